@@ -1,0 +1,170 @@
+// BN254 G1 (y^2 = x^3 + 3) group law on Montgomery-form Fq, Jacobian accumulators.
+//
+// Replaces the halo2curves calls the reference makes at arithmetic.rs:42,56-59,89-92 (double / add /
+// mixed add inside multiexp_serial), msm.rs:78-86 (batch_normalize + best_multiexp) and the point
+// decompression behind transcript/mod.rs:161-162 (`C::from_bytes`).
+#pragma once
+#include "field.cuh"
+
+namespace h2v {
+
+struct G1Affine {
+  Fq x, y;  // Montgomery form; the identity never appears as an affine proof point
+};
+
+struct G1Jac {
+  Fq X, Y, Z;  // Z == 0 <=> identity
+  static H2V_HD G1Jac identity() {
+    G1Jac r;
+    r.X = Fq::one();
+    r.Y = Fq::one();
+    r.Z = Fq::zero();
+    return r;
+  }
+  H2V_HD bool is_identity() const { return Z.is_zero(); }
+  static H2V_HD G1Jac from_affine(const G1Affine& a) {
+    G1Jac r;
+    r.X = a.x;
+    r.Y = a.y;
+    r.Z = Fq::one();
+    return r;
+  }
+};
+
+H2V_HD Fq fq_b3() { return Fq::from_u32(3); }
+
+H2V_HD bool g1_on_curve(const G1Affine& p) {
+  Fq rhs = p.x.sqr() * p.x + fq_b3();
+  return p.y.sqr() == rhs;
+}
+
+// dbl-2009-l (a = 0): 2M + 5S
+H2V_HDN inline G1Jac g1_double(const G1Jac& p) {
+  if (p.is_identity()) return p;
+  Fq A = p.X.sqr();
+  Fq B = p.Y.sqr();
+  Fq C = B.sqr();
+  Fq t = p.X + B;
+  Fq D = (t.sqr() - A - C).dbl();
+  Fq E = A.dbl() + A;
+  Fq F = E.sqr();
+  G1Jac r;
+  r.X = F - D.dbl();
+  Fq C8 = C.dbl().dbl().dbl();
+  r.Y = E * (D - r.X) - C8;
+  r.Z = (p.Y * p.Z).dbl();
+  return r;
+}
+
+// Jacobian += affine (madd-2007-bl style, 7M + 4S) with the exceptional cases handled exactly:
+// equal points -> doubling, opposite points -> identity.  `negate` adds -q.
+H2V_HDN inline G1Jac g1_add_mixed(const G1Jac& p, const G1Affine& q, bool negate = false) {
+  Fq qy = negate ? q.y.neg() : q.y;
+  if (p.is_identity()) {
+    G1Jac r;
+    r.X = q.x;
+    r.Y = qy;
+    r.Z = Fq::one();
+    return r;
+  }
+  Fq Z1Z1 = p.Z.sqr();
+  Fq U2 = q.x * Z1Z1;
+  Fq S2 = qy * p.Z * Z1Z1;
+  Fq H = U2 - p.X;
+  Fq rr = S2 - p.Y;
+  if (H.is_zero()) {
+    if (rr.is_zero()) return g1_double(p);
+    return G1Jac::identity();
+  }
+  Fq HH = H.sqr();
+  Fq HHH = HH * H;
+  Fq V = p.X * HH;
+  G1Jac r;
+  r.X = rr.sqr() - HHH - V.dbl();
+  r.Y = rr * (V - r.X) - p.Y * HHH;
+  r.Z = p.Z * H;
+  return r;
+}
+
+// Jacobian + Jacobian (11M + 5S), exceptional cases handled exactly.
+H2V_HDN inline G1Jac g1_add(const G1Jac& p, const G1Jac& q) {
+  if (p.is_identity()) return q;
+  if (q.is_identity()) return p;
+  Fq Z1Z1 = p.Z.sqr();
+  Fq Z2Z2 = q.Z.sqr();
+  Fq U1 = p.X * Z2Z2;
+  Fq U2 = q.X * Z1Z1;
+  Fq S1 = p.Y * q.Z * Z2Z2;
+  Fq S2 = q.Y * p.Z * Z1Z1;
+  Fq H = U2 - U1;
+  Fq rr = S2 - S1;
+  if (H.is_zero()) {
+    if (rr.is_zero()) return g1_double(p);
+    return G1Jac::identity();
+  }
+  Fq HH = H.sqr();
+  Fq HHH = HH * H;
+  Fq V = U1 * HH;
+  G1Jac r;
+  r.X = rr.sqr() - HHH - V.dbl();
+  r.Y = rr * (V - r.X) - S1 * HHH;
+  r.Z = p.Z * q.Z * H;
+  return r;
+}
+
+H2V_HD G1Jac g1_neg(const G1Jac& p) {
+  G1Jac r = p;
+  r.Y = p.Y.neg();
+  return r;
+}
+
+// Jacobian -> affine; returns false for the identity (x = y = 0 then).
+H2V_HDN inline bool g1_to_affine(const G1Jac& p, G1Affine& out) {
+  if (p.is_identity()) {
+    out.x = Fq::zero();
+    out.y = Fq::zero();
+    return false;
+  }
+  Fq zi = p.Z.inv();
+  Fq zi2 = zi.sqr();
+  out.x = p.X * zi2;
+  out.y = p.Y * zi2 * zi;
+  return true;
+}
+
+// [k]P for a canonical (non-Montgomery) 256-bit scalar, plain left-to-right double-and-add.
+H2V_HDN inline G1Jac g1_mul_canonical(const G1Affine& p, const u32* k) {
+  G1Jac acc = G1Jac::identity();
+  bool started = false;
+  for (int i = 255; i >= 0; i--) {
+    if (started) acc = g1_double(acc);
+    if ((k[i >> 5] >> (i & 31)) & 1) {
+      acc = g1_add_mixed(acc, p);
+      started = true;
+    }
+  }
+  return acc;
+}
+
+// Point decompression, the halo2curves `from_bytes` convention (kept in ONE place):
+// 32 bytes little-endian x; bit 7 of byte 31 = parity of canonical y; bit 6 must be clear.
+// Returns false for every encoding the reference's read_point rejects (invalid encoding, or the
+// identity, which common_point refuses: transcript/mod.rs:161-163,218-219).
+H2V_HDN inline bool g1_decompress(const u8* b, G1Affine& out) {
+  Fq x = Fq::load_le(b);
+  const bool sign = (x.l[7] >> 31) & 1;
+  const bool inf_bit = (x.l[7] >> 30) & 1;
+  x.l[7] &= 0x3FFFFFFFu;
+  if (inf_bit || x.geq_mod()) return false;
+  Fq xm = Fq::from_canonical(x);
+  Fq rhs = xm.sqr() * xm + fq_b3();
+  Fq y = fq_sqrt_candidate(rhs);
+  if (y.sqr() != rhs) return false;  // also rejects the all-zero string: 3 is a non-residue
+  Fq yc = y.to_canonical();
+  if ((bool)(yc.l[0] & 1) != sign) y = y.neg();
+  out.x = xm;
+  out.y = y;
+  return true;
+}
+
+}  // namespace h2v

@@ -1,0 +1,371 @@
+// 256-bit Montgomery field arithmetic for BN254 Fr / Fq, 8 x 32-bit limbs held in registers.
+//
+// The reference has no such code in-tree: it calls into halo2curves (Cargo.toml:15) at
+//   transcript/mod.rs:161-162,171,220-221,228,502   (from_bytes / from_repr / to_repr / from_uniform_bytes)
+//   lib.rs:180,259  vanishing.rs:100  shplonk.rs:215  domain.rs:175-179,202  arithmetic.rs:169  vk.rs:583
+// Everything here is written for sm_100a (CIOS on the IMAD pipe); the same source compiles for the
+// host (plan compiler, host test harness) through the H2V_HD macro.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define H2V_HD __host__ __device__ __forceinline__
+#define H2V_HDN __host__ __device__
+#else
+#define H2V_HD inline
+#define H2V_HDN
+#endif
+
+namespace h2v {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef uint8_t u8;
+
+struct FqP {
+  static H2V_HD constexpr u32 mod(int i) {
+    constexpr u32 v[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return v[i];
+  }
+  static H2V_HD constexpr u32 r1(int i) {
+    constexpr u32 v[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return v[i];
+  }
+  static H2V_HD constexpr u32 r2(int i) {
+    constexpr u32 v[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return v[i];
+  }
+  static H2V_HD constexpr u32 r3(int i) {
+    constexpr u32 v[8] = {0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u, 0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u};
+    return v[i];
+  }
+  static constexpr u32 INV = 0xe4866389u;
+};
+
+struct FrP {
+  static H2V_HD constexpr u32 mod(int i) {
+    constexpr u32 v[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return v[i];
+  }
+  static H2V_HD constexpr u32 r1(int i) {
+    constexpr u32 v[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return v[i];
+  }
+  static H2V_HD constexpr u32 r2(int i) {
+    constexpr u32 v[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return v[i];
+  }
+  static H2V_HD constexpr u32 r3(int i) {
+    constexpr u32 v[8] = {0xb4bf0040u, 0x5e94d8e1u, 0x1cfbb6b8u, 0x2a489cbeu, 0xa19fcfedu, 0x893cc664u, 0x7fcc657cu, 0x0cf8594bu};
+    return v[i];
+  }
+  static constexpr u32 INV = 0xefffffffu;
+};
+
+// -------------------------------------------------------------------------------------------------
+// Device Montgomery multiplication: 8-limb CIOS written against the IMAD pipe with explicit carry
+// chains (mad.lo.cc / madc.hi.cc).  The portable path below is bit-identical and is what the host
+// build uses; tests/test_gpu_field.py cross-checks the two on random and edge inputs.
+// -------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__) && !defined(H2V_NO_PTX)
+#define H2V_PTX 1
+#endif
+
+#ifdef H2V_PTX
+__device__ __forceinline__ u32 ptx_add_cc(u32 a, u32 b) { u32 r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 ptx_addc_cc(u32 a, u32 b) { u32 r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 ptx_addc(u32 a, u32 b) { u32 r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 ptx_sub_cc(u32 a, u32 b) { u32 r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 ptx_subc_cc(u32 a, u32 b) { u32 r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 ptx_subc(u32 a, u32 b) { u32 r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ u32 ptx_mad_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ u32 ptx_madc_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ u32 ptx_mad_hi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ u32 ptx_madc_hi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ u32 ptx_madc_hi(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#endif
+
+template <class P>
+struct Fp {
+  u32 l[8];
+
+  // ---- constants
+  static H2V_HD Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = 0;
+    return r;
+  }
+  static H2V_HD Fp one() {  // Montgomery form of 1
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = P::r1(i);
+    return r;
+  }
+  static H2V_HD Fp r2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = P::r2(i);
+    return r;
+  }
+  static H2V_HD Fp r3() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = P::r3(i);
+    return r;
+  }
+
+  // ---- predicates (on the raw representation)
+  H2V_HD bool is_zero() const {
+    u32 a = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a |= l[i];
+    return a == 0;
+  }
+  H2V_HD bool operator==(const Fp& o) const {
+    u32 a = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a |= l[i] ^ o.l[i];
+    return a == 0;
+  }
+  H2V_HD bool operator!=(const Fp& o) const { return !(*this == o); }
+  // raw >= modulus ?
+  H2V_HD bool geq_mod() const {
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+      if (l[i] > P::mod(i)) return true;
+      if (l[i] < P::mod(i)) return false;
+    }
+    return true;
+  }
+
+  // ---- raw 256-bit helpers
+  static H2V_HD u32 add_raw(u32* r, const u32* a, const u32* b) {  // returns carry
+#ifdef H2V_PTX
+    r[0] = ptx_add_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r[i] = ptx_addc_cc(a[i], b[i]);
+    return ptx_addc(0, 0);
+#else
+    u64 c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      c += (u64)a[i] + b[i];
+      r[i] = (u32)c;
+      c >>= 32;
+    }
+    return (u32)c;
+#endif
+  }
+  static H2V_HD u32 sub_raw(u32* r, const u32* a, const u32* b) {  // returns borrow (1 if a < b)
+#ifdef H2V_PTX
+    r[0] = ptx_sub_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r[i] = ptx_subc_cc(a[i], b[i]);
+    return ptx_subc(0, 0) & 1u;
+#else
+    u64 br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      u64 t = (u64)a[i] - b[i] - br;
+      r[i] = (u32)t;
+      br = (t >> 32) & 1u;
+    }
+    return (u32)br;
+#endif
+  }
+  H2V_HD void cond_sub_mod() {  // if raw >= p: raw -= p
+    u32 m[8], t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = P::mod(i);
+    u32 br = sub_raw(t, l, m);
+    if (!br) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) l[i] = t[i];
+    }
+  }
+
+  // ---- field ops (Montgomery form in, Montgomery form out; inputs < p)
+  friend H2V_HD Fp operator+(const Fp& a, const Fp& b) {
+    Fp r;
+    add_raw(r.l, a.l, b.l);  // p < 2^254: no carry out
+    r.cond_sub_mod();
+    return r;
+  }
+  friend H2V_HD Fp operator-(const Fp& a, const Fp& b) {
+    Fp r;
+    u32 br = sub_raw(r.l, a.l, b.l);
+    if (br) {
+      u32 m[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) m[i] = P::mod(i);
+      add_raw(r.l, r.l, m);
+    }
+    return r;
+  }
+  H2V_HD Fp neg() const { return is_zero() ? *this : (zero() - *this); }
+  H2V_HD Fp dbl() const { return *this + *this; }
+
+  // Montgomery product a*b*2^-256 mod p.  Requires b < p, a < 2^256 (so a*b < 2^256 * p).
+  static H2V_HD Fp mul(const Fp& a, const Fp& b) {
+    Fp r;
+#ifdef H2V_PTX
+    // CIOS, one row per limb of b.  t has 9 live limbs (t8 is the running top word).
+    u32 t[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const u32 bi = b.l[i];
+      // t += a * bi : low halves then high halves, two carry chains
+      t[0] = ptx_mad_lo_cc(a.l[0], bi, t[0]);
+#pragma unroll
+      for (int j = 1; j < 8; j++) t[j] = ptx_madc_lo_cc(a.l[j], bi, t[j]);
+      t[8] = ptx_addc(t[8], 0);
+      t[1] = ptx_mad_hi_cc(a.l[0], bi, t[1]);
+#pragma unroll
+      for (int j = 1; j < 7; j++) t[j + 1] = ptx_madc_hi_cc(a.l[j], bi, t[j + 1]);
+      t[8] = ptx_madc_hi(a.l[7], bi, t[8]);
+      // m = t0 * inv ; t = (t + m * p) >> 32
+      const u32 m = t[0] * P::INV;
+      (void)ptx_mad_lo_cc(m, P::mod(0), t[0]);  // low word becomes 0, keep carry
+#pragma unroll
+      for (int j = 1; j < 8; j++) t[j - 1] = ptx_madc_lo_cc(m, P::mod(j), t[j]);
+      t[7] = ptx_addc_cc(t[8], 0);
+      t[8] = ptx_addc(0, 0);
+      t[0] = ptx_mad_hi_cc(m, P::mod(0), t[0]);
+#pragma unroll
+      for (int j = 1; j < 7; j++) t[j] = ptx_madc_hi_cc(m, P::mod(j), t[j]);
+      t[7] = ptx_madc_hi_cc(m, P::mod(7), t[7]);
+      t[8] = ptx_addc(t[8], 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = t[i];
+#else
+    u32 t[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      u64 c = 0;
+      const u32 bi = b.l[i];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        c += (u64)a.l[j] * bi + t[j];
+        t[j] = (u32)c;
+        c >>= 32;
+      }
+      c += t[8];
+      t[8] = (u32)c;
+      t[9] = (u32)(c >> 32);
+      const u32 m = t[0] * P::INV;
+      c = (u64)m * P::mod(0) + t[0];
+      c >>= 32;
+#pragma unroll
+      for (int j = 1; j < 8; j++) {
+        c += (u64)m * P::mod(j) + t[j];
+        t[j - 1] = (u32)c;
+        c >>= 32;
+      }
+      c += t[8];
+      t[7] = (u32)c;
+      t[8] = t[9] + (u32)(c >> 32);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = t[i];
+#endif
+    r.cond_sub_mod();
+    return r;
+  }
+  friend H2V_HD Fp operator*(const Fp& a, const Fp& b) { return mul(a, b); }
+  H2V_HD Fp sqr() const { return mul(*this, *this); }
+
+  // ---- conversions
+  // canonical integer (little-endian limbs, must be < p) -> Montgomery form
+  static H2V_HD Fp from_canonical(const Fp& c) { return mul(c, r2()); }
+  H2V_HD Fp to_canonical() const {
+    Fp o = zero();
+    o.l[0] = 1;
+    return mul(*this, o);
+  }
+  static H2V_HD Fp from_u32(u32 v) {
+    Fp c = zero();
+    c.l[0] = v;
+    return from_canonical(c);
+  }
+  // 32 little-endian bytes -> raw limbs (no range check, no Montgomery conversion)
+  static H2V_HD Fp load_le(const u8* b) {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      r.l[i] = (u32)b[4 * i] | ((u32)b[4 * i + 1] << 8) | ((u32)b[4 * i + 2] << 16) | ((u32)b[4 * i + 3] << 24);
+    return r;
+  }
+  H2V_HD void store_le(u8* b) const {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      b[4 * i] = (u8)l[i];
+      b[4 * i + 1] = (u8)(l[i] >> 8);
+      b[4 * i + 2] = (u8)(l[i] >> 16);
+      b[4 * i + 3] = (u8)(l[i] >> 24);
+    }
+  }
+  // ff::FromUniformBytes<64>: 512-bit little-endian integer mod p, result in Montgomery form.
+  // lo*R^2*R^-1 + hi*R^3*R^-1 = (lo + hi*2^256)*R  (same decomposition halo2curves uses)
+  static H2V_HD Fp from_uniform(const u8* b64) {
+    Fp lo = load_le(b64), hi = load_le(b64 + 32);
+    return mul(lo, r2()) + mul(hi, r3());
+  }
+
+  // ---- exponentiation by a fixed 256-bit exponent given as 8 limbs (4-bit fixed window)
+  H2V_HDN Fp pow_limbs(const u32* e) const {
+    Fp tab[16];
+    tab[0] = one();
+    tab[1] = *this;
+    for (int i = 2; i < 16; i++) tab[i] = tab[i - 1] * *this;
+    Fp acc = one();
+    bool started = false;
+    for (int w = 63; w >= 0; w--) {
+      u32 d = (e[w >> 3] >> ((w & 7) * 4)) & 0xF;
+      if (started) {
+        acc = acc.sqr();
+        acc = acc.sqr();
+        acc = acc.sqr();
+        acc = acc.sqr();
+      }
+      if (d) {
+        acc = started ? acc * tab[d] : tab[d];
+        started = true;
+      }
+    }
+    return acc;
+  }
+  // small exponent, square-and-multiply (pow_vartime call sites: vk.rs:583, domain.rs:175-179)
+  H2V_HDN Fp pow_u64(u64 e) const {
+    Fp acc = one(), base = *this;
+    while (e) {
+      if (e & 1) acc = acc * base;
+      base = base.sqr();
+      e >>= 1;
+    }
+    return acc;
+  }
+  // inverse by Fermat (a^(p-2)); inv(0) = 0
+  H2V_HDN Fp inv() const {
+    u32 e[8];
+    for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+    e[0] -= 2;  // neither modulus has low limb < 2
+    return pow_limbs(e);
+  }
+};
+
+typedef Fp<FqP> Fq;
+typedef Fp<FrP> Fr;
+
+// Fq square root candidate a^((p+1)/4) (p = 3 mod 4); caller checks candidate^2 == a.
+H2V_HDN inline Fq fq_sqrt_candidate(const Fq& a) {
+  const u32 e[8] = {0xb61f3f52u, 0x4f082305u, 0x5a1c72a3u, 0x65e05aa4u, 0xa0605617u, 0x6e14116du, 0xb84c680au, 0x0c19139cu};
+  return a.pow_limbs(e);
+}
+
+}  // namespace h2v
