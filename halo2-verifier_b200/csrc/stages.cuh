@@ -1,0 +1,435 @@
+// Per-proof stages of the batched verifier, written once as host/device functions and driven by the
+// plan (plan.h).  Kernels in kernels.cu map proofs (or proof points) onto threads; the host build
+// (tests/hostlib) runs the very same code on the CPU for unit tests.
+//
+//   decompress_stage   point decompression behind read_point        transcript/mod.rs:158-166
+//   transcript_stage   Fiat-Shamir replay, challenges               lib.rs:66-253, transcript/mod.rs:205-272,484-515
+//   scalar_stage       instance / Lagrange evals, h(x), multi-open  lib.rs:173-347, domain.rs:187-212, vanishing.rs:92-120,
+//                      reduction to one scalar per MSM base          shplonk.rs:175-267, gwc.rs:54-135
+//
+// Batch layouts (n = proofs in the batch, j = proof index): every per-proof array is "structure of
+// arrays", element (i, j) at [i * n + j], so that consecutive threads touch consecutive 32/64-byte
+// elements.
+#pragma once
+#include "curve.cuh"
+#include "hash.cuh"
+#include "plan.h"
+
+namespace h2v {
+
+static constexpr u32 H2V_NO_BAD_ITEM = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------------------------------------
+// Point slot `slot` of one proof -> affine point.  Returns false when the reference's read_point
+// would fail at this item (truncated proof, invalid encoding, identity).
+H2V_HDN inline bool decompress_stage(const PlanView& pv, const u8* proof, u32 len, u32 slot, G1Affine& out) {
+  const u32 item = pv.sec<u32>(pv.h().off_pt_item)[slot];
+  if ((item + 1) * 32 > len) return false;
+  return g1_decompress(proof + item * 32, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class H>
+struct TranscriptState {
+  H hs;
+  H2V_HDN void init() { hs.init_halo2(); }
+  H2V_HDN void common_scalar_limbs(const u32* canon) {
+    hs.update_byte(2);
+    hs.update_limbs(canon);
+  }
+  H2V_HDN void common_point(const G1Affine& p) {
+    hs.update_byte(1);
+    Fq x = p.x.to_canonical(), y = p.y.to_canonical();
+    hs.update_limbs(x.l);
+    hs.update_limbs(y.l);
+  }
+  H2V_HDN Fr squeeze();
+};
+template <>
+H2V_HDN inline Fr TranscriptState<Blake2b>::squeeze() {
+  hs.update_byte(0);
+  u8 d[64];
+  hs.digest(d);
+  return Fr::from_uniform(d);
+}
+template <>
+H2V_HDN inline Fr TranscriptState<Keccak256>::squeeze() {
+  hs.update_byte(0);
+  u8 d[64];
+  hs.digest_with_suffix(10, d);
+  hs.digest_with_suffix(11, d + 32);
+  return Fr::from_uniform(d);
+}
+
+// Replays the transcript of proof j.  Writes the Montgomery-form proof scalars and challenges into
+// the value table and returns the index of the first item at which the reference would have
+// returned an error (H2V_NO_BAD_ITEM if none), merged with `bad_item` from the decompress stage.
+// `inst_bad` is set when an instance value is not a canonical Fr encoding.
+template <class H>
+H2V_HDN inline u32 transcript_stage(const PlanView& pv, const u8* proof, u32 len, const u8* inst, u32 inst_total,
+                                    const G1Affine* pts, Fr* vals, u32 j, u32 n, u32 bad_item, bool& inst_bad) {
+  const PlanHeader& hd = pv.h();
+  const TranscriptOp* ops = pv.sec<TranscriptOp>(hd.off_tops);
+  TranscriptState<H> ts;
+  ts.init();
+  u32 item = 0, pslot = 0, sslot = 0, cidx = 0;
+  inst_bad = false;
+  for (u32 o = 0; o < hd.n_tops; o++) {
+    const u32 kind = ops[o].kind, count = ops[o].count;
+    if (kind == T_ABS_VK) {
+      Fr c = pv.cst(hd.c_vk_repr).to_canonical();
+      ts.common_scalar_limbs(c.l);
+    } else if (kind == T_ABS_INST) {
+      for (u32 i = 0; i < inst_total; i++) {
+        Fr c = Fr::load_le(inst + 32 * (size_t)i);
+        if (c.geq_mod()) inst_bad = true;
+        ts.common_scalar_limbs(c.l);
+      }
+    } else if (kind == T_POINTS) {
+      for (u32 i = 0; i < count; i++, item++, pslot++) ts.common_point(pts[(size_t)pslot * n + j]);
+    } else if (kind == T_SCALARS) {
+      for (u32 i = 0; i < count; i++, item++, sslot++) {
+        Fr c = Fr::zero();
+        if ((item + 1) * 32 <= len) {
+          c = Fr::load_le(proof + item * 32);
+          if (c.geq_mod()) {
+            if (item < bad_item) bad_item = item;
+            c = Fr::zero();
+          }
+        } else if (item < bad_item) {
+          bad_item = item;
+        }
+        ts.common_scalar_limbs(c.l);
+        vals[(size_t)sslot * n + j] = Fr::from_canonical(c);
+      }
+    } else {  // T_SQUEEZE
+      for (u32 i = 0; i < count; i++, cidx++) vals[(size_t)(hd.v_chal + cidx) * n + j] = ts.squeeze();
+    }
+  }
+  return bad_item;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct ScalarIO {
+  u32 j, n;
+  Fr* vals;     // value table [n_vals][n]
+  Fr* scratch;  // [scratch_rows][n] prefix products of the instance Lagrange denominators
+  Fr* right;    // [n_points][n]   scalar of each proof point in the right MSM
+  Fr* shared;   // [n_shared][n]   scalar of each shared base (fixed | sigma | G)
+  Fr* left;     // [n_mo][n]       scalar of each multi-open point in the left MSM
+  H2V_HD Fr V(u32 idx) const { return vals[(size_t)idx * n + j]; }
+  H2V_HD void setV(u32 idx, const Fr& v) const { vals[(size_t)idx * n + j] = v; }
+};
+
+H2V_HDN inline Fr eval_poly(const PlanView& pv, const ScalarIO& io, u32 pid) {
+  const PlanHeader& hd = pv.h();
+  const PolyRange pr = pv.sec<PolyRange>(hd.off_polys)[pid];
+  const PolyTerm* terms = pv.sec<PolyTerm>(hd.off_terms);
+  const PolyVar* vars = pv.sec<PolyVar>(hd.off_vars);
+  Fr acc = Fr::zero();
+  for (u32 t = pr.term_begin; t < pr.term_end; t++) {
+    Fr prod = pv.cst(terms[t].coeff);
+    for (u32 v = terms[t].var_begin; v < terms[t].var_end; v++) {
+      Fr b = io.V(vars[v].val);
+      const u32 pw = vars[v].pow;
+      prod = prod * (pw == 1 ? b : b.pow_u64(pw));
+    }
+    acc = acc + prod;
+  }
+  return acc;
+}
+
+H2V_HDN inline Fr compress_polys(const PlanView& pv, const ScalarIO& io, u32 begin, u32 end, const Fr& theta) {
+  const u32* list = pv.sec<u32>(pv.h().off_polylist);
+  Fr acc = Fr::zero();
+  for (u32 i = begin; i < end; i++) acc = acc * theta + eval_poly(pv, io, list[i]);
+  return acc;
+}
+
+H2V_HD void acc_scalar(const PlanView& pv, const ScalarIO& io, u32 kind, u32 idx, const Fr& t, const Fr& xn) {
+  const PlanHeader& hd = pv.h();
+  if (kind == CM_PROOF) {
+    Fr* p = &io.right[(size_t)idx * io.n + io.j];
+    *p = *p + t;
+  } else if (kind == CM_FIXED) {
+    Fr* p = &io.shared[(size_t)idx * io.n + io.j];
+    *p = *p + t;
+  } else if (kind == CM_SIGMA) {
+    Fr* p = &io.shared[(size_t)(hd.n_fixed + idx) * io.n + io.j];
+    *p = *p + t;
+  } else {  // CM_HMSM: sum_i xn^i h_i  (vanishing.rs:102-112)
+    Fr s = t;
+    for (u32 i = 0; i < hd.n_h; i++) {
+      Fr* p = &io.right[(size_t)(hd.h_slot + i) * io.n + io.j];
+      *p = *p + s;
+      s = s * xn;
+    }
+  }
+}
+
+// Instance layout of one proof: `inst` points at its first value; column c holds col_len[c] values
+// (equal split of inst_total when col_len == nullptr).
+H2V_HDN inline u32 scalar_stage(const PlanView& pv, const ScalarIO& io, const u8* inst, const u32* col_len, u32 inst_total) {
+  const PlanHeader& hd = pv.h();
+  const u32 n = io.n, j = io.j;
+  const Fr one = Fr::one();
+  for (u32 i = 0; i < hd.n_points; i++) io.right[(size_t)i * n + j] = Fr::zero();
+  for (u32 i = 0; i < hd.n_shared; i++) io.shared[(size_t)i * n + j] = Fr::zero();
+  for (u32 i = 0; i < hd.n_mo; i++) io.left[(size_t)i * n + j] = Fr::zero();
+
+  const Fr x = io.V(hd.v_chal + hd.ch_x);
+  const Fr y = io.V(hd.v_chal + hd.ch_y);
+  const Fr theta = io.V(hd.v_chal + hd.ch_theta);
+  const Fr beta = io.V(hd.v_chal + hd.ch_beta);
+  const Fr gamma = io.V(hd.v_chal + hd.ch_gamma);
+
+  Fr xn = x;  // x^n, n = 2^k  (lib.rs:180,259)
+  for (u32 i = 0; i < hd.k; i++) xn = xn.sqr();
+  const Fr xn_m1 = xn - one;
+  if (xn_m1.is_zero() || x.is_zero()) return ST_WOULD_PANIC;  // vanishing.rs:100
+
+  // u - x*omega^rot for every distinct opening rotation (SHPLONK), z_diff of the first set
+  const u32* rot = pv.sec<u32>(hd.off_rot);
+  Fr um[H2V_MAX_ROT];
+  Fr zdiff0 = one;
+  const RotSet* sets = pv.sec<RotSet>(hd.off_sets);
+  const u32* diffs = pv.sec<u32>(hd.off_diffs);
+  if (hd.multiopen == MO_SHPLONK) {
+    const Fr u = io.V(hd.v_chal + hd.ch_mo2);
+    for (u32 r = 0; r < hd.n_rot; r++) um[r] = u - x * pv.cst(rot[r]);
+    for (u32 d = sets[0].diff_begin; d < sets[0].diff_end; d++) zdiff0 = zdiff0 * um[diffs[d]];
+    if (zdiff0.is_zero()) return ST_WOULD_PANIC;  // shplonk.rs:215
+  }
+
+  // ---- one batched inversion: [x^n-1, x, zdiff0, x-omega^rot (rot=-(bf+1)..0), x-omega^rot (instance range)]
+  // zero denominators of the Lagrange part are skipped and left as zero, like ff::BatchInvert (domain.rs:202)
+  const u32 nl = hd.blinding + 2;
+  Fr pre[3 + H2V_MAX_LEVALS];
+  Fr acc = one;
+  pre[0] = acc; acc = acc * xn_m1;
+  pre[1] = acc; acc = acc * x;
+  pre[2] = acc; acc = acc * zdiff0;
+  for (u32 i = 0; i < nl; i++) {
+    Fr d = x - pv.cst(hd.c_lrot + i);
+    pre[3 + i] = acc;
+    if (!d.is_zero()) acc = acc * d;
+  }
+  // instance range: rotations -max_rot .. max_len + |min_rot| - 1   (lib.rs:199-203)
+  u32 max_len = 0;
+  if (hd.n_inst_cols) {
+    if (col_len) {
+      for (u32 c = 0; c < hd.n_inst_cols; c++) max_len = col_len[c] > max_len ? col_len[c] : max_len;
+    } else {
+      max_len = inst_total / hd.n_inst_cols;
+    }
+  }
+  const u32 li = hd.n_inst_q ? (hd.inst_max_rot + max_len + hd.inst_min_rot_abs) : 0;
+  const Fr omega = pv.cst(hd.c_omega), omega_inv = pv.cst(hd.c_omega_inv);
+  Fr w = omega_inv.pow_u64(hd.inst_max_rot);  // omega^(-max_rot)
+  for (u32 i = 0; i < li; i++) {
+    Fr d = x - w;
+    io.scratch[(size_t)i * n + j] = acc;
+    if (!d.is_zero()) acc = acc * d;
+    w = w * omega;
+  }
+  Fr inv = acc.inv();
+  const Fr common = xn_m1 * pv.cst(hd.c_one_over_n);
+
+  // instance evals (lib.rs:204-217), walking the range backwards
+  Fr ie[H2V_MAX_INST_Q];
+  const InstQuery* iq = pv.sec<InstQuery>(hd.off_instq);
+  for (u32 q = 0; q < hd.n_inst_q; q++) ie[q] = Fr::zero();
+  for (u32 i = li; i-- > 0;) {
+    w = w * omega_inv;  // omega^(i - max_rot)
+    Fr d = x - w;
+    Fr l_i = Fr::zero();
+    if (!d.is_zero()) {
+      l_i = inv * io.scratch[(size_t)i * n + j] * common * w;
+      inv = inv * d;
+    }
+    for (u32 q = 0; q < hd.n_inst_q; q++) {
+      const u32 c = iq[q].column, off = iq[q].offset;
+      u32 cbeg, clen;
+      if (col_len) {
+        cbeg = 0;
+        for (u32 t = 0; t < c; t++) cbeg += col_len[t];
+        clen = col_len[c];
+      } else {
+        clen = max_len;
+        cbeg = c * max_len;
+      }
+      if (i >= off && i - off < clen) {
+        Fr v = Fr::from_canonical(Fr::load_le(inst + 32 * (size_t)(cbeg + (i - off))));
+        ie[q] = ie[q] + v * l_i;
+      }
+    }
+  }
+  for (u32 q = 0; q < hd.n_inst_q; q++) io.setV(hd.v_inst + q, ie[q]);
+
+  // l_last, l_blind, l_0 (lib.rs:261-270)
+  Fr l_last = Fr::zero(), l_blind = Fr::zero(), l_0 = Fr::zero();
+  for (u32 i = nl; i-- > 0;) {
+    const Fr wr = pv.cst(hd.c_lrot + i);
+    Fr d = x - wr;
+    Fr l_i = Fr::zero();
+    if (!d.is_zero()) {
+      l_i = inv * pre[3 + i] * common * wr;
+      inv = inv * d;
+    }
+    if (i == 0) l_last = l_i;
+    else if (i == nl - 1) l_0 = l_i;
+    else l_blind = l_blind + l_i;
+  }
+  const Fr zdiff0_inv = inv * pre[2];
+  inv = inv * zdiff0;
+  const Fr xinv = inv * pre[1];
+  inv = inv * x;
+  const Fr xn_m1_inv = inv;  // pre[0] == 1
+  const Fr active = one - (l_last + l_blind);
+
+  // ---- expected h(x): fold every expression with y (vanishing.rs:99-100)
+  Fr h = Fr::zero();
+  const ExprOp* eops = pv.sec<ExprOp>(hd.off_exprops);
+  const PermCol* pcs = pv.sec<PermCol>(hd.off_permcols);
+  const LookupDesc* lks = pv.sec<LookupDesc>(hd.off_lookups);
+  const Fr delta = pv.cst(hd.c_delta);
+  for (u32 o = 0; o < hd.n_exprops; o++) {
+    const ExprOp& e = eops[o];
+    switch (e.kind) {
+      case E_GATE:
+        h = h * y + eval_poly(pv, io, e.a);
+        break;
+      case E_PERM_FIRST:  // l_0 (1 - z_0)
+        h = h * y + l_0 * (one - io.V(e.a));
+        break;
+      case E_PERM_LAST: {  // l_last (z_l^2 - z_l)
+        Fr z = io.V(e.a);
+        h = h * y + (z.sqr() - z) * l_last;
+        break;
+      }
+      case E_PERM_LINK:  // l_0 (z_i - z_{i-1}(omega^last x))
+        h = h * y + (io.V(e.a) - io.V(e.b)) * l_0;
+        break;
+      case E_PERM_PROD: {  // permutation.rs:239-287
+        Fr left = io.V(e.b);
+        for (u32 c = e.c; c < e.d; c++) left = left * (io.V(pcs[c].col_val) + beta * io.V(pcs[c].sigma_val) + gamma);
+        Fr right = io.V(e.a);
+        Fr cur = beta * x * pv.cst(e.e);
+        for (u32 c = e.c; c < e.d; c++) {
+          right = right * (io.V(pcs[c].col_val) + cur + gamma);
+          cur = cur * delta;
+        }
+        h = h * y + (left - right) * active;
+        break;
+      }
+      case E_LOOKUP: {  // lookup.rs:159-230
+        const LookupDesc& L = lks[e.a];
+        const Fr pe = io.V(L.v_prod), pne = io.V(L.v_prod_next), pie = io.V(L.v_in), piie = io.V(L.v_in_inv), pte = io.V(L.v_tab);
+        Fr lft = pne * (pie + beta) * (pte + gamma);
+        Fr rgt = pe * (compress_polys(pv, io, L.in_begin, L.in_end, theta) + beta) *
+                 (compress_polys(pv, io, L.tab_begin, L.tab_end, theta) + gamma);
+        h = h * y + l_0 * (one - pe);
+        h = h * y + l_last * (pe.sqr() - pe);
+        h = h * y + (lft - rgt) * active;
+        h = h * y + l_0 * (pie - pte);
+        h = h * y + (pie - pte) * (pie - piie) * active;
+        break;
+      }
+      default: {  // E_SHUFFLE, shuffle.rs:148-203
+        const LookupDesc& L = lks[e.a];
+        const Fr pe = io.V(L.v_prod), pne = io.V(L.v_prod_next);
+        Fr lft = pne * (compress_polys(pv, io, L.tab_begin, L.tab_end, theta) + gamma);
+        Fr rgt = pe * (compress_polys(pv, io, L.in_begin, L.in_end, theta) + gamma);
+        h = h * y + l_0 * (one - pe);
+        h = h * y + l_last * (pe.sqr() - pe);
+        h = h * y + (lft - rgt) * active;
+        break;
+      }
+    }
+  }
+  h = h * xn_m1_inv;
+  io.setV(hd.v_expected_h, h);
+
+  // ---- multi-open reduction to one scalar per base
+  const u32 g_idx = hd.n_shared - 1;
+  const u32 mo_slot = hd.n_points - hd.n_mo;
+  if (hd.multiopen == MO_SHPLONK) {
+    const Fr yy = io.V(hd.v_chal + hd.ch_mo0), vv = io.V(hd.v_chal + hd.ch_mo1), u = io.V(hd.v_chal + hd.ch_mo2);
+    const SetPoint* sp = pv.sec<SetPoint>(hd.off_setpts);
+    const SetCommit* sc = pv.sec<SetCommit>(hd.off_setcms);
+    const u32* sev = pv.sec<u32>(hd.off_setevals);
+    Fr r_outer = Fr::zero(), pow_v = one, z_0 = one;
+    for (u32 s = 0; s < hd.n_sets; s++) {
+      const RotSet& S = sets[s];
+      const u32 m = S.pt_end - S.pt_begin;
+      Fr zd = one;
+      if (s == 0) {
+        for (u32 p = S.pt_begin; p < S.pt_end; p++) z_0 = z_0 * um[sp[p].rot_id];
+      } else {
+        for (u32 d = S.diff_begin; d < S.diff_end; d++) zd = zd * um[diffs[d]];
+        zd = zd * zdiff0_inv;
+      }
+      // Lagrange basis of the set's points at u: prod_{t != k} (u - p_t) / prod_{t != k} (p_k - p_t)
+      Fr basis[H2V_MAX_SET_POINTS];
+      Fr xip = one;
+      for (u32 t = 1; t < m; t++) xip = xip * xinv;
+      for (u32 k2 = 0; k2 < m; k2++) {
+        Fr num = pv.cst(sp[S.pt_begin + k2].invden) * xip;
+        for (u32 t = 0; t < m; t++)
+          if (t != k2) num = num * um[sp[S.pt_begin + t].rot_id];
+        basis[k2] = num;
+      }
+      const Fr coef_set = pow_v * zd;
+      Fr pow_y = one;
+      for (u32 c = S.cm_begin; c < S.cm_end; c++) {
+        Fr r_u = Fr::zero();
+        for (u32 k2 = 0; k2 < m; k2++) r_u = r_u + io.V(sev[sc[c].eval_begin + k2]) * basis[k2];
+        const Fr t = pow_y * coef_set;
+        r_outer = r_outer + t * r_u;
+        acc_scalar(pv, io, sc[c].kind, sc[c].idx, t, xn);
+        pow_y = pow_y * yy;
+      }
+      pow_v = pow_v * vv;
+    }
+    io.shared[(size_t)g_idx * n + j] = r_outer.neg();        // (-r_outer) G        shplonk.rs:258
+    io.right[(size_t)mo_slot * n + j] = z_0.neg();           // (-z_0) h1           shplonk.rs:259
+    io.right[(size_t)(mo_slot + 1) * n + j] = u;             // u h2                shplonk.rs:260
+    io.left[(size_t)1 * n + j] = one;                        // left: 1 h2          shplonk.rs:262
+  } else {
+    const Fr vv = io.V(hd.v_chal + hd.ch_mo0), u = io.V(hd.v_chal + hd.ch_mo1);
+    const GwcPoint* gp = pv.sec<GwcPoint>(hd.off_gwcpts);
+    const GwcQuery* gq = pv.sec<GwcQuery>(hd.off_gwcq);
+    Fr pow_u = one, eval_multi = Fr::zero();
+    for (u32 p = 0; p < hd.n_gwc_points; p++) {
+      const Fr z = x * pv.cst(rot[gp[p].rot_id]);
+      Fr pow_v = one, eval_batch = Fr::zero();
+      for (u32 q = gp[p].q_begin; q < gp[p].q_end; q++) {
+        acc_scalar(pv, io, gq[q].kind, gq[q].idx, pow_u * pow_v, xn);
+        eval_batch = eval_batch + pow_v * io.V(gq[q].eval_val);
+        pow_v = pow_v * vv;
+      }
+      eval_multi = eval_multi + pow_u * eval_batch;
+      io.right[(size_t)(mo_slot + p) * n + j] = pow_u * z;  // witness_with_aux   gwc.rs:123
+      io.left[(size_t)p * n + j] = pow_u;                   // witness            gwc.rs:124
+      pow_u = pow_u * u;
+    }
+    io.shared[(size_t)g_idx * n + j] = eval_multi.neg();    // eval_multi * (-G)  gwc.rs:132
+  }
+  return ST_OK;
+}
+
+// RLC coefficient seed expansion: r_i = from_uniform(Blake2b-512(personal "Halo2-Transcript",
+// "h2v-rlc" | seed_le64 | i_le64)); c_j = prod_{i > j} r_i  (strategy.rs:125-136 convention).
+H2V_HDN inline Fr rlc_scalar_from_seed(u64 seed, u64 i) {
+  Blake2b b;
+  b.init_halo2();
+  const char* tag = "h2v-rlc";
+  for (int t = 0; t < 7; t++) b.update_byte((u8)tag[t]);
+  for (int t = 0; t < 8; t++) b.update_byte((u8)(seed >> (8 * t)));
+  for (int t = 0; t < 8; t++) b.update_byte((u8)(i >> (8 * t)));
+  u8 d[64];
+  b.digest(d);
+  return Fr::from_uniform(d);
+}
+
+}  // namespace h2v
