@@ -1,0 +1,333 @@
+"""halo2-verifier_b200: B200-native batch verifier for Halo2 KZG proofs (BN254).
+
+Host-side mirror of the reference's verification surface (ChainSafe/halo2-verifier):
+
+    reference (Rust)                                   here
+    -------------------------------------------------  ------------------------------------------
+    ParamsKZG::{read, from_bytes, read_custom}         ParamsKZG.{read, from_bytes}
+      poly/kzg/commitment.rs:133-232
+    VerifyingKey::{read, from_bytes}                   VerifyingKey.{read, from_bytes}
+      plonk/vk.rs:76-127
+    SerdeFormat  helpers.rs:7-19                       SerdeFormat
+    verify_proof::<Scheme, V, E, T, Strategy>(..)      verify_proof(params, vk, proof, instances,
+      lib.rs:33-46                                                  multiopen=, transcript=)
+    VerifierSHPLONK | VerifierGWC                      multiopen="shplonk" | "gwc"
+    Blake2bRead | Keccak256Read (+Challenge255)        transcript="blake2b" | "keccak256"
+    plonk::Error  plonk/mod.rs:19-32                   Error subclasses
+    (added) verify_proofs_batch                        verify_proofs_batch(..) / BatchVerifier
+
+All arithmetic runs in the CUDA library `libh2v_b200.so` behind the C ABI in include/h2v.h.
+There is NO CPU fallback: importing works anywhere, but creating a verifier without the built
+library or without a CUDA device raises.
+"""
+import ctypes
+import enum
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libh2v_b200.so")
+
+R_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+
+
+class SerdeFormat(enum.IntEnum):
+    Processed = 0
+    RawBytes = 1
+    RawBytesUnchecked = 2
+
+
+class Error(Exception):
+    """plonk::Error (reference plonk/mod.rs:19-32)."""
+
+
+class InvalidInstances(Error):
+    pass
+
+
+class TranscriptError(Error):
+    pass
+
+
+class OpeningError(Error):
+    pass
+
+
+class ConstraintSystemFailure(Error):
+    pass
+
+
+class ReferenceWouldPanic(Error):
+    """Inputs on which the reference unwraps None (vanishing.rs:100, shplonk.rs:215)."""
+
+
+class BackendError(RuntimeError):
+    """Infrastructure failure: library missing, CUDA error, malformed VK / params."""
+
+
+STATUS_ERRORS = {
+    1: InvalidInstances,
+    2: TranscriptError,
+    3: OpeningError,
+    4: ConstraintSystemFailure,
+    5: ReferenceWouldPanic,
+}
+
+_MULTIOPEN = {"shplonk": 0, "gwc": 1}
+_HASH = {"blake2b": 0, "keccak256": 1, "keccak": 1}
+
+_lib = None
+
+
+def load_library():
+    """Loads the CUDA library; fails loudly if it has not been built (see __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BackendError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(LIB_PATH)
+    u8p, u32p, u64p = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
+    lib.h2v_ctx_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
+                                   ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.h2v_ctx_destroy.argtypes = [ctypes.c_void_p]
+    lib.h2v_ctx_destroy.restype = None
+    lib.h2v_last_error.argtypes = [ctypes.c_void_p]
+    lib.h2v_last_error.restype = ctypes.c_char_p
+    lib.h2v_ctx_info.argtypes = [ctypes.c_void_p, u32p]
+    lib.h2v_verify_proof.argtypes = [ctypes.c_void_p, u8p, ctypes.c_size_t, u8p, ctypes.c_size_t, u8p]
+    lib.h2v_verify_batch.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64,
+                                     u8p, u8p, u8p, u8p]
+    lib.h2v_batch_set_columns.argtypes = [ctypes.c_void_p, u32p, u32p]
+    lib.h2v_batch_set_scalar_hook.argtypes = [ctypes.c_void_p, u8p]
+    lib.h2v_accumulate_shard.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64,
+                                         ctypes.c_uint64, ctypes.c_uint64, u8p, u8p]
+    lib.h2v_finalize.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u8p, ctypes.POINTER(ctypes.c_int)]
+    lib.h2v_attribute_shard.argtypes = [ctypes.c_void_p, u8p]
+    lib.h2v_batch_upload.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64]
+    lib.h2v_batch_run.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
+    lib.h2v_batch_download.argtypes = [ctypes.c_void_p, u8p]
+    lib.h2v_last_timings.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.h2v_launch_count.argtypes = [ctypes.c_void_p]
+    lib.h2v_launch_count.restype = ctypes.c_uint64
+    lib.h2v_last_msm_geometry.argtypes = [ctypes.c_void_p, u32p]
+    lib.h2v_selftest_field.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64]
+    lib.h2v_calibrate_imad.argtypes = [ctypes.c_int]
+    lib.h2v_calibrate_imad.restype = ctypes.c_double
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = (
+    "h2v_ctx_create", "h2v_ctx_destroy", "h2v_last_error", "h2v_ctx_info", "h2v_verify_proof", "h2v_verify_batch",
+    "h2v_batch_set_columns", "h2v_batch_set_scalar_hook", "h2v_accumulate_shard", "h2v_finalize", "h2v_attribute_shard",
+    "h2v_batch_upload", "h2v_batch_run", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count",
+    "h2v_last_msm_geometry", "h2v_selftest_field", "h2v_calibrate_imad",
+)
+
+
+@dataclass
+class ParamsKZG:
+    """Verifier-side KZG parameters (reference poly/kzg/commitment.rs:22-29), kept as bytes."""
+
+    data: bytes
+    format: SerdeFormat = SerdeFormat.Processed
+
+    @classmethod
+    def from_bytes(cls, data: bytes, format: SerdeFormat = SerdeFormat.Processed):
+        return cls(bytes(data), SerdeFormat(format))
+
+    @classmethod
+    def read(cls, reader, format: SerdeFormat = SerdeFormat.Processed):
+        size = 4 + (32 + 64 + 64 if format == SerdeFormat.Processed else 64 + 128 + 128)
+        return cls(reader.read(size), SerdeFormat(format))
+
+    @property
+    def k(self):
+        return int.from_bytes(self.data[:4], "little")  # little-endian, commitment.rs:147
+
+
+@dataclass
+class VerifyingKey:
+    """Serialized verifying key (reference plonk/vk.rs:16-26), kept as bytes; parsed by the library."""
+
+    data: bytes
+    format: SerdeFormat = SerdeFormat.RawBytes
+
+    @classmethod
+    def from_bytes(cls, data: bytes, format: SerdeFormat = SerdeFormat.RawBytes):
+        return cls(bytes(data), SerdeFormat(format))
+
+    @classmethod
+    def read(cls, reader, format: SerdeFormat = SerdeFormat.RawBytes):
+        return cls(reader.read(), SerdeFormat(format))
+
+
+def pack_instances(instances) -> (bytes, List[int], Optional[List[int]], Optional[List[int]]):
+    """instances[proof][column][row] of ints (or 32-byte strings) -> (bytes, per-proof scalar counts,
+    per-proof column counts, per-proof per-column lengths)."""
+    out = bytearray()
+    counts, ncols, col_len = [], [], []
+    for proof_inst in instances:
+        c = 0
+        ncols.append(len(proof_inst))
+        for col in proof_inst:
+            col_len.append(len(col))
+            for v in col:
+                out += v if isinstance(v, (bytes, bytearray)) else int(v).to_bytes(32, "little")
+                c += 1
+        counts.append(c)
+    return bytes(out), counts, ncols, col_len
+
+
+@dataclass
+class BatchResult:
+    status: List[int]
+    verdict: bool  # every proof accepted
+    challenges: Optional[bytes] = None
+    accum: Optional[bytes] = None
+    batch_accum: Optional[bytes] = None
+    msm_scalars: Optional[bytes] = None
+
+    def errors(self):
+        return [None if s == 0 else STATUS_ERRORS[s]() for s in self.status]
+
+
+class BatchVerifier:
+    """One (params, vk, multiopen, transcript, device) context: owns the device plan and buffers."""
+
+    def __init__(self, params: ParamsKZG, vk: VerifyingKey, multiopen="shplonk", transcript="blake2b", device=0):
+        self.lib = load_library()
+        self._ctx = ctypes.c_void_p()
+        rc = self.lib.h2v_ctx_create(ctypes.byref(self._ctx), params.data, len(params.data), int(params.format), vk.data,
+                                     len(vk.data), int(vk.format), _MULTIOPEN[multiopen], _HASH[transcript], int(device))
+        if rc != 0:
+            self._ctx = None
+            raise BackendError(self.lib.h2v_last_error(None).decode())
+        info = (ctypes.c_uint32 * 8)()
+        self.lib.h2v_ctx_info(self._ctx, info)
+        (self.k, self.n_points, self.n_scalars, self.n_challenges, self.proof_len, self.n_inst_cols, self.n_shared,
+         self.n_mo) = list(info)
+        self.n_bases = self.n_points + self.n_shared + self.n_mo
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.h2v_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BackendError(self.lib.h2v_last_error(self._ctx).decode())
+
+    @staticmethod
+    def _offsets(sizes):
+        arr = (ctypes.c_uint64 * (len(sizes) + 1))()
+        t = 0
+        for i, s in enumerate(sizes):
+            arr[i] = t
+            t += s
+        arr[len(sizes)] = t
+        return arr
+
+    def _pack(self, proofs, instances):
+        pbytes = b"".join(proofs)
+        poff = self._offsets([len(p) for p in proofs])
+        ibytes, counts, ncols, col_len = pack_instances(instances)
+        ioff = self._offsets(counts)
+        ragged = any(c != self.n_inst_cols for c in ncols) or any(
+            len({len(col) for col in inst}) > 1 for inst in instances
+        )
+        keep = []
+        if ragged:
+            a = (ctypes.c_uint32 * len(ncols))(*ncols)
+            # column lengths are laid out with exactly n_inst_cols entries per proof
+            flat = []
+            for inst in instances:
+                lens = [len(c) for c in inst][: self.n_inst_cols]
+                flat += lens + [0] * (self.n_inst_cols - len(lens))
+            b = (ctypes.c_uint32 * max(1, len(flat)))(*flat)
+            self._check(self.lib.h2v_batch_set_columns(self._ctx, a, b if self.n_inst_cols else None))
+            keep = [a, b]
+        return pbytes, poff, ibytes, ioff, keep
+
+    def verify_batch(self, proofs: Sequence[bytes], instances, rlc_scalars: Optional[Sequence[int]] = None, seed=0,
+                     want_challenges=False, want_accum=False, want_batch_accum=False, want_scalars=False) -> BatchResult:
+        n = len(proofs)
+        assert n == len(instances) and n > 0
+        pbytes, poff, ibytes, ioff, keep = self._pack(proofs, instances)
+        rlc = b"".join(int(r).to_bytes(32, "little") for r in rlc_scalars) if rlc_scalars is not None else None
+        status = (ctypes.c_uint8 * n)()
+        ch = ctypes.create_string_buffer(32 * n * self.n_challenges) if want_challenges else None
+        acc = ctypes.create_string_buffer(128 * n) if want_accum else None
+        bacc = ctypes.create_string_buffer(128) if want_batch_accum else None
+        sc = ctypes.create_string_buffer(32 * n * self.n_bases) if want_scalars else None
+        if sc is not None:
+            self._check(self.lib.h2v_batch_set_scalar_hook(self._ctx, sc))
+        self._check(self.lib.h2v_verify_batch(self._ctx, n, pbytes, poff, ibytes, ioff, rlc, seed, status, ch, acc, bacc))
+        st = list(status)
+        return BatchResult(st, all(s == 0 for s in st), ch.raw if ch else None, acc.raw if acc else None,
+                           bacc.raw if bacc else None, sc.raw if sc else None)
+
+    def accumulate_shard(self, proofs, instances, global_base, global_count, rlc_scalars=None, seed=0):
+        n = len(proofs)
+        pbytes, poff, ibytes, ioff, keep = self._pack(proofs, instances)
+        rlc = b"".join(int(r).to_bytes(32, "little") for r in rlc_scalars) if rlc_scalars is not None else None
+        status = (ctypes.c_uint8 * n)()
+        partial = ctypes.create_string_buffer(128)
+        self._check(self.lib.h2v_accumulate_shard(self._ctx, n, pbytes, poff, ibytes, ioff, rlc, seed, global_base,
+                                                  global_count, status, partial))
+        return list(status), partial.raw
+
+    def finalize(self, partials: Sequence[bytes]):
+        buf = b"".join(partials)
+        bacc = ctypes.create_string_buffer(128)
+        verdict = ctypes.c_int(0)
+        self._check(self.lib.h2v_finalize(self._ctx, len(partials), buf, bacc, ctypes.byref(verdict)))
+        return bool(verdict.value), bacc.raw
+
+    def attribute_shard(self, status):
+        arr = (ctypes.c_uint8 * len(status))(*status)
+        self._check(self.lib.h2v_attribute_shard(self._ctx, arr))
+        return list(arr)
+
+    def timings(self):
+        out = (ctypes.c_float * 8)()
+        self._check(self.lib.h2v_last_timings(self._ctx, out))
+        names = ("total", "decompress", "transcript", "scalar", "rlc_msm", "pairing", "attribution")
+        return dict(zip(names, list(out)))
+
+    def msm_geometry(self):
+        out = (ctypes.c_uint32 * 4)()
+        self.lib.h2v_last_msm_geometry(self._ctx, out)
+        return dict(zip(("window_bits", "windows", "terms", "buckets"), list(out)))
+
+    def launch_count(self):
+        return int(self.lib.h2v_launch_count(self._ctx))
+
+
+def verify_proof(params: ParamsKZG, vk: VerifyingKey, proof: bytes, instances, multiopen="shplonk", transcript="blake2b",
+                 device=0) -> None:
+    """verify_proof with SingleStrategy (reference lib.rs:33-46): returns None or raises a plonk Error.
+    `instances[column][row]`: public inputs of the single circuit instance."""
+    with BatchVerifier(params, vk, multiopen, transcript, device) as bv:
+        res = bv.verify_batch([proof], [instances])
+    if res.status[0] != 0:
+        raise STATUS_ERRORS[res.status[0]]()
+
+
+def verify_proofs_batch(params: ParamsKZG, vk: VerifyingKey, proofs: Sequence[bytes], instances, multiopen="shplonk",
+                        transcript="blake2b", device=0, rlc_scalars=None, seed=0) -> List[Optional[Error]]:
+    """Batch entry point: one folded pairing check for the whole batch (AccumulatorStrategy,
+    strategy.rs:125-140), per-proof attribution when the fold is rejected.  Returns one entry per
+    proof: None (accepted) or the plonk Error the reference's verify_proof would have returned."""
+    with BatchVerifier(params, vk, multiopen, transcript, device) as bv:
+        return bv.verify_batch(proofs, instances, rlc_scalars, seed).errors()

@@ -10,7 +10,7 @@
 
 #if defined(__CUDACC__)
 #define H2V_HD __host__ __device__ __forceinline__
-#define H2V_HDN __host__ __device__
+#define H2V_HDN __host__ __device__ __noinline__
 #else
 #define H2V_HD inline
 #define H2V_HDN
@@ -206,42 +206,9 @@ struct Fp {
   H2V_HD Fp neg() const { return is_zero() ? *this : (zero() - *this); }
   H2V_HD Fp dbl() const { return *this + *this; }
 
-  // Montgomery product a*b*2^-256 mod p.  Requires b < p, a < 2^256 (so a*b < 2^256 * p).
-  static H2V_HD Fp mul(const Fp& a, const Fp& b) {
+  // Portable CIOS (bit-identical reference for the PTX path; the only path of the host build).
+  static H2V_HD Fp mul_portable(const Fp& a, const Fp& b) {
     Fp r;
-#ifdef H2V_PTX
-    // CIOS, one row per limb of b.  t has 9 live limbs (t8 is the running top word).
-    u32 t[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) t[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const u32 bi = b.l[i];
-      // t += a * bi : low halves then high halves, two carry chains
-      t[0] = ptx_mad_lo_cc(a.l[0], bi, t[0]);
-#pragma unroll
-      for (int j = 1; j < 8; j++) t[j] = ptx_madc_lo_cc(a.l[j], bi, t[j]);
-      t[8] = ptx_addc(t[8], 0);
-      t[1] = ptx_mad_hi_cc(a.l[0], bi, t[1]);
-#pragma unroll
-      for (int j = 1; j < 7; j++) t[j + 1] = ptx_madc_hi_cc(a.l[j], bi, t[j + 1]);
-      t[8] = ptx_madc_hi(a.l[7], bi, t[8]);
-      // m = t0 * inv ; t = (t + m * p) >> 32
-      const u32 m = t[0] * P::INV;
-      (void)ptx_mad_lo_cc(m, P::mod(0), t[0]);  // low word becomes 0, keep carry
-#pragma unroll
-      for (int j = 1; j < 8; j++) t[j - 1] = ptx_madc_lo_cc(m, P::mod(j), t[j]);
-      t[7] = ptx_addc_cc(t[8], 0);
-      t[8] = ptx_addc(0, 0);
-      t[0] = ptx_mad_hi_cc(m, P::mod(0), t[0]);
-#pragma unroll
-      for (int j = 1; j < 7; j++) t[j] = ptx_madc_hi_cc(m, P::mod(j), t[j]);
-      t[7] = ptx_madc_hi_cc(m, P::mod(7), t[7]);
-      t[8] = ptx_addc(t[8], 0);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = t[i];
-#else
     u32 t[10];
 #pragma unroll
     for (int i = 0; i < 10; i++) t[i] = 0;
@@ -273,9 +240,50 @@ struct Fp {
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) r.l[i] = t[i];
-#endif
     r.cond_sub_mod();
     return r;
+  }
+
+  // Montgomery product a*b*2^-256 mod p.  Requires b < p, a < 2^256 (so a*b < 2^256 * p).
+  static H2V_HD Fp mul(const Fp& a, const Fp& b) {
+#ifdef H2V_PTX
+    Fp r;
+    // CIOS, one row per limb of b.  t has 9 live limbs (t8 is the running top word).
+    u32 t[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const u32 bi = b.l[i];
+      // t += a * bi : low halves then high halves, two carry chains
+      t[0] = ptx_mad_lo_cc(a.l[0], bi, t[0]);
+#pragma unroll
+      for (int j = 1; j < 8; j++) t[j] = ptx_madc_lo_cc(a.l[j], bi, t[j]);
+      t[8] = ptx_addc(t[8], 0);
+      t[1] = ptx_mad_hi_cc(a.l[0], bi, t[1]);
+#pragma unroll
+      for (int j = 1; j < 7; j++) t[j + 1] = ptx_madc_hi_cc(a.l[j], bi, t[j + 1]);
+      t[8] = ptx_madc_hi(a.l[7], bi, t[8]);
+      // m = t0 * inv ; t = (t + m * p) >> 32
+      const u32 m = t[0] * P::INV;
+      (void)ptx_mad_lo_cc(m, P::mod(0), t[0]);  // low word becomes 0, keep carry
+#pragma unroll
+      for (int j = 1; j < 8; j++) t[j - 1] = ptx_madc_lo_cc(m, P::mod(j), t[j]);
+      t[7] = ptx_addc_cc(t[8], 0);
+      t[8] = ptx_addc(0, 0);
+      t[0] = ptx_mad_hi_cc(m, P::mod(0), t[0]);
+#pragma unroll
+      for (int j = 1; j < 7; j++) t[j] = ptx_madc_hi_cc(m, P::mod(j), t[j]);
+      t[7] = ptx_madc_hi_cc(m, P::mod(7), t[7]);
+      t[8] = ptx_addc(t[8], 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = t[i];
+    r.cond_sub_mod();
+    return r;
+#else
+    return mul_portable(a, b);
+#endif
   }
   friend H2V_HD Fp operator*(const Fp& a, const Fp& b) { return mul(a, b); }
   H2V_HD Fp sqr() const { return mul(*this, *this); }

@@ -1,0 +1,996 @@
+// CUDA kernels (sm_100a) and the C ABI of the batch verifier.  See include/h2v.h for the contract and
+// DESIGN.md for the data layout and per-kernel rooflines.
+//
+// Pipeline of one batch (all on the context's stream, no host round trip until the verdict):
+//   k_init            instance-shape checks                                    lib.rs:51-55
+//   k_decompress      thread per (proof, point): sqrt + curve check            transcript/mod.rs:158-166
+//   k_transcript      thread per proof: Blake2b / Keccak replay -> challenges  lib.rs:66-253
+//   k_scalar          thread per proof: Lagrange, h(x), multi-open scalars     lib.rs:173-347, shplonk.rs / gwc.rs
+//   k_rlc_*           r_i expansion + suffix products c_j                      strategy.rs:125-136
+//   k_shared_reduce   column sums of the shared-base scalars
+//   k_msm_*           one signed-digit Pippenger over every proof's points     arithmetic.rs:7-108, msm.rs:81-86
+//   k_finalize        window combine + 2-pair Miller loop + final exp          msm.rs:185-203
+//   (k_pp_*           per-proof accumulators / pairings: parity hook and rejection attribution)
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "h2v.h"
+#include "plan_build.h"
+#include "stages.cuh"
+#include "tower.cuh"
+
+using namespace h2v;
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_init(PlanView pv, u32 n, const u64* inst_off, const u32* ncols, const u32* col_len, u32* status, u32* bad) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const PlanHeader& hd = pv.h();
+  bad[j] = H2V_NO_BAD_ITEM;
+  const u64 tot = inst_off[j + 1] - inst_off[j];
+  u32 st = ST_OK;
+  if (ncols && ncols[j] != hd.n_inst_cols) {
+    st = ST_INVALID_INSTANCES;
+  } else if (col_len) {
+    u64 s = 0;
+    for (u32 c = 0; c < hd.n_inst_cols; c++) s += col_len[(size_t)j * hd.n_inst_cols + c];
+    if (s != tot) st = ST_INVALID_INSTANCES;
+  } else if (hd.n_inst_cols == 0 ? tot != 0 : (tot % hd.n_inst_cols) != 0) {
+    st = ST_INVALID_INSTANCES;
+  }
+  status[j] = st;
+}
+
+__global__ void __launch_bounds__(128) k_decompress(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, G1Affine* pts, u32* bad) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  const PlanHeader& hd = pv.h();
+  if (t >= n * hd.n_points) return;
+  const u32 j = t % n, slot = t / n;
+  const u64 off = proof_off[j];
+  const u32 len = (u32)(proof_off[j + 1] - off);
+  G1Affine p;
+  if (!decompress_stage(pv, proofs + off, len, slot, p)) {
+    p.x = Fq::zero();
+    p.y = Fq::zero();
+    atomicMin(&bad[j], pv.sec<u32>(hd.off_pt_item)[slot]);
+  }
+  pts[t] = p;
+}
+
+template <class H>
+__global__ void __launch_bounds__(64) k_transcript(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, const u8* inst,
+                                                   const u64* inst_off, const G1Affine* pts, Fr* vals, u32* status, const u32* bad) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  if (status[j] != ST_OK) return;
+  const PlanHeader& hd = pv.h();
+  const u64 off = proof_off[j];
+  bool inst_bad;
+  const u32 b = transcript_stage<H>(pv, proofs + off, (u32)(proof_off[j + 1] - off), inst + 32 * inst_off[j],
+                                    (u32)(inst_off[j + 1] - inst_off[j]), pts, vals, j, n, bad[j], inst_bad);
+  if (inst_bad) status[j] = ST_INVALID_INSTANCES;
+  else if (b != H2V_NO_BAD_ITEM) status[j] = b < hd.first_mo_item ? ST_TRANSCRIPT : ST_OPENING;
+}
+
+__global__ void __launch_bounds__(64) k_scalar(PlanView pv, u32 n, const u8* inst, const u64* inst_off, const u32* col_len, Fr* vals,
+                                               Fr* scratch, Fr* right, Fr* shared, Fr* left, u32* status) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const PlanHeader& hd = pv.h();
+  u32 st = status[j];
+  if (st == ST_OK) {
+    ScalarIO io{j, n, vals, scratch, right, shared, left};
+    st = scalar_stage(pv, io, inst + 32 * inst_off[j], col_len ? col_len + (size_t)j * hd.n_inst_cols : nullptr,
+                      (u32)(inst_off[j + 1] - inst_off[j]));
+    if (st != ST_OK) status[j] = st;
+  }
+  if (st != ST_OK) {  // excluded from the fold
+    for (u32 i = 0; i < hd.n_points; i++) right[(size_t)i * n + j] = Fr::zero();
+    for (u32 i = 0; i < hd.n_shared; i++) shared[(size_t)i * n + j] = Fr::zero();
+    for (u32 i = 0; i < hd.n_mo; i++) left[(size_t)i * n + j] = Fr::zero();
+  }
+}
+
+__global__ void k_rlc_expand(u64 count, u64 seed, const u8* bytes, Fr* r) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  r[i] = bytes ? Fr::from_canonical(Fr::load_le(bytes + 32 * i)) : rlc_scalar_from_seed(seed, i);
+}
+
+// c_j = prod_{i > j} r_i over the GLOBAL batch; one block, chunked suffix scan through shared memory.
+__global__ void __launch_bounds__(1024) k_rlc_scan(const Fr* r, u64 count, u64 base, u32 n, Fr* coef) {
+  __shared__ Fr sh[1024];
+  const u32 t = threadIdx.x;
+  const u64 m = (count + 1023) / 1024;
+  const u64 lo = (u64)t * m < count ? (u64)t * m : count, hi = lo + m < count ? lo + m : count;
+  Fr p = Fr::one();
+  for (u64 i = lo; i < hi; i++) p = p * r[i];
+  sh[t] = p;
+  __syncthreads();
+  for (u32 d = 1; d < 1024; d <<= 1) {  // inclusive suffix products
+    Fr v = sh[t];
+    const bool act = t + d < 1024;
+    Fr o = act ? sh[t + d] : Fr::one();
+    __syncthreads();
+    if (act) sh[t] = v * o;
+    __syncthreads();
+  }
+  Fr run = t + 1 < 1024 ? sh[t + 1] : Fr::one();
+  for (u64 i = hi; i-- > lo;) {
+    if (i >= base && i < base + n) coef[i - base] = run;
+    run = run * r[i];
+  }
+}
+
+// shared_sum[b] = sum_j c_j * shared[b][j]  (canonical form, ready for digit extraction)
+__global__ void __launch_bounds__(256) k_shared_reduce(u32 n, const Fr* shared, const Fr* coef, Fr* shared_sum) {
+  __shared__ Fr sh[256];
+  const u32 b = blockIdx.x, t = threadIdx.x;
+  Fr acc = Fr::zero();
+  for (u32 j = t; j < n; j += 256) acc = acc + shared[(size_t)b * n + j] * coef[j];
+  sh[t] = acc;
+  __syncthreads();
+  for (u32 d = 128; d > 0; d >>= 1) {
+    if (t < d) sh[t] = sh[t] + sh[t + d];
+    __syncthreads();
+  }
+  if (t == 0) shared_sum[b] = sh[0].to_canonical();
+}
+
+struct MsmGeom {
+  u32 c, W, B;        // window bits, windows, buckets per window (2^(c-1))
+  u32 n, P, n_mo, Sh;  // batch shape
+  u32 T;              // terms = n*P + n*n_mo + Sh
+};
+
+__device__ __forceinline__ const G1Affine& msm_point(const MsmGeom& g, u32 t, const G1Affine* pts, const G1Affine* shared_pts) {
+  const u32 nP = g.n * g.P;
+  if (t < nP) return pts[t];
+  const u32 nL = g.n * g.n_mo;
+  if (t < nP + nL) return pts[(size_t)(g.P - g.n_mo) * g.n + (t - nP)];  // (mo_slot + q) * n + j
+  return shared_pts[t - nP - nL];
+}
+
+// signed c-bit digits of every term's scalar (already multiplied by c_j) + bucket histogram
+__global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, const Fr* left, const Fr* coef, const Fr* shared_sum,
+                                                    const G1Affine* shared_pts, int16_t* dig, u32* hist) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.T) return;
+  const u32 nP = g.n * g.P, nL = g.n * g.n_mo;
+  Fr k;
+  u32 ch = 0;
+  if (t < nP) {
+    k = (right[t] * coef[t % g.n]).to_canonical();
+  } else if (t < nP + nL) {
+    k = (left[t - nP] * coef[(t - nP) % g.n]).to_canonical();
+    ch = 1;
+  } else {
+    const G1Affine& sp = shared_pts[t - nP - nL];
+    k = (sp.x.is_zero() && sp.y.is_zero()) ? Fr::zero() : shared_sum[t - nP - nL];  // identity base (all-zero fixed column)
+  }
+  u32 carry = 0;
+  const u32 mask = (1u << g.c) - 1, half = 1u << (g.c - 1);
+  for (u32 w = 0; w < g.W; w++) {
+    const u32 bit = w * g.c;
+    u32 v = 0;
+    if (bit < 256) {
+      const u32 li = bit >> 5, sh = bit & 31;
+      u64 two = k.l[li];
+      if (li + 1 < 8) two |= (u64)k.l[li + 1] << 32;
+      v = (u32)(two >> sh) & mask;
+    }
+    v += carry;
+    int d;
+    if (v > half) {
+      d = (int)v - (int)(1u << g.c);
+      carry = 1;
+    } else {
+      d = (int)v;
+      carry = 0;
+    }
+    dig[(size_t)t * g.W + w] = (int16_t)d;
+    if (d != 0) atomicAdd(&hist[(size_t)(ch * g.W + w) * g.B + (u32)(d < 0 ? -d : d) - 1], 1u);
+  }
+}
+
+// exclusive scan of the histogram (one block); off has nb + 1 entries, cursor is a working copy
+__global__ void __launch_bounds__(1024) k_scan(const u32* hist, u32 nb, u32* off, u32* cursor) {
+  __shared__ u32 sh[1024];
+  const u32 t = threadIdx.x;
+  const u32 m = (nb + 1023) / 1024;
+  const u32 lo = min(nb, t * m), hi = min(nb, lo + m);
+  u32 s = 0;
+  for (u32 i = lo; i < hi; i++) s += hist[i];
+  sh[t] = s;
+  __syncthreads();
+  for (u32 d = 1; d < 1024; d <<= 1) {
+    u32 v = t >= d ? sh[t - d] : 0;
+    __syncthreads();
+    sh[t] += v;
+    __syncthreads();
+  }
+  u32 run = t ? sh[t - 1] : 0;
+  for (u32 i = lo; i < hi; i++) {
+    off[i] = run;
+    cursor[i] = run;
+    run += hist[i];
+  }
+  if (t == 1023) off[nb] = sh[1023];
+}
+
+__global__ void k_msm_scatter(MsmGeom g, const int16_t* dig, u32* cursor, u32* sorted) {
+  const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (u64)g.T * g.W) return;
+  const int d = dig[idx];
+  if (d == 0) return;
+  const u32 t = (u32)(idx / g.W), w = (u32)(idx % g.W);
+  const u32 ch = (t >= g.n * g.P && t < g.n * g.P + g.n * g.n_mo) ? 1 : 0;
+  const u32 b = (ch * g.W + w) * g.B + (u32)(d < 0 ? -d : d) - 1;
+  const u32 pos = atomicAdd(&cursor[b], 1u);
+  sorted[pos] = t | (d < 0 ? 0x80000000u : 0u);
+}
+
+// thread per bucket: sum of its (signed) points, Jacobian += affine
+__global__ void __launch_bounds__(128) k_msm_bucket_sum(MsmGeom g, u32 nb, const u32* off, const u32* sorted, const G1Affine* pts,
+                                                        const G1Affine* shared_pts, G1Jac* buckets) {
+  const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  G1Jac acc = G1Jac::identity();
+  const u32 e0 = off[b], e1 = off[b + 1];
+  for (u32 e = e0; e < e1; e++) {
+    const u32 ent = sorted[e];
+    acc = g1_add_mixed(acc, msm_point(g, ent & 0x7FFFFFFFu, pts, shared_pts), (ent >> 31) != 0);
+  }
+  buckets[b] = acc;
+}
+
+__device__ G1Jac g1_mul_small(const G1Jac& p, u32 k) {
+  G1Jac acc = G1Jac::identity();
+  for (int i = 31; i >= 0; i--) {
+    acc = g1_double(acc);
+    if ((k >> i) & 1) acc = g1_add(acc, p);
+  }
+  return acc;
+}
+
+// block per (channel, window): S_w = sum_{k=1..B} k * bucket_k, chunked running sums + tree reduction
+__global__ void __launch_bounds__(256) k_msm_window_reduce(MsmGeom g, const G1Jac* buckets, G1Jac* window_sums) {
+  __shared__ G1Jac sh[256];
+  const u32 wi = blockIdx.x, t = threadIdx.x;
+  const u32 threads = g.B < 256 ? g.B : 256;
+  const u32 m = g.B / threads;
+  G1Jac total = G1Jac::identity();
+  if (t < threads) {
+    const G1Jac* bk = buckets + (size_t)wi * g.B;
+    G1Jac run = G1Jac::identity(), acc = G1Jac::identity();
+    for (u32 i = (t + 1) * m; i-- > t * m;) {
+      run = g1_add(run, bk[i]);
+      acc = g1_add(acc, run);
+    }
+    total = acc;
+    if (t) total = g1_add(total, g1_mul_small(run, t * m));
+  }
+  sh[t] = total;
+  __syncthreads();
+  for (u32 d = 128; d > 0; d >>= 1) {
+    if (t < d) sh[t] = g1_add(sh[t], sh[t + d]);
+    __syncthreads();
+  }
+  if (t == 0) window_sums[wi] = sh[0];
+}
+
+struct FinalizeArgs {
+  u32 mode;          // 0: combine window sums, 1: add `n_partials` affine partials
+  u32 W, c;          // MSM geometry (mode 0)
+  u32 n_partials;    // mode 1
+  u32 do_pairing;    // 0: only produce the accumulators
+};
+
+__device__ __forceinline__ void store_affine_bytes(const G1Affine& a, bool is_id, u8* out) {
+  if (is_id) {
+    for (int i = 0; i < 64; i++) out[i] = 0;
+    return;
+  }
+  a.x.to_canonical().store_le(out);
+  a.y.to_canonical().store_le(out + 32);
+}
+
+// threads 0,1: one accumulator each (left / right); then thread 0: the pairing check
+__global__ void __launch_bounds__(32) k_finalize(PlanView pv, FinalizeArgs fa, const G1Jac* window_sums, const u8* partials, u8* acc_bytes,
+                                                 u32* verdict) {
+  __shared__ G1Affine aff[2];
+  __shared__ bool skip[2];
+  const u32 t = threadIdx.x;
+  if (t < 2) {
+    // channel order in window_sums / partials: 0 = right, 1 = left; pairing order: pair 0 = left, pair 1 = right
+    G1Jac acc = G1Jac::identity();
+    if (fa.mode == 0) {
+      const G1Jac* ws = window_sums + (size_t)t * fa.W;
+      for (u32 w = fa.W; w-- > 0;) {
+        for (u32 i = 0; i < fa.c; i++) acc = g1_double(acc);
+        acc = g1_add(acc, ws[w]);
+      }
+    } else {
+      for (u32 i = 0; i < fa.n_partials; i++) {
+        const u8* p = partials + (size_t)i * 128 + (t == 0 ? 64 : 0);  // partial = L(64) | R(64)
+        bool z = true;
+        for (int q = 0; q < 64; q++) z = z && p[q] == 0;
+        if (z) continue;
+        G1Affine a;
+        a.x = Fq::from_canonical(Fq::load_le(p));
+        a.y = Fq::from_canonical(Fq::load_le(p + 32));
+        acc = g1_add_mixed(acc, a);
+      }
+    }
+    const u32 pair = t == 0 ? 1 : 0;
+    skip[pair] = !g1_to_affine(acc, aff[pair]);
+    store_affine_bytes(aff[pair], skip[pair], acc_bytes + 64 * pair);  // acc_bytes = L | R
+  }
+  __syncthreads();
+  if (t == 0 && fa.do_pairing) {
+    const PlanHeader& hd = pv.h();
+    const G2Line* lines[2] = {pv.sec<G2Line>(hd.off_lines0), pv.sec<G2Line>(hd.off_lines1)};
+    Fq12 f = miller_loop2(aff, skip, lines);
+    *verdict = final_exponentiation(f).is_one() ? 1u : 0u;
+  }
+}
+
+// ---- per-proof accumulators (parity hook, rejection attribution)
+// thread per (base, proof): unscaled scalar * point, plain double-and-add
+__global__ void __launch_bounds__(128) k_pp_mul(PlanView pv, u32 n, const G1Affine* pts, const Fr* right, const Fr* shared, const Fr* left,
+                                                const u32* status, G1Jac* out) {
+  const PlanHeader& hd = pv.h();
+  const u32 nb = hd.n_points + hd.n_shared + hd.n_mo;
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb * n) return;
+  const u32 j = t % n, b = t / n;
+  G1Jac r = G1Jac::identity();
+  if (status[j] == ST_OK || status[j] == ST_CONSTRAINT_SYSTEM_FAILURE) {
+    Fr k;
+    const G1Affine* p;
+    if (b < hd.n_points) {
+      k = right[(size_t)b * n + j];
+      p = &pts[(size_t)b * n + j];
+    } else if (b < hd.n_points + hd.n_shared) {
+      k = shared[(size_t)(b - hd.n_points) * n + j];
+      p = &pv.sec<G1Affine>(hd.off_shared_pts)[b - hd.n_points];
+    } else {
+      const u32 q = b - hd.n_points - hd.n_shared;
+      k = left[(size_t)q * n + j];
+      p = &pts[(size_t)(hd.n_points - hd.n_mo + q) * n + j];
+    }
+    if (!k.is_zero() && !(p->x.is_zero() && p->y.is_zero())) {
+      k = k.to_canonical();
+      r = g1_mul_canonical(*p, k.l);
+    }
+  }
+  out[t] = r;
+}
+
+// thread per (channel, proof): sum the per-base products; optional affine bytes out
+__global__ void __launch_bounds__(128) k_pp_reduce(PlanView pv, u32 n, const G1Jac* prod, G1Jac* lr, u8* accum_bytes) {
+  const PlanHeader& hd = pv.h();
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * n) return;
+  const u32 j = t % n, ch = t / n;  // ch 0 = left, 1 = right
+  G1Jac acc = G1Jac::identity();
+  const u32 b0 = ch == 0 ? hd.n_points + hd.n_shared : 0;
+  const u32 b1 = ch == 0 ? hd.n_points + hd.n_shared + hd.n_mo : hd.n_points + hd.n_shared;
+  for (u32 b = b0; b < b1; b++) acc = g1_add(acc, prod[(size_t)b * n + j]);
+  lr[(size_t)ch * n + j] = acc;
+  if (accum_bytes) {
+    G1Affine a;
+    const bool id = !g1_to_affine(acc, a);
+    store_affine_bytes(a, id, accum_bytes + (size_t)j * 128 + 64 * ch);
+  }
+}
+
+// thread per proof: DualMSM::check of its own accumulators (SingleStrategy semantics)
+__global__ void __launch_bounds__(64) k_pp_pairing(PlanView pv, u32 n, const G1Jac* lr, u32* status) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  if (status[j] != ST_OK) return;
+  const PlanHeader& hd = pv.h();
+  if (!pairing_check2(lr[j], lr[(size_t)n + j], pv.sec<G2Line>(hd.off_lines0), pv.sec<G2Line>(hd.off_lines1)))
+    status[j] = ST_CONSTRAINT_SYSTEM_FAILURE;
+}
+
+__global__ void k_gather_scalars(PlanView pv, u32 n, const Fr* right, const Fr* shared, const Fr* left, u8* out) {
+  const PlanHeader& hd = pv.h();
+  const u32 nb = hd.n_points + hd.n_shared + hd.n_mo;
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb * n) return;
+  const u32 j = t % n, b = t / n;
+  Fr k = b < hd.n_points ? right[(size_t)b * n + j]
+                         : b < hd.n_points + hd.n_shared ? shared[(size_t)(b - hd.n_points) * n + j]
+                                                         : left[(size_t)(b - hd.n_points - hd.n_shared) * n + j];
+  k.to_canonical().store_le(out + ((size_t)j * nb + b) * 32);
+}
+
+__global__ void k_gather_challenges(PlanView pv, u32 n, const Fr* vals, u8* out) {
+  const PlanHeader& hd = pv.h();
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= hd.n_challenges * n) return;
+  const u32 j = t % n, c = t / n;
+  vals[(size_t)(hd.v_chal + c) * n + j].to_canonical().store_le(out + ((size_t)j * hd.n_challenges + c) * 32);
+}
+
+// ---- self tests / calibration
+template <class F>
+__device__ u32 selftest_one(u64& s, bool edge) {
+  F a, b;
+  for (int i = 0; i < 8; i++) {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    a.l[i] = (u32)(s >> 32);
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    b.l[i] = (u32)(s >> 32);
+  }
+  a.l[7] &= 0x1FFFFFFFu;  // < 2^253 < p
+  b.l[7] &= 0x1FFFFFFFu;
+  if (edge) {
+    const u32 sel = (u32)(s >> 60);
+    if (sel & 1) a = F::zero();
+    if (sel & 2) {
+      b = F::zero() - F::one();  // p - R mod p
+    }
+    if (sel & 4) {
+      for (int i = 0; i < 8; i++) a.l[i] = 0xFFFFFFFFu;  // a may be any 256-bit value
+    }
+  }
+  F x = F::mul(a, b), y = F::mul_portable(a, b);
+  u32 bad = x != y;
+  F s1 = a.geq_mod() ? F::zero() : a;
+  F u = s1 + b, v = u - b;
+  bad += (v != s1);
+  return bad;
+}
+__global__ void k_selftest_field(u32 count, u64 seed, u32* mismatches) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  u64 s = seed + 0x9E3779B97F4A7C15ull * (t + 1);
+  u32 bad = selftest_one<Fq>(s, t % 7 == 0) + selftest_one<Fr>(s, t % 5 == 0);
+  if (bad) atomicAdd(mismatches, bad);
+}
+__global__ void k_imad(u32 iters, u32* out) {
+  u32 a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const u32 m = blockIdx.x * 2654435761u + 12345u, k = threadIdx.x | 1u;
+  for (u32 i = 0; i < iters; i++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      a0 = a0 * m + k; a1 = a1 * m + k; a2 = a2 * m + k; a3 = a3 * m + k;
+      a4 = a4 * m + k; a5 = a5 * m + k; a6 = a6 * m + k; a7 = a7 * m + k;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <class T>
+  T* as() const {
+    return (T*)p;
+  }
+};
+
+struct h2v_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<u8> blob;
+  PlanInfo info{};
+  PlanHeader hd{};
+  std::string err;
+  u64 launches = 0;
+  cudaEvent_t ev[8]{};
+  float timings[8]{};
+  // options for the next batch
+  const u32* opt_ncols = nullptr;
+  const u32* opt_col_len = nullptr;
+  u8* opt_scalar_hook = nullptr;
+  // current batch
+  u32 n = 0;
+  u64 gbase = 0, gcount = 0;
+  bool has_ncols = false, has_col_len = false;
+  u32 scratch_rows = 0;
+  MsmGeom geom{};
+  bool ran = false;
+  // device buffers
+  DevBuf d_plan, d_proofs, d_proof_off, d_inst, d_inst_off, d_ncols, d_col_len, d_pts, d_bad, d_status, d_vals, d_scratch, d_right,
+      d_shared, d_left, d_rlc_bytes, d_r, d_coef, d_shared_sum, d_dig, d_hist, d_off, d_cursor, d_sorted, d_buckets, d_wsums,
+      d_acc_bytes, d_verdict, d_partials, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal;
+  std::vector<u32> h_status;
+  PlanView pv() const { return PlanView{d_plan.as<u8>()}; }
+};
+
+#define CKC(call)                                                                  \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) {                                                       \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+      return -2;                                                                   \
+    }                                                                              \
+  } while (0)
+#define LAUNCH_CHECK()                       \
+  do {                                       \
+    ctx->launches++;                         \
+    CKC(cudaGetLastError());                 \
+  } while (0)
+
+static inline u32 cdiv(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
+
+static MsmGeom choose_geom(u32 n, const PlanHeader& hd) {
+  MsmGeom g{};
+  g.n = n;
+  g.P = hd.n_points;
+  g.n_mo = hd.n_mo;
+  g.Sh = hd.n_shared;
+  g.T = n * hd.n_points + n * hd.n_mo + hd.n_shared;
+  double best = 1e300;
+  for (u32 c = 4; c <= 15; c++) {
+    const u32 W = (255 + c - 1) / c;
+    const double B = (double)(1u << (c - 1));
+    // bucket additions (11 MM each) + bucket reduction (2 full additions of 16 MM per bucket, both channels)
+    const double cost = (double)W * ((double)g.T * 11.0 + 2.0 * B * 2.0 * 16.0);
+    if (cost < best) {
+      best = cost;
+      g.c = c;
+      g.W = W;
+      g.B = 1u << (c - 1);
+    }
+  }
+  const char* force = getenv("H2V_MSM_WINDOW");
+  if (force) {
+    u32 c = (u32)atoi(force);
+    if (c >= 2 && c <= 15) {
+      g.c = c;
+      g.W = (255 + c - 1) / c;
+      g.B = 1u << (c - 1);
+    }
+  }
+  return g;
+}
+
+extern "C" {
+
+const char* h2v_last_error(const h2v_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int h2v_ctx_create(h2v_ctx** out, const uint8_t* params, size_t params_len, int params_format, const uint8_t* vk, size_t vk_len,
+                   int vk_format, int multiopen, int hash, int device) {
+  if (!out || !params || !vk) {
+    g_create_error = "null argument";
+    return -1;
+  }
+  h2v_ctx* ctx = new h2v_ctx();
+  std::string err;
+  if (build_plan(params, params_len, params_format, vk, vk_len, vk_format, multiopen, hash, ctx->blob, ctx->info, err) != 0) {
+    g_create_error = err;
+    delete ctx;
+    return -1;
+  }
+  memcpy(&ctx->hd, ctx->blob.data(), sizeof(PlanHeader));
+  ctx->device = device;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || device < 0 || device >= count) {
+    g_create_error = std::string("no usable CUDA device (this library has no CPU fallback): ") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+    delete ctx;
+    return -2;
+  }
+  auto fail = [&](const char* what, cudaError_t ce) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+    delete ctx;
+    return -2;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  for (auto& ev : ctx->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = ctx->d_plan.ensure(ctx->blob.size())) != cudaSuccess) return fail("cudaMalloc(plan)", e);
+  if ((e = cudaMemcpy(ctx->d_plan.p, ctx->blob.data(), ctx->blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return fail("cudaMemcpy(plan)", e);
+  if ((e = ctx->d_acc_bytes.ensure(128)) != cudaSuccess || (e = ctx->d_verdict.ensure(16)) != cudaSuccess) return fail("cudaMalloc", e);
+  *out = ctx;
+  return 0;
+}
+
+void h2v_ctx_destroy(h2v_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->d_plan, &ctx->d_proofs, &ctx->d_proof_off, &ctx->d_inst, &ctx->d_inst_off, &ctx->d_ncols, &ctx->d_col_len,
+                    &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
+                    &ctx->d_rlc_bytes, &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off,
+                    &ctx->d_cursor, &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict,
+                    &ctx->d_partials, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int h2v_ctx_info(const h2v_ctx* ctx, uint32_t* out8) {
+  if (!ctx || !out8) return -1;
+  out8[0] = ctx->info.k;
+  out8[1] = ctx->info.n_points;
+  out8[2] = ctx->info.n_scalars;
+  out8[3] = ctx->info.n_challenges;
+  out8[4] = ctx->info.proof_len;
+  out8[5] = ctx->info.n_inst_cols;
+  out8[6] = ctx->info.n_shared;
+  out8[7] = ctx->info.n_mo;
+  return 0;
+}
+
+int h2v_batch_set_columns(h2v_ctx* ctx, const uint32_t* inst_ncols, const uint32_t* inst_col_len) {
+  if (!ctx) return -1;
+  ctx->opt_ncols = inst_ncols;
+  ctx->opt_col_len = inst_col_len;
+  return 0;
+}
+int h2v_batch_set_scalar_hook(h2v_ctx* ctx, uint8_t* msm_scalars) {
+  if (!ctx) return -1;
+  ctx->opt_scalar_hook = msm_scalars;
+  return 0;
+}
+
+static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_off, const u8* instances, const u64* inst_off,
+                       const u8* rlc, u64 seed, u64 gbase, u64 gcount) {
+  if (!ctx) return -1;
+  ctx->ran = false;
+  if (n == 0 || !proof_off || !inst_off || (!proofs && proof_off[n]) || gcount < gbase + n) {
+    ctx->err = "bad batch arguments";
+    return -1;
+  }
+  CKC(cudaSetDevice(ctx->device));
+  const PlanHeader& hd = ctx->hd;
+  const size_t pbytes = proof_off[n] - proof_off[0], iscal = inst_off[n] - inst_off[0];
+  if (proof_off[0] != 0 || inst_off[0] != 0 || (iscal && !instances)) {
+    ctx->err = "offset arrays must start at 0";
+    return -1;
+  }
+  // scratch rows for the instance Lagrange range = max column length + rotation margins
+  u32 max_len = 0;
+  if (ctx->opt_col_len) {
+    for (size_t i = 0; i < (size_t)n * hd.n_inst_cols; i++) max_len = std::max(max_len, ctx->opt_col_len[i]);
+  } else if (hd.n_inst_cols) {
+    for (u32 j = 0; j < n; j++) max_len = std::max<u32>(max_len, (u32)((inst_off[j + 1] - inst_off[j]) / hd.n_inst_cols));
+  }
+  ctx->scratch_rows = hd.inst_max_rot + max_len + hd.inst_min_rot_abs + 1;
+  ctx->n = n;
+  ctx->gbase = gbase;
+  ctx->gcount = gcount;
+  ctx->geom = choose_geom(n, hd);
+  const MsmGeom& g = ctx->geom;
+  const u32 nb = 2 * g.W * g.B;
+  CKC(ctx->d_proofs.ensure(pbytes + 64));
+  CKC(ctx->d_proof_off.ensure(8 * (size_t)(n + 1)));
+  CKC(ctx->d_inst.ensure(32 * iscal + 64));
+  CKC(ctx->d_inst_off.ensure(8 * (size_t)(n + 1)));
+  CKC(ctx->d_pts.ensure(sizeof(G1Affine) * (size_t)n * hd.n_points));
+  CKC(ctx->d_bad.ensure(4 * (size_t)n));
+  CKC(ctx->d_status.ensure(4 * (size_t)n));
+  CKC(ctx->d_vals.ensure(32 * (size_t)n * hd.n_vals));
+  CKC(ctx->d_scratch.ensure(32 * (size_t)n * ctx->scratch_rows));
+  CKC(ctx->d_right.ensure(32 * (size_t)n * hd.n_points));
+  CKC(ctx->d_shared.ensure(32 * (size_t)n * hd.n_shared));
+  CKC(ctx->d_left.ensure(32 * (size_t)n * hd.n_mo));
+  CKC(ctx->d_r.ensure(32 * (size_t)gcount));
+  CKC(ctx->d_coef.ensure(32 * (size_t)n));
+  CKC(ctx->d_shared_sum.ensure(32 * (size_t)hd.n_shared));
+  CKC(ctx->d_dig.ensure(2 * (size_t)g.T * g.W));
+  CKC(ctx->d_hist.ensure(4 * (size_t)nb));
+  CKC(ctx->d_off.ensure(4 * (size_t)(nb + 1)));
+  CKC(ctx->d_cursor.ensure(4 * (size_t)nb));
+  CKC(ctx->d_sorted.ensure(4 * (size_t)g.T * g.W));
+  CKC(ctx->d_buckets.ensure(sizeof(G1Jac) * (size_t)nb));
+  CKC(ctx->d_wsums.ensure(sizeof(G1Jac) * (size_t)2 * g.W));
+  cudaStream_t s = ctx->stream;
+  CKC(cudaMemcpyAsync(ctx->d_proofs.p, proofs, pbytes, cudaMemcpyHostToDevice, s));
+  CKC(cudaMemcpyAsync(ctx->d_proof_off.p, proof_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, s));
+  if (iscal) CKC(cudaMemcpyAsync(ctx->d_inst.p, instances, 32 * iscal, cudaMemcpyHostToDevice, s));
+  CKC(cudaMemcpyAsync(ctx->d_inst_off.p, inst_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, s));
+  ctx->has_ncols = ctx->opt_ncols != nullptr;
+  ctx->has_col_len = ctx->opt_col_len != nullptr && hd.n_inst_cols;
+  if (ctx->has_ncols) {
+    CKC(ctx->d_ncols.ensure(4 * (size_t)n));
+    CKC(cudaMemcpyAsync(ctx->d_ncols.p, ctx->opt_ncols, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+  }
+  if (ctx->has_col_len) {
+    CKC(ctx->d_col_len.ensure(4 * (size_t)n * hd.n_inst_cols));
+    CKC(cudaMemcpyAsync(ctx->d_col_len.p, ctx->opt_col_len, 4 * (size_t)n * hd.n_inst_cols, cudaMemcpyHostToDevice, s));
+  }
+  ctx->opt_ncols = nullptr;
+  ctx->opt_col_len = nullptr;
+  if (rlc) {
+    CKC(ctx->d_rlc_bytes.ensure(32 * (size_t)gcount));
+    CKC(cudaMemcpyAsync(ctx->d_rlc_bytes.p, rlc, 32 * (size_t)gcount, cudaMemcpyHostToDevice, s));
+  }
+  k_rlc_expand<<<cdiv(gcount, 128), 128, 0, s>>>(gcount, seed, rlc ? ctx->d_rlc_bytes.as<u8>() : nullptr, ctx->d_r.as<Fr>());
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// every kernel of the batch; do_pairing = 0 leaves the accumulators in d_acc_bytes without a verdict
+static int run_impl(h2v_ctx* ctx, int do_pairing) {
+  if (!ctx || ctx->n == 0) return -1;
+  CKC(cudaSetDevice(ctx->device));
+  const PlanHeader& hd = ctx->hd;
+  const u32 n = ctx->n;
+  cudaStream_t s = ctx->stream;
+  PlanView pv = ctx->pv();
+  const MsmGeom& g = ctx->geom;
+  const u32 nb = 2 * g.W * g.B;
+  CKC(cudaEventRecord(ctx->ev[0], s));
+  k_init<<<cdiv(n, 128), 128, 0, s>>>(pv, n, ctx->d_inst_off.as<u64>(), ctx->has_ncols ? ctx->d_ncols.as<u32>() : nullptr,
+                                      ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
+  LAUNCH_CHECK();
+  k_decompress<<<cdiv((u64)n * hd.n_points, 128), 128, 0, s>>>(pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(),
+                                                                ctx->d_pts.as<G1Affine>(), ctx->d_bad.as<u32>());
+  LAUNCH_CHECK();
+  CKC(cudaEventRecord(ctx->ev[1], s));
+  if (hd.hash == HASH_BLAKE2B)
+    k_transcript<Blake2b><<<cdiv(n, 64), 64, 0, s>>>(pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
+                                                     ctx->d_inst_off.as<u64>(), ctx->d_pts.as<G1Affine>(), ctx->d_vals.as<Fr>(),
+                                                     ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
+  else
+    k_transcript<Keccak256><<<cdiv(n, 64), 64, 0, s>>>(pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
+                                                       ctx->d_inst_off.as<u64>(), ctx->d_pts.as<G1Affine>(), ctx->d_vals.as<Fr>(),
+                                                       ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
+  LAUNCH_CHECK();
+  CKC(cudaEventRecord(ctx->ev[2], s));
+  k_scalar<<<cdiv(n, 64), 64, 0, s>>>(pv, n, ctx->d_inst.as<u8>(), ctx->d_inst_off.as<u64>(),
+                                      ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_vals.as<Fr>(), ctx->d_scratch.as<Fr>(),
+                                      ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_status.as<u32>());
+  LAUNCH_CHECK();
+  CKC(cudaEventRecord(ctx->ev[3], s));
+  k_rlc_scan<<<1, 1024, 0, s>>>(ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, n, ctx->d_coef.as<Fr>());
+  LAUNCH_CHECK();
+  k_shared_reduce<<<hd.n_shared, 256, 0, s>>>(n, ctx->d_shared.as<Fr>(), ctx->d_coef.as<Fr>(), ctx->d_shared_sum.as<Fr>());
+  LAUNCH_CHECK();
+  CKC(cudaMemsetAsync(ctx->d_hist.p, 0, 4 * (size_t)nb, s));
+  k_msm_digits<<<cdiv(g.T, 128), 128, 0, s>>>(g, ctx->d_right.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_coef.as<Fr>(),
+                                              ctx->d_shared_sum.as<Fr>(), pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_dig.as<int16_t>(),
+                                              ctx->d_hist.as<u32>());
+  LAUNCH_CHECK();
+  k_scan<<<1, 1024, 0, s>>>(ctx->d_hist.as<u32>(), nb, ctx->d_off.as<u32>(), ctx->d_cursor.as<u32>());
+  LAUNCH_CHECK();
+  k_msm_scatter<<<cdiv((u64)g.T * g.W, 256), 256, 0, s>>>(g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
+  LAUNCH_CHECK();
+  k_msm_bucket_sum<<<cdiv(nb, 128), 128, 0, s>>>(g, nb, ctx->d_off.as<u32>(), ctx->d_sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
+                                                 pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_buckets.as<G1Jac>());
+  LAUNCH_CHECK();
+  k_msm_window_reduce<<<2 * g.W, 256, 0, s>>>(g, ctx->d_buckets.as<G1Jac>(), ctx->d_wsums.as<G1Jac>());
+  LAUNCH_CHECK();
+  CKC(cudaEventRecord(ctx->ev[4], s));
+  FinalizeArgs fa{0, g.W, g.c, 0, (u32)do_pairing};
+  k_finalize<<<1, 32, 0, s>>>(pv, fa, ctx->d_wsums.as<G1Jac>(), nullptr, ctx->d_acc_bytes.as<u8>(), ctx->d_verdict.as<u32>());
+  LAUNCH_CHECK();
+  CKC(cudaEventRecord(ctx->ev[5], s));
+  CKC(cudaEventRecord(ctx->ev[6], s));
+  ctx->ran = true;
+  return 0;
+}
+
+static int per_proof_impl(h2v_ctx* ctx, bool pairing, u8* accum_host) {
+  CKC(cudaSetDevice(ctx->device));
+  const PlanHeader& hd = ctx->hd;
+  const u32 n = ctx->n;
+  cudaStream_t s = ctx->stream;
+  PlanView pv = ctx->pv();
+  const u32 nbases = hd.n_points + hd.n_shared + hd.n_mo;
+  CKC(ctx->d_pp_prod.ensure(sizeof(G1Jac) * (size_t)n * nbases));
+  CKC(ctx->d_pp_lr.ensure(sizeof(G1Jac) * (size_t)2 * n));
+  if (accum_host) CKC(ctx->d_pp_bytes.ensure(128 * (size_t)n));
+  k_pp_mul<<<cdiv((u64)n * nbases, 128), 128, 0, s>>>(pv, n, ctx->d_pts.as<G1Affine>(), ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(),
+                                                       ctx->d_left.as<Fr>(), ctx->d_status.as<u32>(), ctx->d_pp_prod.as<G1Jac>());
+  LAUNCH_CHECK();
+  k_pp_reduce<<<cdiv(2 * (u64)n, 128), 128, 0, s>>>(pv, n, ctx->d_pp_prod.as<G1Jac>(), ctx->d_pp_lr.as<G1Jac>(),
+                                                    accum_host ? ctx->d_pp_bytes.as<u8>() : nullptr);
+  LAUNCH_CHECK();
+  if (pairing) {
+    k_pp_pairing<<<cdiv(n, 64), 64, 0, s>>>(pv, n, ctx->d_pp_lr.as<G1Jac>(), ctx->d_status.as<u32>());
+    LAUNCH_CHECK();
+  }
+  if (accum_host) CKC(cudaMemcpyAsync(accum_host, ctx->d_pp_bytes.p, 128 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CKC(cudaEventRecord(ctx->ev[6], s));
+  return 0;
+}
+
+static int download_status(h2v_ctx* ctx, u8* status) {
+  ctx->h_status.resize(ctx->n);
+  CKC(cudaMemcpyAsync(ctx->h_status.data(), ctx->d_status.p, 4 * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  if (status)
+    for (u32 j = 0; j < ctx->n; j++) status[j] = (u8)ctx->h_status[j];
+  return 0;
+}
+
+static int hooks_impl(h2v_ctx* ctx, u8* challenges) {
+  const PlanHeader& hd = ctx->hd;
+  const u32 n = ctx->n;
+  cudaStream_t s = ctx->stream;
+  if (challenges) {
+    CKC(ctx->d_chal.ensure(32 * (size_t)n * hd.n_challenges));
+    k_gather_challenges<<<cdiv((u64)n * hd.n_challenges, 128), 128, 0, s>>>(ctx->pv(), n, ctx->d_vals.as<Fr>(), ctx->d_chal.as<u8>());
+    LAUNCH_CHECK();
+    CKC(cudaMemcpyAsync(challenges, ctx->d_chal.p, 32 * (size_t)n * hd.n_challenges, cudaMemcpyDeviceToHost, s));
+  }
+  if (ctx->opt_scalar_hook) {
+    const u32 nbases = hd.n_points + hd.n_shared + hd.n_mo;
+    CKC(ctx->d_hook.ensure(32 * (size_t)n * nbases));
+    k_gather_scalars<<<cdiv((u64)n * nbases, 128), 128, 0, s>>>(ctx->pv(), n, ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(),
+                                                                 ctx->d_left.as<Fr>(), ctx->d_hook.as<u8>());
+    LAUNCH_CHECK();
+    CKC(cudaMemcpyAsync(ctx->opt_scalar_hook, ctx->d_hook.p, 32 * (size_t)n * nbases, cudaMemcpyDeviceToHost, s));
+    ctx->opt_scalar_hook = nullptr;
+  }
+  return 0;
+}
+
+int h2v_verify_batch(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off, const uint8_t* instances,
+                     const uint64_t* inst_off, const uint8_t* rlc_scalars, uint64_t seed, uint8_t* status, uint8_t* challenges,
+                     uint8_t* accum, uint8_t* batch_accum) {
+  int rc;
+  if ((rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, 0, n)) != 0) return rc;
+  if ((rc = run_impl(ctx, 1)) != 0) return rc;
+  if ((rc = hooks_impl(ctx, challenges)) != 0) return rc;
+  u32 verdict = 0;
+  CKC(cudaMemcpyAsync(&verdict, ctx->d_verdict.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (batch_accum) CKC(cudaMemcpyAsync(batch_accum, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  if (!verdict || accum) {  // per-proof accumulators: parity hook, or attribution of a rejected batch
+    if ((rc = per_proof_impl(ctx, !verdict, accum)) != 0) return rc;
+  }
+  return download_status(ctx, status);
+}
+
+int h2v_verify_proof(h2v_ctx* ctx, const uint8_t* proof, size_t proof_len, const uint8_t* instances, size_t n_inst, uint8_t* status) {
+  const u64 poff[2] = {0, proof_len}, ioff[2] = {0, n_inst};
+  return h2v_verify_batch(ctx, 1, proof, poff, instances, ioff, nullptr, 0, status, nullptr, nullptr, nullptr);
+}
+
+int h2v_accumulate_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off, const uint8_t* instances,
+                         const uint64_t* inst_off, const uint8_t* rlc_scalars, uint64_t seed, uint64_t global_base,
+                         uint64_t global_count, uint8_t* status, uint8_t* partial) {
+  int rc;
+  if ((rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, global_base, global_count)) != 0) return rc;
+  if ((rc = run_impl(ctx, 0)) != 0) return rc;
+  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
+  return download_status(ctx, status);
+}
+
+int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uint8_t* batch_accum, int* verdict) {
+  if (!ctx || !partials || !n_partials) return -1;
+  CKC(cudaSetDevice(ctx->device));
+  CKC(ctx->d_partials.ensure(128 * (size_t)n_partials));
+  CKC(cudaMemcpyAsync(ctx->d_partials.p, partials, 128 * (size_t)n_partials, cudaMemcpyHostToDevice, ctx->stream));
+  FinalizeArgs fa{1, 0, 0, n_partials, 1};
+  k_finalize<<<1, 32, 0, ctx->stream>>>(ctx->pv(), fa, nullptr, ctx->d_partials.as<u8>(), ctx->d_acc_bytes.as<u8>(), ctx->d_verdict.as<u32>());
+  LAUNCH_CHECK();
+  u32 v = 0;
+  CKC(cudaMemcpyAsync(&v, ctx->d_verdict.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (batch_accum) CKC(cudaMemcpyAsync(batch_accum, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  if (verdict) *verdict = (int)v;
+  return 0;
+}
+
+int h2v_attribute_shard(h2v_ctx* ctx, uint8_t* status) {
+  if (!ctx || !ctx->ran) return -1;
+  int rc;
+  if ((rc = per_proof_impl(ctx, true, nullptr)) != 0) return rc;
+  return download_status(ctx, status);
+}
+
+int h2v_batch_upload(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off, const uint8_t* instances,
+                     const uint64_t* inst_off, const uint8_t* rlc_scalars, uint64_t seed) {
+  int rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, 0, n);
+  if (rc) return rc;
+  CKC(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int h2v_batch_run(h2v_ctx* ctx, int* verdict) {
+  int rc = run_impl(ctx, 1);
+  if (rc) return rc;
+  u32 v = 0;
+  CKC(cudaMemcpyAsync(&v, ctx->d_verdict.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  if (verdict) *verdict = (int)v;
+  return 0;
+}
+
+int h2v_batch_download(h2v_ctx* ctx, uint8_t* status) {
+  if (!ctx || !ctx->ran) return -1;
+  return download_status(ctx, status);
+}
+
+int h2v_last_timings(const h2v_ctx* cctx, float* out8) {
+  h2v_ctx* ctx = (h2v_ctx*)cctx;
+  if (!ctx || !ctx->ran || !out8) return -1;
+  CKC(cudaSetDevice(ctx->device));
+  CKC(cudaEventSynchronize(ctx->ev[6]));
+  for (int i = 0; i < 8; i++) out8[i] = 0;
+  CKC(cudaEventElapsedTime(&out8[0], ctx->ev[0], ctx->ev[6]));
+  for (int i = 1; i <= 6; i++) CKC(cudaEventElapsedTime(&out8[i], ctx->ev[i - 1], ctx->ev[i]));
+  return 0;
+}
+
+uint64_t h2v_launch_count(const h2v_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int h2v_last_msm_geometry(const h2v_ctx* ctx, uint32_t* out4) {
+  if (!ctx || !out4) return -1;
+  out4[0] = ctx->geom.c;
+  out4[1] = ctx->geom.W;
+  out4[2] = ctx->geom.T;
+  out4[3] = 2 * ctx->geom.W * ctx->geom.B;
+  return 0;
+}
+
+int h2v_selftest_field(int device, uint32_t count, uint64_t seed) {
+  if (cudaSetDevice(device) != cudaSuccess) return -2;
+  u32* d = nullptr;
+  if (cudaMalloc(&d, 4) != cudaSuccess) return -2;
+  cudaMemset(d, 0, 4);
+  k_selftest_field<<<cdiv(count, 128), 128>>>(count, seed, d);
+  u32 h = 0;
+  cudaError_t e = cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) return -2;
+  return (int)h;
+}
+
+double h2v_calibrate_imad(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+  const u32 blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  u32* d = nullptr;
+  if (cudaMalloc(&d, 4 * (size_t)blocks * threads) != cudaSuccess) return -1.0;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  k_imad<<<blocks, threads>>>(64, d);  // warm-up
+  double best = 0;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(a);
+    k_imad<<<blocks, threads>>>(iters, d);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    const double ops = (double)blocks * threads * iters * 64.0;
+    if (ms > 0) best = std::max(best, ops / (ms * 1e-3));
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  return cudaGetLastError() == cudaSuccess ? best : -1.0;
+}
+
+}  // extern "C"

@@ -27,12 +27,12 @@ struct Fq2 {
   H2V_HD Fq2 neg() const { return {c0.neg(), c1.neg()}; }
   H2V_HD Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
   H2V_HD Fq2 conj() const { return {c0, c1.neg()}; }
-  friend H2V_HD Fq2 operator*(const Fq2& a, const Fq2& b) {  // Karatsuba, 3 MM
+  friend H2V_HDN Fq2 operator*(const Fq2& a, const Fq2& b) {  // Karatsuba, 3 MM
     Fq t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;
     Fq t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
     return {t0 - t1, t2 - t0 - t1};
   }
-  H2V_HD Fq2 sqr() const {  // 2 MM
+  H2V_HDN Fq2 sqr() const {  // 2 MM
     Fq t = c0 * c1;
     return {(c0 + c1) * (c0 - c1), t.dbl()};
   }

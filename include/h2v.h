@@ -1,0 +1,129 @@
+/* C ABI of the B200 batch verifier for Halo2 KZG proofs (BN254; SHPLONK / GWC; Blake2b / Keccak).
+ *
+ * The reference (ChainSafe/halo2-verifier) has no FFI: its boundary is the Rust API.  Each entry
+ * point below names the reference interface it stands behind; a `cuda`-feature Rust shim (see
+ * INTEGRATION.md) binds exactly these symbols.
+ *
+ * Conventions: every buffer is caller-owned host memory (pinned preferred); the library copies what
+ * it keeps.  Return value: 0 ok, <0 infrastructure failure (CUDA error, malformed VK/params, bad
+ * argument) with text in h2v_last_error(); per-proof verdicts only through `status`.  A context is
+ * single-owner (one in-flight batch); distinct contexts / devices may be driven from distinct host
+ * threads.  There is no CPU fallback: without a CUDA device h2v_ctx_create fails.
+ */
+#ifndef H2V_H
+#define H2V_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* SerdeFormat (reference helpers.rs:7-19) */
+#define H2V_FORMAT_PROCESSED 0
+#define H2V_FORMAT_RAW_BYTES 1
+#define H2V_FORMAT_RAW_BYTES_UNCHECKED 2
+/* generic parameter V of verify_proof (reference lib.rs:36): VerifierSHPLONK / VerifierGWC */
+#define H2V_MULTIOPEN_SHPLONK 0
+#define H2V_MULTIOPEN_GWC 1
+/* generic parameter T of verify_proof (lib.rs:38): Blake2bRead / Keccak256Read (+ Challenge255) */
+#define H2V_HASH_BLAKE2B 0
+#define H2V_HASH_KECCAK256 1
+
+/* per-proof status: plonk::Error classes (reference plonk/mod.rs:19-32) */
+#define H2V_OK 0
+#define H2V_INVALID_INSTANCES 1          /* lib.rs:51-55 */
+#define H2V_TRANSCRIPT 2                 /* Error::Transcript: any read before the multi-open part fails */
+#define H2V_OPENING 3                    /* Error::Opening: lib.rs:420-424 (h1/h2 or W_i unreadable) */
+#define H2V_CONSTRAINT_SYSTEM_FAILURE 4  /* strategy.rs:164-176: pairing check fails */
+#define H2V_WOULD_PANIC 5                /* reference unwraps None: vanishing.rs:100, shplonk.rs:215 */
+
+typedef struct h2v_ctx h2v_ctx;
+
+/* ParamsKZG::read_custom (poly/kzg/commitment.rs:155-207) + VerifyingKey::read (plonk/vk.rs:76-115)
+ * + EvaluationDomain::new (poly/domain.rs:34-140) + G2Prepared::from (poly/kzg/msm.rs:186-187):
+ * parses both byte strings, compiles the device plan, uploads it to `device`. */
+int h2v_ctx_create(h2v_ctx** out, const uint8_t* params, size_t params_len, int params_format,
+                   const uint8_t* vk, size_t vk_len, int vk_format, int multiopen, int hash, int device);
+void h2v_ctx_destroy(h2v_ctx* ctx);
+/* error text of the last failing call on this context (ctx == NULL: of the last failed h2v_ctx_create) */
+const char* h2v_last_error(const h2v_ctx* ctx);
+/* out[8] = k, points per proof, scalars per proof, challenges per proof, proof length in bytes,
+ * instance columns, shared MSM bases (fixed | sigma | G), multi-open points */
+int h2v_ctx_info(const h2v_ctx* ctx, uint32_t* out8);
+
+/* verify_proof with SingleStrategy (lib.rs:33-46, strategy.rs:164-176) for one proof.
+ * instances: n_inst 32-byte little-endian canonical Fr values, columns concatenated. */
+int h2v_verify_proof(h2v_ctx* ctx, const uint8_t* proof, size_t proof_len, const uint8_t* instances,
+                     size_t n_inst, uint8_t* status);
+
+/* verify_proofs_batch: AccumulatorStrategy::process per proof + finalize (strategy.rs:125-140), and on
+ * a failed batch the per-proof re-check the reference prescribes (poly/strategy.rs:26-30).
+ *   proofs / proof_off    concatenated proof bytes, n+1 byte offsets
+ *   instances / inst_off  concatenated 32-byte LE canonical Fr, n+1 offsets in units of scalars;
+ *                         per proof: columns concatenated, equal length (see h2v_batch_set_columns)
+ *   rlc_scalars           n x 32 B canonical r_i, or NULL to expand them from `seed`; proof j is folded
+ *                         with c_j = prod_{i>j} r_i, the reference's convention
+ *   status                n bytes out
+ *   challenges            optional out, n x C x 32 B canonical, squeeze order            (parity hook)
+ *   accum                 optional out, n x 2 x 64 B per-proof affine (L_j, R_j), x|y LE canonical,
+ *                         all-zero = identity                                            (parity hook)
+ *   batch_accum           optional out, 2 x 64 B folded (L, R) */
+int h2v_verify_batch(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off,
+                     const uint8_t* instances, const uint64_t* inst_off, const uint8_t* rlc_scalars,
+                     uint64_t seed, uint8_t* status, uint8_t* challenges, uint8_t* accum,
+                     uint8_t* batch_accum);
+
+/* Optional ragged instance layout for the NEXT batch call: inst_ncols[n] = columns supplied per proof
+ * (a mismatch with the VK gives H2V_INVALID_INSTANCES, lib.rs:51-55) and inst_col_len[n * columns]
+ * = length of each column.  Either may be NULL (equal split).  Cleared after one batch. */
+int h2v_batch_set_columns(h2v_ctx* ctx, const uint32_t* inst_ncols, const uint32_t* inst_col_len);
+
+/* Optional extra parity hook for the NEXT batch call: per-proof MSM scalars before RLC folding,
+ * n x (points + shared + multi-open) x 32 B canonical: right-channel scalar of every proof point,
+ * then of every shared base, then left-channel scalar of every multi-open point. */
+int h2v_batch_set_scalar_hook(h2v_ctx* ctx, uint8_t* msm_scalars);
+
+/* ---- sharded batches (one context per GPU) -------------------------------------
+ * h2v_accumulate_shard processes proofs [global_base, global_base + n) of a global batch of
+ * global_count proofs with GLOBALLY defined coefficients c_j (rlc_scalars, if given, has
+ * global_count entries) and returns this shard's partial accumulators, 2 x 64 B affine (L_g, R_g),
+ * without running a pairing.  Proof statuses are final except that H2V_OK means "accumulated". */
+int h2v_accumulate_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off,
+                         const uint8_t* instances, const uint64_t* inst_off, const uint8_t* rlc_scalars,
+                         uint64_t seed, uint64_t global_base, uint64_t global_count, uint8_t* status,
+                         uint8_t* partial);
+/* Adds n_partials partial accumulators (gathered over NCCL) and runs the single pairing check
+ * DualMSM::check (msm.rs:185-203).  verdict: 1 accept, 0 reject.  batch_accum optional 2 x 64 B. */
+int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uint8_t* batch_accum,
+                 int* verdict);
+/* After a rejected h2v_finalize: per-proof pairing checks on the shard last processed by this
+ * context; proofs that fail get H2V_CONSTRAINT_SYSTEM_FAILURE in status (n bytes, in/out). */
+int h2v_attribute_shard(h2v_ctx* ctx, uint8_t* status);
+
+/* ---- staged execution for measurement (bench.py): upload, run (device-resident), download ---- */
+int h2v_batch_upload(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off,
+                     const uint8_t* instances, const uint64_t* inst_off, const uint8_t* rlc_scalars,
+                     uint64_t seed);
+/* runs every kernel of the batch on data already resident in HBM; verdict of the batch pairing out */
+int h2v_batch_run(h2v_ctx* ctx, int* verdict);
+int h2v_batch_download(h2v_ctx* ctx, uint8_t* status);
+/* CUDA-event timings (ms) of the last run, on the context's stream:
+ * out[0] total, [1] decompress, [2] transcript, [3] scalar stage, [4] rlc + msm, [5] pairing, [6] attribution */
+int h2v_last_timings(const h2v_ctx* ctx, float* out8);
+/* number of kernel launches issued by this context so far */
+uint64_t h2v_launch_count(const h2v_ctx* ctx);
+/* MSM geometry of the last run: out[0] window bits, [1] windows, [2] terms, [3] buckets */
+int h2v_last_msm_geometry(const h2v_ctx* ctx, uint32_t* out4);
+
+/* ---- device self tests (used by tests/ only) ---------------------------------------------------
+ * Runs the PTX field multiplication against the portable one on `count` pseudo-random and edge
+ * operands for both fields; returns the number of mismatches (0 = pass), <0 on CUDA error. */
+int h2v_selftest_field(int device, uint32_t count, uint64_t seed);
+/* integer multiply-add peak calibration: returns achieved 32-bit IMAD operations per second */
+double h2v_calibrate_imad(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
