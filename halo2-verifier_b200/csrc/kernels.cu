@@ -145,9 +145,15 @@ __global__ void __launch_bounds__(256) k_shared_reduce(u32 n, const Fr* shared, 
 }
 
 struct MsmGeom {
-  u32 c, W, B;        // window bits, windows, buckets per window (2^(c-1))
   u32 n, P, n_mo, Sh;  // batch shape
-  u32 T;              // terms = n*P + n*n_mo + Sh
+  u32 T;               // terms = n*P (right) + n*n_mo (left) + Sh (right, shared bases)
+  // per channel (0 = right, 1 = left): window bits, windows, buckets per window (2^(c-1)),
+  // first global window index, first global bucket index
+  u32 c[2], W[2], B[2], wbase[2], bbase[2];
+  u32 Wmax;  // row stride of the digit table
+  u32 m;     // buckets per reduction chunk
+  __host__ __device__ u32 nb() const { return W[0] * B[0] + W[1] * B[1]; }
+  __host__ __device__ u32 channel_of_term(u32 t) const { return (t >= n * P && t < n * P + n * n_mo) ? 1u : 0u; }
 };
 
 __device__ __forceinline__ const G1Affine& msm_point(const MsmGeom& g, u32 t, const G1Affine* pts, const G1Affine* shared_pts) {
@@ -176,9 +182,9 @@ __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, 
     k = (sp.x.is_zero() && sp.y.is_zero()) ? Fr::zero() : shared_sum[t - nP - nL];  // identity base (all-zero fixed column)
   }
   u32 carry = 0;
-  const u32 mask = (1u << g.c) - 1, half = 1u << (g.c - 1);
-  for (u32 w = 0; w < g.W; w++) {
-    const u32 bit = w * g.c;
+  const u32 c = g.c[ch], mask = (1u << c) - 1, half = 1u << (c - 1);
+  for (u32 w = 0; w < g.W[ch]; w++) {
+    const u32 bit = w * c;
     u32 v = 0;
     if (bit < 256) {
       const u32 li = bit >> 5, sh = bit & 31;
@@ -189,14 +195,14 @@ __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, 
     v += carry;
     int d;
     if (v > half) {
-      d = (int)v - (int)(1u << g.c);
+      d = (int)v - (int)(1u << c);
       carry = 1;
     } else {
       d = (int)v;
       carry = 0;
     }
-    dig[(size_t)t * g.W + w] = (int16_t)d;
-    if (d != 0) atomicAdd(&hist[(size_t)(ch * g.W + w) * g.B + (u32)(d < 0 ? -d : d) - 1], 1u);
+    dig[(size_t)t * g.Wmax + w] = (int16_t)d;
+    if (d != 0) atomicAdd(&hist[g.bbase[ch] + w * g.B[ch] + (u32)(d < 0 ? -d : d) - 1], 1u);
   }
 }
 
@@ -227,12 +233,13 @@ __global__ void __launch_bounds__(1024) k_scan(const u32* hist, u32 nb, u32* off
 
 __global__ void k_msm_scatter(MsmGeom g, const int16_t* dig, u32* cursor, u32* sorted) {
   const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (u64)g.T * g.W) return;
+  if (idx >= (u64)g.T * g.Wmax) return;
+  const u32 t = (u32)(idx / g.Wmax), w = (u32)(idx % g.Wmax);
+  const u32 ch = g.channel_of_term(t);
+  if (w >= g.W[ch]) return;
   const int d = dig[idx];
   if (d == 0) return;
-  const u32 t = (u32)(idx / g.W), w = (u32)(idx % g.W);
-  const u32 ch = (t >= g.n * g.P && t < g.n * g.P + g.n * g.n_mo) ? 1 : 0;
-  const u32 b = (ch * g.W + w) * g.B + (u32)(d < 0 ? -d : d) - 1;
+  const u32 b = g.bbase[ch] + w * g.B[ch] + (u32)(d < 0 ? -d : d) - 1;
   const u32 pos = atomicAdd(&cursor[b], 1u);
   sorted[pos] = t | (d < 0 ? 0x80000000u : 0u);
 }
@@ -253,30 +260,39 @@ __global__ void __launch_bounds__(128) k_msm_bucket_sum(MsmGeom g, u32 nb, const
 
 __device__ G1Jac g1_mul_small(const G1Jac& p, u32 k) {
   G1Jac acc = G1Jac::identity();
-  for (int i = 31; i >= 0; i--) {
+  if (k == 0) return acc;
+  for (int i = 31 - __clz(k); i >= 0; i--) {
     acc = g1_double(acc);
     if ((k >> i) & 1) acc = g1_add(acc, p);
   }
   return acc;
 }
 
-// block per (channel, window): S_w = sum_{k=1..B} k * bucket_k, chunked running sums + tree reduction
-__global__ void __launch_bounds__(256) k_msm_window_reduce(MsmGeom g, const G1Jac* buckets, G1Jac* window_sums) {
+// S_w = sum_{k=1..B} k * bucket_k, in two steps.  Step A, thread per chunk of m buckets: running-sum
+// trick inside the chunk plus (offset * chunk sum).  Step B, block per window: tree reduction.
+__global__ void __launch_bounds__(128) k_msm_chunk_reduce(MsmGeom g, u32 n_chunks, const G1Jac* buckets, G1Jac* partials) {
+  const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_chunks) return;
+  const u32 b0 = q * g.m;
+  const u32 ch = b0 >= g.bbase[1] ? 1u : 0u;
+  const u32 i0 = (b0 - g.bbase[ch]) % g.B[ch];  // index of the chunk's first bucket inside its window
+  G1Jac run = G1Jac::identity(), acc = G1Jac::identity();
+  for (u32 i = g.m; i-- > 0;) {
+    run = g1_add(run, buckets[b0 + i]);
+    acc = g1_add(acc, run);
+  }
+  if (i0) acc = g1_add(acc, g1_mul_small(run, i0));
+  partials[q] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_msm_window_reduce(MsmGeom g, const G1Jac* partials, G1Jac* window_sums) {
   __shared__ G1Jac sh[256];
   const u32 wi = blockIdx.x, t = threadIdx.x;
-  const u32 threads = g.B < 256 ? g.B : 256;
-  const u32 m = g.B / threads;
+  const u32 ch = wi >= g.wbase[1] ? 1u : 0u;
+  const u32 per = g.B[ch] / g.m;  // partials of this window
+  const G1Jac* p = partials + (g.bbase[ch] + (wi - g.wbase[ch]) * g.B[ch]) / g.m;
   G1Jac total = G1Jac::identity();
-  if (t < threads) {
-    const G1Jac* bk = buckets + (size_t)wi * g.B;
-    G1Jac run = G1Jac::identity(), acc = G1Jac::identity();
-    for (u32 i = (t + 1) * m; i-- > t * m;) {
-      run = g1_add(run, bk[i]);
-      acc = g1_add(acc, run);
-    }
-    total = acc;
-    if (t) total = g1_add(total, g1_mul_small(run, t * m));
-  }
+  for (u32 i = t; i < per; i += 256) total = g1_add(total, p[i]);
   sh[t] = total;
   __syncthreads();
   for (u32 d = 128; d > 0; d >>= 1) {
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(256) k_msm_window_reduce(MsmGeom g, const G1Ja
 
 struct FinalizeArgs {
   u32 mode;          // 0: combine window sums, 1: add `n_partials` affine partials
-  u32 W, c;          // MSM geometry (mode 0)
+  u32 W[2], c[2], wbase[2];  // MSM geometry per channel (mode 0)
   u32 n_partials;    // mode 1
   u32 do_pairing;    // 0: only produce the accumulators
 };
@@ -312,9 +328,9 @@ __global__ void __launch_bounds__(32) k_finalize(PlanView pv, FinalizeArgs fa, c
     // channel order in window_sums / partials: 0 = right, 1 = left; pairing order: pair 0 = left, pair 1 = right
     G1Jac acc = G1Jac::identity();
     if (fa.mode == 0) {
-      const G1Jac* ws = window_sums + (size_t)t * fa.W;
-      for (u32 w = fa.W; w-- > 0;) {
-        for (u32 i = 0; i < fa.c; i++) acc = g1_double(acc);
+      const G1Jac* ws = window_sums + fa.wbase[t];
+      for (u32 w = fa.W[t]; w-- > 0;) {
+        for (u32 i = 0; i < fa.c[t]; i++) acc = g1_double(acc);
         acc = g1_add(acc, ws[w]);
       }
     } else {
@@ -519,7 +535,7 @@ struct h2v_ctx {
   // device buffers
   DevBuf d_plan, d_proofs, d_proof_off, d_inst, d_inst_off, d_ncols, d_col_len, d_pts, d_bad, d_status, d_vals, d_scratch, d_right,
       d_shared, d_left, d_rlc_bytes, d_r, d_coef, d_shared_sum, d_dig, d_hist, d_off, d_cursor, d_sorted, d_buckets, d_wsums,
-      d_acc_bytes, d_verdict, d_partials, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal;
+      d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal;
   std::vector<u32> h_status;
   PlanView pv() const { return PlanView{d_plan.as<u8>()}; }
 };
@@ -540,6 +556,27 @@ struct h2v_ctx {
 
 static inline u32 cdiv(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
 
+// Window size per channel.  Model: throughput term (bucket additions 11 MM, bucket reduction 2 x 16 MM
+// per bucket) at ~20 G MM/s plus the serial chain of the fullest bucket at ~0.5 us per MM.  Scalars
+// are uniform below r ~ 0.756 * 2^254, so the top window only has `top` significant bits and its
+// buckets are 2^(c - top) times fuller than average; window sizes with a nearly full top window win.
+static void choose_window(u32 terms, u32& c_out, u32& W_out) {
+  double best = 1e300;
+  for (u32 c = 4; c <= 15; c++) {
+    const u32 W = (255 + c - 1) / c;
+    const double B = (double)(1u << (c - 1));
+    const u32 top = 254 - (W - 1) * c;  // significant bits of the top window (1..c)
+    const double top_buckets = top >= c ? B : 0.756 * (double)(1u << top);
+    const double chain = std::max((double)terms / B, (double)terms * 0.756 / std::max(1.0, top_buckets));
+    const double t = ((double)W * (double)terms * 11.0 + (double)W * B * 32.0) / 20e9 + chain * 11.0 * 0.5e-6;
+    if (t < best) {
+      best = t;
+      c_out = c;
+      W_out = W;
+    }
+  }
+}
+
 static MsmGeom choose_geom(u32 n, const PlanHeader& hd) {
   MsmGeom g{};
   g.n = n;
@@ -547,28 +584,24 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd) {
   g.n_mo = hd.n_mo;
   g.Sh = hd.n_shared;
   g.T = n * hd.n_points + n * hd.n_mo + hd.n_shared;
-  double best = 1e300;
-  for (u32 c = 4; c <= 15; c++) {
-    const u32 W = (255 + c - 1) / c;
-    const double B = (double)(1u << (c - 1));
-    // bucket additions (11 MM each) + bucket reduction (2 full additions of 16 MM per bucket, both channels)
-    const double cost = (double)W * ((double)g.T * 11.0 + 2.0 * B * 2.0 * 16.0);
-    if (cost < best) {
-      best = cost;
-      g.c = c;
-      g.W = W;
-      g.B = 1u << (c - 1);
+  choose_window(n * hd.n_points + hd.n_shared, g.c[0], g.W[0]);
+  choose_window(n * hd.n_mo, g.c[1], g.W[1]);
+  const char* f0 = getenv("H2V_MSM_WINDOW_RIGHT");
+  const char* f1 = getenv("H2V_MSM_WINDOW_LEFT");
+  for (int ch = 0; ch < 2; ch++) {
+    const char* f = ch == 0 ? f0 : f1;
+    if (f && atoi(f) >= 4 && atoi(f) <= 15) {
+      g.c[ch] = (u32)atoi(f);
+      g.W[ch] = (255 + g.c[ch] - 1) / g.c[ch];
     }
+    g.B[ch] = 1u << (g.c[ch] - 1);
   }
-  const char* force = getenv("H2V_MSM_WINDOW");
-  if (force) {
-    u32 c = (u32)atoi(force);
-    if (c >= 2 && c <= 15) {
-      g.c = c;
-      g.W = (255 + c - 1) / c;
-      g.B = 1u << (c - 1);
-    }
-  }
+  g.wbase[0] = 0;
+  g.wbase[1] = g.W[0];
+  g.bbase[0] = 0;
+  g.bbase[1] = g.W[0] * g.B[0];
+  g.Wmax = std::max(g.W[0], g.W[1]);
+  g.m = 8;  // every B is a power of two >= 8
   return g;
 }
 
@@ -624,7 +657,7 @@ void h2v_ctx_destroy(h2v_ctx* ctx) {
                     &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
                     &ctx->d_rlc_bytes, &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off,
                     &ctx->d_cursor, &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict,
-                    &ctx->d_partials, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal};
+                    &ctx->d_partials, &ctx->d_partials_msm, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : ctx->ev)
@@ -686,7 +719,7 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   ctx->gcount = gcount;
   ctx->geom = choose_geom(n, hd);
   const MsmGeom& g = ctx->geom;
-  const u32 nb = 2 * g.W * g.B;
+  const u32 nb = g.nb();
   CKC(ctx->d_proofs.ensure(pbytes + 64));
   CKC(ctx->d_proof_off.ensure(8 * (size_t)(n + 1)));
   CKC(ctx->d_inst.ensure(32 * iscal + 64));
@@ -702,13 +735,14 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   CKC(ctx->d_r.ensure(32 * (size_t)gcount));
   CKC(ctx->d_coef.ensure(32 * (size_t)n));
   CKC(ctx->d_shared_sum.ensure(32 * (size_t)hd.n_shared));
-  CKC(ctx->d_dig.ensure(2 * (size_t)g.T * g.W));
+  CKC(ctx->d_dig.ensure(2 * (size_t)g.T * g.Wmax));
   CKC(ctx->d_hist.ensure(4 * (size_t)nb));
   CKC(ctx->d_off.ensure(4 * (size_t)(nb + 1)));
   CKC(ctx->d_cursor.ensure(4 * (size_t)nb));
-  CKC(ctx->d_sorted.ensure(4 * (size_t)g.T * g.W));
+  CKC(ctx->d_sorted.ensure(4 * (size_t)g.T * g.Wmax));
   CKC(ctx->d_buckets.ensure(sizeof(G1Jac) * (size_t)nb));
-  CKC(ctx->d_wsums.ensure(sizeof(G1Jac) * (size_t)2 * g.W));
+  CKC(ctx->d_wsums.ensure(sizeof(G1Jac) * (size_t)(g.W[0] + g.W[1])));
+  CKC(ctx->d_partials_msm.ensure(sizeof(G1Jac) * (size_t)(nb / g.m)));
   cudaStream_t s = ctx->stream;
   CKC(cudaMemcpyAsync(ctx->d_proofs.p, proofs, pbytes, cudaMemcpyHostToDevice, s));
   CKC(cudaMemcpyAsync(ctx->d_proof_off.p, proof_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, s));
@@ -744,7 +778,7 @@ static int run_impl(h2v_ctx* ctx, int do_pairing) {
   cudaStream_t s = ctx->stream;
   PlanView pv = ctx->pv();
   const MsmGeom& g = ctx->geom;
-  const u32 nb = 2 * g.W * g.B;
+  const u32 nb = g.nb();
   CKC(cudaEventRecord(ctx->ev[0], s));
   k_init<<<cdiv(n, 128), 128, 0, s>>>(pv, n, ctx->d_inst_off.as<u64>(), ctx->has_ncols ? ctx->d_ncols.as<u32>() : nullptr,
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
@@ -779,15 +813,17 @@ static int run_impl(h2v_ctx* ctx, int do_pairing) {
   LAUNCH_CHECK();
   k_scan<<<1, 1024, 0, s>>>(ctx->d_hist.as<u32>(), nb, ctx->d_off.as<u32>(), ctx->d_cursor.as<u32>());
   LAUNCH_CHECK();
-  k_msm_scatter<<<cdiv((u64)g.T * g.W, 256), 256, 0, s>>>(g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
+  k_msm_scatter<<<cdiv((u64)g.T * g.Wmax, 256), 256, 0, s>>>(g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
   LAUNCH_CHECK();
   k_msm_bucket_sum<<<cdiv(nb, 128), 128, 0, s>>>(g, nb, ctx->d_off.as<u32>(), ctx->d_sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
                                                  pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_buckets.as<G1Jac>());
   LAUNCH_CHECK();
-  k_msm_window_reduce<<<2 * g.W, 256, 0, s>>>(g, ctx->d_buckets.as<G1Jac>(), ctx->d_wsums.as<G1Jac>());
+  k_msm_chunk_reduce<<<cdiv(nb / g.m, 128), 128, 0, s>>>(g, nb / g.m, ctx->d_buckets.as<G1Jac>(), ctx->d_partials_msm.as<G1Jac>());
+  LAUNCH_CHECK();
+  k_msm_window_reduce<<<g.W[0] + g.W[1], 256, 0, s>>>(g, ctx->d_partials_msm.as<G1Jac>(), ctx->d_wsums.as<G1Jac>());
   LAUNCH_CHECK();
   CKC(cudaEventRecord(ctx->ev[4], s));
-  FinalizeArgs fa{0, g.W, g.c, 0, (u32)do_pairing};
+  FinalizeArgs fa{0, {g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {g.wbase[0], g.wbase[1]}, 0, (u32)do_pairing};
   k_finalize<<<1, 32, 0, s>>>(pv, fa, ctx->d_wsums.as<G1Jac>(), nullptr, ctx->d_acc_bytes.as<u8>(), ctx->d_verdict.as<u32>());
   LAUNCH_CHECK();
   CKC(cudaEventRecord(ctx->ev[5], s));
@@ -889,7 +925,7 @@ int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uin
   CKC(cudaSetDevice(ctx->device));
   CKC(ctx->d_partials.ensure(128 * (size_t)n_partials));
   CKC(cudaMemcpyAsync(ctx->d_partials.p, partials, 128 * (size_t)n_partials, cudaMemcpyHostToDevice, ctx->stream));
-  FinalizeArgs fa{1, 0, 0, n_partials, 1};
+  FinalizeArgs fa{1, {0, 0}, {0, 0}, {0, 0}, n_partials, 1};
   k_finalize<<<1, 32, 0, ctx->stream>>>(ctx->pv(), fa, nullptr, ctx->d_partials.as<u8>(), ctx->d_acc_bytes.as<u8>(), ctx->d_verdict.as<u32>());
   LAUNCH_CHECK();
   u32 v = 0;
@@ -945,10 +981,10 @@ uint64_t h2v_launch_count(const h2v_ctx* ctx) { return ctx ? ctx->launches : 0; 
 
 int h2v_last_msm_geometry(const h2v_ctx* ctx, uint32_t* out4) {
   if (!ctx || !out4) return -1;
-  out4[0] = ctx->geom.c;
-  out4[1] = ctx->geom.W;
+  out4[0] = ctx->geom.c[0] | (ctx->geom.c[1] << 16);
+  out4[1] = ctx->geom.W[0] | (ctx->geom.W[1] << 16);
   out4[2] = ctx->geom.T;
-  out4[3] = 2 * ctx->geom.W * ctx->geom.B;
+  out4[3] = ctx->geom.nb();
   return 0;
 }
 

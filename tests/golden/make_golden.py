@@ -1,0 +1,45 @@
+"""Generates the committed golden vectors tests/golden/*.json from the Python oracle (oracle/).
+Each file: params / vk bytes, a few proofs (valid and corrupted) with their public inputs, and the
+oracle's outputs: status, transcript challenges, per-base MSM scalars, per-proof accumulators
+(L_j, R_j), RLC scalars and the folded (L, R).  Run:  python tests/golden/make_golden.py"""
+import json, os, random, sys
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle")); sys.path.insert(0, os.path.join(HERE, ".."))
+import bn254 as bn, formats as F, prover_sim as sim, verifier as orc
+from workloads import setup, enc_point, oracle_scalars
+
+CASES = [  # name, shape, k, multiopen, hash, vk format
+    ("vm_k8_shplonk_blake2b", "vm", 8, "shplonk", "blake2b", F.RAW_BYTES),
+    ("vm_k8_gwc_keccak", "vm", 8, "gwc", "keccak", F.PROCESSED),
+    ("sh_k8_shplonk_keccak", "sh", 8, "shplonk", "keccak", F.RAW_BYTES),
+    ("mix_k6_shplonk_blake2b", "mix", 6, "shplonk", "blake2b", F.PROCESSED),
+    ("mix_k6_gwc_blake2b", "mix", 6, "gwc", "blake2b", F.RAW_BYTES),
+]
+for name, shape, k, mo, hk, vkfmt in CASES:
+    params, vk, dl, s = setup(shape, k)
+    rng = random.Random("golden-" + name)
+    n = 4
+    instances = [sim.random_instances(vk, rng, 5 + j) for j in range(n)]
+    proofs = [sim.simulate_proof(params, vk, dl, s, inst, rng, mo, hk) for inst in instances]
+    proofs[1], _ = sim.corrupt(proofs[1], vk, "eval_flip", rng, mo)
+    proofs[3], _ = sim.corrupt(proofs[3], vk, "scalar_ge_r", rng, mo)
+    rs = [rng.randrange(1, bn.R) for _ in range(n)]
+    results = [orc.verify_proof(params, vk, inst, p, mo, hk) for inst, p in zip(instances, proofs)]
+    items, first_mo = sim.proof_layout(vk, mo)
+    n_points = items.count("P"); n_mo = len(items) - first_mo
+    L, Rr, ok = orc.accumulate(params, results, rs)
+    out = {
+        "shape": shape, "k": k, "multiopen": mo, "hash": hk, "vk_format": vkfmt,
+        "params": params.to_bytes().hex(), "vk": vk.to_bytes(vkfmt).hex(),
+        "rlc_scalars": [hex(r) for r in rs], "folded": (enc_point(L) + enc_point(Rr)).hex(), "folded_ok": ok,
+        "proofs": [],
+    }
+    for inst, p, res in zip(instances, proofs, results):
+        e = {"proof": p.hex(), "instances": [[hex(v) for v in col] for col in inst[0]], "status": res.status,
+             "challenges": [hex(c) for c in res.challenges]}
+        if res.left is not None:
+            e["accum"] = (enc_point(res.L) + enc_point(res.R)).hex()
+            e["msm_scalars"] = [hex(v) for v in oracle_scalars(vk, res, n_points, n_mo)]
+        out["proofs"].append(e)
+    json.dump(out, open(os.path.join(HERE, name + ".json"), "w"), indent=0)
+    print(name, [r.status for r in results], "folded_ok", ok)
