@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -23,6 +24,7 @@
 #include "plan_build.h"
 #include "stages.cuh"
 #include "tower.cuh"
+#include "pairing_warp.cuh"
 
 using namespace h2v;
 
@@ -150,6 +152,7 @@ struct MsmGeom {
   // per channel (0 = right, 1 = left): window bits, windows, buckets per window (2^(c-1)),
   // first global window index, first global bucket index
   u32 c[2], W[2], B[2], wbase[2], bbase[2];
+  u32 Z[2];  // scalar lift range: k'' = k + z*r, z in [0, Z), keeps every window (also the top one) uniformly filled
   u32 Wmax;  // row stride of the digit table
   u32 m;     // buckets per reduction chunk
   __host__ __device__ u32 nb() const { return W[0] * B[0] + W[1] * B[1]; }
@@ -181,18 +184,32 @@ __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, 
     const G1Affine& sp = shared_pts[t - nP - nL];
     k = (sp.x.is_zero() && sp.y.is_zero()) ? Fr::zero() : shared_sum[t - nP - nL];  // identity base (all-zero fixed column)
   }
+  if (k.is_zero()) {  // excluded proof / unused slot / identity base: no bucket entries at all
+    for (u32 w = 0; w < g.W[ch]; w++) dig[(size_t)t * g.Wmax + w] = 0;
+    return;
+  }
+  // k'' = k + z*r (r*P = identity: same group element), z spread over [0, Z) so that k'' is uniform in
+  // [0, Z*r) ~ [0, 2^(W*c-1)): every window, including the top one, fills its buckets evenly.
+  u32 kk[9];
+  {
+    const u32 z = ((t * 2654435761u) >> 8) % g.Z[ch];
+    u64 acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      acc += (u64)z * FrP::mod(i) + k.l[i];
+      kk[i] = (u32)acc;
+      acc >>= 32;
+    }
+    kk[8] = (u32)acc;
+  }
   u32 carry = 0;
   const u32 c = g.c[ch], mask = (1u << c) - 1, half = 1u << (c - 1);
   for (u32 w = 0; w < g.W[ch]; w++) {
     const u32 bit = w * c;
-    u32 v = 0;
-    if (bit < 256) {
-      const u32 li = bit >> 5, sh = bit & 31;
-      u64 two = k.l[li];
-      if (li + 1 < 8) two |= (u64)k.l[li + 1] << 32;
-      v = (u32)(two >> sh) & mask;
-    }
-    v += carry;
+    const u32 li = bit >> 5, sh = bit & 31;
+    u64 two = li < 9 ? kk[li] : 0;
+    if (li + 1 < 9) two |= (u64)kk[li + 1] << 32;
+    u32 v = ((u32)(two >> sh) & mask) + carry;
     int d;
     if (v > half) {
       d = (int)v - (int)(1u << c);
@@ -318,20 +335,23 @@ __device__ __forceinline__ void store_affine_bytes(const G1Affine& a, bool is_id
   a.y.to_canonical().store_le(out + 32);
 }
 
-// threads 0,1: one accumulator each (left / right); then thread 0: the pairing check
+// one warp: lanes 0,1 combine the windows of one channel each (serial chain of ~W*c doublings, fully
+// inlined), then the whole warp runs the pairing check cooperatively (pairing_warp.cuh)
 __global__ void __launch_bounds__(32) k_finalize(PlanView pv, FinalizeArgs fa, const G1Jac* window_sums, const u8* partials, u8* acc_bytes,
                                                  u32* verdict) {
   __shared__ G1Affine aff[2];
   __shared__ bool skip[2];
-  const u32 t = threadIdx.x;
+  __shared__ W12 pool[H2V_WPOOL];
+  __shared__ WScratch ws;
+  const int t = threadIdx.x;
   if (t < 2) {
     // channel order in window_sums / partials: 0 = right, 1 = left; pairing order: pair 0 = left, pair 1 = right
     G1Jac acc = G1Jac::identity();
     if (fa.mode == 0) {
-      const G1Jac* ws = window_sums + fa.wbase[t];
+      const G1Jac* wsum = window_sums + fa.wbase[t];
       for (u32 w = fa.W[t]; w-- > 0;) {
-        for (u32 i = 0; i < fa.c[t]; i++) acc = g1_double(acc);
-        acc = g1_add(acc, ws[w]);
+        for (u32 i = 0; i < fa.c[t]; i++) g1_double_inl(acc);
+        acc = g1_add(acc, wsum[w]);
       }
     } else {
       for (u32 i = 0; i < fa.n_partials; i++) {
@@ -345,16 +365,18 @@ __global__ void __launch_bounds__(32) k_finalize(PlanView pv, FinalizeArgs fa, c
         acc = g1_add_mixed(acc, a);
       }
     }
-    const u32 pair = t == 0 ? 1 : 0;
-    skip[pair] = !g1_to_affine(acc, aff[pair]);
-    store_affine_bytes(aff[pair], skip[pair], acc_bytes + 64 * pair);  // acc_bytes = L | R
+    const int pair = t == 0 ? 1 : 0;
+    G1Affine a;
+    const bool id = !g1_to_affine_inl(acc, a);
+    aff[pair] = a;
+    skip[pair] = id;
+    store_affine_bytes(a, id, acc_bytes + 64 * pair);  // acc_bytes = L | R
   }
-  __syncthreads();
-  if (t == 0 && fa.do_pairing) {
+  __syncwarp();
+  if (fa.do_pairing) {
     const PlanHeader& hd = pv.h();
-    const G2Line* lines[2] = {pv.sec<G2Line>(hd.off_lines0), pv.sec<G2Line>(hd.off_lines1)};
-    Fq12 f = miller_loop2(aff, skip, lines);
-    *verdict = final_exponentiation(f).is_one() ? 1u : 0u;
+    const bool ok = w_pairing_check2(aff, skip, pv.sec<G2Line>(hd.off_lines0), pv.sec<G2Line>(hd.off_lines1), pool, &ws, t);
+    if (t == 0) *verdict = ok ? 1u : 0u;
   }
 }
 
@@ -408,14 +430,27 @@ __global__ void __launch_bounds__(128) k_pp_reduce(PlanView pv, u32 n, const G1J
   }
 }
 
-// thread per proof: DualMSM::check of its own accumulators (SingleStrategy semantics)
-__global__ void __launch_bounds__(64) k_pp_pairing(PlanView pv, u32 n, const G1Jac* lr, u32* status) {
-  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+// warp per proof: DualMSM::check of its own accumulators (SingleStrategy semantics, strategy.rs:164-176)
+static constexpr int PP_WARPS = 4;
+__global__ void __launch_bounds__(32 * PP_WARPS) k_pp_pairing(PlanView pv, u32 n, const G1Jac* lr, u32* status) {
+  __shared__ G1Affine aff[PP_WARPS][2];
+  __shared__ bool skip[PP_WARPS][2];
+  __shared__ W12 pool[PP_WARPS][H2V_WPOOL];
+  __shared__ WScratch ws[PP_WARPS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const u32 j = blockIdx.x * PP_WARPS + wid;
   if (j >= n) return;
-  if (status[j] != ST_OK) return;
+  if (status[j] != ST_OK) return;  // warp-uniform
+  if (lane < 2) {
+    G1Affine a;
+    const bool id = !g1_to_affine_inl(lr[(size_t)lane * n + j], a);  // lane 0: left, lane 1: right
+    aff[wid][lane] = a;
+    skip[wid][lane] = id;
+  }
+  __syncwarp();
   const PlanHeader& hd = pv.h();
-  if (!pairing_check2(lr[j], lr[(size_t)n + j], pv.sec<G2Line>(hd.off_lines0), pv.sec<G2Line>(hd.off_lines1)))
-    status[j] = ST_CONSTRAINT_SYSTEM_FAILURE;
+  const bool ok = w_pairing_check2(aff[wid], skip[wid], pv.sec<G2Line>(hd.off_lines0), pv.sec<G2Line>(hd.off_lines1), pool[wid], &ws[wid], lane);
+  if (lane == 0 && !ok) status[j] = ST_CONSTRAINT_SYSTEM_FAILURE;
 }
 
 __global__ void k_gather_scalars(PlanView pv, u32 n, const Fr* right, const Fr* shared, const Fr* left, u8* out) {
@@ -535,7 +570,7 @@ struct h2v_ctx {
   // device buffers
   DevBuf d_plan, d_proofs, d_proof_off, d_inst, d_inst_off, d_ncols, d_col_len, d_pts, d_bad, d_status, d_vals, d_scratch, d_right,
       d_shared, d_left, d_rlc_bytes, d_r, d_coef, d_shared_sum, d_dig, d_hist, d_off, d_cursor, d_sorted, d_buckets, d_wsums,
-      d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal;
+      d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush;
   std::vector<u32> h_status;
   PlanView pv() const { return PlanView{d_plan.as<u8>()}; }
 };
@@ -556,25 +591,31 @@ struct h2v_ctx {
 
 static inline u32 cdiv(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
 
-// Window size per channel.  Model: throughput term (bucket additions 11 MM, bucket reduction 2 x 16 MM
-// per bucket) at ~20 G MM/s plus the serial chain of the fullest bucket at ~0.5 us per MM.  Scalars
-// are uniform below r ~ 0.756 * 2^254, so the top window only has `top` significant bits and its
-// buckets are 2^(c - top) times fuller than average; window sizes with a nearly full top window win.
+// Window size per channel.  Thanks to the scalar lift k'' = k + z*r every window is uniformly filled, so
+// the choice is a pure work trade-off: bucket additions (11 MM) against bucket reduction (2 x 16 MM
+// per bucket plus the per-chunk offset multiplication), with a floor on the per-bucket serial chain.
 static void choose_window(u32 terms, u32& c_out, u32& W_out) {
   double best = 1e300;
   for (u32 c = 4; c <= 15; c++) {
     const u32 W = (255 + c - 1) / c;
     const double B = (double)(1u << (c - 1));
-    const u32 top = 254 - (W - 1) * c;  // significant bits of the top window (1..c)
-    const double top_buckets = top >= c ? B : 0.756 * (double)(1u << top);
-    const double chain = std::max((double)terms / B, (double)terms * 0.756 / std::max(1.0, top_buckets));
-    const double t = ((double)W * (double)terms * 11.0 + (double)W * B * 32.0) / 20e9 + chain * 11.0 * 0.5e-6;
+    const double work = (double)W * ((double)terms * 11.0 + B * (32.0 + 28.0));
+    const double chain = ((double)terms / B + 1.0) * 11.0;  // dependent MM per bucket thread
+    const double t = work / 15e9 + chain * 0.4e-6;
     if (t < best) {
       best = t;
       c_out = c;
       W_out = W;
     }
   }
+}
+
+// Z = floor(2^(W*c-1) / r): k + z*r < 2^(W*c-1) for z < Z, so the top signed digit never carries out.
+static u32 lift_range(u32 c, u32 W) {
+  const int e = (int)(W * c) - 1 - 254;  // 2^(W*c-1) = 2^254 * 2^e, e in [0, 15]
+  const long double ratio = 1.3225375138071345L;  // 2^254 / r
+  u32 z = (u32)std::floor(ratio * (long double)(1u << e) * (1.0L - 1e-9L));
+  return std::max(1u, z);
 }
 
 static MsmGeom choose_geom(u32 n, const PlanHeader& hd) {
@@ -595,6 +636,7 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd) {
       g.W[ch] = (255 + g.c[ch] - 1) / g.c[ch];
     }
     g.B[ch] = 1u << (g.c[ch] - 1);
+    g.Z[ch] = lift_range(g.c[ch], g.W[ch]);
   }
   g.wbase[0] = 0;
   g.wbase[1] = g.W[0];
@@ -657,7 +699,7 @@ void h2v_ctx_destroy(h2v_ctx* ctx) {
                     &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
                     &ctx->d_rlc_bytes, &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off,
                     &ctx->d_cursor, &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict,
-                    &ctx->d_partials, &ctx->d_partials_msm, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal};
+                    &ctx->d_partials, &ctx->d_partials_msm, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal, &ctx->d_flush};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : ctx->ev)
@@ -849,7 +891,7 @@ static int per_proof_impl(h2v_ctx* ctx, bool pairing, u8* accum_host) {
                                                     accum_host ? ctx->d_pp_bytes.as<u8>() : nullptr);
   LAUNCH_CHECK();
   if (pairing) {
-    k_pp_pairing<<<cdiv(n, 64), 64, 0, s>>>(pv, n, ctx->d_pp_lr.as<G1Jac>(), ctx->d_status.as<u32>());
+    k_pp_pairing<<<cdiv(n, PP_WARPS), 32 * PP_WARPS, 0, s>>>(pv, n, ctx->d_pp_lr.as<G1Jac>(), ctx->d_status.as<u32>());
     LAUNCH_CHECK();
   }
   if (accum_host) CKC(cudaMemcpyAsync(accum_host, ctx->d_pp_bytes.p, 128 * (size_t)n, cudaMemcpyDeviceToHost, s));
@@ -916,7 +958,7 @@ int h2v_accumulate_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const 
   int rc;
   if ((rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, global_base, global_count)) != 0) return rc;
   if ((rc = run_impl(ctx, 0)) != 0) return rc;
-  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
+  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_acc_bytes.p, 128, cudaMemcpyDefault, ctx->stream));
   return download_status(ctx, status);
 }
 
@@ -924,7 +966,7 @@ int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uin
   if (!ctx || !partials || !n_partials) return -1;
   CKC(cudaSetDevice(ctx->device));
   CKC(ctx->d_partials.ensure(128 * (size_t)n_partials));
-  CKC(cudaMemcpyAsync(ctx->d_partials.p, partials, 128 * (size_t)n_partials, cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemcpyAsync(ctx->d_partials.p, partials, 128 * (size_t)n_partials, cudaMemcpyDefault, ctx->stream));
   FinalizeArgs fa{1, {0, 0}, {0, 0}, {0, 0}, n_partials, 1};
   k_finalize<<<1, 32, 0, ctx->stream>>>(ctx->pv(), fa, nullptr, ctx->d_partials.as<u8>(), ctx->d_acc_bytes.as<u8>(), ctx->d_verdict.as<u32>());
   LAUNCH_CHECK();
@@ -948,6 +990,31 @@ int h2v_batch_upload(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint
   int rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, 0, n);
   if (rc) return rc;
   CKC(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int h2v_batch_upload_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off, const uint8_t* instances,
+                           const uint64_t* inst_off, const uint8_t* rlc_scalars, uint64_t seed, uint64_t global_base,
+                           uint64_t global_count) {
+  int rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, global_base, global_count);
+  if (rc) return rc;
+  CKC(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int h2v_batch_run_shard(h2v_ctx* ctx, uint8_t* partial) {
+  int rc = run_impl(ctx, 0);
+  if (rc) return rc;
+  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_acc_bytes.p, 128, cudaMemcpyDefault, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int h2v_flush_l2(h2v_ctx* ctx, size_t bytes) {
+  if (!ctx) return -1;
+  CKC(cudaSetDevice(ctx->device));
+  CKC(ctx->d_flush.ensure(bytes));
+  CKC(cudaMemsetAsync(ctx->d_flush.p, 0x5a, bytes, ctx->stream));
   return 0;
 }
 

@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing (one process per GPU): contiguous proof shards, globally defined RLC
+coefficients, and an all-gather of the 128-byte partial accumulators (NCCL on GPUs, gloo in the CPU
+tests).  NCCL cannot reduce with an elliptic-curve addition, hence gather-then-add: rank 0 adds the
+partials and runs the single pairing (`h2v_finalize`).  SURVEY.md section 8(e)."""
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous range [lo, hi) of global proof indices owned by `rank`."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_partials(partial: torch.Tensor, world: int) -> List[bytes]:
+    """partial: uint8[128] = affine (L_g | R_g) of this rank, on the device of the process group's
+    backend.  Returns every rank's partial as bytes, rank order."""
+    assert partial.dtype == torch.uint8 and partial.numel() == 128
+    if world == 1:
+        return [bytes(partial.cpu().numpy().tobytes())]
+    out = [torch.empty_like(partial) for _ in range(world)]
+    dist.all_gather(out, partial)
+    return [bytes(t.cpu().numpy().tobytes()) for t in out]
+
+
+def verify_batch_sharded(bv, proofs, instances, rank: int, world: int, rlc_scalars=None, seed=0):
+    """Every rank calls this with the WHOLE batch description (or at least its own shard's data at
+    the right indices); returns (global verdict, statuses of this rank's shard)."""
+    n = len(proofs)
+    lo, hi = shard_range(n, rank, world)
+    status, partial = bv.accumulate_shard(proofs[lo:hi], instances[lo:hi], lo, n, rlc_scalars=rlc_scalars, seed=seed)
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    t = torch.frombuffer(bytearray(partial), dtype=torch.uint8).to(dev)
+    parts = all_gather_partials(t, world)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    if rank == 0:
+        ok, _ = bv.finalize(parts)
+        flag[0] = 1 if ok else 0
+    if world > 1:
+        dist.broadcast(flag, src=0)
+    ok = bool(flag.item())
+    if not ok:  # rejected fold: every rank attributes inside its own shard, no further exchange
+        status = bv.attribute_shard(status)
+    return ok, status

@@ -88,7 +88,8 @@ int h2v_batch_set_scalar_hook(h2v_ctx* ctx, uint8_t* msm_scalars);
  * h2v_accumulate_shard processes proofs [global_base, global_base + n) of a global batch of
  * global_count proofs with GLOBALLY defined coefficients c_j (rlc_scalars, if given, has
  * global_count entries) and returns this shard's partial accumulators, 2 x 64 B affine (L_g, R_g),
- * without running a pairing.  Proof statuses are final except that H2V_OK means "accumulated". */
+ * without running a pairing.  Proof statuses are final except that H2V_OK means "accumulated".
+ * `partial` (and `partials` of h2v_finalize) may be host or device pointers (unified addressing). */
 int h2v_accumulate_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off,
                          const uint8_t* instances, const uint64_t* inst_off, const uint8_t* rlc_scalars,
                          uint64_t seed, uint64_t global_base, uint64_t global_count, uint8_t* status,
@@ -105,6 +106,14 @@ int h2v_attribute_shard(h2v_ctx* ctx, uint8_t* status);
 int h2v_batch_upload(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off,
                      const uint8_t* instances, const uint64_t* inst_off, const uint8_t* rlc_scalars,
                      uint64_t seed);
+/* same, for one shard of a global batch (see h2v_accumulate_shard) */
+int h2v_batch_upload_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off,
+                           const uint8_t* instances, const uint64_t* inst_off, const uint8_t* rlc_scalars,
+                           uint64_t seed, uint64_t global_base, uint64_t global_count);
+/* runs every kernel of the shard except the pairing; partial: 128 B out, host OR device pointer */
+int h2v_batch_run_shard(h2v_ctx* ctx, uint8_t* partial);
+/* overwrites `bytes` of scratch HBM on the context's stream (L2 flush between timed iterations) */
+int h2v_flush_l2(h2v_ctx* ctx, size_t bytes);
 /* runs every kernel of the batch on data already resident in HBM; verdict of the batch pairing out */
 int h2v_batch_run(h2v_ctx* ctx, int* verdict);
 int h2v_batch_download(h2v_ctx* ctx, uint8_t* status);

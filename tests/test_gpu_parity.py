@@ -1,0 +1,215 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(include/h2v.h) of libh2v_b200.so; the checker is the CPU oracle (oracle/), on the same seeded inputs,
+plus the committed golden vectors, plus size-independent properties at the full batch size."""
+import ctypes
+import json
+import os
+import random
+
+import pytest
+
+import bn254 as bn
+import formats as F
+import prover_sim as sim
+import verifier as orc
+from workloads import enc_point, make_batch, oracle_scalars, setup, split32
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def make_bv(pkg, params, vk, mo, hk, vkfmt=F.RAW_BYTES):
+    return pkg.BatchVerifier(pkg.ParamsKZG.from_bytes(params.to_bytes()), pkg.VerifyingKey.from_bytes(vk.to_bytes(vkfmt), vkfmt),
+                             mo, "keccak256" if hk == "keccak" else hk, device=0)
+
+
+def test_field_ptx_matches_portable(pkg):
+    lib = pkg.load_library()
+    assert lib.h2v_selftest_field(0, 1 << 20, 20261018) == 0
+    assert lib.h2v_calibrate_imad(0) > 1e12
+
+
+def check_against_oracle(bv, params, vk, instances, proofs, mo, hk, rs):
+    n = len(proofs)
+    res = bv.verify_batch(proofs, [i[0] for i in instances], rlc_scalars=rs, want_challenges=True, want_accum=True,
+                          want_batch_accum=True, want_scalars=True)
+    want = [orc.verify_proof(params, vk, inst, p, mo, hk) for inst, p in zip(instances, proofs)]
+    assert res.status == [w.status for w in want]
+    C, nb = bv.n_challenges, bv.n_bases
+    for j, w in enumerate(want):
+        if w.status in (orc.OK, orc.CONSTRAINT_SYSTEM_FAILURE):
+            assert split32(res.challenges[32 * C * j:], C) == w.challenges, f"challenges of proof {j}"
+            assert split32(res.msm_scalars[32 * nb * j:], nb) == oracle_scalars(vk, w, bv.n_points, bv.n_mo), f"scalars of proof {j}"
+            assert res.accum[128 * j: 128 * j + 128] == enc_point(w.L) + enc_point(w.R), f"accumulators of proof {j}"
+    L, R_, ok = orc.accumulate(params, want, rs)
+    assert res.batch_accum == enc_point(L) + enc_point(R_)
+    assert ok == all(w.status != orc.CONSTRAINT_SYSTEM_FAILURE for w in want)
+    return res, want
+
+
+@pytest.mark.parametrize("shape,k", [("vm", 8), ("vm", 10), ("sh", 8), ("mix", 6)])
+@pytest.mark.parametrize("mo", ["shplonk", "gwc"])
+@pytest.mark.parametrize("hk", ["blake2b", "keccak"])
+def test_batch_parity_small(pkg, shape, k, mo, hk):
+    params, vk, instances, proofs, rng = make_batch(shape, k, 6, mo, hk)
+    rs = [rng.randrange(1, bn.R) for _ in proofs]
+    with make_bv(pkg, params, vk, mo, hk, F.RAW_BYTES if mo == "shplonk" else F.PROCESSED) as bv:
+        assert bv.proof_len == len(proofs[0])
+        check_against_oracle(bv, params, vk, instances, proofs, mo, hk, rs)
+        # every rejection class, attributed inside a batch
+        bad = list(proofs)
+        kinds = list(sim.CORRUPTIONS)[: len(bad) - 1]
+        for i, kind in enumerate(kinds):
+            bad[i], _ = sim.corrupt(proofs[i], vk, kind, rng, mo)
+        check_against_oracle(bv, params, vk, instances, bad, mo, hk, rs)
+
+
+def test_all_corruption_classes_and_instances(pkg):
+    params, vk, instances, proofs, rng = make_batch("vm", 8, len(sim.CORRUPTIONS) + 3, "shplonk", "blake2b", seed=5)
+    rs = [rng.randrange(1, bn.R) for _ in proofs]
+    bad, insts = list(proofs), [[list(map(list, i[0]))] for i in instances]
+    for i, kind in enumerate(sim.CORRUPTIONS):
+        bad[i], _ = sim.corrupt(proofs[i], vk, kind, rng)
+    j = len(sim.CORRUPTIONS)
+    insts[j][0][0][0] = (insts[j][0][0][0] + 1) % bn.R  # the reference's negative test (vector_mul.rs:327-330)
+    insts[j + 1] = [[]]  # wrong number of instance columns -> InvalidInstances
+    with make_bv(pkg, params, vk, "shplonk", "blake2b") as bv:
+        res, want = check_against_oracle(bv, params, vk, insts, bad, "shplonk", "blake2b", rs)
+        assert res.status[j] == 4 and res.status[j + 1] == 1 and res.status[j + 2] == 0
+        assert sorted(set(res.status)) == [0, 1, 2, 3, 4]
+        # ragged public inputs: different lengths per proof
+        insts2 = [sim.random_instances(vk, rng, 3 + 5 * t) for t in range(4)]
+        _p, _v, dl, s = setup("vm", 8)
+        proofs2 = [sim.simulate_proof(params, vk, dl, s, inst, rng) for inst in insts2]
+        check_against_oracle(bv, params, vk, insts2, proofs2, "shplonk", "blake2b", rs[:4])
+        # single-proof entry point (SingleStrategy)
+        st = ctypes.c_uint8(9)
+        ib = b"".join(bn.fr_to_repr(v) for col in insts2[0][0] for v in col)
+        assert bv.lib.h2v_verify_proof(bv._ctx, proofs2[0], len(proofs2[0]), ib, len(ib) // 32, ctypes.byref(st)) == 0 and st.value == 0
+        assert bv.lib.h2v_verify_proof(bv._ctx, proofs2[1], len(proofs2[1]), ib, len(ib) // 32, ctypes.byref(st)) == 0 and st.value == 4
+
+
+def test_python_api_mirrors_reference(pkg):
+    params, vk, instances, proofs, rng = make_batch("vm", 8, 3, "gwc", "blake2b", seed=9)
+    P, V = pkg.ParamsKZG.from_bytes(params.to_bytes()), pkg.VerifyingKey.from_bytes(vk.to_bytes(F.PROCESSED), pkg.SerdeFormat.Processed)
+    assert pkg.verify_proof(P, V, proofs[0], instances[0][0], multiopen="gwc") is None
+    bad, _ = sim.corrupt(proofs[1], vk, "eval_flip", rng, "gwc")
+    with pytest.raises(pkg.ConstraintSystemFailure):
+        pkg.verify_proof(P, V, bad, instances[1][0], multiopen="gwc")
+    errs = pkg.verify_proofs_batch(P, V, [proofs[0], bad, proofs[2][:100]], [i[0] for i in instances], multiopen="gwc")
+    assert errs[0] is None and isinstance(errs[1], pkg.ConstraintSystemFailure) and isinstance(errs[2], pkg.TranscriptError)
+
+
+def test_golden_vectors(pkg):
+    for fn in sorted(os.listdir(os.path.join(HERE, "golden"))):
+        if not fn.endswith(".json") or fn == "srs_kat.json":
+            continue
+        g = json.load(open(os.path.join(HERE, "golden", fn)))
+        bv = pkg.BatchVerifier(pkg.ParamsKZG.from_bytes(bytes.fromhex(g["params"])),
+                               pkg.VerifyingKey.from_bytes(bytes.fromhex(g["vk"]), pkg.SerdeFormat(g["vk_format"])),
+                               g["multiopen"], "keccak256" if g["hash"] == "keccak" else g["hash"], device=0)
+        proofs = [bytes.fromhex(e["proof"]) for e in g["proofs"]]
+        insts = [[[int(v, 16) for v in col] for col in e["instances"]] for e in g["proofs"]]
+        res = bv.verify_batch(proofs, insts, rlc_scalars=[int(r, 16) for r in g["rlc_scalars"]], want_challenges=True,
+                              want_accum=True, want_batch_accum=True, want_scalars=True)
+        C, nb = bv.n_challenges, bv.n_bases
+        assert res.status == [e["status"] for e in g["proofs"]], fn
+        assert res.batch_accum.hex() == g["folded"], fn
+        for j, e in enumerate(g["proofs"]):
+            if "accum" in e:
+                assert [hex(c) for c in split32(res.challenges[32 * C * j:], C)] == e["challenges"], fn
+                assert res.accum[128 * j: 128 * j + 128].hex() == e["accum"], fn
+                assert [hex(c) for c in split32(res.msm_scalars[32 * nb * j:], nb)] == e["msm_scalars"], fn
+        bv.close()
+
+
+def test_k18_lookup_heavy(pkg):
+    params, vk, instances, proofs, rng = make_batch("k18", 18, 3, "shplonk", "blake2b")
+    proofs[1], _ = sim.corrupt(proofs[1], vk, "eval_flip", rng)
+    with make_bv(pkg, params, vk, "shplonk", "blake2b") as bv:
+        assert bv.proof_len == 12960
+        check_against_oracle(bv, params, vk, instances, proofs, "shplonk", "blake2b", [rng.randrange(1, bn.R) for _ in proofs])
+
+
+def _big_batch(n, mo):
+    """Full-size batch: 64 distinct oracle-simulated proofs tiled to n (bounded CPU generation time)."""
+    params, vk, instances, proofs, rng = make_batch("vm", 10, 64, mo, "blake2b", seed=77)
+    reps = n // 64
+    return params, vk, instances * reps, proofs * reps, rng
+
+
+@pytest.mark.parametrize("mo", ["shplonk", "gwc"])
+def test_full_batch_4096_properties(pkg, mo):
+    """BASELINE.json configs[1] / [2] size.  Size-independent properties:
+    (1) an all-valid batch is accepted and the fold is linear: fold(A || B) = c * fold(A) + fold(B);
+    (2) the fold over tiled copies equals the oracle fold computed from 64 per-proof accumulators;
+    (3) 1% corrupted proofs -> batch rejected -> attribution flags exactly the injected indices."""
+    n = 4096
+    params, vk, instances, proofs, rng = _big_batch(n, mo)
+    insts = [i[0] for i in instances]
+    rs = [rng.randrange(1, bn.R) for _ in range(n)]
+    with make_bv(pkg, params, vk, mo, "blake2b") as bv:
+        res = bv.verify_batch(proofs, insts, rlc_scalars=rs, want_batch_accum=True)
+        assert res.verdict and res.status == [0] * n
+        # (2) oracle fold from the 64 distinct accumulators
+        want = [orc.verify_proof(params, vk, instances[j], proofs[j], mo, "blake2b", check_pairing=False) for j in range(64)]
+        cs = orc.rlc_coefficients(rs)
+        coef = [sum(cs[j + 64 * t] for t in range(n // 64)) % bn.R for j in range(64)]
+        L = R_ = None
+        for w, c in zip(want, coef):
+            L, R_ = bn.g1_add(L, bn.g1_mul(w.L, c)), bn.g1_add(R_, bn.g1_mul(w.R, c))
+        assert res.batch_accum == enc_point(L) + enc_point(R_)
+        # (1) linearity across a split
+        h = n // 2
+        a = bv.verify_batch(proofs[:h], insts[:h], rlc_scalars=rs[:h], want_batch_accum=True).batch_accum
+        b = bv.verify_batch(proofs[h:], insts[h:], rlc_scalars=rs[h:], want_batch_accum=True).batch_accum
+        dec = lambda e: None if e == bytes(64) else (int.from_bytes(e[:32], "little"), int.from_bytes(e[32:], "little"))
+        c_split = cs[h - 1]  # = prod_{i >= h} r_i: what the first half's last coefficient (1) becomes in the whole batch
+        for off in (0, 64):
+            whole = dec(res.batch_accum[off: off + 64])
+            assert whole == bn.g1_add(bn.g1_mul(dec(a[off: off + 64]), c_split), dec(b[off: off + 64]))
+        # (3) attribution
+        bad_idx = sorted(rng.sample(range(n), n // 100))
+        bad = list(proofs)
+        expect = [0] * n
+        kinds = ["eval_flip", "point_swap", "scalar_ge_r", "point_offcurve", "opening_offcurve", "truncate_body"]
+        for t, i in enumerate(bad_idx):
+            bad[i], expect[i] = sim.corrupt(proofs[i], vk, kinds[t % len(kinds)], rng, mo)
+        res = bv.verify_batch(bad, insts, rlc_scalars=rs)
+        assert not res.verdict and res.status == expect
+
+
+def test_sharded_accumulation_matches_whole_batch(pkg):
+    """SURVEY.md 8e on one GPU: two contexts play two ranks; the folded (L, R) must be identical for
+    every shard count, and a corrupted shard is attributed locally."""
+    n = 256
+    params, vk, instances, proofs, rng = make_batch("vm", 10, 32, "shplonk", "blake2b", seed=3)
+    instances, proofs = instances * 8, proofs * 8
+    insts = [i[0] for i in instances]
+    rs = [rng.randrange(1, bn.R) for _ in range(n)]
+    with make_bv(pkg, params, vk, "shplonk", "blake2b") as b0, make_bv(pkg, params, vk, "shplonk", "blake2b") as b1:
+        whole = b0.verify_batch(proofs, insts, rlc_scalars=rs, want_batch_accum=True)
+        for shards in (2, 4):
+            per = n // shards
+            parts = []
+            for g in range(shards):
+                bv = (b0, b1)[g % 2]
+                st, partial = bv.accumulate_shard(proofs[g * per:(g + 1) * per], insts[g * per:(g + 1) * per], g * per, n, rlc_scalars=rs)
+                assert st == [0] * per
+                parts.append(partial)
+            ok, folded = b0.finalize(parts)
+            assert ok and folded == whole.batch_accum
+        # seed-derived coefficients agree between whole and sharded runs too
+        w2 = b0.verify_batch(proofs, insts, seed=99, want_batch_accum=True)
+        parts = [bv.accumulate_shard(proofs[g * 128:(g + 1) * 128], insts[g * 128:(g + 1) * 128], g * 128, n, seed=99)[1] for g, bv in ((0, b0), (1, b1))]
+        assert b1.finalize(parts) == (True, w2.batch_accum)
+        # corrupted proof in shard 1
+        bad = list(proofs)
+        bad[200], _ = sim.corrupt(proofs[200], vk, "eval_flip", rng)
+        st0, p0 = b0.accumulate_shard(bad[:128], insts[:128], 0, n, rlc_scalars=rs)
+        st1, p1 = b1.accumulate_shard(bad[128:], insts[128:], 128, n, rlc_scalars=rs)
+        ok, _ = b0.finalize([p0, p1])
+        assert not ok
+        assert b0.attribute_shard(st0) == [0] * 128
+        st1 = b1.attribute_shard(st1)
+        assert st1[72] == 4 and sum(st1) == 4
