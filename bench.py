@@ -154,8 +154,9 @@ def run_ours(args):
     gen_s = time.time() - t0
     gcount, gbase = n * world, n * rank
     seed = 7
-    partial_dev = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    gathered = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(world)] if world > 1 else None
+    pbytes = int(lib.h2v_partial_bytes())
+    partial_dev = torch.zeros(pbytes, dtype=torch.uint8, device="cuda")
+    gathered = [torch.zeros(pbytes, dtype=torch.uint8, device="cuda") for _ in range(world)] if world > 1 else None
     verdict = ctypes.c_int(0)
     chk = lambda ctx, rc: ctx._check(rc)
 
@@ -274,7 +275,7 @@ def run_ours(args):
                                    f"10 public inputs, 1,024-byte proofs; BASELINE.json configs[1]",
                        "batch_per_gpu": n, "global_batch": n * world, "contexts_in_flight": n_ctx if world == 1 else 1,
                        "l2": "flushed between steps (256 MiB overwrite on the timed stream)",
-                       "parallelism": f"proof-sharded x{world}, NCCL all-gather of 128-byte partial accumulators, one pairing on rank 0"},
+                       "parallelism": f"proof-sharded x{world}, NCCL all-gather of the per-window partial accumulators (12,320 B per rank), one pairing check on rank 0"},
             "e2e": {"value": total / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": batches[0].h2d_bytes, "d2h_bytes_per_step": batches[0].d2h_bytes,
                     "ms_per_step": dt_e2e / args.steps * 1e3, "p50_latency_ms": statistics.median(lat) * 1e3},
             "gpu_launches": int(launches),

@@ -101,6 +101,9 @@ def load_library():
                                      u8p, u8p, u8p, u8p]
     lib.h2v_batch_set_columns.argtypes = [ctypes.c_void_p, u32p, u32p]
     lib.h2v_batch_set_scalar_hook.argtypes = [ctypes.c_void_p, u8p]
+    lib.h2v_batch_set_shard_hint.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+    lib.h2v_partial_bytes.argtypes = []
+    lib.h2v_partial_bytes.restype = ctypes.c_size_t
     lib.h2v_accumulate_shard.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64,
                                          ctypes.c_uint64, ctypes.c_uint64, u8p, u8p]
     lib.h2v_finalize.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u8p, ctypes.POINTER(ctypes.c_int)]
@@ -125,7 +128,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = (
     "h2v_ctx_create", "h2v_ctx_destroy", "h2v_last_error", "h2v_ctx_info", "h2v_verify_proof", "h2v_verify_batch",
-    "h2v_batch_set_columns", "h2v_batch_set_scalar_hook", "h2v_accumulate_shard", "h2v_finalize", "h2v_attribute_shard",
+    "h2v_batch_set_columns", "h2v_batch_set_scalar_hook", "h2v_batch_set_shard_hint", "h2v_partial_bytes", "h2v_accumulate_shard", "h2v_finalize", "h2v_attribute_shard",
     "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count",
     "h2v_last_msm_geometry", "h2v_selftest_field", "h2v_calibrate_imad",
 )
@@ -281,22 +284,27 @@ class BatchVerifier:
         return BatchResult(st, all(s == 0 for s in st), ch.raw if ch else None, acc.raw if acc else None,
                            bacc.raw if bacc else None, sc.raw if sc else None)
 
-    def accumulate_shard(self, proofs, instances, global_base, global_count, rlc_scalars=None, seed=0):
+    def accumulate_shard(self, proofs, instances, global_base, global_count, rlc_scalars=None, seed=0, shard_hint=0):
+        """Returns (statuses, partial): `partial` is the opaque H2V_PARTIAL_BYTES blob of this shard's
+        per-window bucket sums.  `shard_hint` = size of the largest shard of the global batch when the
+        shards are not all of the same size (every rank must use the same window geometry)."""
         n = len(proofs)
         pbytes, poff, ibytes, ioff, keep = self._pack(proofs, instances)
         rlc = b"".join(int(r).to_bytes(32, "little") for r in rlc_scalars) if rlc_scalars is not None else None
         status = (ctypes.c_uint8 * n)()
-        partial = ctypes.create_string_buffer(128)
+        partial = ctypes.create_string_buffer(self.lib.h2v_partial_bytes())
+        if shard_hint:
+            self._check(self.lib.h2v_batch_set_shard_hint(self._ctx, int(shard_hint)))
         self._check(self.lib.h2v_accumulate_shard(self._ctx, n, pbytes, poff, ibytes, ioff, rlc, seed, global_base,
                                                   global_count, status, partial))
         return list(status), partial.raw
 
-    def finalize(self, partials: Sequence[bytes]):
+    def finalize(self, partials: Sequence[bytes], want_batch_accum=True):
         buf = b"".join(partials)
-        bacc = ctypes.create_string_buffer(128)
+        bacc = ctypes.create_string_buffer(128) if want_batch_accum else None
         verdict = ctypes.c_int(0)
         self._check(self.lib.h2v_finalize(self._ctx, len(partials), buf, bacc, ctypes.byref(verdict)))
-        return bool(verdict.value), bacc.raw
+        return bool(verdict.value), (bacc.raw if bacc is not None else None)
 
     def attribute_shard(self, status):
         arr = (ctypes.c_uint8 * len(status))(*status)

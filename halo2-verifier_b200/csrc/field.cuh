@@ -83,6 +83,50 @@ __device__ __forceinline__ u32 ptx_madc_lo_cc(u32 a, u32 b, u32 c) { u32 r; asm 
 __device__ __forceinline__ u32 ptx_mad_hi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ u32 ptx_madc_hi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ u32 ptx_madc_hi(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
+// ---- building blocks of the even/odd wide multiplication (Fp::mul).  Each carry chain is ONE asm
+// statement, so no carry flag is live between statements and the compiler may interleave chains.
+// ptxas fuses every (mad.lo.cc, madc.hi.cc) pair into one IMAD.WIDE.U32 with carry in/out.
+// acc[0..7] = (a0, a2, a4, a6) * b as four 64-bit products
+__device__ __forceinline__ void wide_mul4(u32 (&acc)[8], u32 a0, u32 a2, u32 a4, u32 a6, u32 b) {
+  asm("mul.lo.u32 %0, %8, %12; mul.hi.u32 %1, %8, %12;\n\t"
+      "mul.lo.u32 %2, %9, %12; mul.hi.u32 %3, %9, %12;\n\t"
+      "mul.lo.u32 %4, %10, %12; mul.hi.u32 %5, %10, %12;\n\t"
+      "mul.lo.u32 %6, %11, %12; mul.hi.u32 %7, %11, %12;"
+      : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
+      : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(b));
+}
+// acc[0..7] += (a0, a2, a4, a6) * b along one carry chain; returns the carry out
+__device__ __forceinline__ u32 wide_mad4_carry(u32 (&acc)[8], u32 a0, u32 a2, u32 a4, u32 a6, u32 b) {
+  u32 cy;
+  asm("mad.lo.cc.u32 %0, %9, %13, %0; madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2; madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4; madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6; madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(cy)
+      : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(b));
+  return cy;
+}
+// same, carry out dropped (the caller knows the sum fits)
+__device__ __forceinline__ void wide_mad4(u32 (&acc)[8], u32 a0, u32 a2, u32 a4, u32 a6, u32 b) {
+  asm("mad.lo.cc.u32 %0, %8, %12, %0; madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %2; madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %4; madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, %6; madc.hi.u32 %7, %11, %12, %7;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+      : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(b));
+}
+// even0 += odd[1] (carry kept), then odd = (odd >> 64) + (a1, a3, a5, a7) * b with that carry folded in
+__device__ __forceinline__ void wide_fold_mad4_rshift(u32& even0, u32 (&odd)[8], u32 a1, u32 a3, u32 a5, u32 a7, u32 b) {
+  asm("add.cc.u32 %8, %8, %1;\n\t"
+      "madc.lo.cc.u32 %0, %9, %13, %2; madc.hi.cc.u32 %1, %9, %13, %3;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %4; madc.hi.cc.u32 %3, %10, %13, %5;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %6; madc.hi.cc.u32 %5, %11, %13, %7;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, 0; madc.hi.u32 %7, %12, %13, 0;"
+      : "+r"(odd[0]), "+r"(odd[1]), "+r"(odd[2]), "+r"(odd[3]), "+r"(odd[4]), "+r"(odd[5]), "+r"(odd[6]), "+r"(odd[7]), "+r"(even0)
+      : "r"(a1), "r"(a3), "r"(a5), "r"(a7), "r"(b));
+}
 #endif
 
 template <class P>
@@ -244,8 +288,55 @@ struct Fp {
     return r;
   }
 
-  // Montgomery product a*b*2^-256 mod p.  Requires b < p, a < 2^256 (so a*b < 2^256 * p).
+#ifdef H2V_PTX
+  // One row of the even/odd wide multiplication: acc += a * bi, then one Montgomery reduction step.
+  // `even` holds the 32-bit columns 0..7 and `odd` the columns 1..8 of the running sum, each as four
+  // 64-bit slots, so every 32x32->64 product lands in one slot and one IMAD.WIDE.U32 accumulates it.
+  // After the reduction step column 0 is zero and the arrays swap roles (the shift by one column).
+  template <bool FIRST>
+  static __device__ __forceinline__ void wide_row(u32 (&even)[8], u32 (&odd)[8], const u32* a, u32 bi) {
+    if (FIRST) {
+      wide_mul4(odd, a[1], a[3], a[5], a[7], bi);
+      wide_mul4(even, a[0], a[2], a[4], a[6], bi);
+    } else {
+      wide_fold_mad4_rshift(even[0], odd, a[1], a[3], a[5], a[7], bi);
+      odd[7] += wide_mad4_carry(even, a[0], a[2], a[4], a[6], bi);
+    }
+    const u32 mi = even[0] * P::INV;
+    wide_mad4(odd, P::mod(1), P::mod(3), P::mod(5), P::mod(7), mi);
+    odd[7] += wide_mad4_carry(even, P::mod(0), P::mod(2), P::mod(4), P::mod(6), mi);
+  }
+#endif
+
+  // Montgomery product a*b*2^-256 mod p for REDUCED operands (a, b < p; exact for a < 2^255).
+  // Device: 128 IMAD.WIDE.U32 + 8 IMAD on the multiply pipe (half the issue slots of a lo/hi CIOS).
   static H2V_HD Fp mul(const Fp& a, const Fp& b) {
+#ifdef H2V_PTX
+    u32 even[8], odd[8];
+    wide_row<true>(even, odd, a.l, b.l[0]);
+    wide_row<false>(odd, even, a.l, b.l[1]);
+    wide_row<false>(even, odd, a.l, b.l[2]);
+    wide_row<false>(odd, even, a.l, b.l[3]);
+    wide_row<false>(even, odd, a.l, b.l[4]);
+    wide_row<false>(odd, even, a.l, b.l[5]);
+    wide_row<false>(even, odd, a.l, b.l[6]);
+    wide_row<false>(odd, even, a.l, b.l[7]);
+    Fp r;
+    asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, %17; addc.cc.u32 %2, %10, %18; addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20; addc.cc.u32 %5, %13, %21; addc.cc.u32 %6, %14, %22; addc.u32 %7, %15, 0;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+        : "r"(even[0]), "r"(even[1]), "r"(even[2]), "r"(even[3]), "r"(even[4]), "r"(even[5]), "r"(even[6]), "r"(even[7]),
+          "r"(odd[1]), "r"(odd[2]), "r"(odd[3]), "r"(odd[4]), "r"(odd[5]), "r"(odd[6]), "r"(odd[7]));
+    r.cond_sub_mod();
+    return r;
+#else
+    return mul_portable(a, b);
+#endif
+  }
+
+  // Montgomery product for an UNREDUCED left operand: b < p, a < 2^256 (so a*b < 2^256 * p).  Used
+  // where raw 256-bit strings enter the field (from_uniform, from_canonical).
+  static H2V_HD Fp mul_any(const Fp& a, const Fp& b) {
 #ifdef H2V_PTX
     Fp r;
     // CIOS, one row per limb of b.  t has 9 live limbs (t8 is the running top word).
@@ -290,7 +381,7 @@ struct Fp {
 
   // ---- conversions
   // canonical integer (little-endian limbs, must be < p) -> Montgomery form
-  static H2V_HD Fp from_canonical(const Fp& c) { return mul(c, r2()); }
+  static H2V_HD Fp from_canonical(const Fp& c) { return mul_any(c, r2()); }
   H2V_HD Fp to_canonical() const {
     Fp o = zero();
     o.l[0] = 1;
@@ -322,7 +413,7 @@ struct Fp {
   // lo*R^2*R^-1 + hi*R^3*R^-1 = (lo + hi*2^256)*R  (same decomposition halo2curves uses)
   static H2V_HD Fp from_uniform(const u8* b64) {
     Fp lo = load_le(b64), hi = load_le(b64 + 32);
-    return mul(lo, r2()) + mul(hi, r3());
+    return mul_any(lo, r2()) + mul_any(hi, r3());
   }
 
   // ---- exponentiation by a fixed 256-bit exponent given as 8 limbs (4-bit fixed window)

@@ -9,7 +9,9 @@
 //   k_rlc_*           r_i expansion + suffix products c_j                      strategy.rs:125-136
 //   k_shared_reduce   column sums of the shared-base scalars
 //   k_msm_*           one signed-digit Pippenger over every proof's points     arithmetic.rs:7-108, msm.rs:81-86
-//   k_finalize        window combine + 2-pair Miller loop + final exp          msm.rs:185-203
+//   k_lines           per Miller iteration: product of the lines of every (channel, window) pair
+//   k_pairing_check   f = f^2 M_i, division-free final exponentiation test     msm.rs:185-203
+//   (k_finalize       explicit window combination -> affine (L, R): parity hook only)
 //   (k_pp_*           per-proof accumulators / pairings: parity hook and rejection attribution)
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -25,6 +27,7 @@
 #include "stages.cuh"
 #include "tower.cuh"
 #include "pairing_warp.cuh"
+#include "pairing_cta.cuh"
 
 using namespace h2v;
 
@@ -319,11 +322,8 @@ __global__ void __launch_bounds__(256) k_msm_window_reduce(MsmGeom g, const G1Ja
   if (t == 0) window_sums[wi] = sh[0];
 }
 
-struct FinalizeArgs {
-  u32 mode;          // 0: combine window sums, 1: add `n_partials` affine partials
-  u32 W[2], c[2], wbase[2];  // MSM geometry per channel (mode 0)
-  u32 n_partials;    // mode 1
-  u32 do_pairing;    // 0: only produce the accumulators
+struct FoldArgs {
+  u32 W[2], c[2], wbase[2];  // MSM geometry per channel
 };
 
 __device__ __forceinline__ void store_affine_bytes(const G1Affine& a, bool is_id, u8* out) {
@@ -335,49 +335,57 @@ __device__ __forceinline__ void store_affine_bytes(const G1Affine& a, bool is_id
   a.y.to_canonical().store_le(out + 32);
 }
 
-// one warp: lanes 0,1 combine the windows of one channel each (serial chain of ~W*c doublings, fully
-// inlined), then the whole warp runs the pairing check cooperatively (pairing_warp.cuh)
-__global__ void __launch_bounds__(32) k_finalize(PlanView pv, FinalizeArgs fa, const G1Jac* window_sums, const u8* partials, u8* acc_bytes,
-                                                 u32* verdict) {
-  __shared__ G1Affine aff[2];
-  __shared__ bool skip[2];
-  __shared__ W12 pool[H2V_WPOOL];
-  __shared__ WScratch ws;
+// Parity hook only (the verdict path never forms these points): explicit window combination
+// acc = sum_w 2^(c w) S_w of each channel (serial chain of ~W*c doublings, thread per channel) and
+// conversion to affine bytes, acc_bytes = L | R  (reference msm.rs:81-95 `eval` of both MSMs).
+__global__ void __launch_bounds__(32) k_fold_accum(FoldArgs fa, const G1Jac* window_sums, u8* acc_bytes) {
   const int t = threadIdx.x;
-  if (t < 2) {
-    // channel order in window_sums / partials: 0 = right, 1 = left; pairing order: pair 0 = left, pair 1 = right
-    G1Jac acc = G1Jac::identity();
-    if (fa.mode == 0) {
-      const G1Jac* wsum = window_sums + fa.wbase[t];
-      for (u32 w = fa.W[t]; w-- > 0;) {
-        for (u32 i = 0; i < fa.c[t]; i++) g1_double_inl(acc);
-        acc = g1_add(acc, wsum[w]);
-      }
-    } else {
-      for (u32 i = 0; i < fa.n_partials; i++) {
-        const u8* p = partials + (size_t)i * 128 + (t == 0 ? 64 : 0);  // partial = L(64) | R(64)
-        bool z = true;
-        for (int q = 0; q < 64; q++) z = z && p[q] == 0;
-        if (z) continue;
-        G1Affine a;
-        a.x = Fq::from_canonical(Fq::load_le(p));
-        a.y = Fq::from_canonical(Fq::load_le(p + 32));
-        acc = g1_add_mixed(acc, a);
-      }
-    }
-    const int pair = t == 0 ? 1 : 0;
-    G1Affine a;
-    const bool id = !g1_to_affine_inl(acc, a);
-    aff[pair] = a;
-    skip[pair] = id;
-    store_affine_bytes(a, id, acc_bytes + 64 * pair);  // acc_bytes = L | R
+  if (t >= 2) return;
+  // channel order in window_sums: 0 = right, 1 = left
+  G1Jac acc = G1Jac::identity();
+  const G1Jac* wsum = window_sums + fa.wbase[t];
+  for (u32 w = fa.W[t]; w-- > 0;) {
+    for (u32 i = 0; i < fa.c[t]; i++) g1_double_inl(acc);
+    acc = g1_add(acc, wsum[w]);
   }
-  __syncwarp();
-  if (fa.do_pairing) {
-    const PlanHeader& hd = pv.h();
-    const bool ok = w_pairing_check2(aff, skip, pv.sec<G2Line>(hd.off_lines0), pv.sec<G2Line>(hd.off_lines1), pool, &ws, t);
-    if (t == 0) *verdict = ok ? 1u : 0u;
+  G1Affine a;
+  const bool id = !g1_to_affine_inl(acc, a);
+  store_affine_bytes(a, id, acc_bytes + 64 * (t == 0 ? 1 : 0));
+}
+
+// ---- partial accumulators of a shard: header + the Jacobian window sums (Montgomery limbs)
+struct PartialHeader {
+  u32 magic, cbits, windows, n_pts, rsv[4];
+};
+static constexpr u32 H2V_PARTIAL_MAGIC = 0x50563248u;
+static_assert(sizeof(PartialHeader) == 32 && sizeof(G1Jac) == 96, "partial layout");
+static_assert(sizeof(PartialHeader) + 128 * sizeof(G1Jac) == H2V_PARTIAL_BYTES, "H2V_PARTIAL_BYTES");
+
+__global__ void k_pack_partial(u32 cbits, u32 windows, u32 npts, const G1Jac* wsums, u8* out) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  u32* o = (u32*)out;
+  if (t < 8) {
+    const u32 hdr[8] = {H2V_PARTIAL_MAGIC, cbits, windows, npts, 0, 0, 0, 0};
+    o[t] = hdr[t];
   }
+  const u32* src = (const u32*)wsums;
+  for (u32 i = t; i < H2V_PARTIAL_BYTES / 4 - 8; i += gridDim.x * blockDim.x) o[8 + i] = i < npts * 24 ? src[i] : 0u;
+}
+
+// window-wise sum of the shards' partials (thread per window); flags a geometry mismatch in *err
+__global__ void __launch_bounds__(128) k_sum_partials(u32 n_partials, u32 cbits, u32 windows, u32 npts, const u8* partials, G1Jac* out, u32* err) {
+  const u32 wi = threadIdx.x;
+  if (wi < n_partials) {
+    const PartialHeader* h = (const PartialHeader*)(partials + (size_t)wi * H2V_PARTIAL_BYTES);
+    if (h->magic != H2V_PARTIAL_MAGIC || h->cbits != cbits || h->windows != windows || h->n_pts != npts) atomicOr(err, 1u);
+  }
+  if (wi >= npts) return;
+  G1Jac acc = G1Jac::identity();
+  for (u32 g = 0; g < n_partials; g++) {
+    const G1Jac* pts = (const G1Jac*)(partials + (size_t)g * H2V_PARTIAL_BYTES + sizeof(PartialHeader));
+    acc = g1_add(acc, pts[wi]);
+  }
+  out[wi] = acc;
 }
 
 // ---- per-proof accumulators (parity hook, rejection attribution)
@@ -495,8 +503,10 @@ __device__ u32 selftest_one(u64& s, bool edge) {
       for (int i = 0; i < 8; i++) a.l[i] = 0xFFFFFFFFu;  // a may be any 256-bit value
     }
   }
-  F x = F::mul(a, b), y = F::mul_portable(a, b);
-  u32 bad = x != y;
+  // mul_any accepts any 256-bit left operand; mul (even/odd wide form) is specified for a < 2^255
+  F y = F::mul_portable(a, b);
+  u32 bad = F::mul_any(a, b) != y;
+  if (!(a.l[7] >> 31)) bad += F::mul(a, b) != y;
   F s1 = a.geq_mod() ? F::zero() : a;
   F u = s1 + b, v = u - b;
   bad += (v != s1);
@@ -567,10 +577,12 @@ struct h2v_ctx {
   u32 scratch_rows = 0;
   MsmGeom geom{};
   bool ran = false;
+  u32 opt_shard_hint = 0;   // geometry as for a shard of this many proofs (common to all ranks)
+  u64 lines_key = ~0ull;    // window geometry the prepared G2 lines in d_lines belong to
   // device buffers
   DevBuf d_plan, d_proofs, d_proof_off, d_inst, d_inst_off, d_ncols, d_col_len, d_pts, d_bad, d_status, d_vals, d_scratch, d_right,
       d_shared, d_left, d_rlc_bytes, d_r, d_coef, d_shared_sum, d_dig, d_hist, d_off, d_cursor, d_sorted, d_buckets, d_wsums,
-      d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush;
+      d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush, d_lines, d_M, d_partial_out, d_wsums_fin;
   std::vector<u32> h_status;
   PlanView pv() const { return PlanView{d_plan.as<u8>()}; }
 };
@@ -618,15 +630,18 @@ static u32 lift_range(u32 c, u32 W) {
   return std::max(1u, z);
 }
 
-static MsmGeom choose_geom(u32 n, const PlanHeader& hd) {
+// n_geom >= n: the window geometry is chosen as for a batch of n_geom proofs (sharded batches: every
+// rank must use the same windows so that partial window sums add up, see h2v_batch_set_shard_hint)
+static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom) {
   MsmGeom g{};
   g.n = n;
   g.P = hd.n_points;
   g.n_mo = hd.n_mo;
   g.Sh = hd.n_shared;
   g.T = n * hd.n_points + n * hd.n_mo + hd.n_shared;
-  choose_window(n * hd.n_points + hd.n_shared, g.c[0], g.W[0]);
-  choose_window(n * hd.n_mo, g.c[1], g.W[1]);
+  if (n_geom < n) n_geom = n;
+  choose_window(n_geom * hd.n_points + hd.n_shared, g.c[0], g.W[0]);
+  choose_window(n_geom * hd.n_mo, g.c[1], g.W[1]);
   const char* f0 = getenv("H2V_MSM_WINDOW_RIGHT");
   const char* f1 = getenv("H2V_MSM_WINDOW_LEFT");
   for (int ch = 0; ch < 2; ch++) {
@@ -645,6 +660,44 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd) {
   g.Wmax = std::max(g.W[0], g.W[1]);
   g.m = 8;  // every B is a power of two >= 8
   return g;
+}
+
+static constexpr int LINES_GROUPS = 8;
+
+static u64 lines_key_of(const MsmGeom& g) { return (u64)g.c[0] | (u64)g.W[0] << 8 | (u64)g.c[1] << 16 | (u64)g.W[1] << 24; }
+
+// Prepared Miller lines of [2^(c w)] Q for the current window geometry (host: G2Prepared-style
+// preparation, once per geometry; cached in the context).
+static int ensure_lines(h2v_ctx* ctx) {
+  const MsmGeom& g = ctx->geom;
+  const u64 key = lines_key_of(g);
+  if (ctx->lines_key == key) return 0;
+  if (g.W[0] + g.W[1] > 128) {
+    ctx->err = "window geometry exceeds 128 (channel, window) pairs";
+    return -1;
+  }
+  std::vector<u8> tab;
+  build_window_lines(ctx->info, g.c[0], g.W[0], g.c[1], g.W[1], tab);
+  CKC(ctx->d_lines.ensure(tab.size()));
+  CKC(ctx->d_M.ensure(sizeof(E12) * H2V_ATE_ITERS));
+  CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128));
+  CKC(ctx->d_partial_out.ensure(H2V_PARTIAL_BYTES));
+  CKC(cudaMemcpyAsync(ctx->d_lines.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+  ctx->lines_key = key;
+  return 0;
+}
+
+// the batch pairing check over `wsums` (W0 + W1 Jacobian window sums) -> d_verdict[0]
+static int launch_pairing(h2v_ctx* ctx, const G1Jac* wsums) {
+  const MsmGeom& g = ctx->geom;
+  cudaStream_t s = ctx->stream;
+  k_lines<LINES_GROUPS><<<H2V_ATE_ITERS, 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s>>>(LinesArgs{g.W[0] + g.W[1]}, wsums, ctx->d_lines.as<G2Line>(),
+                                                                                       ctx->d_M.as<E12>());
+  LAUNCH_CHECK();
+  k_pairing_check<<<1, 64, 0, s>>>(ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>());
+  LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" {
@@ -687,6 +740,8 @@ int h2v_ctx_create(h2v_ctx** out, const uint8_t* params, size_t params_len, int 
   if ((e = cudaMemcpy(ctx->d_plan.p, ctx->blob.data(), ctx->blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
     return fail("cudaMemcpy(plan)", e);
   if ((e = ctx->d_acc_bytes.ensure(128)) != cudaSuccess || (e = ctx->d_verdict.ensure(16)) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaFuncSetAttribute(k_lines<LINES_GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k_lines_smem<LINES_GROUPS>())) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_lines)", e);
   *out = ctx;
   return 0;
 }
@@ -699,7 +754,8 @@ void h2v_ctx_destroy(h2v_ctx* ctx) {
                     &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
                     &ctx->d_rlc_bytes, &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off,
                     &ctx->d_cursor, &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict,
-                    &ctx->d_partials, &ctx->d_partials_msm, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal, &ctx->d_flush};
+                    &ctx->d_partials, &ctx->d_partials_msm, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal, &ctx->d_flush,
+                    &ctx->d_lines, &ctx->d_M, &ctx->d_partial_out, &ctx->d_wsums_fin};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : ctx->ev)
@@ -727,6 +783,12 @@ int h2v_batch_set_columns(h2v_ctx* ctx, const uint32_t* inst_ncols, const uint32
   ctx->opt_col_len = inst_col_len;
   return 0;
 }
+int h2v_batch_set_shard_hint(h2v_ctx* ctx, uint32_t max_shard_proofs) {
+  if (!ctx) return -1;
+  ctx->opt_shard_hint = max_shard_proofs;
+  return 0;
+}
+size_t h2v_partial_bytes(void) { return H2V_PARTIAL_BYTES; }
 int h2v_batch_set_scalar_hook(h2v_ctx* ctx, uint8_t* msm_scalars) {
   if (!ctx) return -1;
   ctx->opt_scalar_hook = msm_scalars;
@@ -759,9 +821,14 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   ctx->n = n;
   ctx->gbase = gbase;
   ctx->gcount = gcount;
-  ctx->geom = choose_geom(n, hd);
+  ctx->geom = choose_geom(n, hd, ctx->opt_shard_hint);
+  ctx->opt_shard_hint = 0;
   const MsmGeom& g = ctx->geom;
   const u32 nb = g.nb();
+  {
+    int lrc = ensure_lines(ctx);
+    if (lrc) return lrc;
+  }
   CKC(ctx->d_proofs.ensure(pbytes + 64));
   CKC(ctx->d_proof_off.ensure(8 * (size_t)(n + 1)));
   CKC(ctx->d_inst.ensure(32 * iscal + 64));
@@ -811,8 +878,11 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   return 0;
 }
 
-// every kernel of the batch; do_pairing = 0 leaves the accumulators in d_acc_bytes without a verdict
-static int run_impl(h2v_ctx* ctx, int do_pairing) {
+// every kernel of the batch.  mode bits: RUN_PAIRING = batch pairing check -> d_verdict; RUN_ACCUM = explicit
+// window combination -> affine (L, R) bytes in d_acc_bytes (parity hook); RUN_PARTIAL = pack the window
+// sums into d_partial_out (sharded batches)
+enum : int { RUN_PAIRING = 1, RUN_ACCUM = 2, RUN_PARTIAL = 4 };
+static int run_impl(h2v_ctx* ctx, int mode) {
   if (!ctx || ctx->n == 0) return -1;
   CKC(cudaSetDevice(ctx->device));
   const PlanHeader& hd = ctx->hd;
@@ -865,10 +935,20 @@ static int run_impl(h2v_ctx* ctx, int do_pairing) {
   k_msm_window_reduce<<<g.W[0] + g.W[1], 256, 0, s>>>(g, ctx->d_partials_msm.as<G1Jac>(), ctx->d_wsums.as<G1Jac>());
   LAUNCH_CHECK();
   CKC(cudaEventRecord(ctx->ev[4], s));
-  FinalizeArgs fa{0, {g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {g.wbase[0], g.wbase[1]}, 0, (u32)do_pairing};
-  k_finalize<<<1, 32, 0, s>>>(pv, fa, ctx->d_wsums.as<G1Jac>(), nullptr, ctx->d_acc_bytes.as<u8>(), ctx->d_verdict.as<u32>());
-  LAUNCH_CHECK();
+  if (mode & RUN_PAIRING) {
+    int prc = launch_pairing(ctx, ctx->d_wsums.as<G1Jac>());
+    if (prc) return prc;
+  }
+  if (mode & RUN_PARTIAL) {
+    k_pack_partial<<<8, 256, 0, s>>>(g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, g.W[0] + g.W[1], ctx->d_wsums.as<G1Jac>(), ctx->d_partial_out.as<u8>());
+    LAUNCH_CHECK();
+  }
   CKC(cudaEventRecord(ctx->ev[5], s));
+  if (mode & RUN_ACCUM) {
+    FoldArgs fa{{g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {g.wbase[0], g.wbase[1]}};
+    k_fold_accum<<<1, 32, 0, s>>>(fa, ctx->d_wsums.as<G1Jac>(), ctx->d_acc_bytes.as<u8>());
+    LAUNCH_CHECK();
+  }
   CKC(cudaEventRecord(ctx->ev[6], s));
   ctx->ran = true;
   return 0;
@@ -935,7 +1015,7 @@ int h2v_verify_batch(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint
                      uint8_t* accum, uint8_t* batch_accum) {
   int rc;
   if ((rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, 0, n)) != 0) return rc;
-  if ((rc = run_impl(ctx, 1)) != 0) return rc;
+  if ((rc = run_impl(ctx, RUN_PAIRING | (batch_accum ? RUN_ACCUM : 0))) != 0) return rc;
   if ((rc = hooks_impl(ctx, challenges)) != 0) return rc;
   u32 verdict = 0;
   CKC(cudaMemcpyAsync(&verdict, ctx->d_verdict.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -957,24 +1037,59 @@ int h2v_accumulate_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const 
                          uint64_t global_count, uint8_t* status, uint8_t* partial) {
   int rc;
   if ((rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, global_base, global_count)) != 0) return rc;
-  if ((rc = run_impl(ctx, 0)) != 0) return rc;
-  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_acc_bytes.p, 128, cudaMemcpyDefault, ctx->stream));
+  if ((rc = run_impl(ctx, RUN_PARTIAL)) != 0) return rc;
+  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_partial_out.p, H2V_PARTIAL_BYTES, cudaMemcpyDefault, ctx->stream));
   return download_status(ctx, status);
 }
 
 int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uint8_t* batch_accum, int* verdict) {
-  if (!ctx || !partials || !n_partials) return -1;
+  if (!ctx || !partials || !n_partials || n_partials > 128) return -1;
   CKC(cudaSetDevice(ctx->device));
-  CKC(ctx->d_partials.ensure(128 * (size_t)n_partials));
-  CKC(cudaMemcpyAsync(ctx->d_partials.p, partials, 128 * (size_t)n_partials, cudaMemcpyDefault, ctx->stream));
-  FinalizeArgs fa{1, {0, 0}, {0, 0}, {0, 0}, n_partials, 1};
-  k_finalize<<<1, 32, 0, ctx->stream>>>(ctx->pv(), fa, nullptr, ctx->d_partials.as<u8>(), ctx->d_acc_bytes.as<u8>(), ctx->d_verdict.as<u32>());
+  cudaStream_t s = ctx->stream;
+  CKC(ctx->d_partials.ensure((size_t)H2V_PARTIAL_BYTES * n_partials));
+  CKC(cudaMemcpyAsync(ctx->d_partials.p, partials, (size_t)H2V_PARTIAL_BYTES * n_partials, cudaMemcpyDefault, s));
+  if (ctx->n == 0) {  // a context that has not processed a shard itself: take the geometry from the first partial
+    PartialHeader h;
+    CKC(cudaMemcpyAsync(&h, ctx->d_partials.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CKC(cudaStreamSynchronize(s));
+    MsmGeom& g = ctx->geom;
+    g = MsmGeom{};
+    g.c[0] = h.cbits & 0xFFFF;
+    g.c[1] = h.cbits >> 16;
+    g.W[0] = h.windows & 0xFFFF;
+    g.W[1] = h.windows >> 16;
+    if (h.magic != H2V_PARTIAL_MAGIC || g.c[0] < 1 || g.c[1] < 1 || g.W[0] + g.W[1] != h.n_pts || h.n_pts > 128) {
+      ctx->err = "malformed partial accumulator";
+      return -1;
+    }
+    g.wbase[1] = g.W[0];
+  }
+  {
+    int lrc = ensure_lines(ctx);
+    if (lrc) return lrc;
+  }
+  const MsmGeom& g = ctx->geom;
+  const u32 npts = g.W[0] + g.W[1];
+  CKC(cudaMemsetAsync(ctx->d_verdict.p, 0, 16, s));
+  k_sum_partials<<<1, 128, 0, s>>>(n_partials, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, npts, ctx->d_partials.as<u8>(), ctx->d_wsums_fin.as<G1Jac>(),
+                                   ctx->d_verdict.as<u32>() + 1);
   LAUNCH_CHECK();
-  u32 v = 0;
-  CKC(cudaMemcpyAsync(&v, ctx->d_verdict.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (batch_accum) CKC(cudaMemcpyAsync(batch_accum, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
-  CKC(cudaStreamSynchronize(ctx->stream));
-  if (verdict) *verdict = (int)v;
+  int prc = launch_pairing(ctx, ctx->d_wsums_fin.as<G1Jac>());
+  if (prc) return prc;
+  if (batch_accum) {
+    FoldArgs fa{{g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {0, g.W[0]}};
+    k_fold_accum<<<1, 32, 0, s>>>(fa, ctx->d_wsums_fin.as<G1Jac>(), ctx->d_acc_bytes.as<u8>());
+    LAUNCH_CHECK();
+    CKC(cudaMemcpyAsync(batch_accum, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, s));
+  }
+  u32 v[2] = {0, 0};
+  CKC(cudaMemcpyAsync(v, ctx->d_verdict.p, 8, cudaMemcpyDeviceToHost, s));
+  CKC(cudaStreamSynchronize(s));
+  if (v[1]) {
+    ctx->err = "partial accumulators were produced with different window geometries (use h2v_batch_set_shard_hint)";
+    return -1;
+  }
+  if (verdict) *verdict = (int)v[0];
   return 0;
 }
 
@@ -1003,9 +1118,9 @@ int h2v_batch_upload_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, cons
 }
 
 int h2v_batch_run_shard(h2v_ctx* ctx, uint8_t* partial) {
-  int rc = run_impl(ctx, 0);
+  int rc = run_impl(ctx, RUN_PARTIAL);
   if (rc) return rc;
-  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_acc_bytes.p, 128, cudaMemcpyDefault, ctx->stream));
+  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_partial_out.p, H2V_PARTIAL_BYTES, cudaMemcpyDefault, ctx->stream));
   CKC(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -1019,7 +1134,7 @@ int h2v_flush_l2(h2v_ctx* ctx, size_t bytes) {
 }
 
 int h2v_batch_run(h2v_ctx* ctx, int* verdict) {
-  int rc = run_impl(ctx, 1);
+  int rc = run_impl(ctx, RUN_PAIRING);
   if (rc) return rc;
   u32 v = 0;
   CKC(cudaMemcpyAsync(&v, ctx->d_verdict.p, 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,0 +1,328 @@
+// Cooperative Fq12 engine and the batch pairing check built on it.
+//
+// The batch verdict is ONE pairing-product check (reference poly/kzg/msm.rs:185-203,
+// `DualMSM::check`) and sits on the critical path of every batch, so it is organised for LATENCY:
+//
+//  * No window combination and no inversion.  The folded MSM leaves one Jacobian sum S_w per
+//    (channel, window); instead of the serial Horner chain  R = sum_w 2^(c w) S_w  (c*W dependent
+//    doublings) the check uses bilinearity,  e(R, Q) = prod_w e(S_w, [2^(c w)] Q):  the G2 multiples
+//    are verifier parameters and their Miller lines are prepared once per window geometry.  Lines
+//    are evaluated at PROJECTIVE G1 points (scaled by Z^3, an Fq factor the final exponentiation
+//    kills), and the final exponentiation is checked without dividing:  f^((p^6-1) M) = 1  <=>
+//    conj(F) = F  with F = f^M = N / D,  i.e.  conj(N) D = N conj(D)  (N, D: the positive- and
+//    negative-exponent halves of the hard-part addition chain).
+//  * k_lines: every Miller-loop iteration's line product  prod_pairs l(S_pair)  is independent of
+//    the running value, so all 65 of them are computed by 65 thread blocks in parallel.
+//  * k_pairing_check: one 64-thread group then walks  f = f^2 * M_i  and the final exponentiation;
+//    every Fq12 product is 54 independent Montgomery multiplications (one per lane) plus one
+//    table-driven linear map (pairing_lin.inc), with the operands kept in Karatsuba-expanded form.
+//
+// Values are identical to the single-thread tower in tower.cuh (tests/hostlib runs the per-lane
+// phase functions on the host against fq12_mul; GPU tests compare verdicts with the oracle).
+#pragma once
+#include "pairing_lin.inc"
+#include "tower.cuh"
+
+namespace h2v {
+
+static constexpr int E12_N = 54;   // expanded coordinates
+static constexpr int E12_NB = 12;  // base coordinates b = 2 * (3 * hh + j) + part  <->  Fq12::a[2 j + hh].c{part}
+
+struct E12 {
+  Fq e[E12_N];
+};
+
+struct LinTables {
+  uint16_t full_start[E12_N + 1];
+  uint16_t exp_start[E12_N + 1];
+  uint16_t full_terms[H2V_LIN_FULL_NTERMS];
+  uint16_t exp_terms[H2V_LIN_EXP_NTERMS];
+};
+#define H2V_LIN_TABLES_INIT {H2V_LIN_FULL_START_INIT, H2V_LIN_EXP_START_INIT, H2V_LIN_FULL_TERMS_INIT, H2V_LIN_EXP_TERMS_INIT}
+
+H2V_HD int e12_base_slot(int b) {  // position of base coordinate b inside the expanded form
+  const int hh = b / 6, j = (b % 6) / 2, part = b & 1;
+  return 3 * (6 * hh + j) + part;
+}
+
+// sum_k coef_k * src[idx_k] mod p for one table row: 64-bit column accumulators, one reduction.
+// Every coefficient is positive (negative terms address the negated copy of the source) and every
+// source value is <= p, so the sum is < 2^9 p.
+H2V_HD Fq lin_row(const uint16_t* start, const uint16_t* terms, int row, const Fq* src) {
+  u64 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = 0;
+  const int k1 = start[row + 1];
+  for (int k = start[row]; k < k1; k++) {
+    const u32 t = terms[k];
+    const u32 c = t >> 8;
+    const u32* v = src[t & 0xFF].l;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] += (u64)c * v[i];
+  }
+  u32 V[9];
+  u64 cy = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    cy += acc[i];
+    V[i] = (u32)cy;
+    cy >>= 32;
+  }
+  V[8] = (u32)cy;
+  // quotient estimate from the top bits: q <= floor(V / p) <= q + 2   (1354 = floor(2^32 / ((p >> 232) + 1)))
+  const u32 q = (u32)(((u64)((V[8] << 24) | (V[7] >> 8)) * 1354u) >> 32);
+  Fq r;
+  u64 mc = 0;
+  u32 br = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    mc += (u64)q * FqP::mod(i);
+    const u32 m = (u32)mc;
+    mc >>= 32;
+    const u64 d = (u64)V[i] - m - br;
+    r.l[i] = (u32)d;
+    br = (u32)(d >> 32) & 1u;
+  }
+  r.cond_sub_mod();  // remainder < 3 p < 2^256
+  r.cond_sub_mod();
+  return r;
+}
+
+// ---- per-lane phases (host/device; the device wrappers below add the barriers)
+// products: pr[lane] = a[lane] * b[lane], pr[54 + lane] = p - pr[lane]
+H2V_HD void e12_mul_p1(Fq* pr, const E12* a, const E12* b, int lane) {
+  const Fq t = Fq::mul(a->e[lane], b->e[lane]);
+  pr[lane] = t;
+  Fq n;
+  u32 m[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) m[i] = FqP::mod(i);
+  Fq::sub_raw(n.l, m, t.l);
+  pr[E12_N + lane] = n;
+}
+H2V_HD void e12_mul_p2(E12* dst, const Fq* pr, const LinTables* lt, int lane) {
+  dst->e[lane] = lin_row(lt->full_start, lt->full_terms, lane, pr);
+}
+H2V_HD void e12_expand_p(E12* dst, const Fq* base12, const LinTables* lt, int lane) {
+  dst->e[lane] = lin_row(lt->exp_start, lt->exp_terms, lane, base12);
+}
+// base coordinate b of conj(x) = x^(p^6), of x^p and of x^(p^2)   (lane = b < 12)
+H2V_HD Fq e12_conj_base(const E12* x, int b) {
+  const Fq v = x->e[e12_base_slot(b)];
+  return b >= 6 ? v.neg() : v;
+}
+H2V_HD Fq e12_frob_base(const E12* x, int b) {
+  const int hh = b / 6, j = (b % 6) / 2, part = b & 1, i = 2 * j + hh;
+  const Fq re = x->e[e12_base_slot(b & ~1)], im = x->e[e12_base_slot(b | 1)];
+  if (i == 0) return part ? im.neg() : re;
+  const Fq2 g = tower_gamma1(i);  // conj(c) * g = (re g0 + im g1) + (re g1 - im g0) u
+  return part ? Fq::mul(re, g.c1) - Fq::mul(im, g.c0) : Fq::mul(re, g.c0) + Fq::mul(im, g.c1);
+}
+H2V_HD Fq e12_frob2_base(const E12* x, int b) {
+  const int hh = b / 6, j = (b % 6) / 2, i = 2 * j + hh;
+  const Fq v = x->e[e12_base_slot(b)];
+  return i == 0 ? v : Fq::mul(v, tower_gamma2(i));
+}
+// base coordinate b of the line value  Y + (nlam * XZ) w + (c * Z3) w^3  at the projective point
+// (X, Y, Z) of G1, given XZ = X Z and Z3 = Z^3 (affine line scaled by Z^3; identity point: line = 1)
+H2V_HD Fq e12_line_base(const G2Line& ln, const Fq& Y, const Fq& XZ, const Fq& Z3, bool identity, int b) {
+  if (identity) return b == 0 ? Fq::one() : Fq::zero();
+  switch (b) {
+    case 0: return Y;                         // a[0].c0
+    case 6: return Fq::mul(ln.nlam.c0, XZ);   // a[1].c0   (hh = 1, j = 0)
+    case 7: return Fq::mul(ln.nlam.c1, XZ);
+    case 8: return Fq::mul(ln.c.c0, Z3);      // a[3].c0   (hh = 1, j = 1)
+    case 9: return Fq::mul(ln.c.c1, Z3);
+    default: return Fq::zero();
+  }
+}
+// Fq12 (six Fq2 coefficients of w^i) <-> base coordinates, for tests and for loading constants
+H2V_HD Fq fq12_base_coord(const Fq12& x, int b) {
+  const int hh = b / 6, j = (b % 6) / 2, part = b & 1;
+  const Fq2& c = x.a[2 * j + hh];
+  return part ? c.c1 : c.c0;
+}
+
+// index of the first prepared line of Miller-loop iteration `it` (0..63; 64 = the two Frobenius lines)
+H2V_HD int ate_line_index(int it) {
+  int n = 0;
+  for (int k = 0; k < it && k < 64; k++) n += 1 + (int)((H2V_ATE_LOOP_LOW >> (63 - k)) & 1);
+  return n;
+}
+H2V_HD int ate_lines_in_iteration(int it) { return it >= 64 ? 2 : 1 + (int)((H2V_ATE_LOOP_LOW >> (63 - it)) & 1); }
+static constexpr int H2V_ATE_ITERS = 65;
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------------------------------------
+// device: a "group" is 64 threads (2 warps) sharing one named barrier
+__device__ const LinTables g_lin_tables = H2V_LIN_TABLES_INIT;
+
+struct Grp {
+  int lane;  // 0..63
+  int bar;   // named barrier id (1..15)
+  const LinTables* lt;
+  Fq* scr;   // 2 * E12_N values of shared scratch
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory"); }
+};
+
+__device__ __forceinline__ void g_mul(const Grp& g, E12* dst, const E12* a, const E12* b) {  // dst may alias a, b
+  if (g.lane < E12_N) e12_mul_p1(g.scr, a, b, g.lane);
+  g.sync();
+  if (g.lane < E12_N) e12_mul_p2(dst, g.scr, g.lt, g.lane);
+  g.sync();
+}
+__device__ __forceinline__ void g_expand(const Grp& g, E12* dst) {  // from base coordinates in scr[0..11]
+  g.sync();
+  if (g.lane < E12_N) e12_expand_p(dst, g.scr, g.lt, g.lane);
+  g.sync();
+}
+__device__ __forceinline__ void g_conj(const Grp& g, E12* dst, const E12* a) {
+  if (g.lane < E12_NB) g.scr[g.lane] = e12_conj_base(a, g.lane);
+  g_expand(g, dst);
+}
+__device__ __noinline__ void g_frob(const Grp& g, E12* dst, const E12* a) {
+  if (g.lane < E12_NB) g.scr[g.lane] = e12_frob_base(a, g.lane);
+  g_expand(g, dst);
+}
+__device__ __noinline__ void g_frob2(const Grp& g, E12* dst, const E12* a) {
+  if (g.lane < E12_NB) g.scr[g.lane] = e12_frob2_base(a, g.lane);
+  g_expand(g, dst);
+}
+__device__ __forceinline__ void g_one(const Grp& g, E12* dst) {
+  if (g.lane < E12_NB) g.scr[g.lane] = g.lane == 0 ? Fq::one() : Fq::zero();
+  g_expand(g, dst);
+}
+__device__ __forceinline__ void g_copy(const Grp& g, E12* dst, const E12* a) {
+  if (g.lane < E12_N) dst->e[g.lane] = a->e[g.lane];
+  g.sync();
+}
+__device__ __noinline__ void g_pow_u(const Grp& g, E12* dst, const E12* x) {  // dst != x
+  g_copy(g, dst, x);
+#pragma unroll 1
+  for (int i = 61; i >= 0; i--) {
+    g_mul(g, dst, dst, dst);
+    if ((H2V_BN_U >> i) & 1) g_mul(g, dst, dst, x);
+  }
+}
+
+// ---- k_lines: M[it] = prod over pairs and over the lines of iteration `it` of line(S_pair)
+struct LinesArgs {
+  u32 n_pairs;  // (channel, window) pairs = window sums; pair p uses lines[p * H2V_ATE_LINES ..]
+};
+struct LinesSmem {  // dynamic shared memory layout of k_lines<GROUPS>
+  LinTables lt;
+  Fq Y[128], XZ[128], Z3[128];
+  u32 ident[128];
+};
+template <int GROUPS>
+__global__ void __launch_bounds__(64 * GROUPS) k_lines(LinesArgs la, const G1Jac* __restrict__ wsums, const G2Line* __restrict__ lines,
+                                                       E12* __restrict__ M) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LinesSmem* sm = (LinesSmem*)smem_raw;
+  E12* accs = (E12*)(sm + 1);            // [GROUPS]
+  E12* tmps = accs + GROUPS;             // [GROUPS]
+  Fq* scrs = (Fq*)(tmps + GROUPS);       // [GROUPS][2 * E12_N]
+  const int t = threadIdx.x, gi = t >> 6;
+  for (int i = t; i < (int)(sizeof(LinTables) / 2); i += blockDim.x) ((uint16_t*)&sm->lt)[i] = ((const uint16_t*)&g_lin_tables)[i];
+  if (t < (int)la.n_pairs) {
+    const G1Jac s = wsums[t];
+    const bool id = s.Z.is_zero();
+    sm->ident[t] = id;
+    sm->Y[t] = s.Y;
+    sm->XZ[t] = Fq::mul(s.X, s.Z);
+    sm->Z3[t] = Fq::mul(Fq::mul(s.Z, s.Z), s.Z);
+  }
+  __syncthreads();
+  Grp g{t & 63, gi + 1, &sm->lt, scrs + gi * 2 * E12_N};
+  E12 *acc = accs + gi, *tmp = tmps + gi;
+  const int it = blockIdx.x;
+  const int n0 = it >= 64 ? H2V_ATE_LINES - 2 : ate_line_index(it), ns = ate_lines_in_iteration(it);
+  const int items = ns * (int)la.n_pairs;
+  bool first = true;
+  for (int item = gi; item < items; item += GROUPS) {
+    const int p = item % (int)la.n_pairs, s = item / (int)la.n_pairs;
+    if (g.lane < E12_NB)
+      g.scr[g.lane] = e12_line_base(lines[(size_t)p * H2V_ATE_LINES + n0 + s], sm->Y[p], sm->XZ[p], sm->Z3[p], sm->ident[p] != 0, g.lane);
+    g_expand(g, first ? acc : tmp);
+    if (!first) g_mul(g, acc, acc, tmp);
+    first = false;
+  }
+  if (first) g_one(g, acc);
+  __syncthreads();
+  for (int s = GROUPS / 2; s >= 1; s >>= 1) {
+    if (gi < s) g_mul(g, acc, acc, accs + gi + s);
+    __syncthreads();
+  }
+  if (gi == 0 && g.lane < E12_N) M[it].e[g.lane] = acc->e[g.lane];
+}
+template <int GROUPS>
+constexpr size_t k_lines_smem() {
+  return sizeof(LinesSmem) + GROUPS * (2 * sizeof(E12) + 2 * E12_N * sizeof(Fq));
+}
+
+// ---- k_pairing_check: Miller accumulation over the prepared iteration products + final check
+__global__ void __launch_bounds__(64) k_pairing_check(const E12* __restrict__ M, u32* verdict) {
+  __shared__ LinTables lt;
+  __shared__ E12 slot[12];
+  __shared__ Fq scr[2 * E12_N];
+  const int t = threadIdx.x;
+  for (int i = t; i < (int)(sizeof(LinTables) / 2); i += 64) ((uint16_t*)&lt)[i] = ((const uint16_t*)&g_lin_tables)[i];
+  __syncthreads();
+  Grp g{t, 1, &lt, scr};
+  E12 *f = &slot[0], *tt = &slot[1], *fu = &slot[2], *fu2 = &slot[3], *fu3 = &slot[4], *a = &slot[5], *b = &slot[6], *y0 = &slot[7],
+      *T0 = &slot[8], *T1 = &slot[9], *N = &slot[10], *m = &slot[11];
+  g_copy(g, f, &M[0]);
+#pragma unroll 1
+  for (int it = 1; it < H2V_ATE_ITERS; it++) {
+    g_copy(g, m, &M[it]);
+    if (it < 64) g_mul(g, f, f, f);
+    g_mul(g, f, f, m);
+  }
+  // t = f^(p^2 + 1); the easy factor p^6 - 1 is replaced by the conjugation test at the end
+  g_frob2(g, a, f);
+  g_mul(g, tt, a, f);
+  g_pow_u(g, fu, tt);
+  g_pow_u(g, fu2, fu);
+  g_pow_u(g, fu3, fu2);
+  // numerator: y0 = t^p t^(p^2) t^(p^3), y2 = (t^(u^2))^(p^2);  N = y0 y2^6
+  g_frob(g, a, tt);
+  g_frob2(g, b, tt);
+  g_mul(g, y0, a, b);
+  g_frob(g, a, b);
+  g_mul(g, y0, y0, a);
+  g_frob2(g, a, fu2);
+  g_mul(g, a, a, a);        // y2^2
+  g_mul(g, b, a, a);        // y2^4
+  g_mul(g, b, b, a);        // y2^6
+  g_mul(g, N, y0, b);
+  // denominator (positive powers of the inverted terms): Y1 = t, Y3 = (t^u)^p, Y4 = t^u (t^(u^2))^p, Y5 = t^(u^2),
+  // Y6 = t^(u^3) (t^(u^3))^p;  D = Y1^2 Y3^12 Y4^18 Y5^30 Y6^36 by the Scott et al. vector chain
+  g_frob(g, a, fu3);
+  g_mul(g, a, fu3, a);      // Y6
+  g_mul(g, T0, a, a);       // Y6^2
+  g_frob(g, a, fu2);
+  g_mul(g, a, fu, a);       // Y4
+  g_mul(g, T0, T0, a);
+  g_mul(g, T0, T0, fu2);    // T0 = Y6^2 Y4 Y5
+  g_frob(g, a, fu);         // Y3
+  g_mul(g, T1, a, fu2);
+  g_mul(g, T1, T1, T0);     // T1 = Y3 Y5 T0
+  g_mul(g, T1, T1, T1);
+  g_mul(g, T1, T1, T0);
+  g_mul(g, T1, T1, T1);     // T1 = (T1^2 T0)^2
+  g_mul(g, T0, T1, tt);     // T0 = T1 Y1
+  g_mul(g, T0, T0, T0);
+  g_mul(g, T0, T0, T1);     // D = T0^2 T1
+  // accept  <=>  conj(N) D == N conj(D)
+  g_conj(g, a, N);
+  g_mul(g, a, a, T0);
+  g_conj(g, b, T0);
+  g_mul(g, b, N, b);
+  bool ok = true;
+  if (t < E12_NB) ok = a->e[e12_base_slot(t)] == b->e[e12_base_slot(t)];
+  ok = __syncthreads_and(ok);
+  if (t == 0) *verdict = ok ? 1u : 0u;
+}
+#endif  // __CUDACC__
+
+}  // namespace h2v

@@ -743,6 +743,8 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
     memcpy(blob.data(), &hd, sizeof(hd));
 
     info.k = k;
+    memcpy(info.q_left, &s_g2, sizeof(info.q_left));
+    memcpy(info.q_right, &ng2, sizeof(info.q_right));
     info.n_points = hd.n_points;
     info.n_scalars = S;
     info.n_challenges = n_squeeze;
@@ -755,6 +757,23 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
     err = e.msg;
     return -1;
   }
+}
+
+void build_window_lines(const PlanInfo& info, u32 c0, u32 W0, u32 c1, u32 W1, std::vector<u8>& out) {
+  const u32 np = W0 + W1;
+  std::vector<G2Affine> q(np);
+  for (int ch = 0; ch < 2; ch++) {
+    G2Affine cur;
+    memcpy(&cur, ch == 0 ? info.q_right : info.q_left, sizeof(cur));
+    const u32 W = ch == 0 ? W0 : W1, c = ch == 0 ? c0 : c1, base = ch == 0 ? 0 : W0;
+    for (u32 w = 0; w < W; w++) {
+      q[base + w] = cur;
+      if (w + 1 < W)
+        for (u32 i = 0; i < c; i++) cur = g2_double_affine(cur);  // order r is prime: never the identity
+    }
+  }
+  out.resize((size_t)np * H2V_ATE_LINES * sizeof(G2Line));
+  g2_prepare_many(q.data(), (int)np, (G2Line*)out.data());
 }
 
 }  // namespace h2v

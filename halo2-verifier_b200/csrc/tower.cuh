@@ -11,6 +11,8 @@
 // `G2Prepared`; the device Miller loop only evaluates prepared lines at the two G1 accumulators.
 #pragma once
 #include "curve.cuh"
+#include <stddef.h>
+
 #include "tower_consts.inc"
 
 namespace h2v {
@@ -223,6 +225,66 @@ inline void g2_prepare(const G2Affine& q, G2Line* lines /* H2V_ATE_LINES */) {
   g2_line_step(t, q2, false, lines[n++]);
 }
 inline bool g2_on_curve(const G2Affine& q) { return q.y.sqr() == q.x.sqr() * q.x + twist_b(); }
+inline G2Affine g2_double_affine(const G2Affine& q) {
+  G2Affine t = q;
+  G2Line unused;
+  g2_line_step(t, t, true, unused);
+  return t;
+}
+// Line tables of `count` points at once (lines[k * H2V_ATE_LINES ..] for q[k]); the slope
+// denominators of one step are inverted together (Montgomery's trick), one Fq2 inversion per step.
+inline void g2_prepare_many(const G2Affine* q, int count, G2Line* lines) {
+  if (count <= 0) return;
+  G2Affine* t = new G2Affine[count];
+  G2Affine* other = new G2Affine[count];
+  Fq2* den = new Fq2[count];
+  Fq2* pre = new Fq2[count];
+  for (int k = 0; k < count; k++) t[k] = q[k];
+  int n = 0;
+  auto step = [&](bool is_double, const G2Affine* rhs) {
+    Fq2 acc = Fq2::one();
+    for (int k = 0; k < count; k++) {
+      den[k] = is_double ? t[k].y.dbl() : rhs[k].x - t[k].x;
+      pre[k] = acc;
+      acc = acc * den[k];
+    }
+    Fq2 inv = acc.inv();
+    for (int k = count; k-- > 0;) {
+      const Fq2 di = inv * pre[k];
+      inv = inv * den[k];
+      Fq2 lam;
+      if (is_double) {
+        Fq2 x2 = t[k].x.sqr();
+        lam = (x2.dbl() + x2) * di;
+      } else {
+        lam = (rhs[k].y - t[k].y) * di;
+      }
+      const Fq2 x3 = lam.sqr() - t[k].x - (is_double ? t[k].x : rhs[k].x);
+      const Fq2 y3 = lam * (t[k].x - x3) - t[k].y;
+      G2Line& out = lines[(size_t)k * H2V_ATE_LINES + n];
+      out.nlam = lam.neg();
+      out.c = lam * t[k].x - t[k].y;
+      t[k].x = x3;
+      t[k].y = y3;
+    }
+    n++;
+  };
+  for (int i = 63; i >= 0; i--) {
+    step(true, nullptr);
+    if ((H2V_ATE_LOOP_LOW >> i) & 1) step(false, q);
+  }
+  for (int k = 0; k < count; k++) other[k] = g2_frob(q[k]);
+  step(false, other);
+  for (int k = 0; k < count; k++) {
+    other[k] = g2_frob(other[k]);
+    other[k].y = other[k].y.neg();
+  }
+  step(false, other);
+  delete[] t;
+  delete[] other;
+  delete[] den;
+  delete[] pre;
+}
 #endif
 
 // ------------------------------------------------------------------------------------------ pairing check

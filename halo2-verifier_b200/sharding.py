@@ -1,7 +1,8 @@
 """Multi-GPU plumbing (one process per GPU): contiguous proof shards, globally defined RLC
-coefficients, and an all-gather of the 128-byte partial accumulators (NCCL on GPUs, gloo in the CPU
-tests).  NCCL cannot reduce with an elliptic-curve addition, hence gather-then-add: rank 0 adds the
-partials and runs the single pairing (`h2v_finalize`).  SURVEY.md section 8(e)."""
+coefficients, and an all-gather of the partial accumulators (NCCL on GPUs, gloo in the CPU tests).
+A partial is the shard's per-window bucket sums (H2V_PARTIAL_BYTES, include/h2v.h).  NCCL cannot
+reduce with an elliptic-curve addition, hence gather-then-add: rank 0 adds the partials window-wise
+and runs the single pairing check (`h2v_finalize`).  SURVEY.md section 8(e)."""
 from typing import List, Tuple
 
 import torch
@@ -16,9 +17,9 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def all_gather_partials(partial: torch.Tensor, world: int) -> List[bytes]:
-    """partial: uint8[128] = affine (L_g | R_g) of this rank, on the device of the process group's
-    backend.  Returns every rank's partial as bytes, rank order."""
-    assert partial.dtype == torch.uint8 and partial.numel() == 128
+    """partial: uint8[H2V_PARTIAL_BYTES] of this rank, on the device of the process group's backend.
+    Returns every rank's partial as bytes, rank order."""
+    assert partial.dtype == torch.uint8 and partial.dim() == 1
     if world == 1:
         return [bytes(partial.cpu().numpy().tobytes())]
     out = [torch.empty_like(partial) for _ in range(world)]
@@ -31,13 +32,14 @@ def verify_batch_sharded(bv, proofs, instances, rank: int, world: int, rlc_scala
     the right indices); returns (global verdict, statuses of this rank's shard)."""
     n = len(proofs)
     lo, hi = shard_range(n, rank, world)
-    status, partial = bv.accumulate_shard(proofs[lo:hi], instances[lo:hi], lo, n, rlc_scalars=rlc_scalars, seed=seed)
+    hint = shard_range(n, 0, world)[1]  # largest shard: common window geometry on every rank
+    status, partial = bv.accumulate_shard(proofs[lo:hi], instances[lo:hi], lo, n, rlc_scalars=rlc_scalars, seed=seed, shard_hint=hint)
     dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     t = torch.frombuffer(bytearray(partial), dtype=torch.uint8).to(dev)
     parts = all_gather_partials(t, world)
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     if rank == 0:
-        ok, _ = bv.finalize(parts)
+        ok, _ = bv.finalize(parts, want_batch_accum=False)
         flag[0] = 1 if ok else 0
     if world > 1:
         dist.broadcast(flag, src=0)

@@ -87,15 +87,26 @@ int h2v_batch_set_scalar_hook(h2v_ctx* ctx, uint8_t* msm_scalars);
 /* ---- sharded batches (one context per GPU) -------------------------------------
  * h2v_accumulate_shard processes proofs [global_base, global_base + n) of a global batch of
  * global_count proofs with GLOBALLY defined coefficients c_j (rlc_scalars, if given, has
- * global_count entries) and returns this shard's partial accumulators, 2 x 64 B affine (L_g, R_g),
- * without running a pairing.  Proof statuses are final except that H2V_OK means "accumulated".
- * `partial` (and `partials` of h2v_finalize) may be host or device pointers (unified addressing). */
+ * global_count entries) and returns this shard's partial accumulators without running a pairing.
+ * A partial is an opaque blob of H2V_PARTIAL_BYTES: a 32-byte header (window geometry) and the
+ * shard's per-window Jacobian bucket sums S_w of both MSM channels, L_g = sum_w 2^(c w) S_w^left,
+ * R_g likewise; the partials of all shards add up window-wise, and the final check pairs each
+ * summed S_w with the prepared multiple [2^(c w)] of its G2 argument, so the explicit (L, R) are
+ * only formed when `batch_accum` is requested.  Every shard of one global batch must use the same
+ * window geometry: shards of equal size do; otherwise call h2v_batch_set_shard_hint with the
+ * largest shard size on every rank.  Proof statuses are final except that H2V_OK means
+ * "accumulated".  `partial` (and `partials` of h2v_finalize) may be host or device pointers. */
+#define H2V_PARTIAL_BYTES 12320
+size_t h2v_partial_bytes(void);
+/* window geometry of the NEXT batch call as for a shard of `max_shard_proofs` proofs; cleared after one batch */
+int h2v_batch_set_shard_hint(h2v_ctx* ctx, uint32_t max_shard_proofs);
 int h2v_accumulate_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off,
                          const uint8_t* instances, const uint64_t* inst_off, const uint8_t* rlc_scalars,
                          uint64_t seed, uint64_t global_base, uint64_t global_count, uint8_t* status,
                          uint8_t* partial);
-/* Adds n_partials partial accumulators (gathered over NCCL) and runs the single pairing check
- * DualMSM::check (msm.rs:185-203).  verdict: 1 accept, 0 reject.  batch_accum optional 2 x 64 B. */
+/* Adds n_partials (<= 128) partial accumulators (gathered over NCCL; n_partials x H2V_PARTIAL_BYTES) and
+ * runs the single pairing check DualMSM::check (msm.rs:185-203).  verdict: 1 accept, 0 reject.
+ * batch_accum: optional 2 x 64 B folded affine (L, R) (parity hook; costs the serial window combination). */
 int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uint8_t* batch_accum,
                  int* verdict);
 /* After a rejected h2v_finalize: per-proof pairing checks on the shard last processed by this
@@ -110,7 +121,7 @@ int h2v_batch_upload(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint
 int h2v_batch_upload_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off,
                            const uint8_t* instances, const uint64_t* inst_off, const uint8_t* rlc_scalars,
                            uint64_t seed, uint64_t global_base, uint64_t global_count);
-/* runs every kernel of the shard except the pairing; partial: 128 B out, host OR device pointer */
+/* runs every kernel of the shard except the pairing; partial: H2V_PARTIAL_BYTES out, host OR device pointer */
 int h2v_batch_run_shard(h2v_ctx* ctx, uint8_t* partial);
 /* overwrites `bytes` of scratch HBM on the context's stream (L2 flush between timed iterations) */
 int h2v_flush_l2(h2v_ctx* ctx, size_t bytes);

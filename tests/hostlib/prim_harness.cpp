@@ -1,5 +1,6 @@
 // Host build of the HD device headers, for CPU-side unit tests (tests only; never shipped).
 #include "tower.cuh"
+#include "pairing_cta.cuh"
 #include "hash.cuh"
 #include <string.h>
 using namespace h2v;
@@ -55,6 +56,86 @@ int t_pairing_check(const u32* Lxy, const u32* Rxy, int l_inf, int r_inf, const 
   Fq12 f = final_exponentiation(miller_loop2(p, skip, lines));
   for (int i = 0; i < 6; i++) { Fq a = f.a[i].c0.to_canonical(), b = f.a[i].c1.to_canonical(); memcpy(gt + 16 * i, a.l, 32); memcpy(gt + 16 * i + 8, b.l, 32); }
   return f.is_one() ? 1 : 0;
+}
+// ---- host emulation of the cooperative Fq12 engine (pairing_cta.cuh): lanes run as loops
+static const LinTables h_lin = H2V_LIN_TABLES_INIT;
+struct HostEngine {
+  Fq scr[2 * E12_N];
+  void mul(E12* dst, const E12* a, const E12* b) {
+    for (int l = 0; l < E12_N; l++) e12_mul_p1(scr, a, b, l);
+    for (int l = 0; l < E12_N; l++) e12_mul_p2(dst, scr, &h_lin, l);
+  }
+  void expand(E12* dst) { for (int l = 0; l < E12_N; l++) e12_expand_p(dst, scr, &h_lin, l); }
+  void conj(E12* dst, const E12* a) { for (int b = 0; b < E12_NB; b++) scr[b] = e12_conj_base(a, b); expand(dst); }
+  void frob(E12* dst, const E12* a) { for (int b = 0; b < E12_NB; b++) scr[b] = e12_frob_base(a, b); expand(dst); }
+  void frob2(E12* dst, const E12* a) { for (int b = 0; b < E12_NB; b++) scr[b] = e12_frob2_base(a, b); expand(dst); }
+  void from_fq12(E12* dst, const Fq12& x) { for (int b = 0; b < E12_NB; b++) scr[b] = fq12_base_coord(x, b); expand(dst); }
+  void pow_u(E12* dst, const E12* x) {
+    *dst = *x;
+    for (int i = 61; i >= 0; i--) { mul(dst, dst, dst); if ((H2V_BN_U >> i) & 1) mul(dst, dst, x); }
+  }
+  Fq12 to_fq12(const E12* x) {
+    Fq12 r;
+    for (int b = 0; b < E12_NB; b++) { const int hh = b / 6, j = (b % 6) / 2; Fq2& c = r.a[2 * j + hh]; ((b & 1) ? c.c1 : c.c0) = x->e[e12_base_slot(b)]; }
+    return r;
+  }
+};
+static Fq12 load_fq12(const u32* c) {  // 12 canonical Fq: a[i].c0, a[i].c1
+  Fq12 r; for (int i = 0; i < 6; i++) { Fq t; memcpy(t.l, c + 16 * i, 32); r.a[i].c0 = Fq::from_canonical(t); memcpy(t.l, c + 16 * i + 8, 32); r.a[i].c1 = Fq::from_canonical(t); }
+  return r;
+}
+static void store_fq12(const Fq12& f, u32* out) {
+  for (int i = 0; i < 6; i++) { Fq a = f.a[i].c0.to_canonical(), b = f.a[i].c1.to_canonical(); memcpy(out + 16 * i, a.l, 32); memcpy(out + 16 * i + 8, b.l, 32); }
+}
+// op: 0 mul, 1 conj, 2 frob, 3 frob2, 4 pow_u
+void t_e12_op(int op, const u32* a, const u32* b, u32* out) {
+  HostEngine he; E12 x, y, z;
+  he.from_fq12(&x, load_fq12(a)); he.from_fq12(&y, load_fq12(b));
+  switch (op) { case 0: he.mul(&z, &x, &y); break; case 1: he.conj(&z, &x); break; case 2: he.frob(&z, &x); break; case 3: he.frob2(&z, &x); break; default: he.pow_u(&z, &x); }
+  // the expanded form must be self-consistent: re-expanding the base coordinates reproduces it
+  E12 chk; he.from_fq12(&chk, he.to_fq12(&z));
+  for (int l = 0; l < E12_N; l++) if (chk.e[l] != z.e[l]) { memset(out, 0xff, 12 * 32); return; }
+  store_fq12(he.to_fq12(&z), out);
+}
+// decomposed pairing-product check: prod_k e(S_k, Q_k) == 1 with S_k Jacobian (X, Y, Z canonical, 24 words
+// each; Z = 0: identity) and Q_k affine G2 (32 words each).  Mirrors k_lines + k_pairing_check.
+int t_pairing_windows(int n, const u32* jac, const u32* g2s) {
+  G2Affine* q = new G2Affine[n];
+  G2Line* lines = new G2Line[(size_t)n * H2V_ATE_LINES];
+  for (int k = 0; k < n; k++) { q[k] = load_g2(g2s + 32 * k); if (!g2_on_curve(q[k])) return -1; }
+  g2_prepare_many(q, n, lines);
+  HostEngine he;
+  static E12 M[H2V_ATE_ITERS];
+  for (int it = 0; it < H2V_ATE_ITERS; it++) {
+    const int n0 = it >= 64 ? H2V_ATE_LINES - 2 : ate_line_index(it), ns = ate_lines_in_iteration(it);
+    bool first = true; E12 acc, tmp;
+    for (int s = 0; s < ns; s++) for (int k = 0; k < n; k++) {
+      Fq X, Y, Z, t; memcpy(t.l, jac + 24 * k, 32); X = Fq::from_canonical(t); memcpy(t.l, jac + 24 * k + 8, 32); Y = Fq::from_canonical(t);
+      memcpy(t.l, jac + 24 * k + 16, 32); Z = Fq::from_canonical(t);
+      const Fq XZ = X * Z, Z3 = Z * Z * Z;
+      for (int b = 0; b < E12_NB; b++) he.scr[b] = e12_line_base(lines[(size_t)k * H2V_ATE_LINES + n0 + s], Y, XZ, Z3, Z.is_zero(), b);
+      he.expand(first ? &acc : &tmp);
+      if (!first) he.mul(&acc, &acc, &tmp);
+      first = false;
+    }
+    M[it] = acc;
+  }
+  E12 f = M[0], tt, fu, fu2, fu3, a, b, y0, T0, T1, N;
+  for (int it = 1; it < H2V_ATE_ITERS; it++) { if (it < 64) he.mul(&f, &f, &f); he.mul(&f, &f, &M[it]); }
+  he.frob2(&a, &f); he.mul(&tt, &a, &f);
+  he.pow_u(&fu, &tt); he.pow_u(&fu2, &fu); he.pow_u(&fu3, &fu2);
+  he.frob(&a, &tt); he.frob2(&b, &tt); he.mul(&y0, &a, &b); he.frob(&a, &b); he.mul(&y0, &y0, &a);
+  he.frob2(&a, &fu2); he.mul(&a, &a, &a); he.mul(&b, &a, &a); he.mul(&b, &b, &a); he.mul(&N, &y0, &b);
+  he.frob(&a, &fu3); he.mul(&a, &fu3, &a); he.mul(&T0, &a, &a);
+  he.frob(&a, &fu2); he.mul(&a, &fu, &a); he.mul(&T0, &T0, &a); he.mul(&T0, &T0, &fu2);
+  he.frob(&a, &fu); he.mul(&T1, &a, &fu2); he.mul(&T1, &T1, &T0);
+  he.mul(&T1, &T1, &T1); he.mul(&T1, &T1, &T0); he.mul(&T1, &T1, &T1);
+  he.mul(&T0, &T1, &tt); he.mul(&T0, &T0, &T0); he.mul(&T0, &T0, &T1);
+  he.conj(&a, &N); he.mul(&a, &a, &T0); he.conj(&b, &T0); he.mul(&b, &N, &b);
+  bool ok = true;
+  for (int c = 0; c < E12_NB; c++) ok = ok && a.e[e12_base_slot(c)] == b.e[e12_base_slot(c)];
+  delete[] q; delete[] lines;
+  return ok ? 1 : 0;
 }
 void t_blake2b(const u8* data, u32 len, u8* out) { Blake2b b; b.init_halo2(); b.update(data, len); b.digest(out); }
 void t_keccak(const u8* data, u32 len, u8 suffix, u8* out) { Keccak256 k; k.init_halo2(); k.update(data, len); k.digest_with_suffix(suffix, out); }

@@ -12,7 +12,7 @@ int s_build(const u8* params, size_t pl, int pf, const u8* vk, size_t vl, int vf
   return build_plan(params, pl, pf, vk, vl, vf, mo, hash, g_blob, g_info, g_err);
 }
 const char* s_err() { return g_err.c_str(); }
-void s_info(u32* out) { memcpy(out, &g_info, sizeof(g_info)); }
+void s_info(u32* out) { memcpy(out, &g_info, 8 * sizeof(u32)); }
 // returns status; outputs canonical LE: challenges [C][32], right [P][32], shared [Sh][32], left [n_mo][32],
 // L,R affine canonical x|y (zeros = identity) and verdict of the pairing in *pair_ok
 int s_verify_one(const u8* proof, u32 len, const u8* inst, u32 inst_total, const u32* col_len, int ncols,

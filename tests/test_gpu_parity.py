@@ -203,6 +203,11 @@ def test_sharded_accumulation_matches_whole_batch(pkg):
         w2 = b0.verify_batch(proofs, insts, seed=99, want_batch_accum=True)
         parts = [bv.accumulate_shard(proofs[g * 128:(g + 1) * 128], insts[g * 128:(g + 1) * 128], g * 128, n, seed=99)[1] for g, bv in ((0, b0), (1, b1))]
         assert b1.finalize(parts) == (True, w2.batch_accum)
+        # uneven shards (86 / 85 / 85): the shard hint gives every rank the same window geometry
+        cuts = [0, 86, 171, 256]
+        parts = [(b0, b1)[g % 2].accumulate_shard(proofs[cuts[g]:cuts[g + 1]], insts[cuts[g]:cuts[g + 1]], cuts[g], n, rlc_scalars=rs, shard_hint=86)[1]
+                 for g in range(3)]
+        assert b0.finalize(parts) == (True, whole.batch_accum)
         # corrupted proof in shard 1
         bad = list(proofs)
         bad[200], _ = sim.corrupt(proofs[200], vk, "eval_flip", rng)

@@ -185,3 +185,63 @@ def test_plan_compiler_rejects_malformed_vk(stage):
     assert stage.s_build(pb, len(pb), 0, vb3, len(vb3), 1, 0, 0) != 0 and b"empty polynomial" in stage.s_err()
     p10 = sim.make_params(10, 5).to_bytes()
     assert stage.s_build(p10, len(p10), 0, vb, len(vb), 1, 0, 0) != 0  # params.k != vk.k
+
+
+# ---- cooperative Fq12 engine (pairing_cta.cuh), lanes emulated on the host
+def F12L(x):
+    return (ctypes.c_uint32 * 96)(*sum([[(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)] for c in x for v in c], []))
+
+
+def F12I(a):
+    return tuple((I(a, 16 * i), I(a, 16 * i + 8)) for i in range(6))
+
+
+def test_e12_engine_matches_oracle_tower(prim):
+    rng = random.Random(77)
+    rnd12 = lambda: tuple((rng.randrange(bn.P), rng.randrange(bn.P)) for _ in range(6))
+    out = (ctypes.c_uint32 * 96)()
+    edge = tuple((bn.P - 1, bn.P - 1) for _ in range(6))
+    cases = [(rnd12(), rnd12()) for _ in range(12)] + [(edge, edge), (bn.F12_ONE, rnd12()), (rnd12(), tuple((0, 0) for _ in range(6)))]
+    for x, y in cases:
+        prim.t_e12_op(0, F12L(x), F12L(y), out); assert F12I(out) == bn.f12_mul(x, y)
+        prim.t_e12_op(1, F12L(x), F12L(y), out); assert F12I(out) == bn.f12_conj(x)
+        prim.t_e12_op(2, F12L(x), F12L(y), out); assert F12I(out) == bn.f12_frob(x)
+        prim.t_e12_op(3, F12L(x), F12L(y), out); assert F12I(out) == bn.f12_frob2(x)
+    x = rnd12()
+    prim.t_e12_op(4, F12L(x), F12L(x), out); assert F12I(out) == bn.f12_pow(x, bn.U)
+
+
+def test_decomposed_pairing_check(prim):
+    """prod_w e(S_w, [2^(c w)] Q) with projective S_w, no inversion: same verdict as the oracle's pairing_check."""
+    rng = random.Random(78)
+    S = sim.FIXTURE_SRS_SECRET
+    sg2, ng2 = bn.g2_mul(bn.G2_GEN, S), bn.g2_neg(bn.G2_GEN)
+
+    def jac(pt):  # random projective representative (X, Y, Z) of an affine point; None -> Z = 0
+        if pt is None:
+            return [1, 1, 0]
+        z = rng.randrange(1, bn.P)
+        return [pt[0] * z * z % bn.P, pt[1] * pow(z, 3, bn.P) % bn.P, z]
+
+    def run(pairs):
+        n = len(pairs)
+        jw = (ctypes.c_uint32 * (24 * n))(*sum([[(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)] for p, _ in pairs for v in jac(p)], []))
+        qw = (ctypes.c_uint32 * (32 * n))(*sum([[(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)] for _, q in pairs for c in q for v in c], []))
+        return prim.t_pairing_windows(n, jw, qw)
+
+    c, W = 7, 3
+    # left = sum 2^(c w) A_w, right = s * left, split into windows on both sides
+    a = [rng.randrange(bn.R) for _ in range(W)]
+    A = [bn.g1_mul_gen(x) for x in a]
+    B = [bn.g1_mul_gen(x * S % bn.R) for x in a]
+    pairs = [(A[w], bn.g2_mul(sg2, 1 << (c * w))) for w in range(W)] + [(B[w], bn.g2_mul(ng2, 1 << (c * w))) for w in range(W)]
+    assert bn.pairing_check(pairs)
+    assert run(pairs) == 1
+    bad = list(pairs)
+    bad[4] = (bn.g1_mul_gen((a[1] * S + 1) % bn.R), bad[4][1])
+    assert not bn.pairing_check(bad)
+    assert run(bad) == 0
+    # identity window sums are skipped; an all-identity product accepts
+    pairs2 = [(A[0], sg2), (None, bn.g2_mul(sg2, 1 << c)), (B[0], ng2), (None, bn.g2_mul(ng2, 1 << c))]
+    assert run(pairs2) == 1
+    assert run([(None, sg2), (None, ng2)]) == 1
