@@ -130,7 +130,7 @@ __device__ __forceinline__ void wide_fold_mad4_rshift(u32& even0, u32 (&odd)[8],
 #endif
 
 template <class P>
-struct Fp {
+struct alignas(16) Fp {  // 16-byte alignment: element loads / stores vectorise to two 128-bit accesses
   u32 l[8];
 
   // ---- constants

@@ -32,13 +32,13 @@ struct E12 {
   Fq e[E12_N];
 };
 
-struct LinTables {
+struct alignas(16) LinTables {  // term lists 8-byte aligned: four terms are fetched with one 64-bit load
+  alignas(8) uint16_t full_terms[H2V_LIN_FULL_NTERMS];
+  alignas(8) uint16_t exp_terms[H2V_LIN_EXP_NTERMS];
   uint16_t full_start[E12_N + 1];
   uint16_t exp_start[E12_N + 1];
-  uint16_t full_terms[H2V_LIN_FULL_NTERMS];
-  uint16_t exp_terms[H2V_LIN_EXP_NTERMS];
 };
-#define H2V_LIN_TABLES_INIT {H2V_LIN_FULL_START_INIT, H2V_LIN_EXP_START_INIT, H2V_LIN_FULL_TERMS_INIT, H2V_LIN_EXP_TERMS_INIT}
+#define H2V_LIN_TABLES_INIT {H2V_LIN_FULL_TERMS_INIT, H2V_LIN_EXP_TERMS_INIT, H2V_LIN_FULL_START_INIT, H2V_LIN_EXP_START_INIT}
 
 H2V_HD int e12_base_slot(int b) {  // position of base coordinate b inside the expanded form
   const int hh = b / 6, j = (b % 6) / 2, part = b & 1;
@@ -53,12 +53,15 @@ H2V_HD Fq lin_row(const uint16_t* start, const uint16_t* terms, int row, const F
 #pragma unroll
   for (int i = 0; i < 8; i++) acc[i] = 0;
   const int k1 = start[row + 1];
-  for (int k = start[row]; k < k1; k++) {
-    const u32 t = terms[k];
-    const u32 c = t >> 8;
-    const u32* v = src[t & 0xFF].l;
+  for (int k = start[row]; k < k1; k += 4) {  // rows are padded to a multiple of 4 terms
+    const u64 tt = *(const u64*)(terms + k);  // 4 packed (index | coefficient << 8) terms
+    const u32 tx = (u32)tt, ty = (u32)(tt >> 32);
+    const Fq v0 = src[tx & 0xFF], v1 = src[(tx >> 16) & 0xFF], v2 = src[ty & 0xFF], v3 = src[(ty >> 16) & 0xFF];
+    const u32 c0 = (tx >> 8) & 0xFF, c1 = tx >> 24, c2 = (ty >> 8) & 0xFF, c3 = ty >> 24;
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] += (u64)c * v[i];
+    for (int i = 0; i < 8; i++) acc[i] += (u64)c0 * v0.l[i] + (u64)c1 * v1.l[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] += (u64)c2 * v2.l[i] + (u64)c3 * v3.l[i];
   }
   u32 V[9];
   u64 cy = 0;

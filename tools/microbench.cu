@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include "field.cuh"
+#include "pairing_cta.cuh"
 using namespace h2v;
 
 __global__ void k_imad_lo(u32 iters, u32* out) {
@@ -72,6 +73,26 @@ __global__ void k_check(u32 count, u32* bad) {
   if (x != y || z != y || fx != fy) atomicAdd(bad, 1u);
 }
 
+// latency of the cooperative Fq12 product: one 64-thread group, `iters` dependent g_mul
+__global__ void __launch_bounds__(64) k_e12_chain(u32 iters, Fq* io, int mode) {
+  __shared__ LinTables lt;
+  __shared__ E12 x, y;
+  __shared__ Fq scr[2 * E12_N];
+  const int t = threadIdx.x;
+  for (int i = t; i < (int)(sizeof(LinTables) / 2); i += 64) ((uint16_t*)&lt)[i] = ((const uint16_t*)&g_lin_tables)[i];
+  if (t < E12_NB) { Fq v = io[t]; v.l[7] &= 0x0FFFFFFF; scr[t] = v; }
+  __syncthreads();
+  Grp g{t, 1, &lt, scr};
+  g_expand(g, &x);
+  g_copy(g, &y, &x);
+  for (u32 i = 0; i < iters; i++) {
+    if (mode == 0) g_mul(g, &x, &x, &y);
+    else if (mode == 1) { if (t < E12_N) e12_mul_p1(scr, &x, &y, t); g.sync(); if (t < E12_N) x.e[t] = scr[t]; g.sync(); }
+    else { if (t < E12_N) e12_mul_p2(&x, scr, &lt, t); g.sync(); }
+  }
+  if (t < E12_N) io[64 + t] = x.e[t];
+}
+
 template <class F>
 static double time_ms(F launch, int reps = 3) {
   cudaEvent_t a, b;
@@ -117,6 +138,10 @@ int main() {
     const double n = (double)blocks * c.threads * iters;
     printf("warps/SM %2d: lo/hi CIOS %.2f G MM/s (chain %.0f ns/MM) | wide %.2f G MM/s (chain %.0f ns/MM) | wide x2 chains %.2f | wide x4 chains %.2f G MM/s\n",
            c.blocks_per_sm * c.threads / 32, n / m0 / 1e6, m0 * 1e6 / iters, n / m1 / 1e6, m1 * 1e6 / iters, 2 * n / m2 / 1e6, 4 * n / m3 / 1e6);
+  }
+  for (int mode = 0; mode < 3; mode++) {
+    double ms = time_ms([&] { k_e12_chain<<<1, 64>>>(1000, io, mode); });
+    printf("cooperative Fq12 engine, %s: %.2f us per op\n", mode == 0 ? "g_mul" : mode == 1 ? "product phase only" : "linear phase only", ms);
   }
   printf("last error: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
