@@ -29,6 +29,7 @@ METRIC = "verified proofs/sec (BN254 SHPLONK, batch 4096)"
 UNIT = "proofs/s"
 SRS_SEED = 2  # SRS secret from seed 2
 R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+IMAD_SLOTS_PER_MM = 272  # 8-limb CIOS: 136 32x32->64 multiply-adds = 272 lo/hi IMAD issue slots
 
 
 def srs_secret(k):
@@ -112,7 +113,7 @@ def algorithmic_mm(bv, n, geom):
         "transcript": n * (P * 2 + S + bv.n_challenges * 2),  # only Montgomery conversions; the hash is ALU work
         "scalar": n * (10 + 330 + 3 * 12 + 40 * 4 + 160),  # x^n, one inversion, Lagrange, expressions, SHPLONK sets (VM shape)
         "rlc_msm": n * (P + bv.n_mo) * 2 + (W0 * t_right + W1 * t_left) * 11 + (W0 * (1 << (c0 - 1)) + W1 * (1 << (c1 - 1))) * 32,
-        "pairing": (W0 * c0 + W1 * c1) * 7 + 2 * 400 + 22000,
+        "pairing": (65 * (W0 + W1) * 58 + 430 * 54),  # k_lines: line value (4) + product (54) per pair and step; check: ~430 Fq12 products
     }
     return mm
 
@@ -142,7 +143,7 @@ def run_ours(args):
     vk_bytes, shared_dlogs = synth.make_vk_bytes(args.shape, k)
     params = pkg.ParamsKZG.from_bytes(synth.params_bytes_raw(k, s), pkg.SerdeFormat.RawBytes)
     vk = pkg.VerifyingKey.from_bytes(vk_bytes, pkg.SerdeFormat.RawBytes)
-    n_ctx = max(1, args.streams)
+    n_ctx = max(1, args.streams) if world == 1 else 1
     bvs = [pkg.BatchVerifier(params, vk, "shplonk", "blake2b", device=local) for _ in range(n_ctx)]
     bv = bvs[0]
     # two distinct accepting batches per rank (seeded), alternated between steps
@@ -160,30 +161,37 @@ def run_ours(args):
     verdict = ctypes.c_int(0)
     chk = lambda ctx, rc: ctx._check(rc)
 
-    def step_resident(ctx, flush=True):
-        if flush:
-            chk(ctx, lib.h2v_flush_l2(ctx._ctx, 256 << 20))
-        if world == 1:
-            chk(ctx, lib.h2v_batch_run(ctx._ctx, ctypes.byref(verdict)))
-            return verdict.value
-        chk(ctx, lib.h2v_batch_run_shard(ctx._ctx, partial_dev.data_ptr()))
+    ext_streams = [torch.cuda.ExternalStream(b.stream_handle(), device=torch.device("cuda", local)) for b in bvs]
+
+    def gather_and_finalize(ctx):
+        """NCCL all-gather of the partials (torch's stream), then the single pairing check on rank 0
+        (context stream, ordered after the gather by an event)."""
         dist.all_gather(gathered, partial_dev)
         if rank == 0:
             cat = torch.cat(gathered)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            ext_streams[0].wait_event(ev)
             chk(ctx, lib.h2v_finalize(ctx._ctx, world, cat.data_ptr(), None, ctypes.byref(verdict)))
         return verdict.value
+
+    def step_resident(ctx, flush=True):
+        v = ctypes.c_int(0)
+        if flush:
+            chk(ctx, lib.h2v_flush_l2(ctx._ctx, 256 << 20))
+        if world == 1:
+            chk(ctx, lib.h2v_batch_run(ctx._ctx, ctypes.byref(v)))
+            return v.value
+        chk(ctx, lib.h2v_batch_run_shard(ctx._ctx, partial_dev.data_ptr()))  # returns after the shard's stream is idle
+        return gather_and_finalize(ctx)
 
     def step_e2e(ctx, pb):
         if world == 1:
             chk(ctx, lib.h2v_verify_batch(ctx._ctx, *pb.args(), None, seed, pb.status.data_ptr(), None, None, None))
             return int(pb.status.max()) == 0
         chk(ctx, lib.h2v_accumulate_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount, pb.status.data_ptr(), partial_dev.data_ptr()))
-        dist.all_gather(gathered, partial_dev)
-        if rank == 0:
-            cat = torch.cat(gathered)
-            chk(ctx, lib.h2v_finalize(ctx._ctx, world, cat.data_ptr(), None, ctypes.byref(verdict)))
-            return verdict.value == 1
-        return True
+        v = gather_and_finalize(ctx)
+        return v == 1 if rank == 0 else True
 
     def sync_all():
         torch.cuda.synchronize()
@@ -197,47 +205,76 @@ def run_ours(args):
         else:
             chk(ctx, lib.h2v_batch_upload_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount))
 
-    def run_steps(fn, count):
+    def timed(fn, count, ctxs):
+        """count steps between barrier + synchronize on both sides; returns (results, seconds on the DEVICE clock:
+        CUDA events on the contexts' streams, first start -> last end; wall seconds)."""
+        sync_all()
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record(ext_streams[0])
+        w0 = time.perf_counter()
+        res_ = run_steps(fn, count, ctxs)
+        ends = []
+        for st in ext_streams[: len(ctxs)] + [torch.cuda.current_stream()]:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(st)
+            ends.append(e)
+        sync_all()
+        wall = time.perf_counter() - w0
+        return res_, max(ev0.elapsed_time(e) for e in ends) * 1e-3, wall
+
+    def run_steps(fn, count, ctxs):
         """count steps spread round-robin over the contexts; each context is driven by its own host
         thread (ctypes releases the GIL), so batches of different contexts overlap on the device."""
-        if n_ctx == 1 or world > 1:
-            return [fn(bvs[0], i) for i in range(count)]
+        if len(ctxs) == 1:
+            return [fn(ctxs[0], i) for i in range(count)]
         out = [None] * count
 
         def worker(ci):
-            for i in range(ci, count, n_ctx):
-                out[i] = fn(bvs[ci], i)
+            for i in range(ci, count, len(ctxs)):
+                out[i] = fn(ctxs[ci], i)
 
-        ths = [threading.Thread(target=worker, args=(ci,)) for ci in range(n_ctx)]
+        ths = [threading.Thread(target=worker, args=(ci,)) for ci in range(len(ctxs))]
         [t.start() for t in ths]
         [t.join() for t in ths]
         return out
 
+    def reduce_max(*vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    W = max(args.warmup, 3)
+    total = n * world * args.steps
     # ---------------- device-resident throughput (`value`)
     for ci, ctx in enumerate(bvs):
         upload(ctx, batches[ci % 2])
-    ok = run_steps(lambda ctx, i: step_resident(ctx), max(args.warmup, 3))
+    ok = run_steps(lambda ctx, i: step_resident(ctx), W * n_ctx, bvs)
     assert rank != 0 or all(v == 1 for v in ok), "warm-up batch was rejected"
-    stage_acc, geom = {}, bv.msm_geometry()
+    geom = bv.msm_geometry()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = sum(b.launch_count() for b in bvs)
-    sync_all()
-    t0 = time.perf_counter()
-    res = run_steps(lambda ctx, i: step_resident(ctx), args.steps)
-    sync_all()
-    dt = time.perf_counter() - t0
-    clocks = sampler.summary()
-    launches = sum(b.launch_count() for b in bvs) - launches0
+    # one batch in flight: latency view (also the only mode at N > 1)
+    res, dt1, _ = timed(lambda ctx, i: step_resident(ctx), args.steps, bvs[:1])
     assert rank != 0 or all(v == 1 for v in res), "a timed batch was rejected"
+    launches = sum(b.launch_count() for b in bvs) - launches0
+    dt = dt1
+    if n_ctx > 1:  # several independent batches in flight (one context + stream + host thread each): throughput view
+        launches0 = sum(b.launch_count() for b in bvs)
+        res, dt, _ = timed(lambda ctx, i: step_resident(ctx), args.steps, bvs)
+        assert all(v == 1 for v in res), "a timed batch was rejected"
+        launches = sum(b.launch_count() for b in bvs) - launches0
+    clocks = sampler.summary()
     # per-stage CUDA-event timings of a few serial steps (roofline of the dominant kernel group)
-    for i in range(3):
+    stage_acc = {}
+    for i in range(5):
         step_resident(bv)
         for name, ms in bv.timings().items():
             stage_acc.setdefault(name, []).append(ms)
     stage_ms = {k_: statistics.median(v) for k_, v in stage_acc.items()}
     # ---------------- end to end through the C ABI from pinned host memory
-    run_steps(lambda ctx, i: step_e2e(ctx, batches[i % 2]), max(args.warmup, 3))
+    run_steps(lambda ctx, i: step_e2e(ctx, batches[i % 2]), W * n_ctx, bvs)
     lat = []
 
     def timed_e2e(ctx, i):
@@ -246,48 +283,58 @@ def run_ours(args):
         lat.append(time.perf_counter() - a)
         return okk
 
-    sync_all()
-    t0 = time.perf_counter()
-    res = run_steps(timed_e2e, args.steps)
-    sync_all()
-    dt_e2e = time.perf_counter() - t0
+    res, _, dt_e2e1 = timed(timed_e2e, args.steps, bvs[:1])  # e2e is what the caller sees: host clock around the calls
     assert all(res), "an end-to-end batch was rejected"
-    times = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dt, dt_e2e = float(times[0]), float(times[1])
-    total = n * world * args.steps
+    p50 = statistics.median(lat) * 1e3
+    dt_e2e = dt_e2e1
+    if n_ctx > 1:
+        res, _, dt_e2e = timed(timed_e2e, args.steps, bvs)
+        assert all(res), "an end-to-end batch was rejected"
+    dt, dt1, dt_e2e, dt_e2e1 = reduce_max(dt, dt1, dt_e2e, dt_e2e1)
 
     out = None
     if rank == 0:
         mm = algorithmic_mm(bv, n, geom)
         dom = max((k_ for k_ in mm if k_ in stage_ms), key=lambda k_: stage_ms[k_])
         imad_peak = lib.h2v_calibrate_imad(local)
-        achieved = mm[dom] * 136 / (stage_ms[dom] * 1e-3)
+        slots = lambda m: m * IMAD_SLOTS_PER_MM
+        achieved = slots(mm[dom]) / (stage_ms[dom] * 1e-3)
+        achieved_all = slots(sum(mm.values())) / (dt / args.steps)
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         eval_bytes = n * (bv.proof_len + 32 * bv.n_inst_cols * 10 + 64 * bv.n_points + 32 * (bv.n_scalars + bv.n_challenges))
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")  # per-launch dram bytes of the stage kernels from one ncu --set full capture
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
         out = {
-            "metric": METRIC, "value": total / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": total / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic (trapdoor-simulated accepting proofs, seeded)",
             "config": {"workload": f"{n} SHPLONK proofs per GPU, vector_mul test-circuit shape ('{args.shape}'), k={k}, Blake2b transcript, "
                                    f"10 public inputs, 1,024-byte proofs; BASELINE.json configs[1]",
-                       "batch_per_gpu": n, "global_batch": n * world, "contexts_in_flight": n_ctx if world == 1 else 1,
-                       "l2": "flushed between steps (256 MiB overwrite on the timed stream)",
+                       "batch_per_gpu": n, "global_batch": n * world, "contexts_in_flight": n_ctx,
+                       "in_flight_note": "a step is one complete 4096-proof batch; `value`/`e2e` keep `contexts_in_flight` independent batches in flight "
+                                         "(one context + CUDA stream + host thread each), `one_in_flight` times strictly serial batches",
+                       "timing": "CUDA events on the contexts' streams (first start -> last end) between barrier + synchronize, max over ranks; "
+                                 "e2e on the host clock around the C-ABI calls",
+                       "l2": "flushed before every step (256 MiB overwrite on the step's stream, inside the timed region)",
                        "parallelism": f"proof-sharded x{world}, NCCL all-gather of the per-window partial accumulators (12,320 B per rank), one pairing check on rank 0"},
             "e2e": {"value": total / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": batches[0].h2d_bytes, "d2h_bytes_per_step": batches[0].d2h_bytes,
-                    "ms_per_step": dt_e2e / args.steps * 1e3, "p50_latency_ms": statistics.median(lat) * 1e3},
+                    "ms_per_step": dt_e2e / args.steps * 1e3, "p50_latency_ms": p50},
+            "one_in_flight": {"value": total / dt1, "ms_per_step": dt1 / args.steps * 1e3, "e2e_value": total / dt_e2e1, "e2e_p50_latency_ms": p50},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stage_ms": {k_: round(v, 4) for k_, v in stage_ms.items()},
             "msm": {"window_bits": [geom["window_bits"] & 0xFFFF, geom["window_bits"] >> 16], "windows": [geom["windows"] & 0xFFFF, geom["windows"] >> 16],
                     "terms": geom["terms"], "buckets": geom["buckets"]},
             "roofline": {"bound": "imad", "kernel": dom, "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s",
-                         "frac": achieved / imad_peak, "traffic": None,
-                         "note": "integer-multiply bound (no HBM/tensor roofline applies): algorithmic 32-bit multiply-adds "
-                                 "(136 per 256-bit Montgomery multiplication) of the dominant kernel group / its CUDA-event time; "
-                                 "peak = unrolled mad.lo.u32 calibration kernel measured in this run"},
+                         "frac": achieved / imad_peak, "traffic": traffic,
+                         "whole_step": {"achieved": achieved_all / 1e12, "frac": achieved_all / imad_peak, "mm_per_proof": sum(mm.values()) / n},
+                         "note": "integer-multiply bound (no HBM/tensor roofline applies, DESIGN.md section 5): algorithmic 256-bit Montgomery "
+                                 "multiplications x 272 IMAD issue slots (136 32x32->64 multiply-adds, lo + hi) of the dominant kernel group / its "
+                                 "CUDA-event time; peak = 32-bit IMAD issue rate measured by the calibration kernel in this run; `whole_step` = "
+                                 "all stages / the timed step"},
             "roofline_hbm": {"bound": "hbm", "kernel": "transcript+scalar (evaluation loads)", "achieved": eval_bytes / ((stage_ms["transcript"] + stage_ms["scalar"]) * 1e-3) / 1e9,
                              "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
                              "frac": eval_bytes / ((stage_ms["transcript"] + stage_ms["scalar"]) * 1e-3) / 1e9 / hbm_peak, "traffic": None},
@@ -390,7 +437,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--shape", default="vm")
     ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("H2V_BENCH_STREAMS", "1")), help="batches in flight (contexts) at N=1")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("H2V_BENCH_STREAMS", "8")), help="batches in flight (contexts) at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--ref-proofs-per-core", type=int, default=8)

@@ -1161,6 +1161,8 @@ int h2v_last_timings(const h2v_ctx* cctx, float* out8) {
 
 uint64_t h2v_launch_count(const h2v_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+void* h2v_ctx_stream(const h2v_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
 int h2v_last_msm_geometry(const h2v_ctx* ctx, uint32_t* out4) {
   if (!ctx || !out4) return -1;
   out4[0] = ctx->geom.c[0] | (ctx->geom.c[1] << 16);

@@ -133,6 +133,9 @@ int h2v_batch_download(h2v_ctx* ctx, uint8_t* status);
 int h2v_last_timings(const h2v_ctx* ctx, float* out8);
 /* number of kernel launches issued by this context so far */
 uint64_t h2v_launch_count(const h2v_ctx* ctx);
+/* the context's cudaStream_t (every kernel and copy of the context is issued on it), so that a caller
+ * can record its own CUDA events around calls or order other work after them */
+void* h2v_ctx_stream(const h2v_ctx* ctx);
 /* MSM geometry of the last run: out[0] window bits, [1] windows, [2] terms, [3] buckets */
 int h2v_last_msm_geometry(const h2v_ctx* ctx, uint32_t* out4);
 
