@@ -218,3 +218,103 @@ def test_sharded_accumulation_matches_whole_batch(pkg):
         assert b0.attribute_shard(st0) == [0] * 128
         st1 = b1.attribute_shard(st1)
         assert st1[72] == 4 and sum(st1) == 4
+
+
+# ---- BASELINE.json full sizes, every proof checked against the C oracle (oracle/c)
+def _pack(proofs, insts):
+    import numpy as np
+
+    pb = np.frombuffer(b"".join(proofs), dtype=np.uint8)
+    poff = np.cumsum([0] + [len(p) for p in proofs]).astype(np.uint64)
+    ib = np.frombuffer(b"".join(v if isinstance(v, (bytes, bytearray)) else int(v).to_bytes(32, "little") for inst in insts for col in inst for v in col),
+                       dtype=np.uint8)
+    ioff = np.cumsum([0] + [sum(len(c) for c in inst) for inst in insts]).astype(np.uint64)
+    return pb, poff, ib, ioff
+
+
+def test_config2_4096_shplonk_every_proof_against_c_oracle(pkg):
+    """BASELINE.json configs[1] (+ the corruption mix of configs[2]): 4096 SHPLONK proofs, k = 10; statuses, challenges,
+    per-proof accumulators and the folded (L, R) of ALL proofs bit-exact against the C restatement."""
+    import c_oracle
+    from importlib import import_module
+
+    synth = import_module("halo2_verifier_b200.synth")
+    n, k = 4096, 10
+    rng = random.Random(4096)
+    s = rng.randrange(1, bn.R)
+    vk_bytes, shared_dlogs = synth.make_vk_bytes("vm", k)
+    pbytes = synth.params_bytes_raw(k, s)
+    vk = F.VerifyingKey.from_bytes(vk_bytes, F.RAW_BYTES)
+    co = c_oracle.COracle(pbytes, 1, vk_bytes, 1)
+    with pkg.BatchVerifier(pkg.ParamsKZG.from_bytes(pbytes, pkg.SerdeFormat.RawBytes), pkg.VerifyingKey.from_bytes(vk_bytes)) as bv:
+        proofs, insts = synth.synthesize_shplonk_batch(bv, shared_dlogs, s, n, seed=("t", 1))
+        C = bv.n_challenges
+        rs = [rng.randrange(1, bn.R) for _ in range(n)]
+        for rnd in range(2):
+            if rnd == 1:  # 1 % corrupted, every rejection class
+                kinds = list(sim.CORRUPTIONS)
+                for t, i in enumerate(sorted(rng.sample(range(n), n // 100))):
+                    proofs[i], _ = sim.corrupt(proofs[i], vk, kinds[t % len(kinds)], rng)
+            res = bv.verify_batch(proofs, insts, rlc_scalars=rs, want_challenges=True, want_accum=True, want_batch_accum=True)
+            st, _secs, lr, ch = co.verify_many(*_pack(proofs, insts), n, threads=os.cpu_count() or 1, want_lr=True, chal_cap=C)
+            assert res.status == [int(x) for x in st]
+            live = [x in (0, 4) for x in res.status]
+            for j in range(n):
+                if live[j]:
+                    assert res.challenges[32 * C * j: 32 * C * (j + 1)] == ch[32 * C * j: 32 * C * (j + 1)], f"challenges of proof {j}"
+                    assert res.accum[128 * j: 128 * (j + 1)] == lr[128 * j: 128 * (j + 1)], f"accumulators of proof {j}"
+            folded, ok = co.fold(lr, rs, live)
+            assert res.batch_accum == folded
+            assert ok == res.verdict or (not ok and not res.verdict)
+            assert (rnd == 0) == res.verdict
+            if rnd == 1:
+                assert sorted(set(res.status)) == [0, 2, 3, 4]
+    co.close()
+
+
+def test_config3_gwc_batch_with_attribution_against_c_oracle(pkg):
+    """BASELINE.json configs[2]: GWC multi-open, corrupted proofs attributed inside the batch (1024 proofs: oracle-simulated
+    proofs are slow to manufacture; 64 distinct proofs tiled, then 1 % corrupted)."""
+    import c_oracle
+
+    n = 1024
+    params, vk, instances, proofs, rng = make_batch("vm", 10, 64, "gwc", "blake2b", seed=31)
+    proofs, insts = (proofs * (n // 64)), [i[0] for i in instances] * (n // 64)
+    kinds = list(sim.CORRUPTIONS)
+    for t, i in enumerate(sorted(rng.sample(range(n), n // 100))):
+        proofs[i], _ = sim.corrupt(proofs[i], vk, kinds[t % len(kinds)], rng, "gwc")
+    rs = [rng.randrange(1, bn.R) for _ in range(n)]
+    co = c_oracle.COracle(params.to_bytes(1), 1, vk.to_bytes(1), 1)
+    with make_bv(pkg, params, vk, "gwc", "blake2b") as bv:
+        C = bv.n_challenges
+        res = bv.verify_batch(proofs, insts, rlc_scalars=rs, want_challenges=True, want_accum=True, want_batch_accum=True)
+        st, _secs, lr, ch = co.verify_many(*_pack(proofs, insts), n, "gwc", "blake2b", threads=os.cpu_count() or 1, want_lr=True, chal_cap=C)
+        assert res.status == [int(x) for x in st] and not res.verdict and res.status.count(0) >= n - n // 100
+        live = [x in (0, 4) for x in res.status]
+        for j in range(n):
+            if live[j]:
+                assert res.challenges[32 * C * j: 32 * C * (j + 1)] == ch[32 * C * j: 32 * C * (j + 1)]
+                assert res.accum[128 * j: 128 * (j + 1)] == lr[128 * j: 128 * (j + 1)]
+        assert res.batch_accum == co.fold(lr, rs, live)[0]
+    co.close()
+
+
+def test_config4_k18_lookup_heavy_batch_against_c_oracle(pkg):
+    """BASELINE.json configs[3] shape: k = 18, 64 advice columns, degree-5 gates, 8 lookups, 66-column permutation
+    (batch of 64: 4 distinct oracle-simulated proofs tiled; the full 1024 only repeats them)."""
+    import c_oracle
+
+    n = 64
+    params, vk, instances, proofs, rng = make_batch("k18", 18, 4, "shplonk", "blake2b", seed=41)
+    proofs, insts = proofs * (n // 4), [i[0] for i in instances] * (n // 4)
+    proofs[7], _ = sim.corrupt(proofs[7], vk, "eval_flip", rng)
+    rs = [rng.randrange(1, bn.R) for _ in range(n)]
+    co = c_oracle.COracle(params.to_bytes(1), 1, vk.to_bytes(1), 1)
+    with make_bv(pkg, params, vk, "shplonk", "blake2b") as bv:
+        C = bv.n_challenges
+        res = bv.verify_batch(proofs, insts, rlc_scalars=rs, want_challenges=True, want_accum=True, want_batch_accum=True)
+        st, _secs, lr, ch = co.verify_many(*_pack(proofs, insts), n, threads=os.cpu_count() or 1, want_lr=True, chal_cap=C)
+        assert res.status == [int(x) for x in st] == [4 if j == 7 else 0 for j in range(n)]
+        assert res.challenges == ch and res.accum == lr
+        assert res.batch_accum == co.fold(lr, rs, [True] * n)[0]
+    co.close()
