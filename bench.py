@@ -24,6 +24,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware work queue per stream in flight (default 8): batches of different contexts must not serialise behind
+# each other (read at CUDA initialisation)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "verified proofs/sec (BN254 SHPLONK, batch 4096)"
 UNIT = "proofs/s"
@@ -143,7 +146,7 @@ def run_ours(args):
     vk_bytes, shared_dlogs = synth.make_vk_bytes(args.shape, k)
     params = pkg.ParamsKZG.from_bytes(synth.params_bytes_raw(k, s), pkg.SerdeFormat.RawBytes)
     vk = pkg.VerifyingKey.from_bytes(vk_bytes, pkg.SerdeFormat.RawBytes)
-    n_ctx = max(1, args.streams) if world == 1 else 1
+    n_ctx = max(1, args.streams)
     bvs = [pkg.BatchVerifier(params, vk, "shplonk", "blake2b", device=local) for _ in range(n_ctx)]
     bv = bvs[0]
     # two distinct accepting batches per rank (seeded), alternated between steps
@@ -156,42 +159,91 @@ def run_ours(args):
     gcount, gbase = n * world, n * rank
     seed = 7
     pbytes = int(lib.h2v_partial_bytes())
-    partial_dev = torch.zeros(pbytes, dtype=torch.uint8, device="cuda")
-    gathered = [torch.zeros(pbytes, dtype=torch.uint8, device="cuda") for _ in range(world)] if world > 1 else None
-    verdict = ctypes.c_int(0)
     chk = lambda ctx, rc: ctx._check(rc)
-
     ext_streams = [torch.cuda.ExternalStream(b.stream_handle(), device=torch.device("cuda", local)) for b in bvs]
+    # Per context: its own partial buffers and (N > 1) its own NCCL communicator, so that the batches in flight
+    # exchange their partials independently; each context is driven by one host thread whose current torch stream
+    # IS the context's stream, which orders shard kernels -> all-gather -> pairing check without extra events.
+    for ci, ctx in enumerate(bvs):
+        ctx.ci = ci
+        ctx.partial_dev = torch.zeros(pbytes, dtype=torch.uint8, device="cuda")
+        ctx.gathered = torch.zeros(world * pbytes, dtype=torch.uint8, device="cuda") if world > 1 else None
+    comm_stream = torch.cuda.Stream(priority=-1) if world > 1 else None
+    comm_group = None
+    if world > 1:  # create the communicator (high-priority NCCL stream: the tiny gather must not queue behind compute) before any worker thread exists
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        comm_group = dist.new_group(backend="nccl", pg_options=opts)
+        with torch.cuda.stream(comm_stream):
+            dist.all_gather_into_tensor(bvs[0].gathered, bvs[0].partial_dev, group=comm_group)
+        torch.cuda.synchronize()
 
-    def gather_and_finalize(ctx):
-        """NCCL all-gather of the partials (torch's stream), then the single pairing check on rank 0
-        (context stream, ordered after the gather by an event)."""
-        dist.all_gather(gathered, partial_dev)
-        if rank == 0:
-            cat = torch.cat(gathered)
+    class Exchange:
+        """The one exchange step of a sharded batch: NCCL all-gather of the per-window partials.  All gathers of all
+        batches in flight go through ONE communicator in global step order, issued by one thread on one stream
+        (several communicators spinning on each other's peers can deadlock on the hardware work queues); the
+        contexts' streams are tied to it with CUDA events, so nothing waits on the host."""
+
+        def __init__(self, count):
+            self.ready = [threading.Event() for _ in range(count)]
+            self.done = [threading.Event() for _ in range(count)]
+            self.ev_ready = [None] * count
+            self.ev_done = [None] * count
+            self.slot = [None] * count
+            self.thread = threading.Thread(target=self.run, args=(count,))
+            self.thread.start()
+
+        def run(self, count):
+            torch.cuda.set_device(local)
+            with torch.cuda.stream(comm_stream):
+                for i in range(count):
+                    self.ready[i].wait()
+                    ctx = self.slot[i]
+                    comm_stream.wait_event(self.ev_ready[i])
+                    dist.all_gather_into_tensor(ctx.gathered, ctx.partial_dev, group=comm_group)
+                    ev = torch.cuda.Event()
+                    ev.record(comm_stream)
+                    self.ev_done[i] = ev
+                    self.done[i].set()
+
+        def gather(self, ctx, i):
+            """called by the context's thread after it enqueued the shard's kernels on its stream"""
             ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
-            ext_streams[0].wait_event(ev)
-            chk(ctx, lib.h2v_finalize(ctx._ctx, world, cat.data_ptr(), None, ctypes.byref(verdict)))
-        return verdict.value
+            ev.record(ext_streams[ctx.ci])
+            self.ev_ready[i], self.slot[i] = ev, ctx
+            self.ready[i].set()
+            self.done[i].wait()
+            ext_streams[ctx.ci].wait_event(self.ev_done[i])
+            return self.ev_done[i]
 
-    def step_resident(ctx, flush=True):
+    xchg = [None]
+
+    def gather_and_finalize(ctx, i):
+        """NCCL all-gather of the partials over NVLink, then the single pairing check on rank 0."""
+        v = ctypes.c_int(1)
+        ev = xchg[0].gather(ctx, i)
+        if rank == i % world:  # every rank holds all partials after the all-gather: the ONE pairing check of global batch i runs on rank i mod N
+            chk(ctx, lib.h2v_finalize(ctx._ctx, world, ctx.gathered.data_ptr(), None, ctypes.byref(v)))
+        else:
+            ev.synchronize()  # this context's buffers are reused by its next step
+        return v.value
+
+    def step_resident(ctx, i=0, flush=True):
         v = ctypes.c_int(0)
         if flush:
             chk(ctx, lib.h2v_flush_l2(ctx._ctx, 256 << 20))
         if world == 1:
             chk(ctx, lib.h2v_batch_run(ctx._ctx, ctypes.byref(v)))
             return v.value
-        chk(ctx, lib.h2v_batch_run_shard(ctx._ctx, partial_dev.data_ptr()))  # returns after the shard's stream is idle
-        return gather_and_finalize(ctx)
+        chk(ctx, lib.h2v_batch_run_shard_async(ctx._ctx, ctx.partial_dev.data_ptr()))  # enqueue only: the gather is event-ordered after it
+        return gather_and_finalize(ctx, i)
 
-    def step_e2e(ctx, pb):
+    def step_e2e(ctx, pb, i=0):
         if world == 1:
             chk(ctx, lib.h2v_verify_batch(ctx._ctx, *pb.args(), None, seed, pb.status.data_ptr(), None, None, None))
             return int(pb.status.max()) == 0
-        chk(ctx, lib.h2v_accumulate_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount, pb.status.data_ptr(), partial_dev.data_ptr()))
-        v = gather_and_finalize(ctx)
-        return v == 1 if rank == 0 else True
+        chk(ctx, lib.h2v_accumulate_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount, pb.status.data_ptr(), ctx.partial_dev.data_ptr()))
+        return gather_and_finalize(ctx, i) == 1
 
     def sync_all():
         torch.cuda.synchronize()
@@ -214,7 +266,7 @@ def run_ours(args):
         w0 = time.perf_counter()
         res_ = run_steps(fn, count, ctxs)
         ends = []
-        for st in ext_streams[: len(ctxs)] + [torch.cuda.current_stream()]:
+        for st in ext_streams[: len(ctxs)] + [torch.cuda.current_stream()] + ([comm_stream] if comm_stream is not None else []):
             e = torch.cuda.Event(enable_timing=True)
             e.record(st)
             ends.append(e)
@@ -225,17 +277,27 @@ def run_ours(args):
     def run_steps(fn, count, ctxs):
         """count steps spread round-robin over the contexts; each context is driven by its own host
         thread (ctypes releases the GIL), so batches of different contexts overlap on the device."""
-        if len(ctxs) == 1:
-            return [fn(ctxs[0], i) for i in range(count)]
         out = [None] * count
+        if world > 1:
+            xchg[0] = Exchange(count)
 
         def worker(ci):
-            for i in range(ci, count, len(ctxs)):
-                out[i] = fn(ctxs[ci], i)
+            torch.cuda.set_device(local)
+            with torch.cuda.stream(ext_streams[ctxs[ci].ci]):
+                for i in range(ci, count, len(ctxs)):
+                    out[i] = fn(ctxs[ci], i)
+
+        if len(ctxs) == 1:
+            worker(0)
+            if world > 1:
+                xchg[0].thread.join()
+            return out
 
         ths = [threading.Thread(target=worker, args=(ci,)) for ci in range(len(ctxs))]
         [t.start() for t in ths]
         [t.join() for t in ths]
+        if world > 1:
+            xchg[0].thread.join()
         return out
 
     def reduce_max(*vals):
@@ -249,37 +311,37 @@ def run_ours(args):
     # ---------------- device-resident throughput (`value`)
     for ci, ctx in enumerate(bvs):
         upload(ctx, batches[ci % 2])
-    ok = run_steps(lambda ctx, i: step_resident(ctx), W * n_ctx, bvs)
-    assert rank != 0 or all(v == 1 for v in ok), "warm-up batch was rejected"
+    ok = run_steps(lambda ctx, i: step_resident(ctx, i), W * n_ctx, bvs)
+    assert all(v == 1 for v in ok), "warm-up batch was rejected"
     geom = bv.msm_geometry()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = sum(b.launch_count() for b in bvs)
     # one batch in flight: latency view (also the only mode at N > 1)
-    res, dt1, _ = timed(lambda ctx, i: step_resident(ctx), args.steps, bvs[:1])
-    assert rank != 0 or all(v == 1 for v in res), "a timed batch was rejected"
+    res, dt1, _ = timed(lambda ctx, i: step_resident(ctx, i), args.steps, bvs[:1])
+    assert all(v == 1 for v in res), "a timed batch was rejected"
     launches = sum(b.launch_count() for b in bvs) - launches0
     dt = dt1
     if n_ctx > 1:  # several independent batches in flight (one context + stream + host thread each): throughput view
         launches0 = sum(b.launch_count() for b in bvs)
-        res, dt, _ = timed(lambda ctx, i: step_resident(ctx), args.steps, bvs)
+        res, dt, _ = timed(lambda ctx, i: step_resident(ctx, i), args.steps, bvs)
         assert all(v == 1 for v in res), "a timed batch was rejected"
         launches = sum(b.launch_count() for b in bvs) - launches0
     clocks = sampler.summary()
     # per-stage CUDA-event timings of a few serial steps (roofline of the dominant kernel group)
     stage_acc = {}
     for i in range(5):
-        step_resident(bv)
+        run_steps(lambda ctx, i_: step_resident(ctx, i_), 1, bvs[:1])
         for name, ms in bv.timings().items():
             stage_acc.setdefault(name, []).append(ms)
     stage_ms = {k_: statistics.median(v) for k_, v in stage_acc.items()}
     # ---------------- end to end through the C ABI from pinned host memory
-    run_steps(lambda ctx, i: step_e2e(ctx, batches[i % 2]), W * n_ctx, bvs)
+    run_steps(lambda ctx, i: step_e2e(ctx, batches[i % 2], i), W * n_ctx, bvs)
     lat = []
 
     def timed_e2e(ctx, i):
         a = time.perf_counter()
-        okk = step_e2e(ctx, batches[i % 2])
+        okk = step_e2e(ctx, batches[i % 2], i)
         lat.append(time.perf_counter() - a)
         return okk
 
@@ -314,12 +376,13 @@ def run_ours(args):
             "config": {"workload": f"{n} SHPLONK proofs per GPU, vector_mul test-circuit shape ('{args.shape}'), k={k}, Blake2b transcript, "
                                    f"10 public inputs, 1,024-byte proofs; BASELINE.json configs[1]",
                        "batch_per_gpu": n, "global_batch": n * world, "contexts_in_flight": n_ctx,
+                       "step": f"one global batch of {n * world} proofs: {n} per GPU, per-window partials all-gathered, ONE pairing check",
                        "in_flight_note": "a step is one complete 4096-proof batch; `value`/`e2e` keep `contexts_in_flight` independent batches in flight "
                                          "(one context + CUDA stream + host thread each), `one_in_flight` times strictly serial batches",
                        "timing": "CUDA events on the contexts' streams (first start -> last end) between barrier + synchronize, max over ranks; "
                                  "e2e on the host clock around the C-ABI calls",
                        "l2": "flushed before every step (256 MiB overwrite on the step's stream, inside the timed region)",
-                       "parallelism": f"proof-sharded x{world}, NCCL all-gather of the per-window partial accumulators (12,320 B per rank), one pairing check on rank 0"},
+                       "parallelism": f"proof-sharded x{world}, NCCL all-gather of the per-window partial accumulators (12,320 B per rank), one pairing check per global batch (on rank step mod N)"},
             "e2e": {"value": total / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": batches[0].h2d_bytes, "d2h_bytes_per_step": batches[0].d2h_bytes,
                     "ms_per_step": dt_e2e / args.steps * 1e3, "p50_latency_ms": p50},
             "one_in_flight": {"value": total / dt1, "ms_per_step": dt1 / args.steps * 1e3, "e2e_value": total / dt_e2e1, "e2e_p50_latency_ms": p50},
@@ -453,6 +516,10 @@ def run_reference(args):
 
 
 def main():
+    # stdout must carry exactly one JSON line: libraries (e.g. NCCL with NCCL_DEBUG set) print there too, so
+    # everything else goes to stderr and the JSON is written to the saved descriptor at the end
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -467,8 +534,9 @@ def main():
     ap.add_argument("--ref-proofs-per-core", type=int, default=64)
     args = ap.parse_args()
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    sys.stdout.flush()
     if out is not None:
-        print(json.dumps(out), flush=True)
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":

@@ -1125,6 +1125,13 @@ int h2v_batch_run_shard(h2v_ctx* ctx, uint8_t* partial) {
   return 0;
 }
 
+int h2v_batch_run_shard_async(h2v_ctx* ctx, uint8_t* partial_device) {
+  int rc = run_impl(ctx, RUN_PARTIAL);
+  if (rc) return rc;
+  if (partial_device) CKC(cudaMemcpyAsync(partial_device, ctx->d_partial_out.p, H2V_PARTIAL_BYTES, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+
 int h2v_flush_l2(h2v_ctx* ctx, size_t bytes) {
   if (!ctx) return -1;
   CKC(cudaSetDevice(ctx->device));

@@ -123,6 +123,9 @@ int h2v_batch_upload_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, cons
                            uint64_t seed, uint64_t global_base, uint64_t global_count);
 /* runs every kernel of the shard except the pairing; partial: H2V_PARTIAL_BYTES out, host OR device pointer */
 int h2v_batch_run_shard(h2v_ctx* ctx, uint8_t* partial);
+/* same, enqueue only: returns without waiting; `partial_device` must be device memory and is valid for work
+ * ordered after this call on the context's stream (h2v_ctx_stream), e.g. an NCCL all-gather issued on it */
+int h2v_batch_run_shard_async(h2v_ctx* ctx, uint8_t* partial_device);
 /* overwrites `bytes` of scratch HBM on the context's stream (L2 flush between timed iterations) */
 int h2v_flush_l2(h2v_ctx* ctx, size_t bytes);
 /* runs every kernel of the batch on data already resident in HBM; verdict of the batch pairing out */
