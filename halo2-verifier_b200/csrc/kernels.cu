@@ -226,29 +226,56 @@ __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, 
   }
 }
 
-// exclusive scan of the histogram (one block); off has nb + 1 entries, cursor is a working copy
-__global__ void __launch_bounds__(1024) k_scan(const u32* hist, u32 nb, u32* off, u32* cursor) {
-  __shared__ u32 sh[1024];
-  const u32 t = threadIdx.x;
-  const u32 m = (nb + 1023) / 1024;
-  const u32 lo = min(nb, t * m), hi = min(nb, lo + m);
-  u32 s = 0;
-  for (u32 i = lo; i < hi; i++) s += hist[i];
-  sh[t] = s;
+// exclusive scan of the bucket histogram in two launches: tiles of 1024 counters are scanned with coalesced
+// loads (warp shuffles), then every tile adds the totals of the tiles before it.  off has nb + 1 entries,
+// cursor is a working copy for the scatter.
+__device__ __forceinline__ u32 block_excl_scan_1024(u32 v, u32* total) {
+  __shared__ u32 wsum[32];
+  const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  u32 x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+    if (lane >= (u32)d) x += y;
+  }
+  if (lane == 31) wsum[wid] = x;
   __syncthreads();
-  for (u32 d = 1; d < 1024; d <<= 1) {
-    u32 v = t >= d ? sh[t - d] : 0;
-    __syncthreads();
-    sh[t] += v;
-    __syncthreads();
+  if (wid == 0) {
+    u32 w = wsum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 y = __shfl_up_sync(0xFFFFFFFFu, w, d);
+      if (lane >= (u32)d) w += y;
+    }
+    wsum[lane] = w;
   }
-  u32 run = t ? sh[t - 1] : 0;
-  for (u32 i = lo; i < hi; i++) {
-    off[i] = run;
-    cursor[i] = run;
-    run += hist[i];
+  __syncthreads();
+  *total = wsum[31];
+  return x - v + (wid ? wsum[wid - 1] : 0);
+}
+__global__ void __launch_bounds__(1024) k_scan_tiles(const u32* hist, u32 nb, u32* off, u32* tile_total) {
+  const u32 i = blockIdx.x * 1024 + threadIdx.x;
+  const u32 v = i < nb ? hist[i] : 0;
+  u32 total;
+  const u32 e = block_excl_scan_1024(v, &total);
+  if (i < nb) off[i] = e;
+  if (threadIdx.x == 0) tile_total[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) k_scan_apply(u32 nb, u32 n_tiles, const u32* tile_total, u32* off, u32* cursor) {
+  __shared__ u32 base_sh;
+  u32 part = 0;
+  for (u32 k = threadIdx.x; k < blockIdx.x; k += 1024) part += tile_total[k];
+  u32 total;
+  block_excl_scan_1024(part, &total);  // only the block total is used
+  if (threadIdx.x == 0) base_sh = total;
+  __syncthreads();
+  const u32 base = base_sh, i = blockIdx.x * 1024 + threadIdx.x;
+  if (i < nb) {
+    const u32 o = off[i] + base;
+    off[i] = o;
+    cursor[i] = o;
   }
-  if (t == 1023) off[nb] = sh[1023];
+  if (blockIdx.x == n_tiles - 1 && threadIdx.x == 0) off[nb] = base + tile_total[blockIdx.x];
 }
 
 __global__ void k_msm_scatter(MsmGeom g, const int16_t* dig, u32* cursor, u32* sorted) {
@@ -559,6 +586,8 @@ struct DevBuf {
 struct h2v_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_aux = nullptr;  // the fold-coefficient scan runs beside the per-proof stages
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<u8> blob;
   PlanInfo info{};
   PlanHeader hd{};
@@ -582,7 +611,7 @@ struct h2v_ctx {
   // device buffers
   DevBuf d_plan, d_proofs, d_proof_off, d_inst, d_inst_off, d_ncols, d_col_len, d_pts, d_bad, d_status, d_vals, d_scratch, d_right,
       d_shared, d_left, d_rlc_bytes, d_r, d_coef, d_shared_sum, d_dig, d_hist, d_off, d_cursor, d_sorted, d_buckets, d_wsums,
-      d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush, d_lines, d_M, d_partial_out, d_wsums_fin;
+      d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush, d_lines, d_M, d_partial_out, d_wsums_fin, d_tiles;
   std::vector<u32> h_status;
   PlanView pv() const { return PlanView{d_plan.as<u8>()}; }
 };
@@ -695,7 +724,7 @@ static int launch_pairing(h2v_ctx* ctx, const G1Jac* wsums) {
   k_lines<LINES_GROUPS><<<H2V_ATE_ITERS, 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s>>>(LinesArgs{g.W[0] + g.W[1]}, wsums, ctx->d_lines.as<G2Line>(),
                                                                                        ctx->d_M.as<E12>());
   LAUNCH_CHECK();
-  k_pairing_check<<<1, 64, 0, s>>>(ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>());
+  k_pairing_check<<<1, 128, 0, s>>>(ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>());
   LAUNCH_CHECK();
   return 0;
 }
@@ -734,6 +763,10 @@ int h2v_ctx_create(h2v_ctx** out, const uint8_t* params, size_t params_len, int 
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess)
+    return fail("cudaEventCreate", e);
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = ctx->d_plan.ensure(ctx->blob.size())) != cudaSuccess) return fail("cudaMalloc(plan)", e);
@@ -750,16 +783,20 @@ void h2v_ctx_destroy(h2v_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream_aux) cudaStreamSynchronize(ctx->stream_aux);
   DevBuf* bufs[] = {&ctx->d_plan, &ctx->d_proofs, &ctx->d_proof_off, &ctx->d_inst, &ctx->d_inst_off, &ctx->d_ncols, &ctx->d_col_len,
                     &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
                     &ctx->d_rlc_bytes, &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off,
                     &ctx->d_cursor, &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict,
                     &ctx->d_partials, &ctx->d_partials_msm, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal, &ctx->d_flush,
-                    &ctx->d_lines, &ctx->d_M, &ctx->d_partial_out, &ctx->d_wsums_fin};
+                    &ctx->d_lines, &ctx->d_M, &ctx->d_partial_out, &ctx->d_wsums_fin, &ctx->d_tiles};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -848,6 +885,7 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   CKC(ctx->d_hist.ensure(4 * (size_t)nb));
   CKC(ctx->d_off.ensure(4 * (size_t)(nb + 1)));
   CKC(ctx->d_cursor.ensure(4 * (size_t)nb));
+  CKC(ctx->d_tiles.ensure(4 * (size_t)(nb / 1024 + 2)));
   CKC(ctx->d_sorted.ensure(4 * (size_t)g.T * g.Wmax));
   CKC(ctx->d_buckets.ensure(sizeof(G1Jac) * (size_t)nb));
   CKC(ctx->d_wsums.ensure(sizeof(G1Jac) * (size_t)(g.W[0] + g.W[1])));
@@ -892,6 +930,12 @@ static int run_impl(h2v_ctx* ctx, int mode) {
   const MsmGeom& g = ctx->geom;
   const u32 nb = g.nb();
   CKC(cudaEventRecord(ctx->ev[0], s));
+  // c_j = prod_{i>j} r_i depends only on the coefficients: scanned on the auxiliary stream while the proofs are parsed
+  CKC(cudaEventRecord(ctx->ev_fork, s));
+  CKC(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
+  k_rlc_scan<<<1, 1024, 0, ctx->stream_aux>>>(ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, n, ctx->d_coef.as<Fr>());
+  LAUNCH_CHECK();
+  CKC(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
   k_init<<<cdiv(n, 128), 128, 0, s>>>(pv, n, ctx->d_inst_off.as<u64>(), ctx->has_ncols ? ctx->d_ncols.as<u32>() : nullptr,
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
   LAUNCH_CHECK();
@@ -914,8 +958,7 @@ static int run_impl(h2v_ctx* ctx, int mode) {
                                       ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_status.as<u32>());
   LAUNCH_CHECK();
   CKC(cudaEventRecord(ctx->ev[3], s));
-  k_rlc_scan<<<1, 1024, 0, s>>>(ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, n, ctx->d_coef.as<Fr>());
-  LAUNCH_CHECK();
+  CKC(cudaStreamWaitEvent(s, ctx->ev_join, 0));
   k_shared_reduce<<<hd.n_shared, 256, 0, s>>>(n, ctx->d_shared.as<Fr>(), ctx->d_coef.as<Fr>(), ctx->d_shared_sum.as<Fr>());
   LAUNCH_CHECK();
   CKC(cudaMemsetAsync(ctx->d_hist.p, 0, 4 * (size_t)nb, s));
@@ -923,7 +966,10 @@ static int run_impl(h2v_ctx* ctx, int mode) {
                                               ctx->d_shared_sum.as<Fr>(), pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_dig.as<int16_t>(),
                                               ctx->d_hist.as<u32>());
   LAUNCH_CHECK();
-  k_scan<<<1, 1024, 0, s>>>(ctx->d_hist.as<u32>(), nb, ctx->d_off.as<u32>(), ctx->d_cursor.as<u32>());
+  const u32 n_tiles = cdiv(nb, 1024);
+  k_scan_tiles<<<n_tiles, 1024, 0, s>>>(ctx->d_hist.as<u32>(), nb, ctx->d_off.as<u32>(), ctx->d_tiles.as<u32>());
+  LAUNCH_CHECK();
+  k_scan_apply<<<n_tiles, 1024, 0, s>>>(nb, n_tiles, ctx->d_tiles.as<u32>(), ctx->d_off.as<u32>(), ctx->d_cursor.as<u32>());
   LAUNCH_CHECK();
   k_msm_scatter<<<cdiv((u64)g.T * g.Wmax, 256), 256, 0, s>>>(g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
   LAUNCH_CHECK();

@@ -45,15 +45,9 @@ H2V_HD int e12_base_slot(int b) {  // position of base coordinate b inside the e
   return 3 * (6 * hh + j) + part;
 }
 
-// sum_k coef_k * src[idx_k] mod p for one table row: 64-bit column accumulators, one reduction.
-// Every coefficient is positive (negative terms address the negated copy of the source) and every
-// source value is <= p, so the sum is < 2^9 p.
-H2V_HD Fq lin_row(const uint16_t* start, const uint16_t* terms, int row, const Fq* src) {
-  u64 acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) acc[i] = 0;
-  const int k1 = start[row + 1];
-  for (int k = start[row]; k < k1; k += 4) {  // rows are padded to a multiple of 4 terms
+// accumulates terms [k0, k1) of a row (k0, k1 multiples of 4: rows are padded) into 64-bit column accumulators
+H2V_HD void lin_row_acc(u64* acc, const uint16_t* terms, int k0, int k1, const Fq* src) {
+  for (int k = k0; k < k1; k += 4) {
     const u64 tt = *(const u64*)(terms + k);  // 4 packed (index | coefficient << 8) terms
     const u32 tx = (u32)tt, ty = (u32)(tt >> 32);
     const Fq v0 = src[tx & 0xFF], v1 = src[(tx >> 16) & 0xFF], v2 = src[ty & 0xFF], v3 = src[(ty >> 16) & 0xFF];
@@ -63,6 +57,9 @@ H2V_HD Fq lin_row(const uint16_t* start, const uint16_t* terms, int row, const F
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] += (u64)c2 * v2.l[i] + (u64)c3 * v3.l[i];
   }
+}
+// column accumulators (value < 2^9 p) -> reduced field element
+H2V_HD Fq lin_reduce(const u64* acc) {
   u32 V[9];
   u64 cy = 0;
 #pragma unroll
@@ -89,6 +86,16 @@ H2V_HD Fq lin_row(const uint16_t* start, const uint16_t* terms, int row, const F
   r.cond_sub_mod();  // remainder < 3 p < 2^256
   r.cond_sub_mod();
   return r;
+}
+// sum_k coef_k * src[idx_k] mod p for one table row: 64-bit column accumulators, one reduction.
+// Every coefficient is positive (negative terms address the negated copy of the source) and every
+// source value is <= p, so the sum is < 2^9 p.
+H2V_HD Fq lin_row(const uint16_t* start, const uint16_t* terms, int row, const Fq* src) {
+  u64 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = 0;
+  lin_row_acc(acc, terms, start[row], start[row + 1], src);
+  return lin_reduce(acc);
 }
 
 // ---- per-lane phases (host/device; the device wrappers below add the barriers)
@@ -161,17 +168,42 @@ static constexpr int H2V_ATE_ITERS = 65;
 __device__ const LinTables g_lin_tables = H2V_LIN_TABLES_INIT;
 
 struct Grp {
-  int lane;  // 0..63
+  int lane;  // 0..nthr-1
   int bar;   // named barrier id (1..15)
   const LinTables* lt;
   Fq* scr;   // 2 * E12_N values of shared scratch
-  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory"); }
+  int nthr;  // 64, or 128: every row of the linear map is split over two lanes (latency-critical single group)
+  u64* part; // nthr == 128: E12_N x 8 partial column accumulators
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthr) : "memory"); }
 };
 
 __device__ __forceinline__ void g_mul(const Grp& g, E12* dst, const E12* a, const E12* b) {  // dst may alias a, b
   if (g.lane < E12_N) e12_mul_p1(g.scr, a, b, g.lane);
   g.sync();
-  if (g.lane < E12_N) e12_mul_p2(dst, g.scr, g.lt, g.lane);
+  if (g.nthr == 64) {
+    if (g.lane < E12_N) e12_mul_p2(dst, g.scr, g.lt, g.lane);
+    g.sync();
+    return;
+  }
+  const int half = g.lane >> 6, row = g.lane & 63;
+  u64 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = 0;
+  if (row < E12_N) {
+    const int k0 = g.lt->full_start[row], k1 = g.lt->full_start[row + 1];
+    const int mid = k0 + (((k1 - k0) / 4 + 1) / 2) * 4;
+    lin_row_acc(acc, g.lt->full_terms, half ? mid : k0, half ? k1 : mid, g.scr);
+    if (half) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) g.part[row * 8 + i] = acc[i];
+    }
+  }
+  g.sync();
+  if (!half && row < E12_N) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] += g.part[row * 8 + i];
+    dst->e[row] = lin_reduce(acc);
+  }
   g.sync();
 }
 __device__ __forceinline__ void g_expand(const Grp& g, E12* dst) {  // from base coordinates in scr[0..11]
@@ -236,7 +268,7 @@ __global__ void __launch_bounds__(64 * GROUPS) k_lines(LinesArgs la, const G1Jac
     sm->Z3[t] = Fq::mul(Fq::mul(s.Z, s.Z), s.Z);
   }
   __syncthreads();
-  Grp g{t & 63, gi + 1, &sm->lt, scrs + gi * 2 * E12_N};
+  Grp g{t & 63, gi + 1, &sm->lt, scrs + gi * 2 * E12_N, 64, nullptr};
   E12 *acc = accs + gi, *tmp = tmps + gi;
   const int it = blockIdx.x;
   const int n0 = it >= 64 ? H2V_ATE_LINES - 2 : ate_line_index(it), ns = ate_lines_in_iteration(it);
@@ -264,14 +296,15 @@ constexpr size_t k_lines_smem() {
 }
 
 // ---- k_pairing_check: Miller accumulation over the prepared iteration products + final check
-__global__ void __launch_bounds__(64) k_pairing_check(const E12* __restrict__ M, u32* verdict) {
+__global__ void __launch_bounds__(128) k_pairing_check(const E12* __restrict__ M, u32* verdict) {
   __shared__ LinTables lt;
   __shared__ E12 slot[12];
   __shared__ Fq scr[2 * E12_N];
+  __shared__ u64 part[E12_N * 8];
   const int t = threadIdx.x;
-  for (int i = t; i < (int)(sizeof(LinTables) / 2); i += 64) ((uint16_t*)&lt)[i] = ((const uint16_t*)&g_lin_tables)[i];
+  for (int i = t; i < (int)(sizeof(LinTables) / 2); i += 128) ((uint16_t*)&lt)[i] = ((const uint16_t*)&g_lin_tables)[i];
   __syncthreads();
-  Grp g{t, 1, &lt, scr};
+  Grp g{t, 1, &lt, scr, 128, part};
   E12 *f = &slot[0], *tt = &slot[1], *fu = &slot[2], *fu2 = &slot[3], *fu3 = &slot[4], *a = &slot[5], *b = &slot[6], *y0 = &slot[7],
       *T0 = &slot[8], *T1 = &slot[9], *N = &slot[10], *m = &slot[11];
   g_copy(g, f, &M[0]);

@@ -74,15 +74,16 @@ __global__ void k_check(u32 count, u32* bad) {
 }
 
 // latency of the cooperative Fq12 product: one 64-thread group, `iters` dependent g_mul
-__global__ void __launch_bounds__(64) k_e12_chain(u32 iters, Fq* io, int mode) {
+__global__ void __launch_bounds__(128) k_e12_chain(u32 iters, Fq* io, int mode) {
   __shared__ LinTables lt;
   __shared__ E12 x, y;
   __shared__ Fq scr[2 * E12_N];
+  __shared__ u64 part[E12_N * 8];
   const int t = threadIdx.x;
-  for (int i = t; i < (int)(sizeof(LinTables) / 2); i += 64) ((uint16_t*)&lt)[i] = ((const uint16_t*)&g_lin_tables)[i];
+  for (int i = t; i < (int)(sizeof(LinTables) / 2); i += blockDim.x) ((uint16_t*)&lt)[i] = ((const uint16_t*)&g_lin_tables)[i];
   if (t < E12_NB) { Fq v = io[t]; v.l[7] &= 0x0FFFFFFF; scr[t] = v; }
   __syncthreads();
-  Grp g{t, 1, &lt, scr};
+  Grp g{t, 1, &lt, scr, (int)blockDim.x, part};
   g_expand(g, &x);
   g_copy(g, &y, &x);
   for (u32 i = 0; i < iters; i++) {
@@ -139,10 +140,12 @@ int main() {
     printf("warps/SM %2d: lo/hi CIOS %.2f G MM/s (chain %.0f ns/MM) | wide %.2f G MM/s (chain %.0f ns/MM) | wide x2 chains %.2f | wide x4 chains %.2f G MM/s\n",
            c.blocks_per_sm * c.threads / 32, n / m0 / 1e6, m0 * 1e6 / iters, n / m1 / 1e6, m1 * 1e6 / iters, 2 * n / m2 / 1e6, 4 * n / m3 / 1e6);
   }
-  for (int mode = 0; mode < 3; mode++) {
-    double ms = time_ms([&] { k_e12_chain<<<1, 64>>>(1000, io, mode); });
-    printf("cooperative Fq12 engine, %s: %.2f us per op\n", mode == 0 ? "g_mul" : mode == 1 ? "product phase only" : "linear phase only", ms);
-  }
+  for (int nthr = 64; nthr <= 128; nthr += 64)
+    for (int mode = 0; mode < 3; mode++) {
+      if (nthr == 128 && mode == 2) continue;
+      double ms = time_ms([&] { k_e12_chain<<<1, nthr>>>(1000, io, mode); });
+      printf("cooperative Fq12 engine, %d threads, %s: %.2f us per op\n", nthr, mode == 0 ? "g_mul" : mode == 1 ? "product phase only" : "linear phase only", ms);
+    }
   printf("last error: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
 }
