@@ -6,6 +6,7 @@
 // Everything here is written for sm_100a (CIOS on the IMAD pipe); the same source compiles for the
 // host (plan compiler, host test harness) through the H2V_HD macro.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -414,6 +415,26 @@ struct alignas(16) Fp {  // 16-byte alignment: element loads / stores vectorise 
   static H2V_HD Fp from_uniform(const u8* b64) {
     Fp lo = load_le(b64), hi = load_le(b64 + 32);
     return mul_any(lo, r2()) + mul_any(hi, r3());
+  }
+
+  // same from 16 little-endian words (hash digests are produced as words on the device)
+  static H2V_HD Fp from_uniform_words(const u32* w16) {
+    Fp lo, hi;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      lo.l[i] = w16[i];
+      hi.l[i] = w16[8 + i];
+    }
+    return mul_any(lo, r2()) + mul_any(hi, r3());
+  }
+  // 32 little-endian bytes -> raw limbs with 32-bit loads when the address allows
+  static H2V_HD Fp load_le_fast(const u8* b) {
+    if (((size_t)b & 3) != 0) return load_le(b);
+    Fp r;
+    const u32* w = (const u32*)b;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = w[i];
+    return r;
   }
 
   // ---- exponentiation by a fixed 256-bit exponent given as 8 limbs (4-bit fixed window)

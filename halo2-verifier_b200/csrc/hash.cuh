@@ -76,27 +76,61 @@ struct Blake2b {
     for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
   }
 
-  H2V_HDN void update_byte(u8 b) {
-    if (buflen == 128) {  // only compress when more input follows (the last block is special)
-      t += 128;
-      compress(false);
-      buflen = 0;
-      for (int i = 0; i < 16; i++) m[i] = 0;
-    }
+  H2V_HD void flush_block() {  // only called when more input follows (the last block is finalised in digest)
+    t += 128;
+    compress(false);
+    buflen = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) m[i] = 0;
+  }
+  H2V_HD void update_byte(u8 b) {
+    if (buflen == 128) flush_block();
     m[buflen >> 3] |= (u64)b << ((buflen & 7) * 8);
     buflen++;
+  }
+  // absorb 4 bytes (little-endian word) at any byte alignment: at most two read-modify-writes of the block buffer
+  H2V_HD void update_u32(u32 w) {
+    if (buflen == 128) flush_block();
+    const u32 sh = (buflen & 7) * 8, wi = buflen >> 3;
+    m[wi] |= (u64)w << sh;
+    if (sh <= 32) {
+      buflen += 4;
+      return;
+    }
+    const u64 hi = (u64)w >> (64 - sh);  // the bytes that did not fit into word wi
+    if (wi + 1 < 16) {
+      m[wi + 1] |= hi;
+      buflen += 4;
+    } else {
+      buflen = 128;
+      flush_block();
+      m[0] = hi;
+      buflen = (sh - 32) / 8;
+    }
   }
   H2V_HDN void update(const u8* data, u32 len) {
     for (u32 i = 0; i < len; i++) update_byte(data[i]);
   }
   // absorb a 256-bit little-endian value given as 8 u32 limbs
   H2V_HDN void update_limbs(const u32* l) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) update_u32(l[i]);
+  }
+  // prefix byte + 256-bit value (the transcript's common_scalar / one coordinate of common_point)
+  H2V_HDN void update_prefixed(u8 prefix, const u32* l) {
+    update_byte(prefix);
+#pragma unroll
+    for (int i = 0; i < 8; i++) update_u32(l[i]);
+  }
+  // digest of a clone as 16 little-endian words; `this` keeps running
+  H2V_HDN void digest_words(u32* out16) const {
+    Blake2b c = *this;
+    c.t += c.buflen;
+    c.compress(true);
+#pragma unroll
     for (int i = 0; i < 8; i++) {
-      u32 w = l[i];
-      update_byte((u8)w);
-      update_byte((u8)(w >> 8));
-      update_byte((u8)(w >> 16));
-      update_byte((u8)(w >> 24));
+      out16[2 * i] = (u32)c.h[i];
+      out16[2 * i + 1] = (u32)(c.h[i] >> 32);
     }
   }
   // digest of a clone; `this` keeps running
@@ -160,9 +194,26 @@ struct Keccak256 {
       s[0] ^= keccak_rc(round);
     }
   }
-  H2V_HDN void update_byte(u8 b) {
+  H2V_HD void update_byte(u8 b) {
     s[pos >> 3] ^= (u64)b << ((pos & 7) * 8);
     pos++;
+    if (pos == 136) {
+      permute();
+      pos = 0;
+    }
+  }
+  H2V_HD void update_u32(u32 w) {  // 4 bytes at any alignment inside the 136-byte rate
+    if (pos + 4 > 136) {
+      update_byte((u8)w);
+      update_byte((u8)(w >> 8));
+      update_byte((u8)(w >> 16));
+      update_byte((u8)(w >> 24));
+      return;
+    }
+    const u32 sh = (pos & 7) * 8, wi = pos >> 3;
+    s[wi] ^= (u64)w << sh;
+    if (sh > 32) s[wi + 1] ^= (u64)w >> (64 - sh);
+    pos += 4;
     if (pos == 136) {
       permute();
       pos = 0;
@@ -172,12 +223,24 @@ struct Keccak256 {
     for (u32 i = 0; i < len; i++) update_byte(data[i]);
   }
   H2V_HDN void update_limbs(const u32* l) {
-    for (int i = 0; i < 8; i++) {
-      u32 w = l[i];
-      update_byte((u8)w);
-      update_byte((u8)(w >> 8));
-      update_byte((u8)(w >> 16));
-      update_byte((u8)(w >> 24));
+#pragma unroll
+    for (int i = 0; i < 8; i++) update_u32(l[i]);
+  }
+  H2V_HDN void update_prefixed(u8 prefix, const u32* l) {
+    update_byte(prefix);
+#pragma unroll
+    for (int i = 0; i < 8; i++) update_u32(l[i]);
+  }
+  H2V_HDN void digest_words_with_suffix(u8 suffix, u32* out8) const {
+    Keccak256 c = *this;
+    c.update_byte(suffix);
+    c.s[c.pos >> 3] ^= (u64)0x01 << ((c.pos & 7) * 8);
+    c.s[16] ^= 0x8000000000000000ull;  // last byte of the 136-byte rate
+    c.permute();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      out8[2 * i] = (u32)c.s[i];
+      out8[2 * i + 1] = (u32)(c.s[i] >> 32);
     }
   }
   // digest of a clone after absorbing one extra byte (the lo / hi challenge prefixes 10 / 11)

@@ -33,14 +33,10 @@ template <class H>
 struct TranscriptState {
   H hs;
   H2V_HDN void init() { hs.init_halo2(); }
-  H2V_HDN void common_scalar_limbs(const u32* canon) {
-    hs.update_byte(2);
-    hs.update_limbs(canon);
-  }
+  H2V_HDN void common_scalar_limbs(const u32* canon) { hs.update_prefixed(2, canon); }
   H2V_HDN void common_point(const G1Affine& p) {
-    hs.update_byte(1);
     Fq x = p.x.to_canonical(), y = p.y.to_canonical();
-    hs.update_limbs(x.l);
+    hs.update_prefixed(1, x.l);
     hs.update_limbs(y.l);
   }
   H2V_HDN Fr squeeze();
@@ -48,17 +44,17 @@ struct TranscriptState {
 template <>
 H2V_HDN inline Fr TranscriptState<Blake2b>::squeeze() {
   hs.update_byte(0);
-  u8 d[64];
-  hs.digest(d);
-  return Fr::from_uniform(d);
+  u32 d[16];
+  hs.digest_words(d);
+  return Fr::from_uniform_words(d);
 }
 template <>
 H2V_HDN inline Fr TranscriptState<Keccak256>::squeeze() {
   hs.update_byte(0);
-  u8 d[64];
-  hs.digest_with_suffix(10, d);
-  hs.digest_with_suffix(11, d + 32);
-  return Fr::from_uniform(d);
+  u32 d[16];
+  hs.digest_words_with_suffix(10, d);
+  hs.digest_words_with_suffix(11, d + 8);
+  return Fr::from_uniform_words(d);
 }
 
 // Replays the transcript of proof j.  Writes the Montgomery-form proof scalars and challenges into
@@ -81,7 +77,7 @@ H2V_HDN inline u32 transcript_stage(const PlanView& pv, const u8* proof, u32 len
       ts.common_scalar_limbs(c.l);
     } else if (kind == T_ABS_INST) {
       for (u32 i = 0; i < inst_total; i++) {
-        Fr c = Fr::load_le(inst + 32 * (size_t)i);
+        Fr c = Fr::load_le_fast(inst + 32 * (size_t)i);
         if (c.geq_mod()) inst_bad = true;
         ts.common_scalar_limbs(c.l);
       }
@@ -91,7 +87,7 @@ H2V_HDN inline u32 transcript_stage(const PlanView& pv, const u8* proof, u32 len
       for (u32 i = 0; i < count; i++, item++, sslot++) {
         Fr c = Fr::zero();
         if ((item + 1) * 32 <= len) {
-          c = Fr::load_le(proof + item * 32);
+          c = Fr::load_le_fast(proof + item * 32);
           if (c.geq_mod()) {
             if (item < bad_item) bad_item = item;
             c = Fr::zero();
