@@ -587,7 +587,8 @@ struct h2v_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream_aux = nullptr;  // the fold-coefficient scan runs beside the per-proof stages
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done = nullptr;
+  bool blocking_sync = false;
   std::vector<u8> blob;
   PlanInfo info{};
   PlanHeader hd{};
@@ -631,6 +632,16 @@ struct h2v_ctx {
   } while (0)
 
 static inline u32 cdiv(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
+
+// Host wait for everything queued on the context's stream.  Default: cudaStreamSynchronize (spins: lowest latency).
+// With many contexts per host (several batches in flight on several GPUs) the spinning threads starve the cores, so
+// a context can be switched to a blocking wait on an event (h2v_ctx_set_blocking_sync).
+static cudaError_t ctx_sync(h2v_ctx* ctx) {
+  if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaEventRecord(ctx->ev_done, ctx->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ctx->ev_done);
+}
 
 // Window size per channel.  Thanks to the scalar lift k'' = k + z*r every window is uniformly filled, so
 // the choice is a pure work trade-off: bucket additions (11 MM) against bucket reduction (2 x 16 MM
@@ -688,6 +699,10 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom) {
   g.bbase[1] = g.W[0] * g.B[0];
   g.Wmax = std::max(g.W[0], g.W[1]);
   g.m = 8;  // every B is a power of two >= 8
+  if (const char* fm = getenv("H2V_MSM_CHUNK")) {
+    const int m = atoi(fm);
+    if (m == 2 || m == 4 || m == 8) g.m = (u32)m;
+  }
   return g;
 }
 
@@ -712,7 +727,7 @@ static int ensure_lines(h2v_ctx* ctx) {
   CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128));
   CKC(ctx->d_partial_out.ensure(H2V_PARTIAL_BYTES));
   CKC(cudaMemcpyAsync(ctx->d_lines.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(ctx_sync(ctx));
   ctx->lines_key = key;
   return 0;
 }
@@ -765,7 +780,8 @@ int h2v_ctx_create(h2v_ctx** out, const uint8_t* params, size_t params_len, int 
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess)
+      (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess)
     return fail("cudaEventCreate", e);
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -796,6 +812,7 @@ void h2v_ctx_destroy(h2v_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
   if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1028,7 +1045,7 @@ static int per_proof_impl(h2v_ctx* ctx, bool pairing, u8* accum_host) {
 static int download_status(h2v_ctx* ctx, u8* status) {
   ctx->h_status.resize(ctx->n);
   CKC(cudaMemcpyAsync(ctx->h_status.data(), ctx->d_status.p, 4 * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
-  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(ctx_sync(ctx));
   if (status)
     for (u32 j = 0; j < ctx->n; j++) status[j] = (u8)ctx->h_status[j];
   return 0;
@@ -1066,7 +1083,7 @@ int h2v_verify_batch(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint
   u32 verdict = 0;
   CKC(cudaMemcpyAsync(&verdict, ctx->d_verdict.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (batch_accum) CKC(cudaMemcpyAsync(batch_accum, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
-  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(ctx_sync(ctx));
   if (!verdict || accum) {  // per-proof accumulators: parity hook, or attribution of a rejected batch
     if ((rc = per_proof_impl(ctx, !verdict, accum)) != 0) return rc;
   }
@@ -1097,7 +1114,7 @@ int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uin
   if (ctx->n == 0) {  // a context that has not processed a shard itself: take the geometry from the first partial
     PartialHeader h;
     CKC(cudaMemcpyAsync(&h, ctx->d_partials.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-    CKC(cudaStreamSynchronize(s));
+    CKC(ctx_sync(ctx));
     MsmGeom& g = ctx->geom;
     g = MsmGeom{};
     g.c[0] = h.cbits & 0xFFFF;
@@ -1130,7 +1147,7 @@ int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uin
   }
   u32 v[2] = {0, 0};
   CKC(cudaMemcpyAsync(v, ctx->d_verdict.p, 8, cudaMemcpyDeviceToHost, s));
-  CKC(cudaStreamSynchronize(s));
+  CKC(ctx_sync(ctx));
   if (v[1]) {
     ctx->err = "partial accumulators were produced with different window geometries (use h2v_batch_set_shard_hint)";
     return -1;
@@ -1150,7 +1167,7 @@ int h2v_batch_upload(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint
                      const uint64_t* inst_off, const uint8_t* rlc_scalars, uint64_t seed) {
   int rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, 0, n);
   if (rc) return rc;
-  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(ctx_sync(ctx));
   return 0;
 }
 
@@ -1159,7 +1176,7 @@ int h2v_batch_upload_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, cons
                            uint64_t global_count) {
   int rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, global_base, global_count);
   if (rc) return rc;
-  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(ctx_sync(ctx));
   return 0;
 }
 
@@ -1167,7 +1184,7 @@ int h2v_batch_run_shard(h2v_ctx* ctx, uint8_t* partial) {
   int rc = run_impl(ctx, RUN_PARTIAL);
   if (rc) return rc;
   if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_partial_out.p, H2V_PARTIAL_BYTES, cudaMemcpyDefault, ctx->stream));
-  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(ctx_sync(ctx));
   return 0;
 }
 
@@ -1191,7 +1208,7 @@ int h2v_batch_run(h2v_ctx* ctx, int* verdict) {
   if (rc) return rc;
   u32 v = 0;
   CKC(cudaMemcpyAsync(&v, ctx->d_verdict.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CKC(cudaStreamSynchronize(ctx->stream));
+  CKC(ctx_sync(ctx));
   if (verdict) *verdict = (int)v;
   return 0;
 }
@@ -1215,6 +1232,12 @@ int h2v_last_timings(const h2v_ctx* cctx, float* out8) {
 uint64_t h2v_launch_count(const h2v_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 void* h2v_ctx_stream(const h2v_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int h2v_ctx_set_blocking_sync(h2v_ctx* ctx, int blocking) {
+  if (!ctx) return -1;
+  ctx->blocking_sync = blocking != 0;
+  return 0;
+}
 
 int h2v_last_msm_geometry(const h2v_ctx* ctx, uint32_t* out4) {
   if (!ctx || !out4) return -1;

@@ -139,6 +139,9 @@ uint64_t h2v_launch_count(const h2v_ctx* ctx);
 /* the context's cudaStream_t (every kernel and copy of the context is issued on it), so that a caller
  * can record its own CUDA events around calls or order other work after them */
 void* h2v_ctx_stream(const h2v_ctx* ctx);
+/* host waits of this context: 0 (default) spin on the stream (lowest latency), 1 block on an event (use when many
+ * contexts share few host cores, e.g. several batches in flight on every GPU of a box) */
+int h2v_ctx_set_blocking_sync(h2v_ctx* ctx, int blocking);
 /* MSM geometry of the last run: out[0] window bits, [1] windows, [2] terms, [3] buckets */
 int h2v_last_msm_geometry(const h2v_ctx* ctx, uint32_t* out4);
 
