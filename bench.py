@@ -234,7 +234,7 @@ def run_ours(args):
 
     def step_resident(ctx, i=0, flush=True):
         v = ctypes.c_int(0)
-        if flush:
+        if flush and not os.environ.get("H2V_BENCH_DIAG_NOFLUSH"):  # (diagnosis only; reported numbers always flush)
             chk(ctx, lib.h2v_flush_l2(ctx._ctx, 256 << 20))
         if world == 1:
             chk(ctx, lib.h2v_batch_run(ctx._ctx, ctypes.byref(v)))

@@ -43,3 +43,31 @@ for name, shape, k, mo, hk, vkfmt in CASES:
         out["proofs"].append(e)
     json.dump(out, open(os.path.join(HERE, name + ".json"), "w"), indent=0)
     print(name, [r.status for r in results], "folded_ok", ok)
+
+# ---- honest proofs of the vector_mul circuit (oracle/honest_prover.py: real witness, real polynomials, k = 8 fixture SRS secret)
+import honest_prover as hp
+rng = random.Random("golden-honest")
+s = sim.FIXTURE_SRS_SECRET
+params, vk, pk = hp.keygen_vm(8, s, 10)
+proofs, instances = [], []
+for j in range(3):
+    lhs = [rng.randrange(bn.R) for _ in range(10)]
+    rhs = [rng.randrange(bn.R) for _ in range(10)]
+    p, inst = hp.prove_vm(params, vk, pk, s, lhs, rhs, rng, cheat_row=(4 if j == 1 else None))
+    proofs.append(p); instances.append(inst)
+inst_wrong = [[list(instances[2][0][0])]]
+inst_wrong[0][0][3] = (inst_wrong[0][0][3] + 1) % bn.R  # the reference's own negative test: wrong public input (vector_mul.rs:327-330)
+proofs.append(proofs[2]); instances.append(inst_wrong)
+rs = [rng.randrange(1, bn.R) for _ in proofs]
+results = [orc.verify_proof(params, vk, inst, p) for inst, p in zip(instances, proofs)]
+assert [r.status for r in results] == [0, 4, 0, 4], [r.status for r in results]
+L, Rr, ok = orc.accumulate(params, results, rs)
+out = {"shape": "vm-honest", "k": 8, "multiopen": "shplonk", "hash": "blake2b", "vk_format": F.RAW_BYTES,
+       "params": params.to_bytes().hex(), "vk": vk.to_bytes(F.RAW_BYTES).hex(),
+       "rlc_scalars": [hex(r) for r in rs], "folded": (enc_point(L) + enc_point(Rr)).hex(), "folded_ok": ok, "proofs": []}
+for inst, p, res in zip(instances, proofs, results):
+    out["proofs"].append({"proof": p.hex(), "instances": [[hex(v) for v in col] for col in inst[0]], "status": res.status,
+                          "challenges": [hex(c) for c in res.challenges], "accum": (enc_point(res.L) + enc_point(res.R)).hex(),
+                          "msm_scalars": [hex(v) for v in oracle_scalars(vk, res, 12, 2)]})
+json.dump(out, open(os.path.join(HERE, "vm_k8_honest_prover.json"), "w"), indent=0)
+print("vm_k8_honest_prover", [r.status for r in results])

@@ -1,0 +1,58 @@
+"""Honest proofs of the vector_mul circuit (oracle/honest_prover.py): a real witness, real polynomials and the
+protocol's own definitions of the permutation / vanishing arguments.  Unlike the trapdoor simulator these only
+verify if the restated verifier expressions vanish on the whole domain for an honest witness."""
+import json
+import os
+import random
+
+import pytest
+
+import bn254 as bn
+import c_oracle
+import formats as F
+import honest_prover as hp
+import prover_sim as sim
+import verifier as orc
+from workloads import enc_point
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("k,rows,hk", [(8, 10, "blake2b"), (6, 3, "keccak"), (5, 1, "blake2b")])
+def test_honest_proof_is_accepted_and_cheats_are_rejected(built, k, rows, hk):
+    rng = random.Random(("honest", k, rows).__repr__())
+    s = sim.FIXTURE_SRS_SECRET if k == 8 else rng.randrange(1, bn.R)
+    params, vk, pk = hp.keygen_vm(k, s, rows)
+    lhs = [rng.randrange(bn.R) for _ in range(rows)]
+    rhs = [rng.randrange(bn.R) for _ in range(rows)]
+    proof, inst = hp.prove_vm(params, vk, pk, s, lhs, rhs, rng, hk)
+    assert inst[0][0] == [a * b % bn.R for a, b in zip(lhs, rhs)]
+    res = orc.verify_proof(params, vk, inst, proof, "shplonk", hk)
+    assert res.status == orc.OK
+    co = c_oracle.COracle(params.to_bytes(1), 1, vk.to_bytes(1), 1)
+    st, chal, lr = co.verify(proof, inst[0], "shplonk", hk)
+    assert (st, chal, lr) == (0, res.challenges, enc_point(res.L) + enc_point(res.R))
+    # wrong public input: the reference's own negative test (tests/vector_mul.rs:327-330)
+    wrong = [[list(inst[0][0])]]
+    wrong[0][0][0] = (wrong[0][0][0] + 1) % bn.R
+    assert orc.verify_proof(params, vk, wrong, proof, "shplonk", hk).status == orc.CONSTRAINT_SYSTEM_FAILURE
+    assert co.verify(proof, wrong[0], "shplonk", hk)[0] == orc.CONSTRAINT_SYSTEM_FAILURE
+    # a witness that violates the gate (and a consistent public input): no polynomial quotient -> rejected
+    bad, bad_inst = hp.prove_vm(params, vk, pk, s, lhs, rhs, rng, hk, cheat_row=rows - 1)
+    assert orc.verify_proof(params, vk, bad_inst, bad, "shplonk", hk).status == orc.CONSTRAINT_SYSTEM_FAILURE
+    assert co.verify(bad, bad_inst[0], "shplonk", hk)[0] == orc.CONSTRAINT_SYSTEM_FAILURE
+    co.close()
+
+
+def test_honest_golden_vector_against_both_oracles(built):
+    g = json.load(open(os.path.join(HERE, "golden", "vm_k8_honest_prover.json")))
+    params = F.ParamsKZG.from_bytes(bytes.fromhex(g["params"]))
+    vk = F.VerifyingKey.from_bytes(bytes.fromhex(g["vk"]), g["vk_format"])
+    co = c_oracle.COracle(bytes.fromhex(g["params"]), 0, bytes.fromhex(g["vk"]), g["vk_format"])
+    for e in g["proofs"]:
+        inst = [[[int(v, 16) for v in col] for col in e["instances"]]]
+        res = orc.verify_proof(params, vk, inst, bytes.fromhex(e["proof"]))
+        assert res.status == e["status"] and [hex(c) for c in res.challenges] == e["challenges"]
+        st, chal, lr = co.verify(bytes.fromhex(e["proof"]), inst[0])
+        assert st == e["status"] and lr.hex() == e["accum"]
+    co.close()
