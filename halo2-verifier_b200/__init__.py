@@ -91,6 +91,8 @@ def load_library():
     u8p, u32p, u64p = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
     lib.h2v_ctx_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
                                    ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.h2v_ctx_create_from_bundle.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int]
     lib.h2v_ctx_destroy.argtypes = [ctypes.c_void_p]
     lib.h2v_ctx_destroy.restype = None
     lib.h2v_last_error.argtypes = [ctypes.c_void_p]
@@ -131,7 +133,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = (
-    "h2v_ctx_create", "h2v_ctx_destroy", "h2v_last_error", "h2v_ctx_info", "h2v_verify_proof", "h2v_verify_batch",
+    "h2v_ctx_create", "h2v_ctx_create_from_bundle", "h2v_ctx_destroy", "h2v_last_error", "h2v_ctx_info", "h2v_verify_proof", "h2v_verify_batch",
     "h2v_batch_set_columns", "h2v_batch_set_scalar_hook", "h2v_batch_set_shard_hint", "h2v_partial_bytes", "h2v_accumulate_shard", "h2v_finalize", "h2v_attribute_shard",
     "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync",
     "h2v_last_msm_geometry", "h2v_selftest_field", "h2v_calibrate_imad",
@@ -173,6 +175,26 @@ class VerifyingKey:
     @classmethod
     def read(cls, reader, format: SerdeFormat = SerdeFormat.RawBytes):
         return cls(reader.read(), SerdeFormat(format))
+
+
+PARAMS_BYTES_LENGTH = 4 + 32 + 64 + 64  # ParamsKZG::bytes_length() (poly/kzg/commitment.rs:209-213)
+
+
+def read_vk_bundle(data: bytes):
+    """Splits a `VALID_VK.bin` bundle (reference serialize/examples/vector_mul.rs:374-393: verifier params in
+    Processed form followed by the VK in RawBytes form) into (ParamsKZG, VerifyingKey)."""
+    if len(data) <= PARAMS_BYTES_LENGTH:
+        raise BackendError("bundle shorter than the verifier params")
+    return (ParamsKZG(bytes(data[:PARAMS_BYTES_LENGTH]), SerdeFormat.Processed),
+            VerifyingKey(bytes(data[PARAMS_BYTES_LENGTH:]), SerdeFormat.RawBytes))
+
+
+def instances_from_pubs(data: bytes):
+    """`VALID_PUBS.bin` of the same example (public inputs as consecutive 32-byte `to_bytes()` values) -> one
+    instance column of ints."""
+    if len(data) % 32:
+        raise BackendError("public-input file is not a multiple of 32 bytes")
+    return [[int.from_bytes(data[i: i + 32], "little") for i in range(0, len(data), 32)]]
 
 
 def pack_instances(instances) -> (bytes, List[int], Optional[List[int]], Optional[List[int]]):

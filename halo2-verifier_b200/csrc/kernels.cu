@@ -795,6 +795,17 @@ int h2v_ctx_create(h2v_ctx** out, const uint8_t* params, size_t params_len, int 
   return 0;
 }
 
+int h2v_ctx_create_from_bundle(h2v_ctx** out, const uint8_t* bundle, size_t bundle_len, int multiopen, int hash, int device) {
+  // serialize/examples/vector_mul.rs:374-393: ParamsKZG::write (Processed, ParamsKZG::bytes_length() = 4 + 32 + 64 + 64
+  // bytes, commitment.rs:209-213) immediately followed by VerifyingKey::write(RawBytes)
+  const size_t plen = 4 + 32 + 64 + 64;
+  if (!out || !bundle || bundle_len <= plen) {
+    g_create_error = "bundle shorter than the verifier params";
+    return -1;
+  }
+  return h2v_ctx_create(out, bundle, plen, H2V_FMT_PROCESSED, bundle + plen, bundle_len - plen, H2V_FMT_RAW_BYTES, multiopen, hash, device);
+}
+
 void h2v_ctx_destroy(h2v_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);

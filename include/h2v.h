@@ -45,6 +45,9 @@ typedef struct h2v_ctx h2v_ctx;
  * parses both byte strings, compiles the device plan, uploads it to `device`. */
 int h2v_ctx_create(h2v_ctx** out, const uint8_t* params, size_t params_len, int params_format,
                    const uint8_t* vk, size_t vk_len, int vk_format, int multiopen, int hash, int device);
+/* Same from the `VALID_VK.bin` bundle the reference's tooling writes (serialize/examples/vector_mul.rs:374-393):
+ * ParamsKZG::write (Processed form, 164 bytes) immediately followed by VerifyingKey::write(SerdeFormat::RawBytes). */
+int h2v_ctx_create_from_bundle(h2v_ctx** out, const uint8_t* bundle, size_t bundle_len, int multiopen, int hash, int device);
 void h2v_ctx_destroy(h2v_ctx* ctx);
 /* error text of the last failing call on this context (ctx == NULL: of the last failed h2v_ctx_create) */
 const char* h2v_last_error(const h2v_ctx* ctx);

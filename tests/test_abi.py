@@ -45,3 +45,17 @@ def test_no_cpu_fallback(built, pkg):
         pkg.BatchVerifier(pkg.ParamsKZG.from_bytes(params.to_bytes()), pkg.VerifyingKey.from_bytes(vk.to_bytes(F.RAW_BYTES)))
     with pytest.raises(pkg.BackendError):
         pkg.verify_proof(pkg.ParamsKZG.from_bytes(params.to_bytes()), pkg.VerifyingKey.from_bytes(vk.to_bytes(F.RAW_BYTES)), bytes(1024), [[1] * 10])
+
+
+def test_vk_bundle_helpers(pkg):
+    import formats as F
+    from workloads import setup
+
+    params, vk, _dl, _s = setup("vm", 8)
+    bundle = params.to_bytes(F.PROCESSED) + vk.to_bytes(F.RAW_BYTES)
+    P, V = pkg.read_vk_bundle(bundle)
+    assert P.data == params.to_bytes(F.PROCESSED) and P.format == pkg.SerdeFormat.Processed and P.k == 8
+    assert V.data == vk.to_bytes(F.RAW_BYTES) and V.format == pkg.SerdeFormat.RawBytes
+    assert pkg.instances_from_pubs((5).to_bytes(32, "little") + (7).to_bytes(32, "little")) == [[5, 7]]
+    with pytest.raises(pkg.BackendError):
+        pkg.read_vk_bundle(bundle[:100])

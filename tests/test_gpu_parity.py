@@ -318,3 +318,30 @@ def test_config4_k18_lookup_heavy_batch_against_c_oracle(pkg):
         assert res.challenges == ch and res.accum == lr
         assert res.batch_accum == co.fold(lr, rs, [True] * n)[0]
     co.close()
+
+
+def test_vk_bundle_and_honest_proof_through_the_c_abi(pkg):
+    """The reference tooling's artefacts (serialize/examples/vector_mul.rs:363-393): VALID_VK.bin = params (Processed) | VK
+    (RawBytes), VALID_PROOF.bin, VALID_PUBS.bin -- here produced by the honest mini-prover -- verified like `verify_proof`."""
+    import honest_prover as hp
+
+    rng = random.Random(77)
+    s = sim.FIXTURE_SRS_SECRET
+    params, vk, pk = hp.keygen_vm(8, s, 10)
+    lhs, rhs = [rng.randrange(bn.R) for _ in range(10)], [rng.randrange(bn.R) for _ in range(10)]
+    proof, inst = hp.prove_vm(params, vk, pk, s, lhs, rhs, rng)
+    bundle = params.to_bytes(F.PROCESSED) + vk.to_bytes(F.RAW_BYTES)
+    pubs = b"".join(bn.fr_to_repr(v) for v in inst[0][0])
+    P, V = pkg.read_vk_bundle(bundle)
+    assert pkg.verify_proof(P, V, proof, pkg.instances_from_pubs(pubs)) is None
+    wrong = pkg.instances_from_pubs(pubs)
+    wrong[0][2] = (wrong[0][2] + 1) % bn.R
+    with pytest.raises(pkg.ConstraintSystemFailure):  # tests/vector_mul.rs:327-330
+        pkg.verify_proof(P, V, proof, wrong)
+    lib = pkg.load_library()
+    ctx = ctypes.c_void_p()
+    assert lib.h2v_ctx_create_from_bundle(ctypes.byref(ctx), bundle, len(bundle), 0, 0, 0) == 0
+    st = ctypes.c_uint8(9)
+    assert lib.h2v_verify_proof(ctx, proof, len(proof), pubs, len(pubs) // 32, ctypes.byref(st)) == 0 and st.value == 0
+    lib.h2v_ctx_destroy(ctx)
+    assert lib.h2v_ctx_create_from_bundle(ctypes.byref(ctx), bundle[:100], 100, 0, 0, 0) != 0
