@@ -71,3 +71,29 @@ for inst, p, res in zip(instances, proofs, results):
                           "msm_scalars": [hex(v) for v in oracle_scalars(vk, res, 12, 2)]})
 json.dump(out, open(os.path.join(HERE, "vm_k8_honest_prover.json"), "w"), indent=0)
 print("vm_k8_honest_prover", [r.status for r in results])
+
+# ---- honest proofs of the lookup + shuffle + rotated-gate circuit (k = 6, seeded SRS secret)
+rng = random.Random("golden-honest-lk")
+s = rng.randrange(1, bn.R)
+circ = hp.lookup_shuffle_circuit(6, 16)
+params, vk, pk = hp.keygen(circ, s)
+proofs, instances = [], []
+for cheat in (None, "lookup", None, "shuffle"):
+    adv, ins = hp.lookup_shuffle_assignment(circ, 16, rng, cheat)
+    proofs.append(hp.prove(params, vk, pk, s, adv, ins, rng, "blake2b", expect_honest=cheat is None))
+    instances.append([ins])
+rs = [rng.randrange(1, bn.R) for _ in proofs]
+results = [orc.verify_proof(params, vk, inst, p) for inst, p in zip(instances, proofs)]
+assert [r.status for r in results] == [0, 4, 0, 4], [r.status for r in results]
+items, first_mo = sim.proof_layout(vk, "shplonk")
+n_points = items.count("P"); n_mo = len(items) - first_mo
+L, Rr, ok = orc.accumulate(params, results, rs)
+out = {"shape": "lookup-shuffle-honest", "k": 6, "multiopen": "shplonk", "hash": "blake2b", "vk_format": F.RAW_BYTES,
+       "params": params.to_bytes().hex(), "vk": vk.to_bytes(F.RAW_BYTES).hex(),
+       "rlc_scalars": [hex(r) for r in rs], "folded": (enc_point(L) + enc_point(Rr)).hex(), "folded_ok": ok, "proofs": []}
+for inst, p, res in zip(instances, proofs, results):
+    out["proofs"].append({"proof": p.hex(), "instances": [[hex(v) for v in col] for col in inst[0]], "status": res.status,
+                          "challenges": [hex(c) for c in res.challenges], "accum": (enc_point(res.L) + enc_point(res.R)).hex(),
+                          "msm_scalars": [hex(v) for v in oracle_scalars(vk, res, n_points, n_mo)]})
+json.dump(out, open(os.path.join(HERE, "lk_k6_honest_prover.json"), "w"), indent=0)
+print("lk_k6_honest_prover", [r.status for r in results])

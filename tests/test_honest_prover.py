@@ -44,8 +44,9 @@ def test_honest_proof_is_accepted_and_cheats_are_rejected(built, k, rows, hk):
     co.close()
 
 
-def test_honest_golden_vector_against_both_oracles(built):
-    g = json.load(open(os.path.join(HERE, "golden", "vm_k8_honest_prover.json")))
+@pytest.mark.parametrize("name", ["vm_k8_honest_prover", "lk_k6_honest_prover"])
+def test_honest_golden_vector_against_both_oracles(built, name):
+    g = json.load(open(os.path.join(HERE, "golden", name + ".json")))
     params = F.ParamsKZG.from_bytes(bytes.fromhex(g["params"]))
     vk = F.VerifyingKey.from_bytes(bytes.fromhex(g["vk"]), g["vk_format"])
     co = c_oracle.COracle(bytes.fromhex(g["params"]), 0, bytes.fromhex(g["vk"]), g["vk_format"])
@@ -55,4 +56,26 @@ def test_honest_golden_vector_against_both_oracles(built):
         assert res.status == e["status"] and [hex(c) for c in res.challenges] == e["challenges"]
         st, chal, lr = co.verify(bytes.fromhex(e["proof"]), inst[0])
         assert st == e["status"] and lr.hex() == e["accum"]
+    co.close()
+
+
+@pytest.mark.parametrize("hk", ["blake2b", "keccak"])
+def test_honest_lookup_shuffle_circuit(built, hk):
+    """lookup.rs:159-271, shuffle.rs:148-225, a rotated gate query and a permutation that includes a fixed column."""
+    rng = random.Random(("honest-lk", hk).__repr__())
+    s = rng.randrange(1, bn.R)
+    circ = hp.lookup_shuffle_circuit(6, 16)
+    params, vk, pk = hp.keygen(circ, s)
+    co = c_oracle.COracle(params.to_bytes(1), 1, vk.to_bytes(1), 1)
+    adv, ins = hp.lookup_shuffle_assignment(circ, 16, rng)
+    proof = hp.prove(params, vk, pk, s, adv, ins, rng, hk)
+    res = orc.verify_proof(params, vk, [ins], proof, "shplonk", hk)
+    assert res.status == orc.OK
+    st, chal, lr = co.verify(proof, ins, "shplonk", hk)
+    assert (st, chal, lr) == (0, res.challenges, enc_point(res.L) + enc_point(res.R))
+    for cheat in ("lookup", "shuffle", "gate", "copy"):
+        adv, ins = hp.lookup_shuffle_assignment(circ, 16, rng, cheat)
+        bad = hp.prove(params, vk, pk, s, adv, ins, rng, hk, expect_honest=False)
+        assert orc.verify_proof(params, vk, [ins], bad, "shplonk", hk).status == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
+        assert co.verify(bad, ins, "shplonk", hk)[0] == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
     co.close()
