@@ -646,20 +646,23 @@ static cudaError_t ctx_sync(h2v_ctx* ctx) {
 // Window size per channel.  Thanks to the scalar lift k'' = k + z*r every window is uniformly filled, so
 // the choice is a pure work trade-off: bucket additions (11 MM) against bucket reduction (2 x 16 MM
 // per bucket plus the per-chunk offset multiplication), with a floor on the per-bucket serial chain.
-static void choose_window(u32 terms, u32& c_out, u32& W_out) {
-  double best = 1e300;
+static double choose_window(u32 terms, u32& c_out, u32& W_out, double chain_floor) {
+  double best = 1e300, best_chain = 0;
   for (u32 c = 4; c <= 15; c++) {
     const u32 W = (255 + c - 1) / c;
     const double B = (double)(1u << (c - 1));
     const double work = (double)W * ((double)terms * 11.0 + B * (32.0 + 28.0));
     const double chain = ((double)terms / B + 1.0) * 11.0;  // dependent MM per bucket thread
-    const double t = work / 15e9 + chain * 0.4e-6;
+    // both channels share the bucket kernels: only a chain longer than the other channel's costs latency
+    const double t = work / 15e9 + std::max(0.0, chain - chain_floor) * 0.4e-6;
     if (t < best) {
       best = t;
+      best_chain = chain;
       c_out = c;
       W_out = W;
     }
   }
+  return best_chain;
 }
 
 // Z = floor(2^(W*c-1) / r): k + z*r < 2^(W*c-1) for z < Z, so the top signed digit never carries out.
@@ -680,8 +683,8 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom) {
   g.Sh = hd.n_shared;
   g.T = n * hd.n_points + n * hd.n_mo + hd.n_shared;
   if (n_geom < n) n_geom = n;
-  choose_window(n_geom * hd.n_points + hd.n_shared, g.c[0], g.W[0]);
-  choose_window(n_geom * hd.n_mo, g.c[1], g.W[1]);
+  const double chain_right = choose_window(n_geom * hd.n_points + hd.n_shared, g.c[0], g.W[0], 0.0);
+  choose_window(n_geom * hd.n_mo, g.c[1], g.W[1], chain_right);
   const char* f0 = getenv("H2V_MSM_WINDOW_RIGHT");
   const char* f1 = getenv("H2V_MSM_WINDOW_LEFT");
   for (int ch = 0; ch < 2; ch++) {
