@@ -345,3 +345,53 @@ def test_vk_bundle_and_honest_proof_through_the_c_abi(pkg):
     assert lib.h2v_verify_proof(ctx, proof, len(proof), pubs, len(pubs) // 32, ctypes.byref(st)) == 0 and st.value == 0
     lib.h2v_ctx_destroy(ctx)
     assert lib.h2v_ctx_create_from_bundle(ctypes.byref(ctx), bundle[:100], 100, 0, 0, 0) != 0
+
+
+def test_edge_cases_empty_inputs_single_proof_all_invalid(pkg):
+    """Edge cases of the batch API: no public inputs at all, a batch of one, a batch in which every proof is unreadable
+    (nothing to fold: the pairing check of two identities accepts, the statuses carry the errors), empty proof bytes."""
+    import honest_prover as hp
+
+    rng = random.Random(5150)
+    s = rng.randrange(1, bn.R)
+    params, vk, pk = hp.keygen_vm(6, s, 0)  # zero multiplications: empty instance column
+    proof, inst = hp.prove_vm(params, vk, pk, s, [], [], rng)
+    assert inst == [[[]]] and orc.verify_proof(params, vk, inst, proof).status == 0
+    with make_bv(pkg, params, vk, "shplonk", "blake2b") as bv:
+        assert bv.verify_batch([proof], [inst[0]]).status == [0]
+        assert bv.verify_batch([proof] * 3, [inst[0]] * 3).status == [0, 0, 0]
+        bad = bv.verify_batch([proof[:40], b"", proof[:-1]], [inst[0]] * 3, want_batch_accum=True)
+        assert bad.status == [2, 2, 3] and bad.batch_accum == bytes(128)
+        mixed = bv.verify_batch([b"", proof], [inst[0]] * 2)
+        assert mixed.status == [2, 0]
+        with pytest.raises(AssertionError):
+            bv.verify_batch([], [])
+        v = ctypes.c_int(7)
+        assert bv.lib.h2v_verify_batch(bv._ctx, 0, None, None, None, None, None, 0, None, None, None, None) != 0  # n = 0 is an argument error
+
+
+def test_config5_shard_sizes_large_batch_tiled(pkg):
+    """BASELINE.json configs[4] shard sizes: 16384 proofs on one GPU (what one of 4 GPUs gets of a 65,536-proof batch),
+    4096 distinct proofs tiled; verdict, statuses and the folded accumulators against the C oracle's fold."""
+    import c_oracle
+    from importlib import import_module
+
+    synth = import_module("halo2_verifier_b200.synth")
+    n0, reps, k = 4096, 4, 10
+    rng = random.Random(16384)
+    s = rng.randrange(1, bn.R)
+    vk_bytes, shared_dlogs = synth.make_vk_bytes("vm", k)
+    pbytes = synth.params_bytes_raw(k, s)
+    co = c_oracle.COracle(pbytes, 1, vk_bytes, 1)
+    with pkg.BatchVerifier(pkg.ParamsKZG.from_bytes(pbytes, pkg.SerdeFormat.RawBytes), pkg.VerifyingKey.from_bytes(vk_bytes)) as bv:
+        proofs, insts = synth.synthesize_shplonk_batch(bv, shared_dlogs, s, n0, seed=("t", 5))
+        st, _secs, lr, _ch = co.verify_many(*_pack(proofs, insts), n0, check_pairing=False, threads=os.cpu_count() or 1, want_lr=True)
+        assert int(st.max()) == 0
+        n = n0 * reps
+        rs = [rng.randrange(1, bn.R) for _ in range(n)]
+        res = bv.verify_batch(proofs * reps, insts * reps, rlc_scalars=rs, want_batch_accum=True)
+        assert res.verdict and res.status == [0] * n
+        assert bv.msm_geometry()["terms"] == n * (bv.n_points + bv.n_mo) + bv.n_shared
+        folded, ok = co.fold(lr * reps, rs, [True] * n)
+        assert ok and res.batch_accum == folded
+    co.close()
