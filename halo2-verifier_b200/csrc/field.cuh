@@ -128,6 +128,64 @@ __device__ __forceinline__ void wide_fold_mad4_rshift(u32& even0, u32 (&odd)[8],
       : "+r"(odd[0]), "+r"(odd[1]), "+r"(odd[2]), "+r"(odd[3]), "+r"(odd[4]), "+r"(odd[5]), "+r"(odd[6]), "+r"(odd[7]), "+r"(even0)
       : "r"(a1), "r"(a3), "r"(a5), "r"(a7), "r"(b));
 }
+// ---- shorter rows for the dedicated squaring (Fp::sqr): the multiplicand vector of row i starts with i
+// zeros, so the first S products of a chain are skipped (the chain starts higher up / only shifts).
+// acc[2S..7] += (terms from slot S on) * b, returns the carry out
+__device__ __forceinline__ u32 wide_mad3_carry(u32 (&acc)[8], u32 a2, u32 a4, u32 a6, u32 b) {
+  u32 cy;
+  asm("mad.lo.cc.u32 %0, %7, %10, %0; madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+      "madc.lo.cc.u32 %2, %8, %10, %2; madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+      "madc.lo.cc.u32 %4, %9, %10, %4; madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+      "addc.u32 %6, 0, 0;"
+      : "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(cy)
+      : "r"(a2), "r"(a4), "r"(a6), "r"(b));
+  return cy;
+}
+__device__ __forceinline__ u32 wide_mad2_carry(u32 (&acc)[8], u32 a4, u32 a6, u32 b) {
+  u32 cy;
+  asm("mad.lo.cc.u32 %0, %5, %7, %0; madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+      "madc.lo.cc.u32 %2, %6, %7, %2; madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+      "addc.u32 %4, 0, 0;"
+      : "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(cy)
+      : "r"(a4), "r"(a6), "r"(b));
+  return cy;
+}
+__device__ __forceinline__ u32 wide_mad1_carry(u32 (&acc)[8], u32 a6, u32 b) {
+  u32 cy;
+  asm("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, 0, 0;"
+      : "+r"(acc[6]), "+r"(acc[7]), "=r"(cy)
+      : "r"(a6), "r"(b));
+  return cy;
+}
+// wide_fold_mad4_rshift with the first 1 / 2 / 3 products skipped (those slots only shift down)
+__device__ __forceinline__ void wide_fold_mad3_rshift(u32& even0, u32 (&odd)[8], u32 a3, u32 a5, u32 a7, u32 b) {
+  asm("add.cc.u32 %8, %8, %1;\n\t"
+      "addc.cc.u32 %0, %2, 0; addc.cc.u32 %1, %3, 0;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %4; madc.hi.cc.u32 %3, %9, %12, %5;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %6; madc.hi.cc.u32 %5, %10, %12, %7;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, 0; madc.hi.u32 %7, %11, %12, 0;"
+      : "+r"(odd[0]), "+r"(odd[1]), "+r"(odd[2]), "+r"(odd[3]), "+r"(odd[4]), "+r"(odd[5]), "+r"(odd[6]), "+r"(odd[7]), "+r"(even0)
+      : "r"(a3), "r"(a5), "r"(a7), "r"(b));
+}
+__device__ __forceinline__ void wide_fold_mad2_rshift(u32& even0, u32 (&odd)[8], u32 a5, u32 a7, u32 b) {
+  asm("add.cc.u32 %8, %8, %1;\n\t"
+      "addc.cc.u32 %0, %2, 0; addc.cc.u32 %1, %3, 0;\n\t"
+      "addc.cc.u32 %2, %4, 0; addc.cc.u32 %3, %5, 0;\n\t"
+      "madc.lo.cc.u32 %4, %9, %11, %6; madc.hi.cc.u32 %5, %9, %11, %7;\n\t"
+      "madc.lo.cc.u32 %6, %10, %11, 0; madc.hi.u32 %7, %10, %11, 0;"
+      : "+r"(odd[0]), "+r"(odd[1]), "+r"(odd[2]), "+r"(odd[3]), "+r"(odd[4]), "+r"(odd[5]), "+r"(odd[6]), "+r"(odd[7]), "+r"(even0)
+      : "r"(a5), "r"(a7), "r"(b));
+}
+__device__ __forceinline__ void wide_fold_mad1_rshift(u32& even0, u32 (&odd)[8], u32 a7, u32 b) {
+  asm("add.cc.u32 %8, %8, %1;\n\t"
+      "addc.cc.u32 %0, %2, 0; addc.cc.u32 %1, %3, 0;\n\t"
+      "addc.cc.u32 %2, %4, 0; addc.cc.u32 %3, %5, 0;\n\t"
+      "addc.cc.u32 %4, %6, 0; addc.cc.u32 %5, %7, 0;\n\t"
+      "madc.lo.cc.u32 %6, %9, %10, 0; madc.hi.u32 %7, %9, %10, 0;"
+      : "+r"(odd[0]), "+r"(odd[1]), "+r"(odd[2]), "+r"(odd[3]), "+r"(odd[4]), "+r"(odd[5]), "+r"(odd[6]), "+r"(odd[7]), "+r"(even0)
+      : "r"(a7), "r"(b));
+}
 #endif
 
 template <class P>
@@ -307,6 +365,33 @@ struct alignas(16) Fp {  // 16-byte alignment: element loads / stores vectorise 
     wide_mad4(odd, P::mod(1), P::mod(3), P::mod(5), P::mod(7), mi);
     odd[7] += wide_mad4_carry(even, P::mod(0), P::mod(2), P::mod(4), P::mod(6), mi);
   }
+  // Row I of the squaring: a^2 = sum_i a_i 2^(32 i) * (a_i 2^(32 i) + [2a with the bits below limb i+1 cleared]),
+  // i.e. a multiplication row whose multiplicand v has v_j = 0 (j < I), v_I = a_I, v_(I+1) = a_(I+1) << 1,
+  // v_j = limb j of 2a (j > I+1): 36 products instead of 64.  Column i only receives products of rows <= i/2,
+  // so the interleaved reduction steps are those of `wide_row`.
+  template <int I>
+  static __device__ __forceinline__ void sqr_row(u32 (&even)[8], u32 (&odd)[8], const u32* a, const u32* d) {
+    u32 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = j < I ? 0u : j == I ? a[j] : j == I + 1 ? (a[j] << 1) : d[j];
+    const u32 bi = a[I];
+    constexpr int SO = I / 2, SE = (I + 1) / 2;  // leading zero products of the odd / even chain
+    if (I == 0) {
+      wide_mul4(odd, v[1], v[3], v[5], v[7], bi);
+      wide_mul4(even, v[0], v[2], v[4], v[6], bi);
+    } else {
+      if (SO == 0) wide_fold_mad4_rshift(even[0], odd, v[1], v[3], v[5], v[7], bi);
+      else if (SO == 1) wide_fold_mad3_rshift(even[0], odd, v[3], v[5], v[7], bi);
+      else if (SO == 2) wide_fold_mad2_rshift(even[0], odd, v[5], v[7], bi);
+      else wide_fold_mad1_rshift(even[0], odd, v[7], bi);
+      if (SE == 1) odd[7] += wide_mad3_carry(even, v[2], v[4], v[6], bi);
+      else if (SE == 2) odd[7] += wide_mad2_carry(even, v[4], v[6], bi);
+      else if (SE == 3) odd[7] += wide_mad1_carry(even, v[6], bi);
+    }
+    const u32 mi = even[0] * P::INV;
+    wide_mad4(odd, P::mod(1), P::mod(3), P::mod(5), P::mod(7), mi);
+    odd[7] += wide_mad4_carry(even, P::mod(0), P::mod(2), P::mod(4), P::mod(6), mi);
+  }
 #endif
 
   // Montgomery product a*b*2^-256 mod p for REDUCED operands (a, b < p; exact for a < 2^255).
@@ -378,7 +463,33 @@ struct alignas(16) Fp {  // 16-byte alignment: element loads / stores vectorise 
 #endif
   }
   friend H2V_HD Fp operator*(const Fp& a, const Fp& b) { return mul(a, b); }
-  H2V_HD Fp sqr() const { return mul(*this, *this); }
+  // Montgomery square (a < p): 100 IMAD.WIDE.U32 + 8 IMAD instead of 128 + 8; same integer result as mul(a, a).
+  H2V_HD Fp sqr() const {
+#ifdef H2V_PTX
+    u32 d[8], even[8], odd[8];
+    d[0] = l[0] << 1;
+#pragma unroll
+    for (int j = 1; j < 8; j++) d[j] = __funnelshift_l(l[j - 1], l[j], 1);  // limbs of 2a (< 2^255)
+    sqr_row<0>(even, odd, l, d);
+    sqr_row<1>(odd, even, l, d);
+    sqr_row<2>(even, odd, l, d);
+    sqr_row<3>(odd, even, l, d);
+    sqr_row<4>(even, odd, l, d);
+    sqr_row<5>(odd, even, l, d);
+    sqr_row<6>(even, odd, l, d);
+    sqr_row<7>(odd, even, l, d);
+    Fp r;
+    asm("add.cc.u32 %0, %8, %16; addc.cc.u32 %1, %9, %17; addc.cc.u32 %2, %10, %18; addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20; addc.cc.u32 %5, %13, %21; addc.cc.u32 %6, %14, %22; addc.u32 %7, %15, 0;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+        : "r"(even[0]), "r"(even[1]), "r"(even[2]), "r"(even[3]), "r"(even[4]), "r"(even[5]), "r"(even[6]), "r"(even[7]),
+          "r"(odd[1]), "r"(odd[2]), "r"(odd[3]), "r"(odd[4]), "r"(odd[5]), "r"(odd[6]), "r"(odd[7]));
+    r.cond_sub_mod();
+    return r;
+#else
+    return mul_portable(*this, *this);
+#endif
+  }
 
   // ---- conversions
   // canonical integer (little-endian limbs, must be < p) -> Montgomery form
@@ -437,26 +548,35 @@ struct alignas(16) Fp {  // 16-byte alignment: element loads / stores vectorise 
     return r;
   }
 
-  // ---- exponentiation by a fixed 256-bit exponent given as 8 limbs (4-bit fixed window)
+  // ---- exponentiation by a 256-bit exponent given as 8 limbs: sliding window of 5 bits over a table of the
+  // 16 odd powers (for (p+1)/4: 250 squarings + 38 + 16 multiplications)
   H2V_HDN Fp pow_limbs(const u32* e) const {
     Fp tab[16];
-    tab[0] = one();
-    tab[1] = *this;
-    for (int i = 2; i < 16; i++) tab[i] = tab[i - 1] * *this;
+    const Fp a2 = sqr();
+    tab[0] = *this;
+    for (int i = 1; i < 16; i++) tab[i] = tab[i - 1] * a2;
+    int i = 255;
+    while (i >= 0 && !((e[i >> 5] >> (i & 31)) & 1)) i--;
     Fp acc = one();
     bool started = false;
-    for (int w = 63; w >= 0; w--) {
-      u32 d = (e[w >> 3] >> ((w & 7) * 4)) & 0xF;
-      if (started) {
+    while (i >= 0) {
+      if (!((e[i >> 5] >> (i & 31)) & 1)) {
         acc = acc.sqr();
-        acc = acc.sqr();
-        acc = acc.sqr();
-        acc = acc.sqr();
+        i--;
+        continue;
       }
-      if (d) {
-        acc = started ? acc * tab[d] : tab[d];
+      int j = i >= 4 ? i - 4 : 0;
+      while (!((e[j >> 5] >> (j & 31)) & 1)) j++;
+      u32 val = 0;
+      for (int b = i; b >= j; b--) val = (val << 1) | ((e[b >> 5] >> (b & 31)) & 1);
+      if (started) {
+        for (int b = j; b <= i; b++) acc = acc.sqr();
+        acc = acc * tab[val >> 1];
+      } else {
+        acc = tab[val >> 1];
         started = true;
       }
+      i = j - 1;
     }
     return acc;
   }

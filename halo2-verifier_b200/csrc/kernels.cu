@@ -535,6 +535,8 @@ __device__ u32 selftest_one(u64& s, bool edge) {
   u32 bad = F::mul_any(a, b) != y;
   if (!(a.l[7] >> 31)) bad += F::mul(a, b) != y;
   F s1 = a.geq_mod() ? F::zero() : a;
+  bad += s1.sqr() != F::mul_portable(s1, s1);  // dedicated squaring row schedule
+  bad += b.sqr() != F::mul_portable(b, b);
   F u = s1 + b, v = u - b;
   bad += (v != s1);
   return bad;

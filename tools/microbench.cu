@@ -45,7 +45,7 @@ __global__ void k_mm(u32 iters, Fq* io) {
   y.l[7] &= 0x0FFFFFFF;
   for (u32 i = 0; i < iters; i++) {
 #pragma unroll
-    for (int c = 0; c < CH; c++) x[c] = MODE == 0 ? Fq::mul_any(x[c], y) : Fq::mul(x[c], y);
+    for (int c = 0; c < CH; c++) x[c] = MODE == 0 ? Fq::mul_any(x[c], y) : MODE == 2 ? x[c].sqr() : Fq::mul(x[c], y);
   }
   Fq r = x[0];
   for (int c = 1; c < CH; c++) r = r + x[c];
@@ -71,6 +71,7 @@ __global__ void k_check(u32 count, u32* bad) {
   fa.l[7] &= 0x0FFFFFFF; fb.l[7] &= 0x0FFFFFFF;
   Fr fx = Fr::mul(fa, fb), fy = Fr::mul_portable(fa, fb);
   if (x != y || z != y || fx != fy) atomicAdd(bad, 1u);
+  if (a.sqr() != Fq::mul_portable(a, a) || b.sqr() != Fq::mul_portable(b, b) || fa.sqr() != Fr::mul_portable(fa, fa)) atomicAdd(bad, 1u);
 }
 
 // latency of the cooperative Fq12 product: one 64-thread group, `iters` dependent g_mul
@@ -117,7 +118,7 @@ int main() {
   u32* bad; cudaMalloc(&bad, 4); cudaMemset(bad, 0, 4);
   k_check<<<4096, 256>>>(1u << 20, bad);
   u32 hb = 0; cudaMemcpy(&hb, bad, 4, cudaMemcpyDeviceToHost);
-  printf("mul vs mul_portable vs mul_any mismatches over 2^20 inputs (Fq and Fr): %u  [%s]\n", hb, cudaGetErrorString(cudaGetLastError()));
+  printf("mul / sqr vs mul_portable vs mul_any mismatches over 2^20 inputs (Fq and Fr): %u  [%s]\n", hb, cudaGetErrorString(cudaGetLastError()));
   {
     const u32 blocks = sms * 8, threads = 256, iters = 2048;
     double ms = time_ms([&] { k_imad_lo<<<blocks, threads>>>(iters, d); });
@@ -136,9 +137,10 @@ int main() {
     double m1 = time_ms([&] { k_mm<1, 1><<<blocks, c.threads>>>(iters, io); });
     double m2 = time_ms([&] { k_mm<1, 2><<<blocks, c.threads>>>(iters, io); });
     double m3 = time_ms([&] { k_mm<1, 4><<<blocks, c.threads>>>(iters, io); });
+    double m4 = time_ms([&] { k_mm<2, 1><<<blocks, c.threads>>>(iters, io); });
     const double n = (double)blocks * c.threads * iters;
-    printf("warps/SM %2d: lo/hi CIOS %.2f G MM/s (chain %.0f ns/MM) | wide %.2f G MM/s (chain %.0f ns/MM) | wide x2 chains %.2f | wide x4 chains %.2f G MM/s\n",
-           c.blocks_per_sm * c.threads / 32, n / m0 / 1e6, m0 * 1e6 / iters, n / m1 / 1e6, m1 * 1e6 / iters, 2 * n / m2 / 1e6, 4 * n / m3 / 1e6);
+    printf("warps/SM %2d: lo/hi CIOS %.2f G MM/s (chain %.0f ns/MM) | wide %.2f G MM/s (chain %.0f ns/MM) | wide x2 chains %.2f | wide x4 chains %.2f G MM/s | sqr %.2f G/s (chain %.0f ns)\n",
+           c.blocks_per_sm * c.threads / 32, n / m0 / 1e6, m0 * 1e6 / iters, n / m1 / 1e6, m1 * 1e6 / iters, 2 * n / m2 / 1e6, 4 * n / m3 / 1e6, n / m4 / 1e6, m4 * 1e6 / iters);
   }
   for (int nthr = 64; nthr <= 128; nthr += 64)
     for (int mode = 0; mode < 3; mode++) {
