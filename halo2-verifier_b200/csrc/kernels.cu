@@ -253,9 +253,13 @@ __device__ __forceinline__ u32 block_excl_scan_1024(u32 v, u32* total) {
   *total = wsum[31];
   return x - v + (wid ? wsum[wid - 1] : 0);
 }
-__global__ void __launch_bounds__(1024) k_scan_tiles(const u32* hist, u32 nb, u32* off, u32* tile_total) {
+// size_bin: bucket sizes are binned in DESCENDING order (bin 0 = 1023 entries or more) for k_bucket_order
+static constexpr u32 SIZE_BINS = 1024;
+__device__ __forceinline__ u32 size_bin(u32 count) { return SIZE_BINS - 1 - (count < SIZE_BINS - 1 ? count : SIZE_BINS - 1); }
+__global__ void __launch_bounds__(1024) k_scan_tiles(const u32* hist, u32 nb, u32* off, u32* tile_total, u32* size_hist) {
   const u32 i = blockIdx.x * 1024 + threadIdx.x;
   const u32 v = i < nb ? hist[i] : 0;
+  if (i < nb) atomicAdd(&size_hist[size_bin(v)], 1u);
   u32 total;
   const u32 e = block_excl_scan_1024(v, &total);
   if (i < nb) off[i] = e;
@@ -278,6 +282,19 @@ __global__ void __launch_bounds__(1024) k_scan_apply(u32 nb, u32 n_tiles, const 
   if (blockIdx.x == n_tiles - 1 && threadIdx.x == 0) off[nb] = base + tile_total[blockIdx.x];
 }
 
+// Buckets ordered by size, largest first (counting sort on the size bins): the threads of a warp of
+// k_msm_bucket_sum then walk chains of (nearly) equal length, and the longest chains start first.
+__global__ void __launch_bounds__(1024) k_bucket_order(u32 nb, const u32* hist, const u32* size_hist, u32* size_cursor, u32* order) {
+  __shared__ u32 base[SIZE_BINS];
+  u32 total;
+  base[threadIdx.x] = block_excl_scan_1024(size_hist[threadIdx.x], &total);
+  __syncthreads();
+  const u32 i = blockIdx.x * 1024 + threadIdx.x;
+  if (i >= nb) return;
+  const u32 bin = size_bin(hist[i]);
+  order[base[bin] + atomicAdd(&size_cursor[bin], 1u)] = i;
+}
+
 __global__ void k_msm_scatter(MsmGeom g, const int16_t* dig, u32* cursor, u32* sorted) {
   const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (u64)g.T * g.Wmax) return;
@@ -292,10 +309,11 @@ __global__ void k_msm_scatter(MsmGeom g, const int16_t* dig, u32* cursor, u32* s
 }
 
 // thread per bucket: sum of its (signed) points, Jacobian += affine
-__global__ void __launch_bounds__(128) k_msm_bucket_sum(MsmGeom g, u32 nb, const u32* off, const u32* sorted, const G1Affine* pts,
-                                                        const G1Affine* shared_pts, G1Jac* buckets) {
-  const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
+__global__ void __launch_bounds__(128) k_msm_bucket_sum(MsmGeom g, u32 nb, const u32* off, const u32* order, const u32* sorted,
+                                                        const G1Affine* pts, const G1Affine* shared_pts, G1Jac* buckets) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb) return;
+  const u32 b = order[t];
   G1Jac acc = G1Jac::identity();
   const u32 e0 = off[b], e1 = off[b + 1];
   for (u32 e = e0; e < e1; e++) {
@@ -613,7 +631,7 @@ struct h2v_ctx {
   u64 lines_key = ~0ull;    // window geometry the prepared G2 lines in d_lines belong to
   // device buffers
   DevBuf d_plan, d_proofs, d_proof_off, d_inst, d_inst_off, d_ncols, d_col_len, d_pts, d_bad, d_status, d_vals, d_scratch, d_right,
-      d_shared, d_left, d_rlc_bytes, d_r, d_coef, d_shared_sum, d_dig, d_hist, d_off, d_cursor, d_sorted, d_buckets, d_wsums,
+      d_shared, d_left, d_rlc_bytes, d_r, d_coef, d_shared_sum, d_dig, d_hist, d_off, d_cursor, d_order, d_sorted, d_buckets, d_wsums,
       d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush, d_lines, d_M, d_partial_out, d_wsums_fin, d_tiles;
   std::vector<u32> h_status;
   PlanView pv() const { return PlanView{d_plan.as<u8>()}; }
@@ -819,7 +837,7 @@ void h2v_ctx_destroy(h2v_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_plan, &ctx->d_proofs, &ctx->d_proof_off, &ctx->d_inst, &ctx->d_inst_off, &ctx->d_ncols, &ctx->d_col_len,
                     &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
                     &ctx->d_rlc_bytes, &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off,
-                    &ctx->d_cursor, &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict,
+                    &ctx->d_cursor, &ctx->d_order, &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict,
                     &ctx->d_partials, &ctx->d_partials_msm, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal, &ctx->d_flush,
                     &ctx->d_lines, &ctx->d_M, &ctx->d_partial_out, &ctx->d_wsums_fin, &ctx->d_tiles};
   for (DevBuf* b : bufs)
@@ -915,7 +933,8 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   CKC(ctx->d_coef.ensure(32 * (size_t)n));
   CKC(ctx->d_shared_sum.ensure(32 * (size_t)hd.n_shared));
   CKC(ctx->d_dig.ensure(2 * (size_t)g.T * g.Wmax));
-  CKC(ctx->d_hist.ensure(4 * (size_t)nb));
+  CKC(ctx->d_hist.ensure(4 * ((size_t)nb + 2 * SIZE_BINS)));
+  CKC(ctx->d_order.ensure(4 * (size_t)nb));
   CKC(ctx->d_off.ensure(4 * (size_t)(nb + 1)));
   CKC(ctx->d_cursor.ensure(4 * (size_t)nb));
   CKC(ctx->d_tiles.ensure(4 * (size_t)(nb / 1024 + 2)));
@@ -994,19 +1013,22 @@ static int run_impl(h2v_ctx* ctx, int mode) {
   CKC(cudaStreamWaitEvent(s, ctx->ev_join, 0));
   k_shared_reduce<<<hd.n_shared, 256, 0, s>>>(n, ctx->d_shared.as<Fr>(), ctx->d_coef.as<Fr>(), ctx->d_shared_sum.as<Fr>());
   LAUNCH_CHECK();
-  CKC(cudaMemsetAsync(ctx->d_hist.p, 0, 4 * (size_t)nb, s));
+  CKC(cudaMemsetAsync(ctx->d_hist.p, 0, 4 * ((size_t)nb + 2 * SIZE_BINS), s));  // bucket histogram | size histogram | size cursors
   k_msm_digits<<<cdiv(g.T, 128), 128, 0, s>>>(g, ctx->d_right.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_coef.as<Fr>(),
                                               ctx->d_shared_sum.as<Fr>(), pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_dig.as<int16_t>(),
                                               ctx->d_hist.as<u32>());
   LAUNCH_CHECK();
   const u32 n_tiles = cdiv(nb, 1024);
-  k_scan_tiles<<<n_tiles, 1024, 0, s>>>(ctx->d_hist.as<u32>(), nb, ctx->d_off.as<u32>(), ctx->d_tiles.as<u32>());
+  k_scan_tiles<<<n_tiles, 1024, 0, s>>>(ctx->d_hist.as<u32>(), nb, ctx->d_off.as<u32>(), ctx->d_tiles.as<u32>(), ctx->d_hist.as<u32>() + nb);
   LAUNCH_CHECK();
   k_scan_apply<<<n_tiles, 1024, 0, s>>>(nb, n_tiles, ctx->d_tiles.as<u32>(), ctx->d_off.as<u32>(), ctx->d_cursor.as<u32>());
   LAUNCH_CHECK();
+  k_bucket_order<<<n_tiles, 1024, 0, s>>>(nb, ctx->d_hist.as<u32>(), ctx->d_hist.as<u32>() + nb, ctx->d_hist.as<u32>() + nb + SIZE_BINS,
+                                          ctx->d_order.as<u32>());
+  LAUNCH_CHECK();
   k_msm_scatter<<<cdiv((u64)g.T * g.Wmax, 256), 256, 0, s>>>(g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
   LAUNCH_CHECK();
-  k_msm_bucket_sum<<<cdiv(nb, 128), 128, 0, s>>>(g, nb, ctx->d_off.as<u32>(), ctx->d_sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
+  k_msm_bucket_sum<<<cdiv(nb, 128), 128, 0, s>>>(g, nb, ctx->d_off.as<u32>(), ctx->d_order.as<u32>(), ctx->d_sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
                                                  pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_buckets.as<G1Jac>());
   LAUNCH_CHECK();
   k_msm_chunk_reduce<<<cdiv(nb / g.m, 128), 128, 0, s>>>(g, nb / g.m, ctx->d_buckets.as<G1Jac>(), ctx->d_partials_msm.as<G1Jac>());
