@@ -149,6 +149,8 @@ def run_ours(args):
     n_ctx = max(1, args.streams)
     bvs = [pkg.BatchVerifier(params, vk, "shplonk", "blake2b", device=local) for _ in range(n_ctx)]
     bv = bvs[0]
+    if os.environ.get("H2V_BENCH_DIAG_NOGRAPH"):
+        [b.set_graphs(False) for b in bvs]
     # host threads: one per context and rank; when they outnumber the cores, waits must block instead of spin
     blocking = n_ctx * world > max(1, (os.cpu_count() or 1) // 2)
     for b in bvs:
@@ -334,12 +336,22 @@ def run_ours(args):
         assert all(v == 1 for v in res), "a timed batch was rejected"
         launches = sum(b.launch_count() for b in bvs) - launches0
     clocks = sampler.summary()
+    # the same CUDA-event stage timings, of the LAST batch of every context of the run with all batches in flight
+    inflight_acc = {}
+    for b in (bvs if os.environ.get("H2V_BENCH_DIAG_NOGRAPH") else []):  # (diagnosis only: needs direct launches)
+        for name, ms in b.timings().items():
+            inflight_acc.setdefault(name, []).append(ms)
+    stage_ms_in_flight = {k_: statistics.median(v) for k_, v in inflight_acc.items()}
     # per-stage CUDA-event timings of a few serial steps (roofline of the dominant kernel group)
     stage_acc = {}
-    for i in range(5):
+    bv.set_graphs(False)  # direct launches: a graph replay has no events between its kernels
+    for i in range(6):
         run_steps(lambda ctx, i_: step_resident(ctx, i_), 1, bvs[:1])
+        if i == 0:
+            continue
         for name, ms in bv.timings().items():
             stage_acc.setdefault(name, []).append(ms)
+    bv.set_graphs(True)
     stage_ms = {k_: statistics.median(v) for k_, v in stage_acc.items()}
     # ---------------- end to end through the C ABI from pinned host memory
     run_steps(lambda ctx, i: step_e2e(ctx, batches[i % 2], i), W * n_ctx, bvs)
@@ -399,6 +411,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stage_ms": {k_: round(v, 4) for k_, v in stage_ms.items()},
+            "stage_ms_all_in_flight": {k_: round(v, 4) for k_, v in stage_ms_in_flight.items()},
             "msm": {"window_bits": [geom["window_bits"] & 0xFFFF, geom["window_bits"] >> 16], "windows": [geom["windows"] & 0xFFFF, geom["windows"] >> 16],
                     "terms": geom["terms"], "buckets": geom["buckets"]},
             "roofline": {"bound": "imad", "kernel": dom, "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s",

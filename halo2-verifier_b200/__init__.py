@@ -124,6 +124,7 @@ def load_library():
     lib.h2v_ctx_stream.argtypes = [ctypes.c_void_p]
     lib.h2v_ctx_stream.restype = ctypes.c_void_p
     lib.h2v_ctx_set_blocking_sync.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.h2v_ctx_set_graphs.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.h2v_last_msm_geometry.argtypes = [ctypes.c_void_p, u32p]
     lib.h2v_selftest_field.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64]
     lib.h2v_calibrate_imad.argtypes = [ctypes.c_int]
@@ -135,7 +136,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "h2v_ctx_create", "h2v_ctx_create_from_bundle", "h2v_ctx_destroy", "h2v_last_error", "h2v_ctx_info", "h2v_verify_proof", "h2v_verify_batch",
     "h2v_batch_set_columns", "h2v_batch_set_scalar_hook", "h2v_batch_set_shard_hint", "h2v_partial_bytes", "h2v_accumulate_shard", "h2v_finalize", "h2v_attribute_shard",
-    "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync",
+    "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync", "h2v_ctx_set_graphs",
     "h2v_last_msm_geometry", "h2v_selftest_field", "h2v_calibrate_imad",
 )
 
@@ -350,6 +351,10 @@ class BatchVerifier:
 
     def launch_count(self):
         return int(self.lib.h2v_launch_count(self._ctx))
+
+    def set_graphs(self, on):
+        """CUDA-graph replay of the batch kernels (default on); off = direct launches with per-stage event timings."""
+        self._check(self.lib.h2v_ctx_set_graphs(self._ctx, 1 if on else 0))
 
     def stream_handle(self):
         """cudaStream_t of this context as an integer (wrap with torch.cuda.ExternalStream to record events on it)."""

@@ -31,6 +31,16 @@
 
 using namespace h2v;
 
+// Minimum resident blocks per SM of the latency-bound per-proof kernels (a register cap).  Measured on B200 with
+// 16 batches in flight: capping k_scalar at 128 / 96 / 64 and k_transcript at 80 / 64 registers spills almost
+// nothing but leaves the throughput unchanged (5.0 M proofs/s) and costs 5-10 % of their solo latency: left uncapped.
+#ifndef H2V_TRANSCRIPT_MINB
+#define H2V_TRANSCRIPT_MINB 1
+#endif
+#ifndef H2V_SCALAR_MINB
+#define H2V_SCALAR_MINB 1
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
@@ -70,7 +80,7 @@ __global__ void __launch_bounds__(128) k_decompress(PlanView pv, u32 n, const u8
 }
 
 template <class H>
-__global__ void __launch_bounds__(64) k_transcript(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, const u8* inst,
+__global__ void __launch_bounds__(64, H2V_TRANSCRIPT_MINB) k_transcript(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, const u8* inst,
                                                    const u64* inst_off, const G1Affine* pts, Fr* vals, u32* status, const u32* bad) {
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -84,7 +94,7 @@ __global__ void __launch_bounds__(64) k_transcript(PlanView pv, u32 n, const u8*
   else if (b != H2V_NO_BAD_ITEM) status[j] = b < hd.first_mo_item ? ST_TRANSCRIPT : ST_OPENING;
 }
 
-__global__ void __launch_bounds__(64) k_scalar(PlanView pv, u32 n, const u8* inst, const u64* inst_off, const u32* col_len, Fr* vals,
+__global__ void __launch_bounds__(64, H2V_SCALAR_MINB) k_scalar(PlanView pv, u32 n, const u8* inst, const u64* inst_off, const u32* col_len, Fr* vals,
                                                Fr* scratch, Fr* right, Fr* shared, Fr* left, u32* status) {
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
@@ -629,6 +639,15 @@ struct h2v_ctx {
   bool ran = false;
   u32 opt_shard_hint = 0;   // geometry as for a shard of this many proofs (common to all ranks)
   u64 lines_key = ~0ull;    // window geometry the prepared G2 lines in d_lines belong to
+  // CUDA graphs: the ~20 kernels of a batch are captured once per (mode, shape, buffers) and replayed with one launch
+  bool use_graphs = true;
+  bool capturing = false;
+  bool stages_timed = false;  // ev[1..5] of the last run are valid (direct launches only)
+  struct GraphSlot {
+    u64 key = 0;
+    u64 kernels = 0;
+    cudaGraphExec_t exec = nullptr;
+  } graphs[8];
   // device buffers
   DevBuf d_plan, d_proofs, d_proof_off, d_inst, d_inst_off, d_ncols, d_col_len, d_pts, d_bad, d_status, d_vals, d_scratch, d_right,
       d_shared, d_left, d_rlc_bytes, d_r, d_coef, d_shared_sum, d_dig, d_hist, d_off, d_cursor, d_order, d_sorted, d_buckets, d_wsums,
@@ -671,10 +690,10 @@ static double choose_window(u32 terms, u32& c_out, u32& W_out, double chain_floo
   for (u32 c = 4; c <= 15; c++) {
     const u32 W = (255 + c - 1) / c;
     const double B = (double)(1u << (c - 1));
-    const double work = (double)W * ((double)terms * 11.0 + B * (32.0 + 28.0));
+    const double work = (double)W * ((double)terms * 11.0 + B * 150.0);  // per bucket: measured (window sweep on B200), not just 2 additions
     const double chain = ((double)terms / B + 1.0) * 11.0;  // dependent MM per bucket thread
     // both channels share the bucket kernels: only a chain longer than the other channel's costs latency
-    const double t = work / 15e9 + std::max(0.0, chain - chain_floor) * 0.4e-6;
+    const double t = work / 10e9 + std::max(0.0, chain - chain_floor) * 0.4e-6;
     if (t < best) {
       best = t;
       best_chain = chain;
@@ -814,6 +833,16 @@ int h2v_ctx_create(h2v_ctx** out, const uint8_t* params, size_t params_len, int 
   if ((e = ctx->d_acc_bytes.ensure(128)) != cudaSuccess || (e = ctx->d_verdict.ensure(16)) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaFuncSetAttribute(k_lines<LINES_GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k_lines_smem<LINES_GROUPS>())) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_lines)", e);
+  if (const char* cv = getenv("H2V_SMEM_CARVEOUT")) {  // experiment: one shared-memory carveout for every kernel of the pipeline
+    const int pct = atoi(cv);
+    const void* fns[] = {(const void*)k_init, (const void*)k_decompress, (const void*)k_transcript<Blake2b>, (const void*)k_transcript<Keccak256>,
+                         (const void*)k_scalar, (const void*)k_rlc_scan, (const void*)k_shared_reduce, (const void*)k_msm_digits,
+                         (const void*)k_scan_tiles, (const void*)k_scan_apply, (const void*)k_bucket_order, (const void*)k_msm_scatter,
+                         (const void*)k_msm_bucket_sum, (const void*)k_msm_chunk_reduce, (const void*)k_msm_window_reduce,
+                         (const void*)k_lines<LINES_GROUPS>, (const void*)k_pairing_check, (const void*)k_rlc_expand};
+    for (const void* f : fns)
+      if ((e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return fail("carveout", e);
+  }
   *out = ctx;
   return 0;
 }
@@ -840,6 +869,8 @@ void h2v_ctx_destroy(h2v_ctx* ctx) {
                     &ctx->d_cursor, &ctx->d_order, &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict,
                     &ctx->d_partials, &ctx->d_partials_msm, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal, &ctx->d_flush,
                     &ctx->d_lines, &ctx->d_M, &ctx->d_partial_out, &ctx->d_wsums_fin, &ctx->d_tiles};
+  for (auto& gsl : ctx->graphs)
+    if (gsl.exec) cudaGraphExecDestroy(gsl.exec);
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : ctx->ev)
@@ -972,16 +1003,14 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
 // window combination -> affine (L, R) bytes in d_acc_bytes (parity hook); RUN_PARTIAL = pack the window
 // sums into d_partial_out (sharded batches)
 enum : int { RUN_PAIRING = 1, RUN_ACCUM = 2, RUN_PARTIAL = 4 };
-static int run_impl(h2v_ctx* ctx, int mode) {
-  if (!ctx || ctx->n == 0) return -1;
-  CKC(cudaSetDevice(ctx->device));
+static int enqueue_batch(h2v_ctx* ctx, int mode) {
   const PlanHeader& hd = ctx->hd;
   const u32 n = ctx->n;
   cudaStream_t s = ctx->stream;
   PlanView pv = ctx->pv();
   const MsmGeom& g = ctx->geom;
   const u32 nb = g.nb();
-  CKC(cudaEventRecord(ctx->ev[0], s));
+  if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[0], s));
   // c_j = prod_{i>j} r_i depends only on the coefficients: scanned on the auxiliary stream while the proofs are parsed
   CKC(cudaEventRecord(ctx->ev_fork, s));
   CKC(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
@@ -994,7 +1023,7 @@ static int run_impl(h2v_ctx* ctx, int mode) {
   k_decompress<<<cdiv((u64)n * hd.n_points, 128), 128, 0, s>>>(pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(),
                                                                 ctx->d_pts.as<G1Affine>(), ctx->d_bad.as<u32>());
   LAUNCH_CHECK();
-  CKC(cudaEventRecord(ctx->ev[1], s));
+  if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[1], s));
   if (hd.hash == HASH_BLAKE2B)
     k_transcript<Blake2b><<<cdiv(n, 64), 64, 0, s>>>(pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
                                                      ctx->d_inst_off.as<u64>(), ctx->d_pts.as<G1Affine>(), ctx->d_vals.as<Fr>(),
@@ -1004,12 +1033,12 @@ static int run_impl(h2v_ctx* ctx, int mode) {
                                                        ctx->d_inst_off.as<u64>(), ctx->d_pts.as<G1Affine>(), ctx->d_vals.as<Fr>(),
                                                        ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
   LAUNCH_CHECK();
-  CKC(cudaEventRecord(ctx->ev[2], s));
+  if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[2], s));
   k_scalar<<<cdiv(n, 64), 64, 0, s>>>(pv, n, ctx->d_inst.as<u8>(), ctx->d_inst_off.as<u64>(),
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_vals.as<Fr>(), ctx->d_scratch.as<Fr>(),
                                       ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_status.as<u32>());
   LAUNCH_CHECK();
-  CKC(cudaEventRecord(ctx->ev[3], s));
+  if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[3], s));
   CKC(cudaStreamWaitEvent(s, ctx->ev_join, 0));
   k_shared_reduce<<<hd.n_shared, 256, 0, s>>>(n, ctx->d_shared.as<Fr>(), ctx->d_coef.as<Fr>(), ctx->d_shared_sum.as<Fr>());
   LAUNCH_CHECK();
@@ -1035,7 +1064,7 @@ static int run_impl(h2v_ctx* ctx, int mode) {
   LAUNCH_CHECK();
   k_msm_window_reduce<<<g.W[0] + g.W[1], 256, 0, s>>>(g, ctx->d_partials_msm.as<G1Jac>(), ctx->d_wsums.as<G1Jac>());
   LAUNCH_CHECK();
-  CKC(cudaEventRecord(ctx->ev[4], s));
+  if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[4], s));
   if (mode & RUN_PAIRING) {
     int prc = launch_pairing(ctx, ctx->d_wsums.as<G1Jac>());
     if (prc) return prc;
@@ -1044,13 +1073,84 @@ static int run_impl(h2v_ctx* ctx, int mode) {
     k_pack_partial<<<8, 256, 0, s>>>(g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, g.W[0] + g.W[1], ctx->d_wsums.as<G1Jac>(), ctx->d_partial_out.as<u8>());
     LAUNCH_CHECK();
   }
-  CKC(cudaEventRecord(ctx->ev[5], s));
+  if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[5], s));
   if (mode & RUN_ACCUM) {
     FoldArgs fa{{g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {g.wbase[0], g.wbase[1]}};
     k_fold_accum<<<1, 32, 0, s>>>(fa, ctx->d_wsums.as<G1Jac>(), ctx->d_acc_bytes.as<u8>());
     LAUNCH_CHECK();
   }
+  if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[6], s));
+  return 0;
+}
+
+
+static u64 graph_key(const h2v_ctx* ctx, int mode) {
+  u64 h = 0xcbf29ce484222325ull;
+  auto mix = [&h](u64 v) {
+    h ^= v;
+    h *= 0x100000001b3ull;
+    h ^= h >> 29;
+  };
+  const MsmGeom& g = ctx->geom;
+  mix((u64)mode);
+  mix(ctx->n);
+  mix(ctx->gcount);
+  mix(ctx->gbase);
+  mix(ctx->scratch_rows);
+  mix((u64)ctx->has_ncols | (u64)ctx->has_col_len << 1);
+  for (int ch = 0; ch < 2; ch++) mix((u64)g.c[ch] | (u64)g.W[ch] << 8 | (u64)g.Z[ch] << 16);
+  mix((u64)g.T | (u64)g.m << 32);
+  const DevBuf* bufs[] = {&ctx->d_plan, &ctx->d_proofs, &ctx->d_proof_off, &ctx->d_inst, &ctx->d_inst_off, &ctx->d_ncols, &ctx->d_col_len,
+                          &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
+                          &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off, &ctx->d_cursor, &ctx->d_order,
+                          &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict, &ctx->d_partials_msm, &ctx->d_lines,
+                          &ctx->d_M, &ctx->d_partial_out, &ctx->d_tiles};
+  for (const DevBuf* b : bufs) mix((u64)(size_t)b->p);
+  return h | 1;
+}
+
+// Every kernel of the batch on the context's stream: replay of the captured graph (one launch) or, with graphs
+// off (per-stage event timings wanted), the direct launches.
+static int run_impl(h2v_ctx* ctx, int mode) {
+  if (!ctx || ctx->n == 0) return -1;
+  CKC(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (!ctx->use_graphs) {
+    int rc = enqueue_batch(ctx, mode);
+    if (rc) return rc;
+    ctx->stages_timed = true;
+    ctx->ran = true;
+    return 0;
+  }
+  h2v_ctx::GraphSlot& gs = ctx->graphs[mode & 7];
+  const u64 key = graph_key(ctx, mode);
+  if (!gs.exec || gs.key != key) {
+    if (gs.exec) cudaGraphExecDestroy(gs.exec);
+    gs.exec = nullptr;
+    const u64 before = ctx->launches;
+    CKC(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    const int rc = enqueue_batch(ctx, mode);
+    ctx->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    gs.kernels = ctx->launches - before;
+    ctx->launches = before;
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    CKC(ce);
+    const cudaError_t ie = cudaGraphInstantiate(&gs.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CKC(ie);
+    gs.key = key;
+  }
+  CKC(cudaEventRecord(ctx->ev[0], s));
+  CKC(cudaGraphLaunch(gs.exec, s));
   CKC(cudaEventRecord(ctx->ev[6], s));
+  ctx->launches += gs.kernels;
+  ctx->stages_timed = false;
   ctx->ran = true;
   return 0;
 }
@@ -1263,13 +1363,20 @@ int h2v_last_timings(const h2v_ctx* cctx, float* out8) {
   CKC(cudaEventSynchronize(ctx->ev[6]));
   for (int i = 0; i < 8; i++) out8[i] = 0;
   CKC(cudaEventElapsedTime(&out8[0], ctx->ev[0], ctx->ev[6]));
-  for (int i = 1; i <= 6; i++) CKC(cudaEventElapsedTime(&out8[i], ctx->ev[i - 1], ctx->ev[i]));
+  if (ctx->stages_timed)  // a graph replay has no events between its kernels: only the total is known
+    for (int i = 1; i <= 6; i++) CKC(cudaEventElapsedTime(&out8[i], ctx->ev[i - 1], ctx->ev[i]));
   return 0;
 }
 
 uint64_t h2v_launch_count(const h2v_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 void* h2v_ctx_stream(const h2v_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int h2v_ctx_set_graphs(h2v_ctx* ctx, int on) {
+  if (!ctx) return -1;
+  ctx->use_graphs = on != 0;
+  return 0;
+}
 
 int h2v_ctx_set_blocking_sync(h2v_ctx* ctx, int blocking) {
   if (!ctx) return -1;

@@ -145,6 +145,11 @@ void* h2v_ctx_stream(const h2v_ctx* ctx);
 /* host waits of this context: 0 (default) spin on the stream (lowest latency), 1 block on an event (use when many
  * contexts share few host cores, e.g. several batches in flight on every GPU of a box) */
 int h2v_ctx_set_blocking_sync(h2v_ctx* ctx, int blocking);
+/* CUDA graphs (default 1): the kernels of a batch are captured once per (entry point, batch shape, buffers) and
+ * replayed with ONE launch per batch, which removes ~40 driver calls per batch from the host threads (with many
+ * batches in flight those calls, serialised by the driver, bounded the throughput).  0 = direct launches with a CUDA
+ * event after every stage: required for the per-stage values of h2v_last_timings (a replay only yields the total). */
+int h2v_ctx_set_graphs(h2v_ctx* ctx, int on);
 /* MSM geometry of the last run: out[0] window bits, [1] windows, [2] terms, [3] buckets */
 int h2v_last_msm_geometry(const h2v_ctx* ctx, uint32_t* out4);
 

@@ -395,3 +395,25 @@ def test_config5_shard_sizes_large_batch_tiled(pkg):
         folded, ok = co.fold(lr * reps, rs, [True] * n)
         assert ok and res.batch_accum == folded
     co.close()
+
+
+def test_graph_replay_equals_direct_launches(pkg):
+    """The batch kernels run as a replayed CUDA graph by default.  Same results as the direct launches (statuses,
+    challenges, accumulators, folded pair), re-capture when the batch shape changes, and repeated replays over new
+    proof bytes in the same buffers; only the direct launches carry per-stage event timings."""
+    params, vk, instances, proofs, rng = make_batch("vm", 8, 9, "shplonk", "blake2b")
+    rs = [rng.randrange(1, bn.R) for _ in proofs]
+    bad = list(proofs)
+    bad[2], _ = sim.corrupt(proofs[2], vk, list(sim.CORRUPTIONS)[0], rng, "shplonk")
+    with make_bv(pkg, params, vk, "shplonk", "blake2b") as bv:
+        runs = {}
+        for graphs in (True, False, True):
+            bv.set_graphs(graphs)
+            for name, pr, n in (("all", proofs, 9), ("bad", bad, 9), ("short", proofs, 5), ("all2", proofs, 9)):
+                res = bv.verify_batch(pr[:n], [i[0] for i in instances[:n]], rlc_scalars=rs[:n], want_challenges=True, want_accum=True, want_batch_accum=True)
+                got = (res.verdict, tuple(res.status), bytes(res.challenges), bytes(res.accum), bytes(res.batch_accum))
+                assert runs.setdefault(name, got) == got, (name, graphs)
+                t = bv.timings()
+                assert t["total"] > 0 and (t["scalar"] > 0) == (not graphs)
+        assert runs["all"][0] and not runs["bad"][0] and runs["bad"][1][2] != 0 and runs["all"] == runs["all2"]
+        check_against_oracle(bv, params, vk, instances, bad, "shplonk", "blake2b", rs)
