@@ -336,6 +336,16 @@ def run_ours(args):
         assert all(v == 1 for v in res), "a timed batch was rejected"
         launches = sum(b.launch_count() for b in bvs) - launches0
     clocks = sampler.summary()
+    if os.environ.get("H2V_BENCH_DIAG_TIMELINE") and rank == 0:  # (diagnosis only) per-block timeline of 2 steps per context
+        import numpy as np
+
+        cap = 1 << 20
+        chk(bv, lib.h2v_debug_timeline_start(local, cap))
+        run_steps(lambda ctx, i: step_resident(ctx, i), 3 * n_ctx, bvs)
+        buf = np.zeros(cap * 8, dtype=np.uint32)
+        cnt = ctypes.c_uint32(0)
+        chk(bv, lib.h2v_debug_timeline_stop(local, buf.ctypes.data, cap, ctypes.byref(cnt)))
+        np.save(os.environ["H2V_BENCH_DIAG_TIMELINE"], buf[: cnt.value * 8].reshape(-1, 8))
     # the same CUDA-event stage timings, of the LAST batch of every context of the run with all batches in flight
     inflight_acc = {}
     for b in (bvs if os.environ.get("H2V_BENCH_DIAG_NOGRAPH") else []):  # (diagnosis only: needs direct launches)

@@ -42,9 +42,55 @@ using namespace h2v;
 #endif
 
 // ------------------------------------------------------------------------------------------------
+// diagnostics: per-block timeline (off unless h2v_debug_timeline_start was called).  Thread 0 of every block of the
+// instrumented kernels appends {kernel id, block, SM, context tag, start, end} on the global nanosecond timer; used
+// to see how the kernels of many batches in flight share the SMs (bench.py, H2V_BENCH_DIAG_TIMELINE).
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the batch pipeline first waits for the kernel before it in the
+// stream (a no-op when it was launched without the attribute) and then lets the kernel after it be placed on the
+// SMs, where that one waits in turn.  The next kernel is thus resident when its predecessor ends: with many batches
+// in flight the stream-ordered hand-over cost ~350 us per kernel boundary (measured with the block timeline below).
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+struct TlRec {
+  u32 kid, block, smid, tag;
+  u64 t0, t1;
+};
+__device__ TlRec* g_tl_buf = nullptr;
+__device__ u32 g_tl_cap = 0;
+__device__ u32 g_tl_count = 0;
+struct TlScope {
+  u64 t0;
+  u32 kid, tag;
+  bool on;
+  __device__ __forceinline__ TlScope(u32 kid_, const void* tagp) {
+    on = threadIdx.x == 0 && g_tl_buf != nullptr;
+    if (on) {
+      kid = kid_;
+      tag = (u32)((size_t)tagp >> 8);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    }
+  }
+  __device__ __forceinline__ ~TlScope() {
+    if (on) {
+      u64 t1;
+      u32 sm;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      const u32 i = atomicAdd(&g_tl_count, 1u);
+      if (i < g_tl_cap) g_tl_buf[i] = TlRec{kid, blockIdx.x, sm, tag, t0, t1};
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
 __global__ void k_init(PlanView pv, u32 n, const u64* inst_off, const u32* ncols, const u32* col_len, u32* status, u32* bad) {
+  pdl_prologue();
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const PlanHeader& hd = pv.h();
@@ -64,6 +110,8 @@ __global__ void k_init(PlanView pv, u32 n, const u64* inst_off, const u32* ncols
 }
 
 __global__ void __launch_bounds__(128) k_decompress(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, G1Affine* pts, u32* bad) {
+  pdl_prologue();
+  TlScope tl_(1, pts);
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   const PlanHeader& hd = pv.h();
   if (t >= n * hd.n_points) return;
@@ -82,6 +130,8 @@ __global__ void __launch_bounds__(128) k_decompress(PlanView pv, u32 n, const u8
 template <class H>
 __global__ void __launch_bounds__(64, H2V_TRANSCRIPT_MINB) k_transcript(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, const u8* inst,
                                                    const u64* inst_off, const G1Affine* pts, Fr* vals, u32* status, const u32* bad) {
+  pdl_prologue();
+  TlScope tl_(2, pts);
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   if (status[j] != ST_OK) return;
@@ -96,6 +146,8 @@ __global__ void __launch_bounds__(64, H2V_TRANSCRIPT_MINB) k_transcript(PlanView
 
 __global__ void __launch_bounds__(64, H2V_SCALAR_MINB) k_scalar(PlanView pv, u32 n, const u8* inst, const u64* inst_off, const u32* col_len, Fr* vals,
                                                Fr* scratch, Fr* right, Fr* shared, Fr* left, u32* status) {
+  pdl_prologue();
+  TlScope tl_(3, right);
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const PlanHeader& hd = pv.h();
@@ -120,24 +172,26 @@ __global__ void k_rlc_expand(u64 count, u64 seed, const u8* bytes, Fr* r) {
 }
 
 // c_j = prod_{i > j} r_i over the GLOBAL batch; one block, chunked suffix scan through shared memory.
-__global__ void __launch_bounds__(1024) k_rlc_scan(const Fr* r, u64 count, u64 base, u32 n, Fr* coef) {
-  __shared__ Fr sh[1024];
+static constexpr u32 RLC_NT = 256;
+__global__ void __launch_bounds__(RLC_NT) k_rlc_scan(const Fr* r, u64 count, u64 base, u32 n, Fr* coef) {
+  pdl_prologue();
+  __shared__ Fr sh[RLC_NT];
   const u32 t = threadIdx.x;
-  const u64 m = (count + 1023) / 1024;
+  const u64 m = (count + RLC_NT - 1) / RLC_NT;
   const u64 lo = (u64)t * m < count ? (u64)t * m : count, hi = lo + m < count ? lo + m : count;
   Fr p = Fr::one();
   for (u64 i = lo; i < hi; i++) p = p * r[i];
   sh[t] = p;
   __syncthreads();
-  for (u32 d = 1; d < 1024; d <<= 1) {  // inclusive suffix products
+  for (u32 d = 1; d < RLC_NT; d <<= 1) {  // inclusive suffix products
     Fr v = sh[t];
-    const bool act = t + d < 1024;
+    const bool act = t + d < RLC_NT;
     Fr o = act ? sh[t + d] : Fr::one();
     __syncthreads();
     if (act) sh[t] = v * o;
     __syncthreads();
   }
-  Fr run = t + 1 < 1024 ? sh[t + 1] : Fr::one();
+  Fr run = t + 1 < RLC_NT ? sh[t + 1] : Fr::one();
   for (u64 i = hi; i-- > lo;) {
     if (i >= base && i < base + n) coef[i - base] = run;
     run = run * r[i];
@@ -146,6 +200,7 @@ __global__ void __launch_bounds__(1024) k_rlc_scan(const Fr* r, u64 count, u64 b
 
 // shared_sum[b] = sum_j c_j * shared[b][j]  (canonical form, ready for digit extraction)
 __global__ void __launch_bounds__(256) k_shared_reduce(u32 n, const Fr* shared, const Fr* coef, Fr* shared_sum) {
+  pdl_prologue();
   __shared__ Fr sh[256];
   const u32 b = blockIdx.x, t = threadIdx.x;
   Fr acc = Fr::zero();
@@ -183,6 +238,8 @@ __device__ __forceinline__ const G1Affine& msm_point(const MsmGeom& g, u32 t, co
 // signed c-bit digits of every term's scalar (already multiplied by c_j) + bucket histogram
 __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, const Fr* left, const Fr* coef, const Fr* shared_sum,
                                                     const G1Affine* shared_pts, int16_t* dig, u32* hist) {
+  pdl_prologue();
+  TlScope tl_(4, right);
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= g.T) return;
   const u32 nP = g.n * g.P, nL = g.n * g.n_mo;
@@ -239,7 +296,9 @@ __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, 
 // exclusive scan of the bucket histogram in two launches: tiles of 1024 counters are scanned with coalesced
 // loads (warp shuffles), then every tile adds the totals of the tiles before it.  off has nb + 1 entries,
 // cursor is a working copy for the scatter.
-__device__ __forceinline__ u32 block_excl_scan_1024(u32 v, u32* total) {
+// exclusive scan over the NT threads of a block (NT a multiple of 32, at most 1024)
+template <int NT>
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32* total) {
   __shared__ u32 wsum[32];
   const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   u32 x = v;
@@ -251,7 +310,7 @@ __device__ __forceinline__ u32 block_excl_scan_1024(u32 v, u32* total) {
   if (lane == 31) wsum[wid] = x;
   __syncthreads();
   if (wid == 0) {
-    u32 w = wsum[lane];
+    u32 w = lane < NT / 32 ? wsum[lane] : 0;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const u32 y = __shfl_up_sync(0xFFFFFFFFu, w, d);
@@ -261,66 +320,108 @@ __device__ __forceinline__ u32 block_excl_scan_1024(u32 v, u32* total) {
   }
   __syncthreads();
   *total = wsum[31];
-  return x - v + (wid ? wsum[wid - 1] : 0);
+  const u32 r = x - v + (wid ? wsum[wid - 1] : 0);
+  __syncthreads();  // wsum is reused by the next call
+  return r;
 }
+// Tiles of SCAN_TILE counters are scanned by blocks of SCAN_NT threads, SCAN_PER consecutive counters per thread.
+// Blocks are kept small everywhere in the pipeline: with many batches in flight a 1024-thread block has to wait
+// for half an SM to drain before it can be placed.
+static constexpr u32 SCAN_NT = 256, SCAN_PER = 4, SCAN_TILE = SCAN_NT * SCAN_PER;
 // size_bin: bucket sizes are binned in DESCENDING order (bin 0 = 1023 entries or more) for k_bucket_order
 static constexpr u32 SIZE_BINS = 1024;
 __device__ __forceinline__ u32 size_bin(u32 count) { return SIZE_BINS - 1 - (count < SIZE_BINS - 1 ? count : SIZE_BINS - 1); }
-__global__ void __launch_bounds__(1024) k_scan_tiles(const u32* hist, u32 nb, u32* off, u32* tile_total, u32* size_hist) {
-  const u32 i = blockIdx.x * 1024 + threadIdx.x;
-  const u32 v = i < nb ? hist[i] : 0;
-  if (i < nb) atomicAdd(&size_hist[size_bin(v)], 1u);
+__global__ void __launch_bounds__(SCAN_NT) k_scan_tiles(const u32* hist, u32 nb, u32* off, u32* tile_total, u32* size_hist) {
+  pdl_prologue();
+  const u32 i0 = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
+  u32 v[SCAN_PER], sum = 0;
+#pragma unroll
+  for (u32 q = 0; q < SCAN_PER; q++) {
+    v[q] = i0 + q < nb ? hist[i0 + q] : 0;
+    if (i0 + q < nb) atomicAdd(&size_hist[size_bin(v[q])], 1u);
+    sum += v[q];
+  }
   u32 total;
-  const u32 e = block_excl_scan_1024(v, &total);
-  if (i < nb) off[i] = e;
+  u32 e = block_excl_scan<SCAN_NT>(sum, &total);
+#pragma unroll
+  for (u32 q = 0; q < SCAN_PER; q++) {
+    if (i0 + q < nb) off[i0 + q] = e;
+    e += v[q];
+  }
   if (threadIdx.x == 0) tile_total[blockIdx.x] = total;
 }
-__global__ void __launch_bounds__(1024) k_scan_apply(u32 nb, u32 n_tiles, const u32* tile_total, u32* off, u32* cursor) {
+__global__ void __launch_bounds__(SCAN_NT) k_scan_apply(u32 nb, u32 n_tiles, const u32* tile_total, u32* off, u32* cursor) {
+  pdl_prologue();
   __shared__ u32 base_sh;
   u32 part = 0;
-  for (u32 k = threadIdx.x; k < blockIdx.x; k += 1024) part += tile_total[k];
+  for (u32 k = threadIdx.x; k < blockIdx.x; k += SCAN_NT) part += tile_total[k];
   u32 total;
-  block_excl_scan_1024(part, &total);  // only the block total is used
+  block_excl_scan<SCAN_NT>(part, &total);  // only the block total is used
   if (threadIdx.x == 0) base_sh = total;
   __syncthreads();
-  const u32 base = base_sh, i = blockIdx.x * 1024 + threadIdx.x;
-  if (i < nb) {
-    const u32 o = off[i] + base;
-    off[i] = o;
-    cursor[i] = o;
+  const u32 base = base_sh;
+#pragma unroll
+  for (u32 q = 0; q < SCAN_PER; q++) {
+    const u32 i = blockIdx.x * SCAN_TILE + q * SCAN_NT + threadIdx.x;
+    if (i < nb) {
+      const u32 o = off[i] + base;
+      off[i] = o;
+      cursor[i] = o;
+    }
   }
   if (blockIdx.x == n_tiles - 1 && threadIdx.x == 0) off[nb] = base + tile_total[blockIdx.x];
 }
 
 // Buckets ordered by size, largest first (counting sort on the size bins): the threads of a warp of
 // k_msm_bucket_sum then walk chains of (nearly) equal length, and the longest chains start first.
-__global__ void __launch_bounds__(1024) k_bucket_order(u32 nb, const u32* hist, const u32* size_hist, u32* size_cursor, u32* order) {
+__global__ void __launch_bounds__(SCAN_NT) k_bucket_order(u32 nb, const u32* hist, const u32* size_hist, u32* size_cursor, u32* order) {
+  pdl_prologue();
+  static_assert(SIZE_BINS == SCAN_TILE, "one tile of size bins");
   __shared__ u32 base[SIZE_BINS];
-  u32 total;
-  base[threadIdx.x] = block_excl_scan_1024(size_hist[threadIdx.x], &total);
+  u32 v[SCAN_PER], sum = 0, total;
+#pragma unroll
+  for (u32 q = 0; q < SCAN_PER; q++) {
+    v[q] = size_hist[threadIdx.x * SCAN_PER + q];
+    sum += v[q];
+  }
+  u32 e = block_excl_scan<SCAN_NT>(sum, &total);
+#pragma unroll
+  for (u32 q = 0; q < SCAN_PER; q++) {
+    base[threadIdx.x * SCAN_PER + q] = e;
+    e += v[q];
+  }
   __syncthreads();
-  const u32 i = blockIdx.x * 1024 + threadIdx.x;
-  if (i >= nb) return;
-  const u32 bin = size_bin(hist[i]);
-  order[base[bin] + atomicAdd(&size_cursor[bin], 1u)] = i;
+#pragma unroll
+  for (u32 q = 0; q < SCAN_PER; q++) {
+    const u32 i = blockIdx.x * SCAN_TILE + q * SCAN_NT + threadIdx.x;
+    if (i < nb) {
+      const u32 bin = size_bin(hist[i]);
+      order[base[bin] + atomicAdd(&size_cursor[bin], 1u)] = i;
+    }
+  }
 }
 
-__global__ void k_msm_scatter(MsmGeom g, const int16_t* dig, u32* cursor, u32* sorted) {
-  const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (u64)g.T * g.Wmax) return;
-  const u32 t = (u32)(idx / g.Wmax), w = (u32)(idx % g.Wmax);
-  const u32 ch = g.channel_of_term(t);
-  if (w >= g.W[ch]) return;
-  const int d = dig[idx];
-  if (d == 0) return;
-  const u32 b = g.bbase[ch] + w * g.B[ch] + (u32)(d < 0 ? -d : d) - 1;
-  const u32 pos = atomicAdd(&cursor[b], 1u);
-  sorted[pos] = t | (d < 0 ? 0x80000000u : 0u);
+__global__ void __launch_bounds__(256) k_msm_scatter(MsmGeom g, const int16_t* dig, u32* cursor, u32* sorted) {
+  pdl_prologue();
+  TlScope tl_(5, sorted);
+  const u64 total = (u64)g.T * g.Wmax;
+  for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
+    const u32 t = (u32)(idx / g.Wmax), w = (u32)(idx % g.Wmax);
+    const u32 ch = g.channel_of_term(t);
+    if (w >= g.W[ch]) continue;
+    const int d = dig[idx];
+    if (d == 0) continue;
+    const u32 b = g.bbase[ch] + w * g.B[ch] + (u32)(d < 0 ? -d : d) - 1;
+    const u32 pos = atomicAdd(&cursor[b], 1u);
+    sorted[pos] = t | (d < 0 ? 0x80000000u : 0u);
+  }
 }
 
 // thread per bucket: sum of its (signed) points, Jacobian += affine
 __global__ void __launch_bounds__(128) k_msm_bucket_sum(MsmGeom g, u32 nb, const u32* off, const u32* order, const u32* sorted,
                                                         const G1Affine* pts, const G1Affine* shared_pts, G1Jac* buckets) {
+  pdl_prologue();
+  TlScope tl_(6, pts);
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nb) return;
   const u32 b = order[t];
@@ -346,6 +447,8 @@ __device__ G1Jac g1_mul_small(const G1Jac& p, u32 k) {
 // S_w = sum_{k=1..B} k * bucket_k, in two steps.  Step A, thread per chunk of m buckets: running-sum
 // trick inside the chunk plus (offset * chunk sum).  Step B, block per window: tree reduction.
 __global__ void __launch_bounds__(128) k_msm_chunk_reduce(MsmGeom g, u32 n_chunks, const G1Jac* buckets, G1Jac* partials) {
+  pdl_prologue();
+  TlScope tl_(7, buckets);
   const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_chunks) return;
   const u32 b0 = q * g.m;
@@ -360,17 +463,19 @@ __global__ void __launch_bounds__(128) k_msm_chunk_reduce(MsmGeom g, u32 n_chunk
   partials[q] = acc;
 }
 
-__global__ void __launch_bounds__(256) k_msm_window_reduce(MsmGeom g, const G1Jac* partials, G1Jac* window_sums) {
-  __shared__ G1Jac sh[256];
+__global__ void __launch_bounds__(128) k_msm_window_reduce(MsmGeom g, const G1Jac* partials, G1Jac* window_sums) {
+  pdl_prologue();
+  TlScope tl_(8, window_sums);
+  __shared__ G1Jac sh[128];
   const u32 wi = blockIdx.x, t = threadIdx.x;
   const u32 ch = wi >= g.wbase[1] ? 1u : 0u;
   const u32 per = g.B[ch] / g.m;  // partials of this window
   const G1Jac* p = partials + (g.bbase[ch] + (wi - g.wbase[ch]) * g.B[ch]) / g.m;
   G1Jac total = G1Jac::identity();
-  for (u32 i = t; i < per; i += 256) total = g1_add(total, p[i]);
+  for (u32 i = t; i < per; i += 128) total = g1_add(total, p[i]);
   sh[t] = total;
   __syncthreads();
-  for (u32 d = 128; d > 0; d >>= 1) {
+  for (u32 d = 64; d > 0; d >>= 1) {
     if (t < d) sh[t] = g1_add(sh[t], sh[t + d]);
     __syncthreads();
   }
@@ -394,6 +499,7 @@ __device__ __forceinline__ void store_affine_bytes(const G1Affine& a, bool is_id
 // acc = sum_w 2^(c w) S_w of each channel (serial chain of ~W*c doublings, thread per channel) and
 // conversion to affine bytes, acc_bytes = L | R  (reference msm.rs:81-95 `eval` of both MSMs).
 __global__ void __launch_bounds__(32) k_fold_accum(FoldArgs fa, const G1Jac* window_sums, u8* acc_bytes) {
+  pdl_prologue();
   const int t = threadIdx.x;
   if (t >= 2) return;
   // channel order in window_sums: 0 = right, 1 = left
@@ -417,6 +523,7 @@ static_assert(sizeof(PartialHeader) == 32 && sizeof(G1Jac) == 96, "partial layou
 static_assert(sizeof(PartialHeader) + 128 * sizeof(G1Jac) == H2V_PARTIAL_BYTES, "H2V_PARTIAL_BYTES");
 
 __global__ void k_pack_partial(u32 cbits, u32 windows, u32 npts, const G1Jac* wsums, u8* out) {
+  pdl_prologue();
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   u32* o = (u32*)out;
   if (t < 8) {
@@ -641,6 +748,7 @@ struct h2v_ctx {
   u64 lines_key = ~0ull;    // window geometry the prepared G2 lines in d_lines belong to
   // CUDA graphs: the ~20 kernels of a batch are captured once per (mode, shape, buffers) and replayed with one launch
   bool use_graphs = true;
+  bool use_pdl = true;  // programmatic dependent launch between the kernels of a batch (pdl_prologue)
   bool capturing = false;
   bool stages_timed = false;  // ev[1..5] of the last run are valid (direct launches only)
   struct GraphSlot {
@@ -671,6 +779,28 @@ struct h2v_ctx {
   } while (0)
 
 static inline u32 cdiv(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
+
+// kernel launch with (pdl) or without the programmatic-stream-serialization attribute
+template <class... KArgs, class... Args>
+static cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#define KLAUNCH_P(pdl, kern, grid, block, smem, st, ...)                       \
+  do {                                                                         \
+    ctx->launches++;                                                           \
+    CKC(launch_k(pdl, kern, grid, block, smem, st, __VA_ARGS__));              \
+  } while (0)
+#define KLAUNCH(kern, grid, block, smem, st, ...) KLAUNCH_P(ctx->use_pdl, kern, grid, block, smem, st, __VA_ARGS__)
 
 // Host wait for everything queued on the context's stream.  Default: cudaStreamSynchronize (spins: lowest latency).
 // With many contexts per host (several batches in flight on several GPUs) the spinning threads starve the cores, so
@@ -748,7 +878,7 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom) {
   return g;
 }
 
-static constexpr int LINES_GROUPS = 8;
+static constexpr int LINES_GROUPS = 4;
 
 static u64 lines_key_of(const MsmGeom& g) { return (u64)g.c[0] | (u64)g.W[0] << 8 | (u64)g.c[1] << 16 | (u64)g.W[1] << 24; }
 
@@ -778,11 +908,9 @@ static int ensure_lines(h2v_ctx* ctx) {
 static int launch_pairing(h2v_ctx* ctx, const G1Jac* wsums) {
   const MsmGeom& g = ctx->geom;
   cudaStream_t s = ctx->stream;
-  k_lines<LINES_GROUPS><<<H2V_ATE_ITERS, 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s>>>(LinesArgs{g.W[0] + g.W[1]}, wsums, ctx->d_lines.as<G2Line>(),
+  KLAUNCH((k_lines<LINES_GROUPS>), H2V_ATE_ITERS, 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s, LinesArgs{g.W[0] + g.W[1]}, wsums, ctx->d_lines.as<G2Line>(),
                                                                                        ctx->d_M.as<E12>());
-  LAUNCH_CHECK();
-  k_pairing_check<<<1, 128, 0, s>>>(ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>());
-  LAUNCH_CHECK();
+  KLAUNCH(k_pairing_check, 1, 128, 0, s, ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>());
   return 0;
 }
 
@@ -833,16 +961,6 @@ int h2v_ctx_create(h2v_ctx** out, const uint8_t* params, size_t params_len, int 
   if ((e = ctx->d_acc_bytes.ensure(128)) != cudaSuccess || (e = ctx->d_verdict.ensure(16)) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaFuncSetAttribute(k_lines<LINES_GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k_lines_smem<LINES_GROUPS>())) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_lines)", e);
-  if (const char* cv = getenv("H2V_SMEM_CARVEOUT")) {  // experiment: one shared-memory carveout for every kernel of the pipeline
-    const int pct = atoi(cv);
-    const void* fns[] = {(const void*)k_init, (const void*)k_decompress, (const void*)k_transcript<Blake2b>, (const void*)k_transcript<Keccak256>,
-                         (const void*)k_scalar, (const void*)k_rlc_scan, (const void*)k_shared_reduce, (const void*)k_msm_digits,
-                         (const void*)k_scan_tiles, (const void*)k_scan_apply, (const void*)k_bucket_order, (const void*)k_msm_scatter,
-                         (const void*)k_msm_bucket_sum, (const void*)k_msm_chunk_reduce, (const void*)k_msm_window_reduce,
-                         (const void*)k_lines<LINES_GROUPS>, (const void*)k_pairing_check, (const void*)k_rlc_expand};
-    for (const void* f : fns)
-      if ((e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return fail("carveout", e);
-  }
   *out = ctx;
   return 0;
 }
@@ -1014,70 +1132,54 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   // c_j = prod_{i>j} r_i depends only on the coefficients: scanned on the auxiliary stream while the proofs are parsed
   CKC(cudaEventRecord(ctx->ev_fork, s));
   CKC(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
-  k_rlc_scan<<<1, 1024, 0, ctx->stream_aux>>>(ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, n, ctx->d_coef.as<Fr>());
-  LAUNCH_CHECK();
+  CKC(cudaMemsetAsync(ctx->d_hist.p, 0, 4 * ((size_t)nb + 2 * SIZE_BINS), ctx->stream_aux));  // bucket histogram | size histogram | size cursors
+  KLAUNCH_P(false, k_rlc_scan, 1, RLC_NT, 0, ctx->stream_aux, ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, n, ctx->d_coef.as<Fr>());
   CKC(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
-  k_init<<<cdiv(n, 128), 128, 0, s>>>(pv, n, ctx->d_inst_off.as<u64>(), ctx->has_ncols ? ctx->d_ncols.as<u32>() : nullptr,
+  KLAUNCH(k_init, cdiv(n, 128), 128, 0, s, pv, n, ctx->d_inst_off.as<u64>(), ctx->has_ncols ? ctx->d_ncols.as<u32>() : nullptr,
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
-  LAUNCH_CHECK();
-  k_decompress<<<cdiv((u64)n * hd.n_points, 128), 128, 0, s>>>(pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(),
+  KLAUNCH(k_decompress, cdiv((u64)n * hd.n_points, 128), 128, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(),
                                                                 ctx->d_pts.as<G1Affine>(), ctx->d_bad.as<u32>());
-  LAUNCH_CHECK();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[1], s));
   if (hd.hash == HASH_BLAKE2B)
-    k_transcript<Blake2b><<<cdiv(n, 64), 64, 0, s>>>(pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
+    KLAUNCH((k_transcript<Blake2b>), cdiv(n, 64), 64, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
                                                      ctx->d_inst_off.as<u64>(), ctx->d_pts.as<G1Affine>(), ctx->d_vals.as<Fr>(),
                                                      ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
   else
-    k_transcript<Keccak256><<<cdiv(n, 64), 64, 0, s>>>(pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
+    KLAUNCH((k_transcript<Keccak256>), cdiv(n, 64), 64, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
                                                        ctx->d_inst_off.as<u64>(), ctx->d_pts.as<G1Affine>(), ctx->d_vals.as<Fr>(),
                                                        ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
-  LAUNCH_CHECK();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[2], s));
-  k_scalar<<<cdiv(n, 64), 64, 0, s>>>(pv, n, ctx->d_inst.as<u8>(), ctx->d_inst_off.as<u64>(),
+  KLAUNCH(k_scalar, cdiv(n, 64), 64, 0, s, pv, n, ctx->d_inst.as<u8>(), ctx->d_inst_off.as<u64>(),
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_vals.as<Fr>(), ctx->d_scratch.as<Fr>(),
                                       ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_status.as<u32>());
-  LAUNCH_CHECK();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[3], s));
   CKC(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-  k_shared_reduce<<<hd.n_shared, 256, 0, s>>>(n, ctx->d_shared.as<Fr>(), ctx->d_coef.as<Fr>(), ctx->d_shared_sum.as<Fr>());
-  LAUNCH_CHECK();
-  CKC(cudaMemsetAsync(ctx->d_hist.p, 0, 4 * ((size_t)nb + 2 * SIZE_BINS), s));  // bucket histogram | size histogram | size cursors
-  k_msm_digits<<<cdiv(g.T, 128), 128, 0, s>>>(g, ctx->d_right.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_coef.as<Fr>(),
+  KLAUNCH(k_shared_reduce, hd.n_shared, 256, 0, s, n, ctx->d_shared.as<Fr>(), ctx->d_coef.as<Fr>(), ctx->d_shared_sum.as<Fr>());
+  KLAUNCH(k_msm_digits, cdiv(g.T, 128), 128, 0, s, g, ctx->d_right.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_coef.as<Fr>(),
                                               ctx->d_shared_sum.as<Fr>(), pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_dig.as<int16_t>(),
                                               ctx->d_hist.as<u32>());
-  LAUNCH_CHECK();
-  const u32 n_tiles = cdiv(nb, 1024);
-  k_scan_tiles<<<n_tiles, 1024, 0, s>>>(ctx->d_hist.as<u32>(), nb, ctx->d_off.as<u32>(), ctx->d_tiles.as<u32>(), ctx->d_hist.as<u32>() + nb);
-  LAUNCH_CHECK();
-  k_scan_apply<<<n_tiles, 1024, 0, s>>>(nb, n_tiles, ctx->d_tiles.as<u32>(), ctx->d_off.as<u32>(), ctx->d_cursor.as<u32>());
-  LAUNCH_CHECK();
-  k_bucket_order<<<n_tiles, 1024, 0, s>>>(nb, ctx->d_hist.as<u32>(), ctx->d_hist.as<u32>() + nb, ctx->d_hist.as<u32>() + nb + SIZE_BINS,
+  const u32 n_tiles = cdiv(nb, SCAN_TILE);
+  KLAUNCH(k_scan_tiles, n_tiles, SCAN_NT, 0, s, ctx->d_hist.as<u32>(), nb, ctx->d_off.as<u32>(), ctx->d_tiles.as<u32>(), ctx->d_hist.as<u32>() + nb);
+  KLAUNCH(k_scan_apply, n_tiles, SCAN_NT, 0, s, nb, n_tiles, ctx->d_tiles.as<u32>(), ctx->d_off.as<u32>(), ctx->d_cursor.as<u32>());
+  KLAUNCH(k_bucket_order, n_tiles, SCAN_NT, 0, s, nb, ctx->d_hist.as<u32>(), ctx->d_hist.as<u32>() + nb, ctx->d_hist.as<u32>() + nb + SIZE_BINS,
                                           ctx->d_order.as<u32>());
-  LAUNCH_CHECK();
-  k_msm_scatter<<<cdiv((u64)g.T * g.Wmax, 256), 256, 0, s>>>(g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
-  LAUNCH_CHECK();
-  k_msm_bucket_sum<<<cdiv(nb, 128), 128, 0, s>>>(g, nb, ctx->d_off.as<u32>(), ctx->d_order.as<u32>(), ctx->d_sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
+  KLAUNCH(k_msm_scatter, std::min<u32>(cdiv((u64)g.T * g.Wmax, 256), 148 * 4), 256, 0, s, g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
+  KLAUNCH(k_msm_bucket_sum, cdiv(nb, 128), 128, 0, s, g, nb, ctx->d_off.as<u32>(), ctx->d_order.as<u32>(), ctx->d_sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
                                                  pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_buckets.as<G1Jac>());
-  LAUNCH_CHECK();
-  k_msm_chunk_reduce<<<cdiv(nb / g.m, 128), 128, 0, s>>>(g, nb / g.m, ctx->d_buckets.as<G1Jac>(), ctx->d_partials_msm.as<G1Jac>());
-  LAUNCH_CHECK();
-  k_msm_window_reduce<<<g.W[0] + g.W[1], 256, 0, s>>>(g, ctx->d_partials_msm.as<G1Jac>(), ctx->d_wsums.as<G1Jac>());
-  LAUNCH_CHECK();
+  KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, ctx->d_buckets.as<G1Jac>(), ctx->d_partials_msm.as<G1Jac>());
+  KLAUNCH(k_msm_window_reduce, g.W[0] + g.W[1], 128, 0, s, g, ctx->d_partials_msm.as<G1Jac>(), ctx->d_wsums.as<G1Jac>());
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[4], s));
   if (mode & RUN_PAIRING) {
     int prc = launch_pairing(ctx, ctx->d_wsums.as<G1Jac>());
     if (prc) return prc;
   }
   if (mode & RUN_PARTIAL) {
-    k_pack_partial<<<8, 256, 0, s>>>(g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, g.W[0] + g.W[1], ctx->d_wsums.as<G1Jac>(), ctx->d_partial_out.as<u8>());
-    LAUNCH_CHECK();
+    KLAUNCH(k_pack_partial, 8, 256, 0, s, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, g.W[0] + g.W[1], ctx->d_wsums.as<G1Jac>(), ctx->d_partial_out.as<u8>());
   }
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[5], s));
   if (mode & RUN_ACCUM) {
     FoldArgs fa{{g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {g.wbase[0], g.wbase[1]}};
-    k_fold_accum<<<1, 32, 0, s>>>(fa, ctx->d_wsums.as<G1Jac>(), ctx->d_acc_bytes.as<u8>());
-    LAUNCH_CHECK();
+    KLAUNCH(k_fold_accum, 1, 32, 0, s, fa, ctx->d_wsums.as<G1Jac>(), ctx->d_acc_bytes.as<u8>());
   }
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[6], s));
   return 0;
@@ -1372,9 +1474,42 @@ uint64_t h2v_launch_count(const h2v_ctx* ctx) { return ctx ? ctx->launches : 0; 
 
 void* h2v_ctx_stream(const h2v_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+int h2v_debug_timeline_start(int device, uint32_t capacity) {
+  if (cudaSetDevice(device) != cudaSuccess) return -2;
+  TlRec* buf = nullptr;
+  u32 zero = 0;
+  if (cudaMalloc(&buf, sizeof(TlRec) * (size_t)capacity) != cudaSuccess) return -2;
+  cudaDeviceSynchronize();
+  cudaMemcpyToSymbol(g_tl_count, &zero, 4);
+  cudaMemcpyToSymbol(g_tl_cap, &capacity, 4);
+  cudaMemcpyToSymbol(g_tl_buf, &buf, sizeof(buf));
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
+}
+/* stops recording and copies up to `capacity` 32-byte records {u32 kernel, block, sm, tag; u64 start_ns, end_ns} */
+int h2v_debug_timeline_stop(int device, void* out, uint32_t capacity, uint32_t* count) {
+  if (cudaSetDevice(device) != cudaSuccess) return -2;
+  cudaDeviceSynchronize();
+  TlRec* buf = nullptr;
+  TlRec* none = nullptr;
+  u32 n = 0, cap = 0;
+  cudaMemcpyFromSymbol(&buf, g_tl_buf, sizeof(buf));
+  cudaMemcpyFromSymbol(&n, g_tl_count, 4);
+  cudaMemcpyFromSymbol(&cap, g_tl_cap, 4);
+  cudaMemcpyToSymbol(g_tl_buf, &none, sizeof(none));
+  if (!buf) return -1;
+  if (n > cap) n = cap;
+  if (n > capacity) n = capacity;
+  if (out && n) cudaMemcpy(out, buf, sizeof(TlRec) * (size_t)n, cudaMemcpyDeviceToHost);
+  if (count) *count = n;
+  cudaFree(buf);
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
+}
+
 int h2v_ctx_set_graphs(h2v_ctx* ctx, int on) {
   if (!ctx) return -1;
-  ctx->use_graphs = on != 0;
+  ctx->use_graphs = (on & 1) != 0;
+  ctx->use_pdl = (on & 2) == 0;  // diagnosis: bit 1 switches programmatic dependent launch off
+  for (auto& gsl : ctx->graphs) gsl.key = 0;
   return 0;
 }
 

@@ -252,6 +252,8 @@ struct LinesSmem {  // dynamic shared memory layout of k_lines<GROUPS>
 template <int GROUPS>
 __global__ void __launch_bounds__(64 * GROUPS) k_lines(LinesArgs la, const G1Jac* __restrict__ wsums, const G2Line* __restrict__ lines,
                                                        E12* __restrict__ M) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch, see pdl_prologue() in kernels.cu
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LinesSmem* sm = (LinesSmem*)smem_raw;
   E12* accs = (E12*)(sm + 1);            // [GROUPS]
@@ -297,6 +299,8 @@ constexpr size_t k_lines_smem() {
 
 // ---- k_pairing_check: Miller accumulation over the prepared iteration products + final check
 __global__ void __launch_bounds__(128) k_pairing_check(const E12* __restrict__ M, u32* verdict) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch, see pdl_prologue() in kernels.cu
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ LinTables lt;
   __shared__ E12 slot[12];
   __shared__ Fq scr[2 * E12_N];

@@ -150,6 +150,11 @@ int h2v_ctx_set_blocking_sync(h2v_ctx* ctx, int blocking);
  * batches in flight those calls, serialised by the driver, bounded the throughput).  0 = direct launches with a CUDA
  * event after every stage: required for the per-stage values of h2v_last_timings (a replay only yields the total). */
 int h2v_ctx_set_graphs(h2v_ctx* ctx, int on);
+/* diagnostics: per-block timeline of the per-proof and MSM kernels on `device` (all contexts).  start allocates a
+ * log of `capacity` records and switches recording on; stop switches it off and copies up to `capacity` 32-byte
+ * records {u32 kernel id, block, SM, context tag; u64 start_ns, end_ns} (global nanosecond timer) into `out`. */
+int h2v_debug_timeline_start(int device, uint32_t capacity);
+int h2v_debug_timeline_stop(int device, void* out, uint32_t capacity, uint32_t* count);
 /* MSM geometry of the last run: out[0] window bits, [1] windows, [2] terms, [3] buckets */
 int h2v_last_msm_geometry(const h2v_ctx* ctx, uint32_t* out4);
 
