@@ -87,6 +87,7 @@ class PackedBatch:
         import numpy as np
 
         self.n = len(proofs)
+        self.src = (proofs, instances)
         self.proofs = pinned_bytes(torch, b"".join(proofs))
         inst = b"".join(v for inst in instances for col in inst for v in col)
         self.inst = pinned_bytes(torch, inst)
@@ -162,6 +163,21 @@ def run_ours(args):
         proofs, instances = synth.synthesize_shplonk_batch(bv, shared_dlogs, s, n, seed=(rank, b))
         batches.append(PackedBatch(torch, proofs, instances))
     gen_s = time.time() - t0
+    # fold groups (N = 1): G consecutive independent 4096-proof batches per set of kernel launches (own fold and own
+    # pairing check each); the packed upload alternates the two distinct batches
+    G = max(1, args.fold_groups) if world == 1 else 1
+    while args.steps % G:  # exactly `steps` batches are timed
+        G -= 1
+    if G > 1:
+        gbatches = []
+        for b in range(2):
+            pr, ins = [], []
+            for q in range(G):
+                pr += batches[(b + q) % 2].src[0]
+                ins += batches[(b + q) % 2].src[1]
+            gbatches.append(PackedBatch(torch, pr, ins))
+    else:
+        gbatches = batches
     gcount, gbase = n * world, n * rank
     seed = 7
     pbytes = int(lib.h2v_partial_bytes())
@@ -246,6 +262,8 @@ def run_ours(args):
 
     def step_e2e(ctx, pb, i=0):
         if world == 1:
+            if pb.n > n:
+                chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
             chk(ctx, lib.h2v_verify_batch(ctx._ctx, *pb.args(), None, seed, pb.status.data_ptr(), None, None, None))
             return int(pb.status.max()) == 0
         chk(ctx, lib.h2v_accumulate_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount, pb.status.data_ptr(), ctx.partial_dev.data_ptr()))
@@ -259,6 +277,8 @@ def run_ours(args):
 
     def upload(ctx, pb):
         if world == 1:
+            if pb.n > n:
+                chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
             chk(ctx, lib.h2v_batch_upload(ctx._ctx, *pb.args(), None, seed))
         else:
             chk(ctx, lib.h2v_batch_upload_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount))
@@ -313,11 +333,11 @@ def run_ours(args):
         return [float(x) for x in t]
 
     W = max(args.warmup, 3)
+    runs = args.steps // G  # launch sets of G batches each; a step is ONE batch of n proofs per GPU
     total = n * world * args.steps
     # ---------------- device-resident throughput (`value`)
-    for ci, ctx in enumerate(bvs):
-        upload(ctx, batches[ci % 2])
-    ok = run_steps(lambda ctx, i: step_resident(ctx, i), W * n_ctx, bvs)
+    upload(bv, batches[0])
+    ok = run_steps(lambda ctx, i: step_resident(ctx, i), W, bvs[:1])
     assert all(v == 1 for v in ok), "warm-up batch was rejected"
     geom = bv.msm_geometry()
     sampler = ClockSampler(local)
@@ -330,9 +350,13 @@ def run_ours(args):
     assert all(v == 1 for v in res), "a timed batch was rejected"
     launches = sum(b.launch_count() for b in bvs) - launches0
     dt = dt1
-    if n_ctx > 1:  # several independent batches in flight (one context + stream + host thread each): throughput view
+    if n_ctx > 1 or G > 1:  # several independent batches in flight (fold groups per launch set x contexts): throughput view
+        for ci, ctx in enumerate(bvs):
+            upload(ctx, gbatches[ci % 2])
+        ok = run_steps(lambda ctx, i: step_resident(ctx, i), W * n_ctx, bvs)
+        assert all(v == 1 for v in ok), "warm-up batch was rejected"
         launches0 = sum(b.launch_count() for b in bvs)
-        res, dt, _ = timed(lambda ctx, i: step_resident(ctx, i), args.steps, bvs)
+        res, dt, _ = timed(lambda ctx, i: step_resident(ctx, i), runs, bvs)
         assert all(v == 1 for v in res), "a timed batch was rejected"
         launches = sum(b.launch_count() for b in bvs) - launches0
     clocks = sampler.summary()
@@ -354,6 +378,7 @@ def run_ours(args):
     stage_ms_in_flight = {k_: statistics.median(v) for k_, v in inflight_acc.items()}
     # per-stage CUDA-event timings of a few serial steps (roofline of the dominant kernel group)
     stage_acc = {}
+    upload(bv, batches[0])
     bv.set_graphs(False)  # direct launches: a graph replay has no events between its kernels
     for i in range(6):
         run_steps(lambda ctx, i_: step_resident(ctx, i_), 1, bvs[:1])
@@ -364,12 +389,12 @@ def run_ours(args):
     bv.set_graphs(True)
     stage_ms = {k_: statistics.median(v) for k_, v in stage_acc.items()}
     # ---------------- end to end through the C ABI from pinned host memory
-    run_steps(lambda ctx, i: step_e2e(ctx, batches[i % 2], i), W * n_ctx, bvs)
+    run_steps(lambda ctx, i: step_e2e(ctx, batches[i % 2], i), W, bvs[:1])
     lat = []
 
-    def timed_e2e(ctx, i):
+    def timed_e2e(ctx, i, pbs=batches):
         a = time.perf_counter()
-        okk = step_e2e(ctx, batches[i % 2], i)
+        okk = step_e2e(ctx, pbs[i % 2], i)
         lat.append(time.perf_counter() - a)
         return okk
 
@@ -379,8 +404,9 @@ def run_ours(args):
     assert all(res), "an end-to-end batch was rejected"
     p50 = statistics.median(lat) * 1e3
     dt_e2e = dt_e2e1
-    if n_ctx > 1:
-        res, _, dt_e2e = timed(timed_e2e, args.steps, bvs)
+    if n_ctx > 1 or G > 1:
+        run_steps(lambda ctx, i: step_e2e(ctx, gbatches[i % 2], i), W * n_ctx, bvs)
+        res, _, dt_e2e = timed(lambda ctx, i: timed_e2e(ctx, i, gbatches), runs, bvs)
         assert all(res), "an end-to-end batch was rejected"
     dt, dt1, dt_e2e, dt_e2e1 = reduce_max(dt, dt1, dt_e2e, dt_e2e1)
 
@@ -407,10 +433,11 @@ def run_ours(args):
             "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic (trapdoor-simulated accepting proofs, seeded)",
             "config": {"workload": f"{n} SHPLONK proofs per GPU, vector_mul test-circuit shape ('{args.shape}'), k={k}, Blake2b transcript, "
                                    f"10 public inputs, 1,024-byte proofs; BASELINE.json configs[1]",
-                       "batch_per_gpu": n, "global_batch": n * world, "contexts_in_flight": n_ctx, "host_waits": "blocking" if blocking else "spinning",
+                       "batch_per_gpu": n, "global_batch": n * world, "contexts_in_flight": n_ctx, "fold_groups_per_launch_set": G, "host_waits": "blocking" if blocking else "spinning",
                        "step": f"one global batch of {n * world} proofs: {n} per GPU, per-window partials all-gathered, ONE pairing check",
-                       "in_flight_note": "a step is one complete 4096-proof batch; `value`/`e2e` keep `contexts_in_flight` independent batches in flight "
-                                         "(one context + CUDA stream + host thread each), `one_in_flight` times strictly serial batches",
+                       "in_flight_note": "a step is one complete 4096-proof batch (own fold coefficients, own pairing check, own verdict); `value`/`e2e` keep "
+                                         "`contexts_in_flight` x `fold_groups_per_launch_set` independent batches in flight: every context (CUDA stream + host thread) "
+                                         "runs `fold_groups_per_launch_set` batches per set of kernel launches (h2v_batch_set_fold_groups); `one_in_flight` times strictly serial single batches",
                        "timing": "CUDA events on the contexts' streams (first start -> last end) between barrier + synchronize, max over ranks; "
                                  "e2e on the host clock around the C-ABI calls",
                        "l2": "flushed before every step (256 MiB overwrite on the step's stream, inside the timed region)",
@@ -564,6 +591,8 @@ def main():
     ap.add_argument("--shape", default="vm")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--streams", type=int, default=int(os.environ.get("H2V_BENCH_STREAMS", "16")), help="batches in flight (contexts) at N=1")
+    ap.add_argument("--fold-groups", type=int, default=int(os.environ.get("H2V_BENCH_FOLD_GROUPS", "4")),
+                    help="independent batches (own fold + pairing check each) per set of kernel launches at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--ref-proofs-per-core", type=int, default=64)

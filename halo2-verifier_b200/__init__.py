@@ -104,6 +104,8 @@ def load_library():
     lib.h2v_batch_set_columns.argtypes = [ctypes.c_void_p, u32p, u32p]
     lib.h2v_batch_set_scalar_hook.argtypes = [ctypes.c_void_p, u8p]
     lib.h2v_batch_set_shard_hint.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+    lib.h2v_batch_set_fold_groups.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+    lib.h2v_last_group_verdicts.argtypes = [ctypes.c_void_p, u8p, ctypes.c_uint32]
     lib.h2v_partial_bytes.argtypes = []
     lib.h2v_partial_bytes.restype = ctypes.c_size_t
     lib.h2v_accumulate_shard.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64,
@@ -138,7 +140,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "h2v_ctx_create", "h2v_ctx_create_from_bundle", "h2v_ctx_destroy", "h2v_last_error", "h2v_ctx_info", "h2v_verify_proof", "h2v_verify_batch",
     "h2v_batch_set_columns", "h2v_batch_set_scalar_hook", "h2v_batch_set_shard_hint", "h2v_partial_bytes", "h2v_accumulate_shard", "h2v_finalize", "h2v_attribute_shard",
-    "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync", "h2v_ctx_set_graphs", "h2v_debug_timeline_start", "h2v_debug_timeline_stop",
+    "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync", "h2v_ctx_set_graphs", "h2v_batch_set_fold_groups", "h2v_last_group_verdicts", "h2v_debug_timeline_start", "h2v_debug_timeline_stop",
     "h2v_last_msm_geometry", "h2v_selftest_field", "h2v_calibrate_imad",
 )
 
@@ -225,6 +227,7 @@ class BatchResult:
     accum: Optional[bytes] = None
     batch_accum: Optional[bytes] = None
     msm_scalars: Optional[bytes] = None
+    group_verdicts: Optional[List[bool]] = None  # one per fold group (fold_groups > 1)
 
     def errors(self):
         return [None if s == 0 else STATUS_ERRORS[s]() for s in self.status]
@@ -296,9 +299,13 @@ class BatchVerifier:
         return pbytes, poff, ibytes, ioff, keep
 
     def verify_batch(self, proofs: Sequence[bytes], instances, rlc_scalars: Optional[Sequence[int]] = None, seed=0,
-                     want_challenges=False, want_accum=False, want_batch_accum=False, want_scalars=False) -> BatchResult:
+                     want_challenges=False, want_accum=False, want_batch_accum=False, want_scalars=False, fold_groups=1) -> BatchResult:
+        """`fold_groups` = G: the proofs are G consecutive independent batches of len(proofs) / G proofs (own fold, own
+        pairing check) that share every kernel launch; `group_verdicts` holds their G batch verdicts."""
         n = len(proofs)
         assert n == len(instances) and n > 0
+        if fold_groups > 1:
+            self._check(self.lib.h2v_batch_set_fold_groups(self._ctx, int(fold_groups)))
         pbytes, poff, ibytes, ioff, keep = self._pack(proofs, instances)
         rlc = b"".join(int(r).to_bytes(32, "little") for r in rlc_scalars) if rlc_scalars is not None else None
         status = (ctypes.c_uint8 * n)()
@@ -310,8 +317,10 @@ class BatchVerifier:
             self._check(self.lib.h2v_batch_set_scalar_hook(self._ctx, sc))
         self._check(self.lib.h2v_verify_batch(self._ctx, n, pbytes, poff, ibytes, ioff, rlc, seed, status, ch, acc, bacc))
         st = list(status)
+        gv = (ctypes.c_uint8 * max(1, int(fold_groups)))()
+        ng = self.lib.h2v_last_group_verdicts(self._ctx, gv, len(gv))
         return BatchResult(st, all(s == 0 for s in st), ch.raw if ch else None, acc.raw if acc else None,
-                           bacc.raw if bacc else None, sc.raw if sc else None)
+                           bacc.raw if bacc else None, sc.raw if sc else None, [bool(v) for v in gv[:ng]])
 
     def accumulate_shard(self, proofs, instances, global_base, global_count, rlc_scalars=None, seed=0, shard_hint=0):
         """Returns (statuses, partial): `partial` is the opaque H2V_PARTIAL_BYTES blob of this shard's

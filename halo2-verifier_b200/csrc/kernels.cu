@@ -173,9 +173,12 @@ __global__ void k_rlc_expand(u64 count, u64 seed, const u8* bytes, Fr* r) {
 
 // c_j = prod_{i > j} r_i over the GLOBAL batch; one block, chunked suffix scan through shared memory.
 static constexpr u32 RLC_NT = 256;
+// (fold groups: block g scans the n coefficients of its own group; then count = n, base = 0)
 __global__ void __launch_bounds__(RLC_NT) k_rlc_scan(const Fr* r, u64 count, u64 base, u32 n, Fr* coef) {
   pdl_prologue();
   __shared__ Fr sh[RLC_NT];
+  r += (size_t)blockIdx.x * n;
+  coef += (size_t)blockIdx.x * n;
   const u32 t = threadIdx.x;
   const u64 m = (count + RLC_NT - 1) / RLC_NT;
   const u64 lo = (u64)t * m < count ? (u64)t * m : count, hi = lo + m < count ? lo + m : count;
@@ -199,24 +202,29 @@ __global__ void __launch_bounds__(RLC_NT) k_rlc_scan(const Fr* r, u64 count, u64
 }
 
 // shared_sum[b] = sum_j c_j * shared[b][j]  (canonical form, ready for digit extraction)
-__global__ void __launch_bounds__(256) k_shared_reduce(u32 n, const Fr* shared, const Fr* coef, Fr* shared_sum) {
+__global__ void __launch_bounds__(256) k_shared_reduce(u32 n, u32 N, u32 Sh, const Fr* shared, const Fr* coef, Fr* shared_sum) {
   pdl_prologue();
   __shared__ Fr sh[256];
-  const u32 b = blockIdx.x, t = threadIdx.x;
+  const u32 b = blockIdx.x, grp = blockIdx.y, t = threadIdx.x;
   Fr acc = Fr::zero();
-  for (u32 j = t; j < n; j += 256) acc = acc + shared[(size_t)b * n + j] * coef[j];
+  for (u32 j = t; j < n; j += 256) acc = acc + shared[(size_t)b * N + grp * n + j] * coef[grp * n + j];
   sh[t] = acc;
   __syncthreads();
   for (u32 d = 128; d > 0; d >>= 1) {
     if (t < d) sh[t] = sh[t] + sh[t + d];
     __syncthreads();
   }
-  if (t == 0) shared_sum[b] = sh[0].to_canonical();
+  if (t == 0) shared_sum[grp * Sh + b] = sh[0].to_canonical();
 }
 
+// Fold groups: the N = G * n proofs of an upload may be G consecutive independent batches of n proofs (own fold
+// coefficients, own MSM, own pairing check, own verdict) that share every kernel launch: the per-proof kernels run
+// over all N proofs, the MSM kernels over G * T terms and G * nb() buckets, the pairing kernels over G blocks.
+// Everything in MsmGeom is PER GROUP except G and N (the stride of the per-proof arrays).
 struct MsmGeom {
-  u32 n, P, n_mo, Sh;  // batch shape
-  u32 T;               // terms = n*P (right) + n*n_mo (left) + Sh (right, shared bases)
+  u32 n, P, n_mo, Sh;  // shape of one fold group
+  u32 G, N;            // fold groups, proofs of the upload (G * n)
+  u32 T;               // terms of one group = n*P (right) + n*n_mo (left) + Sh (right, shared bases)
   // per channel (0 = right, 1 = left): window bits, windows, buckets per window (2^(c-1)),
   // first global window index, first global bucket index
   u32 c[2], W[2], B[2], wbase[2], bbase[2];
@@ -224,15 +232,19 @@ struct MsmGeom {
   u32 Wmax;  // row stride of the digit table
   u32 m;     // buckets per reduction chunk
   __host__ __device__ u32 nb() const { return W[0] * B[0] + W[1] * B[1]; }
-  __host__ __device__ u32 channel_of_term(u32 t) const { return (t >= n * P && t < n * P + n * n_mo) ? 1u : 0u; }
+  __host__ __device__ u32 channel_of_term(u32 tl) const { return (tl >= n * P && tl < n * P + n * n_mo) ? 1u : 0u; }  // tl = term inside its group
 };
 
 __device__ __forceinline__ const G1Affine& msm_point(const MsmGeom& g, u32 t, const G1Affine* pts, const G1Affine* shared_pts) {
+  const u32 grp = t / g.T, tl = t % g.T;
   const u32 nP = g.n * g.P;
-  if (t < nP) return pts[t];
+  if (tl < nP) return pts[(size_t)(tl / g.n) * g.N + grp * g.n + tl % g.n];
   const u32 nL = g.n * g.n_mo;
-  if (t < nP + nL) return pts[(size_t)(g.P - g.n_mo) * g.n + (t - nP)];  // (mo_slot + q) * n + j
-  return shared_pts[t - nP - nL];
+  if (tl < nP + nL) {
+    const u32 q = (tl - nP) / g.n, jl = (tl - nP) % g.n;
+    return pts[(size_t)(g.P - g.n_mo + q) * g.N + grp * g.n + jl];  // (mo_slot + q) * N + j
+  }
+  return shared_pts[tl - nP - nL];
 }
 
 // signed c-bit digits of every term's scalar (already multiplied by c_j) + bucket histogram
@@ -241,18 +253,21 @@ __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, 
   pdl_prologue();
   TlScope tl_(4, right);
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= g.T) return;
+  if (t >= g.G * g.T) return;
+  const u32 grp = t / g.T, tl = t % g.T;
   const u32 nP = g.n * g.P, nL = g.n * g.n_mo;
   Fr k;
   u32 ch = 0;
-  if (t < nP) {
-    k = (right[t] * coef[t % g.n]).to_canonical();
-  } else if (t < nP + nL) {
-    k = (left[t - nP] * coef[(t - nP) % g.n]).to_canonical();
+  if (tl < nP) {
+    const u32 j = grp * g.n + tl % g.n;
+    k = (right[(size_t)(tl / g.n) * g.N + j] * coef[j]).to_canonical();
+  } else if (tl < nP + nL) {
+    const u32 j = grp * g.n + (tl - nP) % g.n;
+    k = (left[(size_t)((tl - nP) / g.n) * g.N + j] * coef[j]).to_canonical();
     ch = 1;
   } else {
-    const G1Affine& sp = shared_pts[t - nP - nL];
-    k = (sp.x.is_zero() && sp.y.is_zero()) ? Fr::zero() : shared_sum[t - nP - nL];  // identity base (all-zero fixed column)
+    const G1Affine& sp = shared_pts[tl - nP - nL];
+    k = (sp.x.is_zero() && sp.y.is_zero()) ? Fr::zero() : shared_sum[grp * g.Sh + tl - nP - nL];  // identity base (all-zero fixed column)
   }
   if (k.is_zero()) {  // excluded proof / unused slot / identity base: no bucket entries at all
     for (u32 w = 0; w < g.W[ch]; w++) dig[(size_t)t * g.Wmax + w] = 0;
@@ -289,7 +304,7 @@ __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, 
       carry = 0;
     }
     dig[(size_t)t * g.Wmax + w] = (int16_t)d;
-    if (d != 0) atomicAdd(&hist[g.bbase[ch] + w * g.B[ch] + (u32)(d < 0 ? -d : d) - 1], 1u);
+    if (d != 0) atomicAdd(&hist[grp * g.nb() + g.bbase[ch] + w * g.B[ch] + (u32)(d < 0 ? -d : d) - 1], 1u);
   }
 }
 
@@ -404,14 +419,14 @@ __global__ void __launch_bounds__(SCAN_NT) k_bucket_order(u32 nb, const u32* his
 __global__ void __launch_bounds__(256) k_msm_scatter(MsmGeom g, const int16_t* dig, u32* cursor, u32* sorted) {
   pdl_prologue();
   TlScope tl_(5, sorted);
-  const u64 total = (u64)g.T * g.Wmax;
+  const u64 total = (u64)g.G * g.T * g.Wmax;
   for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
     const u32 t = (u32)(idx / g.Wmax), w = (u32)(idx % g.Wmax);
-    const u32 ch = g.channel_of_term(t);
+    const u32 ch = g.channel_of_term(t % g.T);
     if (w >= g.W[ch]) continue;
     const int d = dig[idx];
     if (d == 0) continue;
-    const u32 b = g.bbase[ch] + w * g.B[ch] + (u32)(d < 0 ? -d : d) - 1;
+    const u32 b = (t / g.T) * g.nb() + g.bbase[ch] + w * g.B[ch] + (u32)(d < 0 ? -d : d) - 1;
     const u32 pos = atomicAdd(&cursor[b], 1u);
     sorted[pos] = t | (d < 0 ? 0x80000000u : 0u);
   }
@@ -451,9 +466,9 @@ __global__ void __launch_bounds__(128) k_msm_chunk_reduce(MsmGeom g, u32 n_chunk
   TlScope tl_(7, buckets);
   const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_chunks) return;
-  const u32 b0 = q * g.m;
-  const u32 ch = b0 >= g.bbase[1] ? 1u : 0u;
-  const u32 i0 = (b0 - g.bbase[ch]) % g.B[ch];  // index of the chunk's first bucket inside its window
+  const u32 b0 = q * g.m, bl = b0 % g.nb();  // bl: inside its fold group
+  const u32 ch = bl >= g.bbase[1] ? 1u : 0u;
+  const u32 i0 = (bl - g.bbase[ch]) % g.B[ch];  // index of the chunk's first bucket inside its window
   G1Jac run = G1Jac::identity(), acc = G1Jac::identity();
   for (u32 i = g.m; i-- > 0;) {
     run = g1_add(run, buckets[b0 + i]);
@@ -467,10 +482,11 @@ __global__ void __launch_bounds__(128) k_msm_window_reduce(MsmGeom g, const G1Ja
   pdl_prologue();
   TlScope tl_(8, window_sums);
   __shared__ G1Jac sh[128];
-  const u32 wi = blockIdx.x, t = threadIdx.x;
+  const u32 Wt = g.W[0] + g.W[1];
+  const u32 grp = blockIdx.x / Wt, wi = blockIdx.x % Wt, t = threadIdx.x;
   const u32 ch = wi >= g.wbase[1] ? 1u : 0u;
   const u32 per = g.B[ch] / g.m;  // partials of this window
-  const G1Jac* p = partials + (g.bbase[ch] + (wi - g.wbase[ch]) * g.B[ch]) / g.m;
+  const G1Jac* p = partials + (grp * g.nb() + g.bbase[ch] + (wi - g.wbase[ch]) * g.B[ch]) / g.m;
   G1Jac total = G1Jac::identity();
   for (u32 i = t; i < per; i += 128) total = g1_add(total, p[i]);
   sh[t] = total;
@@ -479,7 +495,7 @@ __global__ void __launch_bounds__(128) k_msm_window_reduce(MsmGeom g, const G1Ja
     if (t < d) sh[t] = g1_add(sh[t], sh[t + d]);
     __syncthreads();
   }
-  if (t == 0) window_sums[wi] = sh[0];
+  if (t == 0) window_sums[blockIdx.x] = sh[0];
 }
 
 struct FoldArgs {
@@ -552,15 +568,16 @@ __global__ void __launch_bounds__(128) k_sum_partials(u32 n_partials, u32 cbits,
 
 // ---- per-proof accumulators (parity hook, rejection attribution)
 // thread per (base, proof): unscaled scalar * point, plain double-and-add
+// (gverdict != null: proofs of fold groups whose batch check accepted are skipped; gsize = proofs per group)
 __global__ void __launch_bounds__(128) k_pp_mul(PlanView pv, u32 n, const G1Affine* pts, const Fr* right, const Fr* shared, const Fr* left,
-                                                const u32* status, G1Jac* out) {
+                                                const u32* status, G1Jac* out, const u32* gverdict, u32 gsize) {
   const PlanHeader& hd = pv.h();
   const u32 nb = hd.n_points + hd.n_shared + hd.n_mo;
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nb * n) return;
   const u32 j = t % n, b = t / n;
   G1Jac r = G1Jac::identity();
-  if (status[j] == ST_OK || status[j] == ST_CONSTRAINT_SYSTEM_FAILURE) {
+  if ((status[j] == ST_OK || status[j] == ST_CONSTRAINT_SYSTEM_FAILURE) && !(gverdict && gverdict[j / gsize])) {
     Fr k;
     const G1Affine* p;
     if (b < hd.n_points) {
@@ -602,7 +619,7 @@ __global__ void __launch_bounds__(128) k_pp_reduce(PlanView pv, u32 n, const G1J
 
 // warp per proof: DualMSM::check of its own accumulators (SingleStrategy semantics, strategy.rs:164-176)
 static constexpr int PP_WARPS = 4;
-__global__ void __launch_bounds__(32 * PP_WARPS) k_pp_pairing(PlanView pv, u32 n, const G1Jac* lr, u32* status) {
+__global__ void __launch_bounds__(32 * PP_WARPS) k_pp_pairing(PlanView pv, u32 n, const G1Jac* lr, u32* status, const u32* gverdict, u32 gsize) {
   __shared__ G1Affine aff[PP_WARPS][2];
   __shared__ bool skip[PP_WARPS][2];
   __shared__ W12 pool[PP_WARPS][H2V_WPOOL];
@@ -610,7 +627,7 @@ __global__ void __launch_bounds__(32 * PP_WARPS) k_pp_pairing(PlanView pv, u32 n
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const u32 j = blockIdx.x * PP_WARPS + wid;
   if (j >= n) return;
-  if (status[j] != ST_OK) return;  // warp-uniform
+  if (status[j] != ST_OK || (gverdict && gverdict[j / gsize])) return;  // warp-uniform
   if (lane < 2) {
     G1Affine a;
     const bool id = !g1_to_affine_inl(lr[(size_t)lane * n + j], a);  // lane 0: left, lane 1: right
@@ -744,11 +761,13 @@ struct h2v_ctx {
   u32 scratch_rows = 0;
   MsmGeom geom{};
   bool ran = false;
+  u32 opt_fold_groups = 0;  // next upload: that many consecutive independent fold groups (h2v_batch_set_fold_groups)
+  std::vector<u32> h_verdicts;  // per fold group, of the last run
   u32 opt_shard_hint = 0;   // geometry as for a shard of this many proofs (common to all ranks)
   u64 lines_key = ~0ull;    // window geometry the prepared G2 lines in d_lines belong to
   // CUDA graphs: the ~20 kernels of a batch are captured once per (mode, shape, buffers) and replayed with one launch
   bool use_graphs = true;
-  bool use_pdl = true;  // programmatic dependent launch between the kernels of a batch (pdl_prologue)
+  bool use_pdl = false;  // programmatic dependent launch between the kernels of a batch (pdl_prologue)
   bool capturing = false;
   bool stages_timed = false;  // ev[1..5] of the last run are valid (direct launches only)
   struct GraphSlot {
@@ -844,9 +863,11 @@ static u32 lift_range(u32 c, u32 W) {
 
 // n_geom >= n: the window geometry is chosen as for a batch of n_geom proofs (sharded batches: every
 // rank must use the same windows so that partial window sums add up, see h2v_batch_set_shard_hint)
-static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom) {
+static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom, u32 groups = 1) {
   MsmGeom g{};
   g.n = n;
+  g.G = groups;
+  g.N = n * groups;
   g.P = hd.n_points;
   g.n_mo = hd.n_mo;
   g.Sh = hd.n_shared;
@@ -905,12 +926,24 @@ static int ensure_lines(h2v_ctx* ctx) {
 }
 
 // the batch pairing check over `wsums` (W0 + W1 Jacobian window sums) -> d_verdict[0]
-static int launch_pairing(h2v_ctx* ctx, const G1Jac* wsums) {
+static int launch_pairing(h2v_ctx* ctx, const G1Jac* wsums, u32 groups) {
   const MsmGeom& g = ctx->geom;
   cudaStream_t s = ctx->stream;
-  KLAUNCH((k_lines<LINES_GROUPS>), H2V_ATE_ITERS, 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s, LinesArgs{g.W[0] + g.W[1]}, wsums, ctx->d_lines.as<G2Line>(),
+  KLAUNCH((k_lines<LINES_GROUPS>), dim3(H2V_ATE_ITERS, groups), 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s, LinesArgs{g.W[0] + g.W[1]}, wsums, ctx->d_lines.as<G2Line>(),
                                                                                        ctx->d_M.as<E12>());
-  KLAUNCH(k_pairing_check, 1, 128, 0, s, ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>());
+  KLAUNCH(k_pairing_check, groups, 128, 0, s, ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>());
+  return 0;
+}
+
+// verdicts of all fold groups of the last run -> ctx->h_verdicts; *all = every group accepted (waits for the stream)
+static int read_verdicts(h2v_ctx* ctx, u32* all) {
+  const u32 G = ctx->geom.G ? ctx->geom.G : 1;
+  ctx->h_verdicts.assign(G, 0);
+  CKC(cudaMemcpyAsync(ctx->h_verdicts.data(), ctx->d_verdict.p, 4 * (size_t)G, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(ctx_sync(ctx));
+  u32 a = 1;
+  for (u32 v : ctx->h_verdicts) a &= v ? 1u : 0u;
+  *all = a;
   return 0;
 }
 
@@ -1020,6 +1053,18 @@ int h2v_batch_set_columns(h2v_ctx* ctx, const uint32_t* inst_ncols, const uint32
   ctx->opt_col_len = inst_col_len;
   return 0;
 }
+int h2v_batch_set_fold_groups(h2v_ctx* ctx, uint32_t groups) {
+  if (!ctx) return -1;
+  ctx->opt_fold_groups = groups;
+  return 0;
+}
+int h2v_last_group_verdicts(const h2v_ctx* ctx, uint8_t* out, uint32_t capacity) {
+  if (!ctx || !ctx->ran) return -1;
+  const u32 G = (u32)ctx->h_verdicts.size();
+  for (u32 i = 0; i < G && i < capacity; i++) out[i] = ctx->h_verdicts[i] ? 1 : 0;
+  return (int)G;
+}
+
 int h2v_batch_set_shard_hint(h2v_ctx* ctx, uint32_t max_shard_proofs) {
   if (!ctx) return -1;
   ctx->opt_shard_hint = max_shard_proofs;
@@ -1058,10 +1103,16 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   ctx->n = n;
   ctx->gbase = gbase;
   ctx->gcount = gcount;
-  ctx->geom = choose_geom(n, hd, ctx->opt_shard_hint);
+  u32 groups = ctx->opt_fold_groups ? ctx->opt_fold_groups : 1;
+  ctx->opt_fold_groups = 0;
+  if (groups > 1 && (n % groups != 0 || gcount != n || gbase != 0 || groups > 1024)) {
+    ctx->err = "fold groups: the batch must split into equal groups and cannot be a shard of a larger batch";
+    return -1;
+  }
+  ctx->geom = choose_geom(n / groups, hd, ctx->opt_shard_hint, groups);
   ctx->opt_shard_hint = 0;
   const MsmGeom& g = ctx->geom;
-  const u32 nb = g.nb();
+  const u32 nb = g.nb() * g.G;  // buckets of all fold groups
   {
     int lrc = ensure_lines(ctx);
     if (lrc) return lrc;
@@ -1080,16 +1131,18 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   CKC(ctx->d_left.ensure(32 * (size_t)n * hd.n_mo));
   CKC(ctx->d_r.ensure(32 * (size_t)gcount));
   CKC(ctx->d_coef.ensure(32 * (size_t)n));
-  CKC(ctx->d_shared_sum.ensure(32 * (size_t)hd.n_shared));
-  CKC(ctx->d_dig.ensure(2 * (size_t)g.T * g.Wmax));
+  CKC(ctx->d_shared_sum.ensure(32 * (size_t)hd.n_shared * g.G));
+  CKC(ctx->d_dig.ensure(2 * (size_t)g.G * g.T * g.Wmax));
+  CKC(ctx->d_M.ensure(sizeof(E12) * H2V_ATE_ITERS * (size_t)g.G));
+  CKC(ctx->d_verdict.ensure(4 * (size_t)g.G + 16));
   CKC(ctx->d_hist.ensure(4 * ((size_t)nb + 2 * SIZE_BINS)));
   CKC(ctx->d_order.ensure(4 * (size_t)nb));
   CKC(ctx->d_off.ensure(4 * (size_t)(nb + 1)));
   CKC(ctx->d_cursor.ensure(4 * (size_t)nb));
   CKC(ctx->d_tiles.ensure(4 * (size_t)(nb / 1024 + 2)));
-  CKC(ctx->d_sorted.ensure(4 * (size_t)g.T * g.Wmax));
+  CKC(ctx->d_sorted.ensure(4 * (size_t)g.G * g.T * g.Wmax));
   CKC(ctx->d_buckets.ensure(sizeof(G1Jac) * (size_t)nb));
-  CKC(ctx->d_wsums.ensure(sizeof(G1Jac) * (size_t)(g.W[0] + g.W[1])));
+  CKC(ctx->d_wsums.ensure(sizeof(G1Jac) * (size_t)(g.W[0] + g.W[1]) * g.G));
   CKC(ctx->d_partials_msm.ensure(sizeof(G1Jac) * (size_t)(nb / g.m)));
   cudaStream_t s = ctx->stream;
   CKC(cudaMemcpyAsync(ctx->d_proofs.p, proofs, pbytes, cudaMemcpyHostToDevice, s));
@@ -1127,13 +1180,20 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   cudaStream_t s = ctx->stream;
   PlanView pv = ctx->pv();
   const MsmGeom& g = ctx->geom;
-  const u32 nb = g.nb();
+  const u32 nb = g.nb() * g.G;
+  if ((mode & (RUN_ACCUM | RUN_PARTIAL)) && g.G != 1) {
+    ctx->err = "folded accumulators / shard partials are defined for a single fold group";
+    return -1;
+  }
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[0], s));
   // c_j = prod_{i>j} r_i depends only on the coefficients: scanned on the auxiliary stream while the proofs are parsed
   CKC(cudaEventRecord(ctx->ev_fork, s));
   CKC(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
   CKC(cudaMemsetAsync(ctx->d_hist.p, 0, 4 * ((size_t)nb + 2 * SIZE_BINS), ctx->stream_aux));  // bucket histogram | size histogram | size cursors
-  KLAUNCH_P(false, k_rlc_scan, 1, RLC_NT, 0, ctx->stream_aux, ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, n, ctx->d_coef.as<Fr>());
+  if (g.G == 1)
+    KLAUNCH_P(false, k_rlc_scan, 1, RLC_NT, 0, ctx->stream_aux, ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, n, ctx->d_coef.as<Fr>());
+  else
+    KLAUNCH_P(false, k_rlc_scan, g.G, RLC_NT, 0, ctx->stream_aux, ctx->d_r.as<Fr>(), (u64)g.n, (u64)0, g.n, ctx->d_coef.as<Fr>());
   CKC(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
   KLAUNCH(k_init, cdiv(n, 128), 128, 0, s, pv, n, ctx->d_inst_off.as<u64>(), ctx->has_ncols ? ctx->d_ncols.as<u32>() : nullptr,
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
@@ -1154,8 +1214,9 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
                                       ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_status.as<u32>());
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[3], s));
   CKC(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-  KLAUNCH(k_shared_reduce, hd.n_shared, 256, 0, s, n, ctx->d_shared.as<Fr>(), ctx->d_coef.as<Fr>(), ctx->d_shared_sum.as<Fr>());
-  KLAUNCH(k_msm_digits, cdiv(g.T, 128), 128, 0, s, g, ctx->d_right.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_coef.as<Fr>(),
+  if (hd.n_shared)
+    KLAUNCH(k_shared_reduce, dim3(hd.n_shared, g.G), 256, 0, s, g.n, g.N, (u32)hd.n_shared, ctx->d_shared.as<Fr>(), ctx->d_coef.as<Fr>(), ctx->d_shared_sum.as<Fr>());
+  KLAUNCH(k_msm_digits, cdiv((u64)g.G * g.T, 128), 128, 0, s, g, ctx->d_right.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_coef.as<Fr>(),
                                               ctx->d_shared_sum.as<Fr>(), pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_dig.as<int16_t>(),
                                               ctx->d_hist.as<u32>());
   const u32 n_tiles = cdiv(nb, SCAN_TILE);
@@ -1163,14 +1224,14 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   KLAUNCH(k_scan_apply, n_tiles, SCAN_NT, 0, s, nb, n_tiles, ctx->d_tiles.as<u32>(), ctx->d_off.as<u32>(), ctx->d_cursor.as<u32>());
   KLAUNCH(k_bucket_order, n_tiles, SCAN_NT, 0, s, nb, ctx->d_hist.as<u32>(), ctx->d_hist.as<u32>() + nb, ctx->d_hist.as<u32>() + nb + SIZE_BINS,
                                           ctx->d_order.as<u32>());
-  KLAUNCH(k_msm_scatter, std::min<u32>(cdiv((u64)g.T * g.Wmax, 256), 148 * 4), 256, 0, s, g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
+  KLAUNCH(k_msm_scatter, std::min<u32>(cdiv((u64)g.G * g.T * g.Wmax, 256), 148 * 4), 256, 0, s, g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
   KLAUNCH(k_msm_bucket_sum, cdiv(nb, 128), 128, 0, s, g, nb, ctx->d_off.as<u32>(), ctx->d_order.as<u32>(), ctx->d_sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
                                                  pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_buckets.as<G1Jac>());
   KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, ctx->d_buckets.as<G1Jac>(), ctx->d_partials_msm.as<G1Jac>());
-  KLAUNCH(k_msm_window_reduce, g.W[0] + g.W[1], 128, 0, s, g, ctx->d_partials_msm.as<G1Jac>(), ctx->d_wsums.as<G1Jac>());
+  KLAUNCH(k_msm_window_reduce, (g.W[0] + g.W[1]) * g.G, 128, 0, s, g, ctx->d_partials_msm.as<G1Jac>(), ctx->d_wsums.as<G1Jac>());
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[4], s));
   if (mode & RUN_PAIRING) {
-    int prc = launch_pairing(ctx, ctx->d_wsums.as<G1Jac>());
+    int prc = launch_pairing(ctx, ctx->d_wsums.as<G1Jac>(), g.G);
     if (prc) return prc;
   }
   if (mode & RUN_PARTIAL) {
@@ -1202,6 +1263,7 @@ static u64 graph_key(const h2v_ctx* ctx, int mode) {
   mix((u64)ctx->has_ncols | (u64)ctx->has_col_len << 1);
   for (int ch = 0; ch < 2; ch++) mix((u64)g.c[ch] | (u64)g.W[ch] << 8 | (u64)g.Z[ch] << 16);
   mix((u64)g.T | (u64)g.m << 32);
+  mix((u64)g.G | (u64)g.N << 32);
   const DevBuf* bufs[] = {&ctx->d_plan, &ctx->d_proofs, &ctx->d_proof_off, &ctx->d_inst, &ctx->d_inst_off, &ctx->d_ncols, &ctx->d_col_len,
                           &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
                           &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off, &ctx->d_cursor, &ctx->d_order,
@@ -1267,14 +1329,16 @@ static int per_proof_impl(h2v_ctx* ctx, bool pairing, u8* accum_host) {
   CKC(ctx->d_pp_prod.ensure(sizeof(G1Jac) * (size_t)n * nbases));
   CKC(ctx->d_pp_lr.ensure(sizeof(G1Jac) * (size_t)2 * n));
   if (accum_host) CKC(ctx->d_pp_bytes.ensure(128 * (size_t)n));
+  // attribution only inside the fold groups whose batch check rejected (all proofs when the accumulators are wanted)
+  const u32* gv = (!accum_host && ctx->geom.G > 1 && ctx->geom.G * ctx->geom.n == n) ? ctx->d_verdict.as<u32>() : nullptr;
   k_pp_mul<<<cdiv((u64)n * nbases, 128), 128, 0, s>>>(pv, n, ctx->d_pts.as<G1Affine>(), ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(),
-                                                       ctx->d_left.as<Fr>(), ctx->d_status.as<u32>(), ctx->d_pp_prod.as<G1Jac>());
+                                                       ctx->d_left.as<Fr>(), ctx->d_status.as<u32>(), ctx->d_pp_prod.as<G1Jac>(), gv, ctx->geom.n);
   LAUNCH_CHECK();
   k_pp_reduce<<<cdiv(2 * (u64)n, 128), 128, 0, s>>>(pv, n, ctx->d_pp_prod.as<G1Jac>(), ctx->d_pp_lr.as<G1Jac>(),
                                                     accum_host ? ctx->d_pp_bytes.as<u8>() : nullptr);
   LAUNCH_CHECK();
   if (pairing) {
-    k_pp_pairing<<<cdiv(n, PP_WARPS), 32 * PP_WARPS, 0, s>>>(pv, n, ctx->d_pp_lr.as<G1Jac>(), ctx->d_status.as<u32>());
+    k_pp_pairing<<<cdiv(n, PP_WARPS), 32 * PP_WARPS, 0, s>>>(pv, n, ctx->d_pp_lr.as<G1Jac>(), ctx->d_status.as<u32>(), gv, ctx->geom.n);
     LAUNCH_CHECK();
   }
   if (accum_host) CKC(cudaMemcpyAsync(accum_host, ctx->d_pp_bytes.p, 128 * (size_t)n, cudaMemcpyDeviceToHost, s));
@@ -1321,9 +1385,8 @@ int h2v_verify_batch(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint
   if ((rc = run_impl(ctx, RUN_PAIRING | (batch_accum ? RUN_ACCUM : 0))) != 0) return rc;
   if ((rc = hooks_impl(ctx, challenges)) != 0) return rc;
   u32 verdict = 0;
-  CKC(cudaMemcpyAsync(&verdict, ctx->d_verdict.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (batch_accum) CKC(cudaMemcpyAsync(batch_accum, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
-  CKC(ctx_sync(ctx));
+  if ((rc = read_verdicts(ctx, &verdict)) != 0) return rc;
   if (!verdict || accum) {  // per-proof accumulators: parity hook, or attribution of a rejected batch
     if ((rc = per_proof_impl(ctx, !verdict, accum)) != 0) return rc;
   }
@@ -1377,7 +1440,7 @@ int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uin
   k_sum_partials<<<1, 128, 0, s>>>(n_partials, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, npts, ctx->d_partials.as<u8>(), ctx->d_wsums_fin.as<G1Jac>(),
                                    ctx->d_verdict.as<u32>() + 1);
   LAUNCH_CHECK();
-  int prc = launch_pairing(ctx, ctx->d_wsums_fin.as<G1Jac>());
+  int prc = launch_pairing(ctx, ctx->d_wsums_fin.as<G1Jac>(), 1);
   if (prc) return prc;
   if (batch_accum) {
     FoldArgs fa{{g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {0, g.W[0]}};
@@ -1447,8 +1510,7 @@ int h2v_batch_run(h2v_ctx* ctx, int* verdict) {
   int rc = run_impl(ctx, RUN_PAIRING);
   if (rc) return rc;
   u32 v = 0;
-  CKC(cudaMemcpyAsync(&v, ctx->d_verdict.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CKC(ctx_sync(ctx));
+  if ((rc = read_verdicts(ctx, &v)) != 0) return rc;
   if (verdict) *verdict = (int)v;
   return 0;
 }

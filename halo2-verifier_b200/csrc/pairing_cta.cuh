@@ -260,6 +260,8 @@ __global__ void __launch_bounds__(64 * GROUPS) k_lines(LinesArgs la, const G1Jac
   E12* tmps = accs + GROUPS;             // [GROUPS]
   Fq* scrs = (Fq*)(tmps + GROUPS);       // [GROUPS][2 * E12_N]
   const int t = threadIdx.x, gi = t >> 6;
+  wsums += (size_t)blockIdx.y * la.n_pairs;  // fold group blockIdx.y: its window sums, its iteration products
+  M += (size_t)blockIdx.y * H2V_ATE_ITERS;
   for (int i = t; i < (int)(sizeof(LinTables) / 2); i += blockDim.x) ((uint16_t*)&sm->lt)[i] = ((const uint16_t*)&g_lin_tables)[i];
   if (t < (int)la.n_pairs) {
     const G1Jac s = wsums[t];
@@ -306,6 +308,8 @@ __global__ void __launch_bounds__(128) k_pairing_check(const E12* __restrict__ M
   __shared__ Fq scr[2 * E12_N];
   __shared__ u64 part[E12_N * 8];
   const int t = threadIdx.x;
+  M += (size_t)blockIdx.x * H2V_ATE_ITERS;  // one block per fold group
+  verdict += blockIdx.x;
   for (int i = t; i < (int)(sizeof(LinTables) / 2); i += 128) ((uint16_t*)&lt)[i] = ((const uint16_t*)&g_lin_tables)[i];
   __syncthreads();
   Grp g{t, 1, &lt, scr, 128, part};

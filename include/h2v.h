@@ -101,6 +101,16 @@ int h2v_batch_set_scalar_hook(h2v_ctx* ctx, uint8_t* msm_scalars);
  * "accumulated".  `partial` (and `partials` of h2v_finalize) may be host or device pointers. */
 #define H2V_PARTIAL_BYTES 12320
 size_t h2v_partial_bytes(void);
+/* Fold groups (one-shot option for the next upload; default 1).  With groups = G the n proofs of the upload are G
+ * consecutive INDEPENDENT batches of n / G proofs: each has its own fold coefficients (the reference's
+ * AccumulatorStrategy run once per group, strategy.rs:125-136), its own MSM and its own pairing check, and all of
+ * them share every kernel launch.  This is how several 4096-proof batches fill the GPU together: the per-proof
+ * kernels run over all n proofs, the bucket kernels over G bucket sets, the pairing kernels over G blocks.
+ * h2v_verify_batch / h2v_batch_run report the AND of the group verdicts, per-proof statuses are unchanged
+ * (attribution runs only inside rejected groups); h2v_last_group_verdicts copies the G verdicts (1 = accepted) and
+ * returns G.  n must be a multiple of G; not combinable with shards or the folded-accumulator hook. */
+int h2v_batch_set_fold_groups(h2v_ctx* ctx, uint32_t groups);
+int h2v_last_group_verdicts(const h2v_ctx* ctx, uint8_t* out, uint32_t capacity);
 /* window geometry of the NEXT batch call as for a shard of `max_shard_proofs` proofs; cleared after one batch */
 int h2v_batch_set_shard_hint(h2v_ctx* ctx, uint32_t max_shard_proofs);
 int h2v_accumulate_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off,

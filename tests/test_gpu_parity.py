@@ -417,3 +417,37 @@ def test_graph_replay_equals_direct_launches(pkg):
                 assert t["total"] > 0 and (t["scalar"] > 0) == (not graphs)
         assert runs["all"][0] and not runs["bad"][0] and runs["bad"][1][2] != 0 and runs["all"] == runs["all2"]
         check_against_oracle(bv, params, vk, instances, bad, "shplonk", "blake2b", rs)
+
+
+@pytest.mark.parametrize("mo", ["shplonk", "gwc"])
+def test_fold_groups_equal_separate_batches(pkg, mo):
+    """G independent batches in ONE set of kernel launches (h2v_batch_set_fold_groups): per-proof statuses, challenges
+    and accumulators equal those of G separate calls, every group gets the verdict of its own fold (a bad proof only
+    rejects its own group, attribution stays inside it), fold coefficients restart in every group."""
+    G, n = 3, 5
+    params, vk, instances, proofs, rng = make_batch("vm", 8, G * n, mo, "blake2b")
+    insts = [i[0] for i in instances]
+    rs = [rng.randrange(1, bn.R) for _ in proofs]
+    bad = list(proofs)
+    bad[n + 2], _ = sim.corrupt(proofs[n + 2], vk, "eval_flip", rng, mo)  # only the pairing check of its group can see it
+    with make_bv(pkg, params, vk, mo, "blake2b") as bv:
+        for pr in (proofs, bad):
+            whole = bv.verify_batch(pr, insts, rlc_scalars=rs, want_challenges=True, want_accum=True, fold_groups=G)
+            C = bv.n_challenges
+            want_gv = []
+            for g_ in range(G):
+                sl = slice(g_ * n, (g_ + 1) * n)
+                part = bv.verify_batch(pr[sl], insts[sl], rlc_scalars=rs[sl], want_challenges=True, want_accum=True, want_batch_accum=True)
+                assert whole.status[sl] == part.status
+                assert whole.challenges[32 * C * g_ * n: 32 * C * (g_ + 1) * n] == part.challenges
+                assert whole.accum[128 * g_ * n: 128 * (g_ + 1) * n] == part.accum
+                want_gv.append(part.verdict)
+            assert whole.group_verdicts == want_gv and whole.verdict == all(want_gv)
+        assert want_gv == [True, False, True]
+        # the grouped run without the accumulator hook: attribution restricted to the rejected group
+        res = bv.verify_batch(bad, insts, rlc_scalars=rs, fold_groups=G)
+        assert res.group_verdicts == [True, False, True] and [i for i, s_ in enumerate(res.status) if s_] == [n + 2]
+        want = [orc.verify_proof(params, vk, inst, p, mo, "blake2b").status for inst, p in zip(instances, bad)]
+        assert res.status == want
+        with pytest.raises(Exception):
+            bv.verify_batch(proofs, insts, fold_groups=4)  # 15 proofs do not split into 4 groups
