@@ -163,9 +163,9 @@ def run_ours(args):
         proofs, instances = synth.synthesize_shplonk_batch(bv, shared_dlogs, s, n, seed=(rank, b))
         batches.append(PackedBatch(torch, proofs, instances))
     gen_s = time.time() - t0
-    # fold groups (N = 1): G consecutive independent 4096-proof batches per set of kernel launches (own fold and own
-    # pairing check each); the packed upload alternates the two distinct batches
-    G = max(1, args.fold_groups) if world == 1 else 1
+    # fold groups: G consecutive independent batches per set of kernel launches (own fold and own pairing check each;
+    # at N > 1 group q is this rank's shard of global batch q); the packed upload alternates the two distinct batches
+    G = max(1, args.fold_groups)
     while args.steps % G:  # exactly `steps` batches are timed
         G -= 1
     if G > 1:
@@ -188,8 +188,10 @@ def run_ours(args):
     # IS the context's stream, which orders shard kernels -> all-gather -> pairing check without extra events.
     for ci, ctx in enumerate(bvs):
         ctx.ci = ci
-        ctx.partial_dev = torch.zeros(pbytes, dtype=torch.uint8, device="cuda")
-        ctx.gathered = torch.zeros(world * pbytes, dtype=torch.uint8, device="cuda") if world > 1 else None
+        # partial / gathered buffers per group count in use: 1 (single batches: latency view) and G (throughput view)
+        ctx.cur_groups = 1
+        ctx.partial_by = {q: torch.zeros(q * pbytes, dtype=torch.uint8, device="cuda") for q in {1, G}}
+        ctx.gathered_by = {q: (torch.zeros(world * q * pbytes, dtype=torch.uint8, device="cuda") if world > 1 else None) for q in {1, G}}
     comm_stream = torch.cuda.Stream(priority=-1) if world > 1 else None
     comm_group = None
     if world > 1:  # create the communicator (high-priority NCCL stream: the tiny gather must not queue behind compute) before any worker thread exists
@@ -197,7 +199,7 @@ def run_ours(args):
         opts.is_high_priority_stream = True
         comm_group = dist.new_group(backend="nccl", pg_options=opts)
         with torch.cuda.stream(comm_stream):
-            dist.all_gather_into_tensor(bvs[0].gathered, bvs[0].partial_dev, group=comm_group)
+            dist.all_gather_into_tensor(bvs[0].gathered_by[1], bvs[0].partial_by[1], group=comm_group)
         torch.cuda.synchronize()
 
     class Exchange:
@@ -222,7 +224,7 @@ def run_ours(args):
                     self.ready[i].wait()
                     ctx = self.slot[i]
                     comm_stream.wait_event(self.ev_ready[i])
-                    dist.all_gather_into_tensor(ctx.gathered, ctx.partial_dev, group=comm_group)
+                    dist.all_gather_into_tensor(ctx.gathered_by[ctx.cur_groups], ctx.partial_by[ctx.cur_groups], group=comm_group)
                     ev = torch.cuda.Event(blocking=blocking)
                     ev.record(comm_stream)
                     self.ev_done[i] = ev
@@ -245,7 +247,7 @@ def run_ours(args):
         v = ctypes.c_int(1)
         ev = xchg[0].gather(ctx, i)
         if rank == i % world:  # every rank holds all partials after the all-gather: the ONE pairing check of global batch i runs on rank i mod N
-            chk(ctx, lib.h2v_finalize(ctx._ctx, world, ctx.gathered.data_ptr(), None, ctypes.byref(v)))
+            chk(ctx, lib.h2v_finalize_groups(ctx._ctx, world, ctx.cur_groups, ctx.gathered_by[ctx.cur_groups].data_ptr(), None, ctypes.byref(v)))
         else:
             ev.synchronize()  # this context's buffers are reused by its next step
         return v.value
@@ -257,7 +259,7 @@ def run_ours(args):
         if world == 1:
             chk(ctx, lib.h2v_batch_run(ctx._ctx, ctypes.byref(v)))
             return v.value
-        chk(ctx, lib.h2v_batch_run_shard_async(ctx._ctx, ctx.partial_dev.data_ptr()))  # enqueue only: the gather is event-ordered after it
+        chk(ctx, lib.h2v_batch_run_shard_async(ctx._ctx, ctx.partial_by[ctx.cur_groups].data_ptr()))  # enqueue only: the gather is event-ordered after it
         return gather_and_finalize(ctx, i)
 
     def step_e2e(ctx, pb, i=0):
@@ -266,7 +268,10 @@ def run_ours(args):
                 chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
             chk(ctx, lib.h2v_verify_batch(ctx._ctx, *pb.args(), None, seed, pb.status.data_ptr(), None, None, None))
             return int(pb.status.max()) == 0
-        chk(ctx, lib.h2v_accumulate_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount, pb.status.data_ptr(), ctx.partial_dev.data_ptr()))
+        ctx.cur_groups = pb.n // n
+        if pb.n > n:
+            chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
+        chk(ctx, lib.h2v_accumulate_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount, pb.status.data_ptr(), ctx.partial_by[ctx.cur_groups].data_ptr()))
         return gather_and_finalize(ctx, i) == 1
 
     def sync_all():
@@ -281,6 +286,9 @@ def run_ours(args):
                 chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
             chk(ctx, lib.h2v_batch_upload(ctx._ctx, *pb.args(), None, seed))
         else:
+            ctx.cur_groups = pb.n // n
+            if pb.n > n:
+                chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
             chk(ctx, lib.h2v_batch_upload_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount))
 
     def timed(fn, count, ctxs):
@@ -441,7 +449,7 @@ def run_ours(args):
                        "timing": "CUDA events on the contexts' streams (first start -> last end) between barrier + synchronize, max over ranks; "
                                  "e2e on the host clock around the C-ABI calls",
                        "l2": "flushed before every step (256 MiB overwrite on the step's stream, inside the timed region)",
-                       "parallelism": f"proof-sharded x{world}, NCCL all-gather of the per-window partial accumulators (12,320 B per rank), one pairing check per global batch (on rank step mod N)"},
+                       "parallelism": f"proof-sharded x{world}, NCCL all-gather of the per-window partial accumulators (12,320 B per rank and global batch), one pairing check per global batch (the checks of launch set i run on rank i mod N)"},
             "e2e": {"value": total / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": batches[0].h2d_bytes, "d2h_bytes_per_step": batches[0].d2h_bytes,
                     "ms_per_step": dt_e2e / args.steps * 1e3, "p50_latency_ms": p50},
             "one_in_flight": {"value": total / dt1, "ms_per_step": dt1 / args.steps * 1e3, "e2e_value": total / dt_e2e1, "e2e_p50_latency_ms": p50},
@@ -590,9 +598,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--shape", default="vm")
     ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("H2V_BENCH_STREAMS", "16")), help="batches in flight (contexts) at N=1")
-    ap.add_argument("--fold-groups", type=int, default=int(os.environ.get("H2V_BENCH_FOLD_GROUPS", "4")),
-                    help="independent batches (own fold + pairing check each) per set of kernel launches at N=1")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("H2V_BENCH_STREAMS", "8")), help="contexts (CUDA stream + host thread each) per GPU")
+    ap.add_argument("--fold-groups", type=int, default=int(os.environ.get("H2V_BENCH_FOLD_GROUPS", "8")),
+                    help="independent batches (own fold + pairing check each) per set of kernel launches of a context")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--ref-proofs-per-core", type=int, default=64)

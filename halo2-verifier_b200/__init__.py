@@ -106,6 +106,7 @@ def load_library():
     lib.h2v_batch_set_shard_hint.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
     lib.h2v_batch_set_fold_groups.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
     lib.h2v_last_group_verdicts.argtypes = [ctypes.c_void_p, u8p, ctypes.c_uint32]
+    lib.h2v_finalize_groups.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, u8p, u8p, ctypes.POINTER(ctypes.c_int)]
     lib.h2v_partial_bytes.argtypes = []
     lib.h2v_partial_bytes.restype = ctypes.c_size_t
     lib.h2v_accumulate_shard.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64,
@@ -140,7 +141,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "h2v_ctx_create", "h2v_ctx_create_from_bundle", "h2v_ctx_destroy", "h2v_last_error", "h2v_ctx_info", "h2v_verify_proof", "h2v_verify_batch",
     "h2v_batch_set_columns", "h2v_batch_set_scalar_hook", "h2v_batch_set_shard_hint", "h2v_partial_bytes", "h2v_accumulate_shard", "h2v_finalize", "h2v_attribute_shard",
-    "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync", "h2v_ctx_set_graphs", "h2v_batch_set_fold_groups", "h2v_last_group_verdicts", "h2v_debug_timeline_start", "h2v_debug_timeline_stop",
+    "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync", "h2v_ctx_set_graphs", "h2v_batch_set_fold_groups", "h2v_last_group_verdicts", "h2v_finalize_groups", "h2v_debug_timeline_start", "h2v_debug_timeline_stop",
     "h2v_last_msm_geometry", "h2v_selftest_field", "h2v_calibrate_imad",
 )
 
@@ -322,7 +323,7 @@ class BatchVerifier:
         return BatchResult(st, all(s == 0 for s in st), ch.raw if ch else None, acc.raw if acc else None,
                            bacc.raw if bacc else None, sc.raw if sc else None, [bool(v) for v in gv[:ng]])
 
-    def accumulate_shard(self, proofs, instances, global_base, global_count, rlc_scalars=None, seed=0, shard_hint=0):
+    def accumulate_shard(self, proofs, instances, global_base, global_count, rlc_scalars=None, seed=0, shard_hint=0, fold_groups=1):
         """Returns (statuses, partial): `partial` is the opaque H2V_PARTIAL_BYTES blob of this shard's
         per-window bucket sums.  `shard_hint` = size of the largest shard of the global batch when the
         shards are not all of the same size (every rank must use the same window geometry)."""
@@ -330,7 +331,9 @@ class BatchVerifier:
         pbytes, poff, ibytes, ioff, keep = self._pack(proofs, instances)
         rlc = b"".join(int(r).to_bytes(32, "little") for r in rlc_scalars) if rlc_scalars is not None else None
         status = (ctypes.c_uint8 * n)()
-        partial = ctypes.create_string_buffer(self.lib.h2v_partial_bytes())
+        partial = ctypes.create_string_buffer(self.lib.h2v_partial_bytes() * max(1, int(fold_groups)))
+        if fold_groups > 1:  # group q = this rank's shard of global batch q; rlc_scalars: fold_groups x global_count values
+            self._check(self.lib.h2v_batch_set_fold_groups(self._ctx, int(fold_groups)))
         if shard_hint:
             self._check(self.lib.h2v_batch_set_shard_hint(self._ctx, int(shard_hint)))
         self._check(self.lib.h2v_accumulate_shard(self._ctx, n, pbytes, poff, ibytes, ioff, rlc, seed, global_base,
@@ -343,6 +346,14 @@ class BatchVerifier:
         verdict = ctypes.c_int(0)
         self._check(self.lib.h2v_finalize(self._ctx, len(partials), buf, bacc, ctypes.byref(verdict)))
         return bool(verdict.value), (bacc.raw if bacc is not None else None)
+
+    def finalize_groups(self, partials: Sequence[bytes], fold_groups):
+        """partials: one accumulate_shard(..., fold_groups=G) output per rank; returns the G batch verdicts"""
+        buf = b"".join(partials)
+        gv = (ctypes.c_uint8 * int(fold_groups))()
+        verdict = ctypes.c_int(0)
+        self._check(self.lib.h2v_finalize_groups(self._ctx, len(partials), int(fold_groups), buf, gv, ctypes.byref(verdict)))
+        return [bool(v) for v in gv]
 
     def attribute_shard(self, status):
         arr = (ctypes.c_uint8 * len(status))(*status)

@@ -173,11 +173,12 @@ __global__ void k_rlc_expand(u64 count, u64 seed, const u8* bytes, Fr* r) {
 
 // c_j = prod_{i > j} r_i over the GLOBAL batch; one block, chunked suffix scan through shared memory.
 static constexpr u32 RLC_NT = 256;
-// (fold groups: block g scans the n coefficients of its own group; then count = n, base = 0)
+// (fold groups: block g scans the `count` coefficients of its own global batch, r + g * count, and writes the n of
+// this rank's shard of it, coef + g * n)
 __global__ void __launch_bounds__(RLC_NT) k_rlc_scan(const Fr* r, u64 count, u64 base, u32 n, Fr* coef) {
   pdl_prologue();
   __shared__ Fr sh[RLC_NT];
-  r += (size_t)blockIdx.x * n;
+  r += (size_t)blockIdx.x * count;
   coef += (size_t)blockIdx.x * n;
   const u32 t = threadIdx.x;
   const u64 m = (count + RLC_NT - 1) / RLC_NT;
@@ -540,6 +541,8 @@ static_assert(sizeof(PartialHeader) + 128 * sizeof(G1Jac) == H2V_PARTIAL_BYTES, 
 
 __global__ void k_pack_partial(u32 cbits, u32 windows, u32 npts, const G1Jac* wsums, u8* out) {
   pdl_prologue();
+  wsums += (size_t)blockIdx.y * npts;  // fold group blockIdx.y
+  out += (size_t)blockIdx.y * H2V_PARTIAL_BYTES;
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   u32* o = (u32*)out;
   if (t < 8) {
@@ -551,16 +554,20 @@ __global__ void k_pack_partial(u32 cbits, u32 windows, u32 npts, const G1Jac* ws
 }
 
 // window-wise sum of the shards' partials (thread per window); flags a geometry mismatch in *err
+// (fold groups: block q sums group q; the partials are rank-major, [rank][group])
 __global__ void __launch_bounds__(128) k_sum_partials(u32 n_partials, u32 cbits, u32 windows, u32 npts, const u8* partials, G1Jac* out, u32* err) {
   const u32 wi = threadIdx.x;
+  const size_t rank_stride = (size_t)gridDim.x * H2V_PARTIAL_BYTES;
+  partials += (size_t)blockIdx.x * H2V_PARTIAL_BYTES;
+  out += (size_t)blockIdx.x * npts;
   if (wi < n_partials) {
-    const PartialHeader* h = (const PartialHeader*)(partials + (size_t)wi * H2V_PARTIAL_BYTES);
+    const PartialHeader* h = (const PartialHeader*)(partials + (size_t)wi * rank_stride);
     if (h->magic != H2V_PARTIAL_MAGIC || h->cbits != cbits || h->windows != windows || h->n_pts != npts) atomicOr(err, 1u);
   }
   if (wi >= npts) return;
   G1Jac acc = G1Jac::identity();
   for (u32 g = 0; g < n_partials; g++) {
-    const G1Jac* pts = (const G1Jac*)(partials + (size_t)g * H2V_PARTIAL_BYTES + sizeof(PartialHeader));
+    const G1Jac* pts = (const G1Jac*)(partials + (size_t)g * rank_stride + sizeof(PartialHeader));
     acc = g1_add(acc, pts[wi]);
   }
   out[wi] = acc;
@@ -763,6 +770,7 @@ struct h2v_ctx {
   bool ran = false;
   u32 opt_fold_groups = 0;  // next upload: that many consecutive independent fold groups (h2v_batch_set_fold_groups)
   std::vector<u32> h_verdicts;  // per fold group, of the last run
+  bool verdicts_on_device = false;  // d_verdict holds the group verdicts of the batch in this context's buffers
   u32 opt_shard_hint = 0;   // geometry as for a shard of this many proofs (common to all ranks)
   u64 lines_key = ~0ull;    // window geometry the prepared G2 lines in d_lines belong to
   // CUDA graphs: the ~20 kernels of a batch are captured once per (mode, shape, buffers) and replayed with one launch
@@ -899,7 +907,7 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom, u32 groups =
   return g;
 }
 
-static constexpr int LINES_GROUPS = 4;
+static constexpr int LINES_GROUPS = 8;
 
 static u64 lines_key_of(const MsmGeom& g) { return (u64)g.c[0] | (u64)g.W[0] << 8 | (u64)g.c[1] << 16 | (u64)g.W[1] << 24; }
 
@@ -1081,8 +1089,10 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
                        const u8* rlc, u64 seed, u64 gbase, u64 gcount) {
   if (!ctx) return -1;
   ctx->ran = false;
-  if (n == 0 || !proof_off || !inst_off || (!proofs && proof_off[n]) || gcount < gbase + n) {
-    ctx->err = "bad batch arguments";
+  const u32 groups = ctx->opt_fold_groups ? ctx->opt_fold_groups : 1;  // gbase / gcount describe ONE fold group (global batch)
+  ctx->opt_fold_groups = 0;
+  if (n == 0 || !proof_off || !inst_off || (!proofs && proof_off[n]) || groups > 1024 || n % groups != 0 || gcount < gbase + n / groups) {
+    ctx->err = "bad batch arguments (with fold groups the batch must split into equal groups)";
     return -1;
   }
   CKC(cudaSetDevice(ctx->device));
@@ -1103,12 +1113,7 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   ctx->n = n;
   ctx->gbase = gbase;
   ctx->gcount = gcount;
-  u32 groups = ctx->opt_fold_groups ? ctx->opt_fold_groups : 1;
-  ctx->opt_fold_groups = 0;
-  if (groups > 1 && (n % groups != 0 || gcount != n || gbase != 0 || groups > 1024)) {
-    ctx->err = "fold groups: the batch must split into equal groups and cannot be a shard of a larger batch";
-    return -1;
-  }
+  ctx->verdicts_on_device = false;
   ctx->geom = choose_geom(n / groups, hd, ctx->opt_shard_hint, groups);
   ctx->opt_shard_hint = 0;
   const MsmGeom& g = ctx->geom;
@@ -1129,7 +1134,8 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   CKC(ctx->d_right.ensure(32 * (size_t)n * hd.n_points));
   CKC(ctx->d_shared.ensure(32 * (size_t)n * hd.n_shared));
   CKC(ctx->d_left.ensure(32 * (size_t)n * hd.n_mo));
-  CKC(ctx->d_r.ensure(32 * (size_t)gcount));
+  CKC(ctx->d_r.ensure(32 * (size_t)gcount * groups));
+  CKC(ctx->d_partial_out.ensure((size_t)H2V_PARTIAL_BYTES * groups));
   CKC(ctx->d_coef.ensure(32 * (size_t)n));
   CKC(ctx->d_shared_sum.ensure(32 * (size_t)hd.n_shared * g.G));
   CKC(ctx->d_dig.ensure(2 * (size_t)g.G * g.T * g.Wmax));
@@ -1161,11 +1167,12 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   }
   ctx->opt_ncols = nullptr;
   ctx->opt_col_len = nullptr;
+  const u64 n_r = gcount * groups;  // fold coefficients of every group's whole global batch
   if (rlc) {
-    CKC(ctx->d_rlc_bytes.ensure(32 * (size_t)gcount));
-    CKC(cudaMemcpyAsync(ctx->d_rlc_bytes.p, rlc, 32 * (size_t)gcount, cudaMemcpyHostToDevice, s));
+    CKC(ctx->d_rlc_bytes.ensure(32 * (size_t)n_r));
+    CKC(cudaMemcpyAsync(ctx->d_rlc_bytes.p, rlc, 32 * (size_t)n_r, cudaMemcpyHostToDevice, s));
   }
-  k_rlc_expand<<<cdiv(gcount, 128), 128, 0, s>>>(gcount, seed, rlc ? ctx->d_rlc_bytes.as<u8>() : nullptr, ctx->d_r.as<Fr>());
+  k_rlc_expand<<<cdiv(n_r, 128), 128, 0, s>>>(n_r, seed, rlc ? ctx->d_rlc_bytes.as<u8>() : nullptr, ctx->d_r.as<Fr>());
   LAUNCH_CHECK();
   return 0;
 }
@@ -1181,8 +1188,8 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   PlanView pv = ctx->pv();
   const MsmGeom& g = ctx->geom;
   const u32 nb = g.nb() * g.G;
-  if ((mode & (RUN_ACCUM | RUN_PARTIAL)) && g.G != 1) {
-    ctx->err = "folded accumulators / shard partials are defined for a single fold group";
+  if ((mode & RUN_ACCUM) && g.G != 1) {
+    ctx->err = "the folded accumulator hook is defined for a single fold group";
     return -1;
   }
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[0], s));
@@ -1190,10 +1197,7 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   CKC(cudaEventRecord(ctx->ev_fork, s));
   CKC(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
   CKC(cudaMemsetAsync(ctx->d_hist.p, 0, 4 * ((size_t)nb + 2 * SIZE_BINS), ctx->stream_aux));  // bucket histogram | size histogram | size cursors
-  if (g.G == 1)
-    KLAUNCH_P(false, k_rlc_scan, 1, RLC_NT, 0, ctx->stream_aux, ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, n, ctx->d_coef.as<Fr>());
-  else
-    KLAUNCH_P(false, k_rlc_scan, g.G, RLC_NT, 0, ctx->stream_aux, ctx->d_r.as<Fr>(), (u64)g.n, (u64)0, g.n, ctx->d_coef.as<Fr>());
+  KLAUNCH_P(false, k_rlc_scan, g.G, RLC_NT, 0, ctx->stream_aux, ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, g.n, ctx->d_coef.as<Fr>());
   CKC(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
   KLAUNCH(k_init, cdiv(n, 128), 128, 0, s, pv, n, ctx->d_inst_off.as<u64>(), ctx->has_ncols ? ctx->d_ncols.as<u32>() : nullptr,
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
@@ -1224,7 +1228,7 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   KLAUNCH(k_scan_apply, n_tiles, SCAN_NT, 0, s, nb, n_tiles, ctx->d_tiles.as<u32>(), ctx->d_off.as<u32>(), ctx->d_cursor.as<u32>());
   KLAUNCH(k_bucket_order, n_tiles, SCAN_NT, 0, s, nb, ctx->d_hist.as<u32>(), ctx->d_hist.as<u32>() + nb, ctx->d_hist.as<u32>() + nb + SIZE_BINS,
                                           ctx->d_order.as<u32>());
-  KLAUNCH(k_msm_scatter, std::min<u32>(cdiv((u64)g.G * g.T * g.Wmax, 256), 148 * 4), 256, 0, s, g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
+  KLAUNCH(k_msm_scatter, std::min<u32>(cdiv((u64)g.G * g.T * g.Wmax, 256), 148 * 16), 256, 0, s, g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
   KLAUNCH(k_msm_bucket_sum, cdiv(nb, 128), 128, 0, s, g, nb, ctx->d_off.as<u32>(), ctx->d_order.as<u32>(), ctx->d_sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
                                                  pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_buckets.as<G1Jac>());
   KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, ctx->d_buckets.as<G1Jac>(), ctx->d_partials_msm.as<G1Jac>());
@@ -1235,7 +1239,7 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
     if (prc) return prc;
   }
   if (mode & RUN_PARTIAL) {
-    KLAUNCH(k_pack_partial, 8, 256, 0, s, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, g.W[0] + g.W[1], ctx->d_wsums.as<G1Jac>(), ctx->d_partial_out.as<u8>());
+    KLAUNCH(k_pack_partial, dim3(8, g.G), 256, 0, s, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, g.W[0] + g.W[1], ctx->d_wsums.as<G1Jac>(), ctx->d_partial_out.as<u8>());
   }
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[5], s));
   if (mode & RUN_ACCUM) {
@@ -1283,6 +1287,7 @@ static int run_impl(h2v_ctx* ctx, int mode) {
     int rc = enqueue_batch(ctx, mode);
     if (rc) return rc;
     ctx->stages_timed = true;
+    ctx->verdicts_on_device = (mode & RUN_PAIRING) != 0;
     ctx->ran = true;
     return 0;
   }
@@ -1315,6 +1320,7 @@ static int run_impl(h2v_ctx* ctx, int mode) {
   CKC(cudaEventRecord(ctx->ev[6], s));
   ctx->launches += gs.kernels;
   ctx->stages_timed = false;
+  ctx->verdicts_on_device = (mode & RUN_PAIRING) != 0;
   ctx->ran = true;
   return 0;
 }
@@ -1330,7 +1336,7 @@ static int per_proof_impl(h2v_ctx* ctx, bool pairing, u8* accum_host) {
   CKC(ctx->d_pp_lr.ensure(sizeof(G1Jac) * (size_t)2 * n));
   if (accum_host) CKC(ctx->d_pp_bytes.ensure(128 * (size_t)n));
   // attribution only inside the fold groups whose batch check rejected (all proofs when the accumulators are wanted)
-  const u32* gv = (!accum_host && ctx->geom.G > 1 && ctx->geom.G * ctx->geom.n == n) ? ctx->d_verdict.as<u32>() : nullptr;
+  const u32* gv = (!accum_host && ctx->verdicts_on_device && ctx->geom.G > 1 && ctx->geom.G * ctx->geom.n == n) ? ctx->d_verdict.as<u32>() : nullptr;
   k_pp_mul<<<cdiv((u64)n * nbases, 128), 128, 0, s>>>(pv, n, ctx->d_pts.as<G1Affine>(), ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(),
                                                        ctx->d_left.as<Fr>(), ctx->d_status.as<u32>(), ctx->d_pp_prod.as<G1Jac>(), gv, ctx->geom.n);
   LAUNCH_CHECK();
@@ -1381,7 +1387,7 @@ int h2v_verify_batch(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint
                      const uint64_t* inst_off, const uint8_t* rlc_scalars, uint64_t seed, uint8_t* status, uint8_t* challenges,
                      uint8_t* accum, uint8_t* batch_accum) {
   int rc;
-  if ((rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, 0, n)) != 0) return rc;
+  if ((rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, 0, n / (ctx->opt_fold_groups ? ctx->opt_fold_groups : 1))) != 0) return rc;
   if ((rc = run_impl(ctx, RUN_PAIRING | (batch_accum ? RUN_ACCUM : 0))) != 0) return rc;
   if ((rc = hooks_impl(ctx, challenges)) != 0) return rc;
   u32 verdict = 0;
@@ -1404,16 +1410,16 @@ int h2v_accumulate_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const 
   int rc;
   if ((rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, global_base, global_count)) != 0) return rc;
   if ((rc = run_impl(ctx, RUN_PARTIAL)) != 0) return rc;
-  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_partial_out.p, H2V_PARTIAL_BYTES, cudaMemcpyDefault, ctx->stream));
+  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_partial_out.p, (size_t)H2V_PARTIAL_BYTES * ctx->geom.G, cudaMemcpyDefault, ctx->stream));
   return download_status(ctx, status);
 }
 
-int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uint8_t* batch_accum, int* verdict) {
-  if (!ctx || !partials || !n_partials || n_partials > 128) return -1;
+static int finalize_impl(h2v_ctx* ctx, u32 n_partials, u32 groups, const u8* partials, u8* batch_accum, int* verdict, u8* group_verdicts) {
+  if (!ctx || !partials || !n_partials || n_partials > 128 || !groups || groups > 1024 || (batch_accum && groups != 1)) return -1;
   CKC(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  CKC(ctx->d_partials.ensure((size_t)H2V_PARTIAL_BYTES * n_partials));
-  CKC(cudaMemcpyAsync(ctx->d_partials.p, partials, (size_t)H2V_PARTIAL_BYTES * n_partials, cudaMemcpyDefault, s));
+  CKC(ctx->d_partials.ensure((size_t)H2V_PARTIAL_BYTES * n_partials * groups));
+  CKC(cudaMemcpyAsync(ctx->d_partials.p, partials, (size_t)H2V_PARTIAL_BYTES * n_partials * groups, cudaMemcpyDefault, s));
   if (ctx->n == 0) {  // a context that has not processed a shard itself: take the geometry from the first partial
     PartialHeader h;
     CKC(cudaMemcpyAsync(&h, ctx->d_partials.p, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -1436,11 +1442,15 @@ int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uin
   }
   const MsmGeom& g = ctx->geom;
   const u32 npts = g.W[0] + g.W[1];
-  CKC(cudaMemsetAsync(ctx->d_verdict.p, 0, 16, s));
-  k_sum_partials<<<1, 128, 0, s>>>(n_partials, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, npts, ctx->d_partials.as<u8>(), ctx->d_wsums_fin.as<G1Jac>(),
-                                   ctx->d_verdict.as<u32>() + 1);
+  CKC(ctx->d_verdict.ensure(4 * (size_t)groups + 16));
+  CKC(ctx->d_M.ensure(sizeof(E12) * H2V_ATE_ITERS * (size_t)groups));
+  CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
+  CKC(cudaMemsetAsync(ctx->d_verdict.p, 0, 4 * (size_t)groups + 16, s));
+  ctx->verdicts_on_device = false;  // d_verdict now belongs to the global batches being finalized
+  k_sum_partials<<<groups, 128, 0, s>>>(n_partials, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, npts, ctx->d_partials.as<u8>(), ctx->d_wsums_fin.as<G1Jac>(),
+                                        ctx->d_verdict.as<u32>() + groups);
   LAUNCH_CHECK();
-  int prc = launch_pairing(ctx, ctx->d_wsums_fin.as<G1Jac>(), 1);
+  int prc = launch_pairing(ctx, ctx->d_wsums_fin.as<G1Jac>(), groups);
   if (prc) return prc;
   if (batch_accum) {
     FoldArgs fa{{g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {0, g.W[0]}};
@@ -1448,15 +1458,27 @@ int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uin
     LAUNCH_CHECK();
     CKC(cudaMemcpyAsync(batch_accum, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, s));
   }
-  u32 v[2] = {0, 0};
-  CKC(cudaMemcpyAsync(v, ctx->d_verdict.p, 8, cudaMemcpyDeviceToHost, s));
+  std::vector<u32> v(groups + 1, 0);
+  CKC(cudaMemcpyAsync(v.data(), ctx->d_verdict.p, 4 * (size_t)(groups + 1), cudaMemcpyDeviceToHost, s));
   CKC(ctx_sync(ctx));
-  if (v[1]) {
+  if (v[groups]) {
     ctx->err = "partial accumulators were produced with different window geometries (use h2v_batch_set_shard_hint)";
     return -1;
   }
-  if (verdict) *verdict = (int)v[0];
+  u32 all = 1;
+  for (u32 q = 0; q < groups; q++) {
+    all &= v[q] ? 1u : 0u;
+    if (group_verdicts) group_verdicts[q] = v[q] ? 1 : 0;
+  }
+  if (verdict) *verdict = (int)all;
   return 0;
+}
+
+int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uint8_t* batch_accum, int* verdict) {
+  return finalize_impl(ctx, n_partials, 1, partials, batch_accum, verdict, nullptr);
+}
+int h2v_finalize_groups(h2v_ctx* ctx, uint32_t n_partials, uint32_t groups, const uint8_t* partials, uint8_t* group_verdicts, int* verdict) {
+  return finalize_impl(ctx, n_partials, groups, partials, nullptr, verdict, group_verdicts);
 }
 
 int h2v_attribute_shard(h2v_ctx* ctx, uint8_t* status) {
@@ -1468,7 +1490,7 @@ int h2v_attribute_shard(h2v_ctx* ctx, uint8_t* status) {
 
 int h2v_batch_upload(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off, const uint8_t* instances,
                      const uint64_t* inst_off, const uint8_t* rlc_scalars, uint64_t seed) {
-  int rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, 0, n);
+  int rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, 0, n / (ctx && ctx->opt_fold_groups ? ctx->opt_fold_groups : 1));
   if (rc) return rc;
   CKC(ctx_sync(ctx));
   return 0;
@@ -1486,7 +1508,7 @@ int h2v_batch_upload_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, cons
 int h2v_batch_run_shard(h2v_ctx* ctx, uint8_t* partial) {
   int rc = run_impl(ctx, RUN_PARTIAL);
   if (rc) return rc;
-  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_partial_out.p, H2V_PARTIAL_BYTES, cudaMemcpyDefault, ctx->stream));
+  if (partial) CKC(cudaMemcpyAsync(partial, ctx->d_partial_out.p, (size_t)H2V_PARTIAL_BYTES * ctx->geom.G, cudaMemcpyDefault, ctx->stream));
   CKC(ctx_sync(ctx));
   return 0;
 }
@@ -1494,7 +1516,7 @@ int h2v_batch_run_shard(h2v_ctx* ctx, uint8_t* partial) {
 int h2v_batch_run_shard_async(h2v_ctx* ctx, uint8_t* partial_device) {
   int rc = run_impl(ctx, RUN_PARTIAL);
   if (rc) return rc;
-  if (partial_device) CKC(cudaMemcpyAsync(partial_device, ctx->d_partial_out.p, H2V_PARTIAL_BYTES, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (partial_device) CKC(cudaMemcpyAsync(partial_device, ctx->d_partial_out.p, (size_t)H2V_PARTIAL_BYTES * ctx->geom.G, cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
 

@@ -108,9 +108,14 @@ size_t h2v_partial_bytes(void);
  * kernels run over all n proofs, the bucket kernels over G bucket sets, the pairing kernels over G blocks.
  * h2v_verify_batch / h2v_batch_run report the AND of the group verdicts, per-proof statuses are unchanged
  * (attribution runs only inside rejected groups); h2v_last_group_verdicts copies the G verdicts (1 = accepted) and
- * returns G.  n must be a multiple of G; not combinable with shards or the folded-accumulator hook. */
+ * returns G.  n must be a multiple of G; not combinable with the folded-accumulator hook.
+ * With shards (h2v_accumulate_shard / h2v_batch_upload_shard) group q is this rank's shard of global batch q:
+ * global_base / global_count describe ONE global batch, rlc_scalars holds G x global_count coefficients, the partial
+ * output is G consecutive H2V_PARTIAL_BYTES blobs, and h2v_finalize_groups takes the ranks' outputs concatenated
+ * ([rank][group]) and runs the G pairing checks in one set of launches (group_verdicts: G bytes, may be NULL). */
 int h2v_batch_set_fold_groups(h2v_ctx* ctx, uint32_t groups);
 int h2v_last_group_verdicts(const h2v_ctx* ctx, uint8_t* out, uint32_t capacity);
+int h2v_finalize_groups(h2v_ctx* ctx, uint32_t n_partials, uint32_t groups, const uint8_t* partials, uint8_t* group_verdicts, int* verdict);
 /* window geometry of the NEXT batch call as for a shard of `max_shard_proofs` proofs; cleared after one batch */
 int h2v_batch_set_shard_hint(h2v_ctx* ctx, uint32_t max_shard_proofs);
 int h2v_accumulate_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off,

@@ -451,3 +451,32 @@ def test_fold_groups_equal_separate_batches(pkg, mo):
         assert res.status == want
         with pytest.raises(Exception):
             bv.verify_batch(proofs, insts, fold_groups=4)  # 15 proofs do not split into 4 groups
+
+
+def test_sharded_fold_groups(pkg):
+    """Fold groups across shards: G global batches, every rank holds its shard of each and processes all of them in one
+    set of launches; the G partials per rank are concatenated ([rank][group]) and finalized together.  Verdicts equal
+    those of the unsharded grouped run and of the separate batches; a corrupted proof rejects only its global batch."""
+    G, n, shards = 3, 64, 2
+    per = n // shards
+    params, vk, instances, proofs, rng = make_batch("vm", 10, 32, "shplonk", "blake2b", seed=5)
+    proofs, insts = proofs * 6, [i[0] for i in instances] * 6  # G * n = 192 proofs, global batch q = proofs[q*n:(q+1)*n]
+    rs = [rng.randrange(1, bn.R) for _ in range(G * n)]
+    bad = list(proofs)
+    bad[n + 40], _ = sim.corrupt(proofs[n + 40], vk, "eval_flip", rng)
+    with make_bv(pkg, params, vk, "shplonk", "blake2b") as b0, make_bv(pkg, params, vk, "shplonk", "blake2b") as b1:
+        for pr, want in ((proofs, [True, True, True]), (bad, [True, False, True])):
+            whole = b0.verify_batch(pr, insts, rlc_scalars=rs, fold_groups=G)
+            assert whole.group_verdicts == want
+            parts = []
+            for rank, bv in ((0, b0), (1, b1)):
+                sel = [q * n + rank * per + j for q in range(G) for j in range(per)]  # this rank's shard of every global batch
+                st, partial = bv.accumulate_shard([pr[i] for i in sel], [insts[i] for i in sel], rank * per, n, rlc_scalars=rs, fold_groups=G)
+                assert st == [0] * len(sel) and len(partial) == G * pkg.load_library().h2v_partial_bytes()
+                parts.append(partial)
+            assert b1.finalize_groups(parts, G) == want
+            # the same global batches one at a time through the single-group shard API
+            for q in range(G):
+                single = [bv.accumulate_shard(pr[q * n + r_ * per: q * n + (r_ + 1) * per], insts[q * n + r_ * per: q * n + (r_ + 1) * per], r_ * per, n,
+                                              rlc_scalars=rs[q * n:(q + 1) * n])[1] for r_, bv in ((0, b0), (1, b1))]
+                assert b0.finalize(single)[0] == want[q]
