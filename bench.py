@@ -113,9 +113,9 @@ def algorithmic_mm(bv, n, geom):
     W0, W1 = geom["windows"] & 0xFFFF, geom["windows"] >> 16
     t_right, t_left = n * P + bv.n_shared, n * bv.n_mo // 2  # half of the left multi-open slots carry scalar 0 (h1)
     mm = {
-        "decompress": n * P * (254 + 64 + 14 + 8),  # sqrt by 4-bit window (254 S + 64 M + 14 table) + curve check / conversions
+        "decompress": n * P * (250 + 38 + 16 + 9),  # sqrt by 5-bit sliding window (250 S + 38 M + 16 table) + curve check / conversions; a squaring counts as one MM
         "transcript": n * (P * 2 + S + bv.n_challenges * 2),  # only Montgomery conversions; the hash is ALU work
-        "scalar": n * (10 + 330 + 3 * 12 + 40 * 4 + 160),  # x^n, one inversion, Lagrange, expressions, SHPLONK sets (VM shape)
+        "scalar": n * (10 + 310 + 3 * 12 + 40 * 4 + 160),  # x^n, one inversion, Lagrange, expressions, SHPLONK sets (VM shape)
         "rlc_msm": n * (P + bv.n_mo) * 2 + (W0 * t_right + W1 * t_left) * 11 + (W0 * (1 << (c0 - 1)) + W1 * (1 << (c1 - 1))) * 32,
         "pairing": (65 * (W0 + W1) * 58 + 430 * 54),  # k_lines: line value (4) + product (54) per pair and step; check: ~430 Fq12 products
     }
