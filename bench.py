@@ -122,6 +122,12 @@ def algorithmic_mm(bv, n, geom):
     return mm
 
 
+def bucket_sum_mm(bv, n, geom):
+    """k_msm_bucket_sum alone: one mixed addition (7 MM + 4 S, counted as 11 MM) per bucket entry"""
+    W0, W1 = geom["windows"] & 0xFFFF, geom["windows"] >> 16
+    return (W0 * (n * bv.n_points + bv.n_shared) + W1 * (n * bv.n_mo // 2)) * 11
+
+
 def run_ours(args):
     import torch
     import __graft_entry__ as g
@@ -384,18 +390,33 @@ def run_ours(args):
         for name, ms in b.timings().items():
             inflight_acc.setdefault(name, []).append(ms)
     stage_ms_in_flight = {k_: statistics.median(v) for k_, v in inflight_acc.items()}
-    # per-stage CUDA-event timings of a few serial steps (roofline of the dominant kernel group)
-    stage_acc = {}
+    # per-stage / per-kernel device times of a few serial single batches under graph replay, from the on-device block
+    # timeline (global nanosecond timer: first block start -> last block end of every kernel; no host in the loop)
+    import numpy as np
+
     upload(bv, batches[0])
-    bv.set_graphs(False)  # direct launches: a graph replay has no events between its kernels
-    for i in range(6):
+    run_steps(lambda ctx, i_: step_resident(ctx, i_), 2, bvs[:1])
+    stage_acc, kern_acc = {}, {}
+    cap = 1 << 18
+    tlbuf = np.zeros(cap * 8, dtype=np.uint32)
+    for i in range(5):
+        chk(bv, lib.h2v_debug_timeline_start(local, cap))
         run_steps(lambda ctx, i_: step_resident(ctx, i_), 1, bvs[:1])
-        if i == 0:
+        cnt = ctypes.c_uint32(0)
+        chk(bv, lib.h2v_debug_timeline_stop(local, tlbuf.ctypes.data, cap, ctypes.byref(cnt)))
+        rec = tlbuf[: cnt.value * 8].reshape(-1, 8).astype(np.uint64)
+        kid, t0, t1 = rec[:, 0], rec[:, 4] | (rec[:, 5] << np.uint64(32)), rec[:, 6] | (rec[:, 7] << np.uint64(32))
+        span = {int(k_): (int(t0[kid == k_].min()), int(t1[kid == k_].max())) for k_ in np.unique(kid)}
+        if not all(k_ in span for k_ in range(1, 11)):
             continue
-        for name, ms in bv.timings().items():
-            stage_acc.setdefault(name, []).append(ms)
-    bv.set_graphs(True)
+        ms = lambda a, b: (b - a) * 1e-6
+        for name, v in (("total", ms(span[1][0], span[10][1])), ("decompress", ms(*span[1])), ("transcript", ms(span[1][1], span[2][1])),
+                        ("scalar", ms(span[2][1], span[3][1])), ("rlc_msm", ms(span[3][1], span[8][1])), ("pairing", ms(span[8][1], span[10][1]))):
+            stage_acc.setdefault(name, []).append(v)
+        for name, k_ in (("k_decompress", 1), ("k_transcript", 2), ("k_scalar", 3), ("k_msm_bucket_sum", 6), ("k_msm_chunk_reduce", 7), ("k_lines", 9), ("k_pairing_check", 10)):
+            kern_acc.setdefault(name, []).append(ms(*span[k_]))
     stage_ms = {k_: statistics.median(v) for k_, v in stage_acc.items()}
+    kern_ms = {k_: statistics.median(v) for k_, v in kern_acc.items()}
     # ---------------- end to end through the C ABI from pinned host memory
     run_steps(lambda ctx, i: step_e2e(ctx, batches[i % 2], i), W, bvs[:1])
     lat = []
@@ -423,10 +444,11 @@ def run_ours(args):
         mm = algorithmic_mm(bv, n, geom)
         # dominant kernel group = the stage that carries the largest share of the algorithmic work (the one that bounds
         # throughput with several batches in flight); every stage's own time / work / fraction is listed under "stages"
-        dom = max((k_ for k_ in mm if k_ in stage_ms), key=lambda k_: mm[k_])
         imad_peak = lib.h2v_calibrate_imad(local)
         slots = lambda m: m * IMAD_SLOTS_PER_MM
-        achieved = slots(mm[dom]) / (stage_ms[dom] * 1e-3)
+        kern_mm = {"k_decompress": mm["decompress"], "k_msm_bucket_sum": bucket_sum_mm(bv, n, geom)}  # the two multiplier-bound kernels
+        dom = max(kern_mm, key=lambda k_: kern_mm[k_])
+        achieved = slots(kern_mm[dom]) / (kern_ms[dom] * 1e-3)
         achieved_all = slots(sum(mm.values())) / (dt / args.steps)
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
@@ -456,18 +478,22 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stage_ms": {k_: round(v, 4) for k_, v in stage_ms.items()},
+            "kernel_ms": {k_: round(v, 4) for k_, v in kern_ms.items()},
             "stage_ms_all_in_flight": {k_: round(v, 4) for k_, v in stage_ms_in_flight.items()},
             "msm": {"window_bits": [geom["window_bits"] & 0xFFFF, geom["window_bits"] >> 16], "windows": [geom["windows"] & 0xFFFF, geom["windows"] >> 16],
                     "terms": geom["terms"], "buckets": geom["buckets"]},
             "roofline": {"bound": "imad", "kernel": dom, "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s",
                          "frac": achieved / imad_peak, "traffic": traffic,
                          "whole_step": {"achieved": achieved_all / 1e12, "frac": achieved_all / imad_peak, "mm_per_proof": sum(mm.values()) / n},
+                         "kernels": {k_: {"ms_one_in_flight": round(kern_ms[k_], 4), "mm": int(kern_mm[k_]),
+                                          "frac": slots(kern_mm[k_]) / (kern_ms[k_] * 1e-3) / imad_peak} for k_ in kern_mm},
                          "stages": {k_: {"ms_one_in_flight": round(stage_ms[k_], 4), "mm": int(mm[k_]),
                                          "frac": slots(mm[k_]) / (stage_ms[k_] * 1e-3) / imad_peak} for k_ in mm if k_ in stage_ms},
                          "note": "integer-multiply bound (no HBM/tensor roofline applies, DESIGN.md section 5): algorithmic 256-bit Montgomery "
-                                 "multiplications x 272 IMAD issue slots (136 32x32->64 multiply-adds, lo + hi) of the kernel group with the largest "
-                                 "share of the work / its CUDA-event time with one batch in flight; peak = 32-bit IMAD issue rate measured by the calibration kernel in this run; `whole_step` = "
-                                 "all stages / the timed step"},
+                                 "multiplications (a squaring counted as one) x 272 IMAD issue slots (136 32x32->64 multiply-adds, lo + hi) of the "
+                                 "kernel with the largest share of the work / its duration on the device's global timer (first block start -> last block end, h2v_debug_timeline) "
+                                 "in serial single batches under graph replay (in the timed region 64 batches overlap, so a kernel's own duration is not defined there); "
+                                 "peak = 32-bit IMAD issue rate measured by the calibration kernel in this run; `whole_step` = all stages / the timed step (CUDA events)"},
             "roofline_hbm": {"bound": "hbm", "kernel": "transcript+scalar (evaluation loads)", "achieved": eval_bytes / ((stage_ms["transcript"] + stage_ms["scalar"]) * 1e-3) / 1e9,
                              "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
                              "frac": eval_bytes / ((stage_ms["transcript"] + stage_ms["scalar"]) * 1e-3) / 1e9 / hbm_peak, "traffic": None},

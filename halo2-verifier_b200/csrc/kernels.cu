@@ -27,6 +27,7 @@
 #include "stages.cuh"
 #include "tower.cuh"
 #include "pairing_warp.cuh"
+#include "timeline.cuh"
 #include "pairing_cta.cuh"
 
 using namespace h2v;
@@ -54,37 +55,6 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-
-struct TlRec {
-  u32 kid, block, smid, tag;
-  u64 t0, t1;
-};
-__device__ TlRec* g_tl_buf = nullptr;
-__device__ u32 g_tl_cap = 0;
-__device__ u32 g_tl_count = 0;
-struct TlScope {
-  u64 t0;
-  u32 kid, tag;
-  bool on;
-  __device__ __forceinline__ TlScope(u32 kid_, const void* tagp) {
-    on = threadIdx.x == 0 && g_tl_buf != nullptr;
-    if (on) {
-      kid = kid_;
-      tag = (u32)((size_t)tagp >> 8);
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    }
-  }
-  __device__ __forceinline__ ~TlScope() {
-    if (on) {
-      u64 t1;
-      u32 sm;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-      const u32 i = atomicAdd(&g_tl_count, 1u);
-      if (i < g_tl_cap) g_tl_buf[i] = TlRec{kid, blockIdx.x, sm, tag, t0, t1};
-    }
-  }
-};
 
 // ------------------------------------------------------------------------------------------------
 // kernels

@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(64 * GROUPS) k_lines(LinesArgs la, const G1Jac
                                                        E12* __restrict__ M) {
   asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch, see pdl_prologue() in kernels.cu
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  ::TlScope tl_(9, M);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LinesSmem* sm = (LinesSmem*)smem_raw;
   E12* accs = (E12*)(sm + 1);            // [GROUPS]
@@ -303,6 +304,7 @@ constexpr size_t k_lines_smem() {
 __global__ void __launch_bounds__(128) k_pairing_check(const E12* __restrict__ M, u32* verdict) {
   asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch, see pdl_prologue() in kernels.cu
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  ::TlScope tl_(10, M);
   __shared__ LinTables lt;
   __shared__ E12 slot[12];
   __shared__ Fq scr[2 * E12_N];
