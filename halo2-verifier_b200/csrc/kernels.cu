@@ -812,7 +812,10 @@ static cudaError_t ctx_sync(h2v_ctx* ctx) {
 // Window size per channel.  Thanks to the scalar lift k'' = k + z*r every window is uniformly filled, so
 // the choice is a pure work trade-off: bucket additions (11 MM) against bucket reduction (2 x 16 MM
 // per bucket plus the per-chunk offset multiplication), with a floor on the per-bucket serial chain.
-static double choose_window(u32 terms, u32& c_out, u32& W_out, double chain_floor) {
+// chain_weight: 1 = throughput (several fold groups share the launches: total work decides), 2 = latency (a single
+// batch: the longest bucket chain is on the critical path).  Measured, 4096 VM proofs: c = 11 -> 5.91 M proofs/s and
+// 3.08 ms alone, c = 12 -> 5.80 M and 2.92 ms.
+static double choose_window(u32 terms, u32& c_out, u32& W_out, double chain_floor, double chain_weight) {
   double best = 1e300, best_chain = 0;
   for (u32 c = 4; c <= 15; c++) {
     const u32 W = (255 + c - 1) / c;
@@ -820,7 +823,7 @@ static double choose_window(u32 terms, u32& c_out, u32& W_out, double chain_floo
     const double work = (double)W * ((double)terms * 11.0 + B * 150.0);  // per bucket: measured (window sweep on B200), not just 2 additions
     const double chain = ((double)terms / B + 1.0) * 11.0;  // dependent MM per bucket thread
     // both channels share the bucket kernels: only a chain longer than the other channel's costs latency
-    const double t = work / 10e9 + std::max(0.0, chain - chain_floor) * 0.4e-6;
+    const double t = work / 10e9 + std::max(0.0, chain - chain_floor) * 0.4e-6 * chain_weight;
     if (t < best) {
       best = t;
       best_chain = chain;
@@ -851,8 +854,9 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom, u32 groups =
   g.Sh = hd.n_shared;
   g.T = n * hd.n_points + n * hd.n_mo + hd.n_shared;
   if (n_geom < n) n_geom = n;
-  const double chain_right = choose_window(n_geom * hd.n_points + hd.n_shared, g.c[0], g.W[0], 0.0);
-  choose_window(n_geom * hd.n_mo, g.c[1], g.W[1], chain_right);
+  const double cw = groups > 1 ? 1.0 : 2.0;
+  const double chain_right = choose_window(n_geom * hd.n_points + hd.n_shared, g.c[0], g.W[0], 0.0, cw);
+  choose_window(n_geom * hd.n_mo, g.c[1], g.W[1], chain_right, cw);
   const char* f0 = getenv("H2V_MSM_WINDOW_RIGHT");
   const char* f1 = getenv("H2V_MSM_WINDOW_LEFT");
   for (int ch = 0; ch < 2; ch++) {
@@ -1171,6 +1175,8 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   CKC(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
   KLAUNCH(k_init, cdiv(n, 128), 128, 0, s, pv, n, ctx->d_inst_off.as<u64>(), ctx->has_ncols ? ctx->d_ncols.as<u32>() : nullptr,
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
+  // (one-warp blocks were measured for the two multiplier-bound kernels: no change, 0.300 ms / 0.364 ms alone.  A single
+  // batch is 2.6 warps of decompression per SM sub-partition: the quantisation to 3 bounds the kernel at ~86 % of the pipe.)
   KLAUNCH(k_decompress, cdiv((u64)n * hd.n_points, 128), 128, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(),
                                                                 ctx->d_pts.as<G1Affine>(), ctx->d_bad.as<u32>());
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[1], s));
