@@ -47,3 +47,34 @@ def verify_batch_sharded(bv, proofs, instances, rank: int, world: int, rlc_scala
     if not ok:  # rejected fold: every rank attributes inside its own shard, no further exchange
         status = bv.attribute_shard(status)
     return ok, status
+
+
+def split_group_partials(rank_blob: bytes, groups: int) -> List[bytes]:
+    """One rank's output of a launch set with `groups` fold groups = `groups` consecutive partials."""
+    assert len(rank_blob) % groups == 0
+    step = len(rank_blob) // groups
+    return [rank_blob[q * step:(q + 1) * step] for q in range(groups)]
+
+
+def verify_batches_sharded(bv, batches, rank: int, world: int, rlc_scalars=None, seed=0):
+    """`batches`: G global batches [(proofs, instances), ...] of EQUAL size n, each sharded over the ranks; every rank
+    processes its shard of all G batches in ONE set of kernel launches (fold groups, include/h2v.h), the G partials per
+    rank are all-gathered as one blob ([rank][group]) and rank 0 runs the G pairing checks together.  `rlc_scalars`:
+    G * n coefficients (batch-major) or None.  Returns (G verdicts, statuses of this rank's shard of every batch)."""
+    G, n = len(batches), len(batches[0][0])
+    assert all(len(p) == n and len(i) == n for p, i in batches) and n % world == 0, "equal batches, equal shards"
+    lo, hi = shard_range(n, rank, world)
+    proofs = [p for pr, _ in batches for p in pr[lo:hi]]
+    insts = [i for _, ins in batches for i in ins[lo:hi]]
+    status, blob = bv.accumulate_shard(proofs, insts, lo, n, rlc_scalars=rlc_scalars, seed=seed, fold_groups=G)
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    parts = all_gather_partials(torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev), world)
+    flags = torch.zeros(G, dtype=torch.int32, device=dev)
+    if rank == 0:
+        flags[:] = torch.tensor([1 if v else 0 for v in bv.finalize_groups(parts, G)], dtype=torch.int32)
+    if world > 1:
+        dist.broadcast(flags, src=0)
+    verdicts = [bool(v) for v in flags.tolist()]
+    if not all(verdicts):  # attribution inside this rank's shards (proofs of accepted batches stay accepted)
+        status = bv.attribute_shard(status)
+    return verdicts, [status[q * (hi - lo):(q + 1) * (hi - lo)] for q in range(G)]

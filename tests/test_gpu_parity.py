@@ -480,3 +480,21 @@ def test_sharded_fold_groups(pkg):
                 single = [bv.accumulate_shard(pr[q * n + r_ * per: q * n + (r_ + 1) * per], insts[q * n + r_ * per: q * n + (r_ + 1) * per], r_ * per, n,
                                               rlc_scalars=rs[q * n:(q + 1) * n])[1] for r_, bv in ((0, b0), (1, b1))]
                 assert b0.finalize(single)[0] == want[q]
+
+
+def test_verify_batches_sharded_world1(pkg):
+    """sharding.verify_batches_sharded (the reference-facing helper for G global batches per launch set) at world size 1"""
+    from importlib import import_module
+
+    sharding = import_module("halo2_verifier_b200.sharding")
+    G, n = 2, 8
+    params, vk, instances, proofs, rng = make_batch("vm", 8, G * n, "gwc", "keccak")
+    insts = [i[0] for i in instances]
+    bad = list(proofs)
+    bad[3], _ = sim.corrupt(proofs[3], vk, "eval_flip", rng, "gwc")
+    with make_bv(pkg, params, vk, "gwc", "keccak", F.PROCESSED) as bv:
+        batches = [(bad[q * n:(q + 1) * n], insts[q * n:(q + 1) * n]) for q in range(G)]
+        verdicts, status = sharding.verify_batches_sharded(bv, batches, 0, 1, seed=5)
+        assert verdicts == [False, True]
+        want = [orc.verify_proof(params, vk, inst, p, "gwc", "keccak").status for inst, p in zip(instances, bad)]
+        assert status[0] + status[1] == want and status[0][3] == orc.CONSTRAINT_SYSTEM_FAILURE
