@@ -171,19 +171,23 @@ def run_ours(args):
     gen_s = time.time() - t0
     # fold groups: G consecutive independent batches per set of kernel launches (own fold and own pairing check each;
     # at N > 1 group q is this rank's shard of global batch q); the packed upload alternates the two distinct batches
-    G = max(1, args.fold_groups)
-    while args.steps % G:  # exactly `steps` batches are timed
-        G -= 1
-    if G > 1:
-        gbatches = []
-        for b in range(2):
-            pr, ins = [], []
-            for q in range(G):
-                pr += batches[(b + q) % 2].src[0]
-                ins += batches[(b + q) % 2].src[1]
-            gbatches.append(PackedBatch(torch, pr, ins))
-    else:
-        gbatches = batches
+    G = max(1, min(args.fold_groups, args.steps))
+    if n_ctx == 1:
+        while args.steps % G:
+            G -= 1
+    # exactly `steps` batches are timed: steps // G launch sets of G groups, and, when G does not divide steps, ONE launch
+    # set of the remaining groups, which the last context runs (the other contexts share the full sets)
+    G_rem = args.steps % G
+
+    def packed_groups(first, count):
+        pr, ins = [], []
+        for q in range(count):
+            pr += batches[(first + q) % 2].src[0]
+            ins += batches[(first + q) % 2].src[1]
+        return PackedBatch(torch, pr, ins)
+
+    gbatches = [packed_groups(b, G) for b in range(2)] if G > 1 else batches
+    rbatch = packed_groups(0, G_rem) if G_rem > 1 else batches[0]
     gcount, gbase = n * world, n * rank
     seed = 7
     pbytes = int(lib.h2v_partial_bytes())
@@ -196,8 +200,8 @@ def run_ours(args):
         ctx.ci = ci
         # partial / gathered buffers per group count in use: 1 (single batches: latency view) and G (throughput view)
         ctx.cur_groups = 1
-        ctx.partial_by = {q: torch.zeros(q * pbytes, dtype=torch.uint8, device="cuda") for q in {1, G}}
-        ctx.gathered_by = {q: (torch.zeros(world * q * pbytes, dtype=torch.uint8, device="cuda") if world > 1 else None) for q in {1, G}}
+        ctx.partial_by = {q: torch.zeros(q * pbytes, dtype=torch.uint8, device="cuda") for q in {1, G, max(1, G_rem)}}
+        ctx.gathered_by = {q: (torch.zeros(world * q * pbytes, dtype=torch.uint8, device="cuda") if world > 1 else None) for q in {1, G, max(1, G_rem)}}
     comm_stream = torch.cuda.Stream(priority=-1) if world > 1 else None
     comm_group = None
     if world > 1:  # create the communicator (high-priority NCCL stream: the tiny gather must not queue behind compute) before any worker thread exists
@@ -297,14 +301,14 @@ def run_ours(args):
                 chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
             chk(ctx, lib.h2v_batch_upload_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount))
 
-    def timed(fn, count, ctxs):
+    def timed(fn, count, ctxs, assign=None):
         """count steps between barrier + synchronize on both sides; returns (results, seconds on the DEVICE clock:
         CUDA events on the contexts' streams, first start -> last end; wall seconds)."""
         sync_all()
         ev0 = torch.cuda.Event(enable_timing=True)
         ev0.record(ext_streams[0])
         w0 = time.perf_counter()
-        res_ = run_steps(fn, count, ctxs)
+        res_ = run_steps(fn, count, ctxs, assign)
         ends = []
         for st in ext_streams[: len(ctxs)] + [torch.cuda.current_stream()] + ([comm_stream] if comm_stream is not None else []):
             e = torch.cuda.Event(enable_timing=True)
@@ -314,18 +318,21 @@ def run_ours(args):
         wall = time.perf_counter() - w0
         return res_, max(ev0.elapsed_time(e) for e in ends) * 1e-3, wall
 
-    def run_steps(fn, count, ctxs):
-        """count steps spread round-robin over the contexts; each context is driven by its own host
-        thread (ctypes releases the GIL), so batches of different contexts overlap on the device."""
+    def run_steps(fn, count, ctxs, assign=None):
+        """count launch sets spread over the contexts (round-robin, or set i on context assign[i]); each context is
+        driven by its own host thread (ctypes releases the GIL), so batches of different contexts overlap on the device."""
         out = [None] * count
         if world > 1:
             xchg[0] = Exchange(count)
+        if assign is None:
+            assign = [i % len(ctxs) for i in range(count)]
 
         def worker(ci):
             torch.cuda.set_device(local)
             with torch.cuda.stream(ext_streams[ctxs[ci].ci]):
-                for i in range(ci, count, len(ctxs)):
-                    out[i] = fn(ctxs[ci], i)
+                for i in range(count):
+                    if assign[i] == ci:
+                        out[i] = fn(ctxs[ci], i)
 
         if len(ctxs) == 1:
             worker(0)
@@ -347,7 +354,11 @@ def run_ours(args):
         return [float(x) for x in t]
 
     W = max(args.warmup, 3)
-    runs = args.steps // G  # launch sets of G batches each; a step is ONE batch of n proofs per GPU
+    full = args.steps // G  # launch sets of G batches each; a step is ONE batch of n proofs per GPU
+    runs = full + (1 if G_rem else 0)
+    n_full = n_ctx - 1 if G_rem else n_ctx  # contexts that run the full sets
+    assign = [i % n_full for i in range(full)] + ([n_ctx - 1] if G_rem else [])
+    warm_assign = [ci for _ in range(W) for ci in range(n_ctx)]
     total = n * world * args.steps
     # ---------------- device-resident throughput (`value`)
     upload(bv, batches[0])
@@ -366,12 +377,12 @@ def run_ours(args):
     dt = dt1
     if n_ctx > 1 or G > 1:  # several independent batches in flight (fold groups per launch set x contexts): throughput view
         for ci, ctx in enumerate(bvs):
-            upload(ctx, gbatches[ci % 2])
-        ok = run_steps(lambda ctx, i: step_resident(ctx, i), W * n_ctx, bvs)
+            upload(ctx, rbatch if (G_rem and ci == n_ctx - 1) else gbatches[ci % 2])
+        ok = run_steps(lambda ctx, i: step_resident(ctx, i), W * n_ctx, bvs, warm_assign)
         assert all(v == 1 for v in ok), "warm-up batch was rejected"
         geom_tp = bv.msm_geometry()
         launches0 = sum(b.launch_count() for b in bvs)
-        res, dt, _ = timed(lambda ctx, i: step_resident(ctx, i), runs, bvs)
+        res, dt, _ = timed(lambda ctx, i: step_resident(ctx, i), runs, bvs, assign)
         assert all(v == 1 for v in res), "a timed batch was rejected"
         launches = sum(b.launch_count() for b in bvs) - launches0
     clocks = sampler.summary()
@@ -435,8 +446,9 @@ def run_ours(args):
     p50 = statistics.median(lat) * 1e3
     dt_e2e = dt_e2e1
     if n_ctx > 1 or G > 1:
-        run_steps(lambda ctx, i: step_e2e(ctx, gbatches[i % 2], i), W * n_ctx, bvs)
-        res, _, dt_e2e = timed(lambda ctx, i: timed_e2e(ctx, i, gbatches), runs, bvs)
+        pick = lambda ctx, i: [rbatch, rbatch] if (G_rem and ctx.ci == n_ctx - 1) else gbatches
+        run_steps(lambda ctx, i: step_e2e(ctx, pick(ctx, i)[i % 2], i), W * n_ctx, bvs, warm_assign)
+        res, _, dt_e2e = timed(lambda ctx, i: timed_e2e(ctx, i, pick(ctx, i)), runs, bvs, assign)
         assert all(res), "an end-to-end batch was rejected"
     dt, dt1, dt_e2e, dt_e2e1 = reduce_max(dt, dt1, dt_e2e, dt_e2e1)
 
