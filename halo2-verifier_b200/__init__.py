@@ -91,6 +91,8 @@ def load_library():
     u8p, u32p, u64p = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
     lib.h2v_ctx_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
                                    ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.h2v_ctx_create_multi.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
+                                         ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32]
     lib.h2v_ctx_create_from_bundle.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int]
     lib.h2v_ctx_destroy.argtypes = [ctypes.c_void_p]
@@ -141,7 +143,7 @@ def load_library():
 EXPORTED_SYMBOLS = (
     "h2v_ctx_create", "h2v_ctx_create_from_bundle", "h2v_ctx_destroy", "h2v_last_error", "h2v_ctx_info", "h2v_verify_proof", "h2v_verify_batch",
     "h2v_batch_set_columns", "h2v_batch_set_scalar_hook", "h2v_batch_set_shard_hint", "h2v_partial_bytes", "h2v_accumulate_shard", "h2v_finalize", "h2v_attribute_shard",
-    "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync", "h2v_ctx_set_graphs", "h2v_batch_set_fold_groups", "h2v_last_group_verdicts", "h2v_finalize_groups", "h2v_debug_timeline_start", "h2v_debug_timeline_stop",
+    "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync", "h2v_ctx_set_graphs", "h2v_ctx_create_multi", "h2v_batch_set_fold_groups", "h2v_last_group_verdicts", "h2v_finalize_groups", "h2v_debug_timeline_start", "h2v_debug_timeline_stop",
     "h2v_last_msm_geometry", "h2v_selftest_field", "h2v_calibrate_imad",
 )
 
@@ -237,11 +239,15 @@ class BatchResult:
 class BatchVerifier:
     """One (params, vk, multiopen, transcript, device) context: owns the device plan and buffers."""
 
-    def __init__(self, params: ParamsKZG, vk: VerifyingKey, multiopen="shplonk", transcript="blake2b", device=0):
+    def __init__(self, params: ParamsKZG, vk: VerifyingKey, multiopen="shplonk", transcript="blake2b", device=0, circuit_instances=1):
+        """circuit_instances = m > 1: every proof carries m circuit instances in one transcript (`instances.len()` of the
+        reference's verify_proof); the `instances` entry of a proof is then a list of m column lists."""
         self.lib = load_library()
         self._ctx = ctypes.c_void_p()
-        rc = self.lib.h2v_ctx_create(ctypes.byref(self._ctx), params.data, len(params.data), int(params.format), vk.data,
-                                     len(vk.data), int(vk.format), _MULTIOPEN[multiopen], _HASH[transcript], int(device))
+        self.circuit_instances = int(circuit_instances)
+        rc = self.lib.h2v_ctx_create_multi(ctypes.byref(self._ctx), params.data, len(params.data), int(params.format), vk.data,
+                                           len(vk.data), int(vk.format), _MULTIOPEN[multiopen], _HASH[transcript], int(device),
+                                           self.circuit_instances)
         if rc != 0:
             self._ctx = None
             raise BackendError(self.lib.h2v_last_error(None).decode())
@@ -279,6 +285,8 @@ class BatchVerifier:
         return arr
 
     def _pack(self, proofs, instances):
+        if self.circuit_instances > 1:  # instance-major "virtual" columns (lib.rs:76-82)
+            instances = [[col for inst in proof_insts for col in inst] for proof_insts in instances]
         pbytes = b"".join(proofs)
         poff = self._offsets([len(p) for p in proofs])
         ibytes, counts, ncols, col_len = pack_instances(instances)

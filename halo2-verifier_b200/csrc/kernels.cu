@@ -935,13 +935,18 @@ const char* h2v_last_error(const h2v_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int h2v_ctx_create(h2v_ctx** out, const uint8_t* params, size_t params_len, int params_format, const uint8_t* vk, size_t vk_len,
                    int vk_format, int multiopen, int hash, int device) {
+  return h2v_ctx_create_multi(out, params, params_len, params_format, vk, vk_len, vk_format, multiopen, hash, device, 1);
+}
+
+int h2v_ctx_create_multi(h2v_ctx** out, const uint8_t* params, size_t params_len, int params_format, const uint8_t* vk, size_t vk_len,
+                         int vk_format, int multiopen, int hash, int device, uint32_t circuit_instances) {
   if (!out || !params || !vk) {
     g_create_error = "null argument";
     return -1;
   }
   h2v_ctx* ctx = new h2v_ctx();
   std::string err;
-  if (build_plan(params, params_len, params_format, vk, vk_len, vk_format, multiopen, hash, ctx->blob, ctx->info, err) != 0) {
+  if (build_plan(params, params_len, params_format, vk, vk_len, vk_format, multiopen, hash, ctx->blob, ctx->info, err, circuit_instances) != 0) {
     g_create_error = err;
     delete ctx;
     return -1;

@@ -209,9 +209,13 @@ u32 append(std::vector<u8>& blob, const std::vector<T>& v) {
 
 }  // namespace
 
+// `m` = circuit instances carried by ONE proof transcript (`instances.len()` of verify_proof, lib.rs:63,92,117,134):
+// advice / lookup / permutation / shuffle commitments and evaluations, the instance columns, the expressions and the
+// queries repeat per instance in the reference's interleaving; fixed columns, sigma, the random polynomial and h are shared.
 int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vkb, size_t vk_len, int vk_fmt,
-               int multiopen, int hash, std::vector<u8>& blob, PlanInfo& info, std::string& err) {
+               int multiopen, int hash, std::vector<u8>& blob, PlanInfo& info, std::string& err, u32 m) {
   try {
+    H2V_REQUIRE(m >= 1 && m <= 16, "circuit instances per proof out of range (1..16)");
     H2V_REQUIRE(multiopen == MO_SHPLONK || multiopen == MO_GWC, "unknown multiopen scheme");
     H2V_REQUIRE(hash == HASH_BLAKE2B || hash == HASH_KECCAK, "unknown transcript hash");
     // ---------------- params (kzg/commitment.rs:155-207)
@@ -316,7 +320,7 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
     for (auto& q : advice_queries) H2V_REQUIRE(q.col < num_advice_columns, "advice query column out of range");
     for (auto& q : fixed_queries) H2V_REQUIRE(q.first < n_fixed_commit, "fixed query column out of range");
     for (auto& q : instance_queries) H2V_REQUIRE(q.first < num_instance_columns, "instance query column out of range");
-    H2V_REQUIRE(I <= H2V_MAX_INST_Q, "too many instance queries for this build");
+    H2V_REQUIRE((u64)I * m <= H2V_MAX_INST_Q, "too many instance queries for this build");
 
     // blinding_factors (vk.rs:396-401), phases (vk.rs:403-411)
     u32 bf = 1;
@@ -387,11 +391,12 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
     };
     op(T_ABS_VK, 0);
     op(T_ABS_INST, 0);
-    std::vector<u32> advice_slot(num_advice_columns, 0xFFFFFFFFu), user_ch_sq(num_challenges, 0xFFFFFFFFu);
+    std::vector<u32> advice_slot((size_t)m * num_advice_columns, 0xFFFFFFFFu), user_ch_sq(num_challenges, 0xFFFFFFFFu);  // [pi][column]
     for (u32 phase = 0; phase <= max_phase; phase++) {
       u32 cnt = 0;
-      for (u32 c = 0; c < num_advice_columns; c++)
-        if (advice_phase[c] == phase) advice_slot[c] = (u32)pt_item.size() + cnt++;
+      for (u32 pi = 0; pi < m; pi++)  // lib.rs:91-103: every instance's advice commitments of this phase
+        for (u32 c = 0; c < num_advice_columns; c++)
+          if (advice_phase[c] == phase) advice_slot[(size_t)pi * num_advice_columns + c] = (u32)pt_item.size() + cnt++;
       op(T_POINTS, cnt);
       cnt = 0;
       for (u32 c = 0; c < num_challenges; c++)
@@ -400,16 +405,16 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
     }
     hd.ch_theta = n_squeeze;
     op(T_SQUEEZE, 1);
-    const u32 slot_lookup_permuted = (u32)pt_item.size();  // 2 per lookup: input, table
-    op(T_POINTS, 2 * L);
+    const u32 slot_lookup_permuted = (u32)pt_item.size();  // per instance, 2 per lookup: input, table
+    op(T_POINTS, 2 * L * m);
     hd.ch_beta = n_squeeze;
     hd.ch_gamma = n_squeeze + 1;
     op(T_SQUEEZE, 2);
-    const u32 slot_perm = (u32)pt_item.size();
-    const u32 slot_lookup_prod = slot_perm + n_sets;
-    const u32 slot_shuffle_prod = slot_lookup_prod + L;
-    const u32 slot_random = slot_shuffle_prod + SH;
-    op(T_POINTS, n_sets + L + SH + 1);
+    const u32 slot_perm = (u32)pt_item.size();              // [pi][set]
+    const u32 slot_lookup_prod = slot_perm + n_sets * m;    // [pi][lookup]
+    const u32 slot_shuffle_prod = slot_lookup_prod + L * m; // [pi][shuffle]
+    const u32 slot_random = slot_shuffle_prod + SH * m;
+    op(T_POINTS, (n_sets + L + SH) * m + 1);
     hd.ch_y = n_squeeze;
     op(T_SQUEEZE, 1);
     hd.h_slot = (u32)pt_item.size();
@@ -418,42 +423,46 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
     hd.ch_x = n_squeeze;
     op(T_SQUEEZE, 1);
     // scalar slots
-    const u32 s_advice = 0, s_fixed = A, s_random = A + F, s_sigma = A + F + 1, s_perm = s_sigma + n_perm;
+    // (lib.rs:219-253: advice evals per instance, fixed, random, sigma, then per instance permutation / lookup / shuffle evals)
+    const u32 s_advice = 0, s_fixed = A * m, s_random = s_fixed + F, s_sigma = s_random + 1, s_perm = s_sigma + n_perm;
     const u32 n_perm_evals = n_sets ? 3 * n_sets - 1 : 0;
-    const u32 s_lookup = s_perm + n_perm_evals, s_shuffle = s_lookup + 5 * L;
-    const u32 S = s_shuffle + 2 * SH;
+    const u32 s_lookup = s_perm + n_perm_evals * m, s_shuffle = s_lookup + 5 * L * m;
+    const u32 S = s_shuffle + 2 * SH * m;
     op(T_SCALARS, S);
     hd.first_mo_item = item;
 
     // ---------------- query list (lib.rs:349-414)
-    auto perm_eval = [&](u32 set, u32 which) { return s_perm + 3 * set + which; };  // eval, next, last
+    auto perm_eval = [&](u32 pi, u32 set, u32 which) { return s_perm + pi * n_perm_evals + 3 * set + which; };  // eval, next, last
     std::vector<Query> queries;
     const u32 V_EXPECTED_H_TMP = 0xFFFFFFF0u;
-    for (u32 qi = 0; qi < A; qi++) {
-      const AQ& q = advice_queries[qi];
-      H2V_REQUIRE(advice_slot[q.col] != 0xFFFFFFFFu, "advice column without commitment");
-      queries.push_back({CM_PROOF, advice_slot[q.col], q.rot, s_advice + qi});
-    }
-    for (u32 s = 0; s < n_sets; s++) {
-      queries.push_back({CM_PROOF, slot_perm + s, 0, perm_eval(s, 0)});
-      queries.push_back({CM_PROOF, slot_perm + s, 1, perm_eval(s, 1)});
-    }
-    for (u32 s = n_sets; s-- > 0;) {
-      if (s == n_sets - 1) continue;  // all but the last set, in reverse (permutation.rs:318)
-      queries.push_back({CM_PROOF, slot_perm + s, -(int32_t)(bf + 1), perm_eval(s, 2)});
-    }
-    for (u32 l = 0; l < L; l++) {  // lookup.rs:232-271
-      const u32 e = s_lookup + 5 * l, pin = slot_lookup_permuted + 2 * l, ptab = pin + 1, pprod = slot_lookup_prod + l;
-      queries.push_back({CM_PROOF, pprod, 0, e + 0});
-      queries.push_back({CM_PROOF, pin, 0, e + 2});
-      queries.push_back({CM_PROOF, ptab, 0, e + 4});
-      queries.push_back({CM_PROOF, pin, -1, e + 3});
-      queries.push_back({CM_PROOF, pprod, 1, e + 1});
-    }
-    for (u32 s = 0; s < SH; s++) {  // shuffle.rs:205-225
-      const u32 e = s_shuffle + 2 * s;
-      queries.push_back({CM_PROOF, slot_shuffle_prod + s, 0, e});
-      queries.push_back({CM_PROOF, slot_shuffle_prod + s, 1, e + 1});
+    for (u32 pi = 0; pi < m; pi++) {
+      for (u32 qi = 0; qi < A; qi++) {
+        const AQ& q = advice_queries[qi];
+        const u32 slot = advice_slot[(size_t)pi * num_advice_columns + q.col];
+        H2V_REQUIRE(slot != 0xFFFFFFFFu, "advice column without commitment");
+        queries.push_back({CM_PROOF, slot, q.rot, s_advice + pi * A + qi});
+      }
+      for (u32 s = 0; s < n_sets; s++) {
+        queries.push_back({CM_PROOF, slot_perm + pi * n_sets + s, 0, perm_eval(pi, s, 0)});
+        queries.push_back({CM_PROOF, slot_perm + pi * n_sets + s, 1, perm_eval(pi, s, 1)});
+      }
+      for (u32 s = n_sets; s-- > 0;) {
+        if (s == n_sets - 1) continue;  // all but the last set, in reverse (permutation.rs:318)
+        queries.push_back({CM_PROOF, slot_perm + pi * n_sets + s, -(int32_t)(bf + 1), perm_eval(pi, s, 2)});
+      }
+      for (u32 l = 0; l < L; l++) {  // lookup.rs:232-271
+        const u32 e = s_lookup + 5 * (pi * L + l), pin = slot_lookup_permuted + 2 * (pi * L + l), ptab = pin + 1, pprod = slot_lookup_prod + pi * L + l;
+        queries.push_back({CM_PROOF, pprod, 0, e + 0});
+        queries.push_back({CM_PROOF, pin, 0, e + 2});
+        queries.push_back({CM_PROOF, ptab, 0, e + 4});
+        queries.push_back({CM_PROOF, pin, -1, e + 3});
+        queries.push_back({CM_PROOF, pprod, 1, e + 1});
+      }
+      for (u32 s = 0; s < SH; s++) {  // shuffle.rs:205-225
+        const u32 e = s_shuffle + 2 * (pi * SH + s);
+        queries.push_back({CM_PROOF, slot_shuffle_prod + pi * SH + s, 0, e});
+        queries.push_back({CM_PROOF, slot_shuffle_prod + pi * SH + s, 1, e + 1});
+      }
     }
     for (u32 qi = 0; qi < F; qi++) queries.push_back({CM_FIXED, fixed_queries[qi].first, fixed_queries[qi].second, s_fixed + qi});
     for (u32 i = 0; i < n_perm; i++) queries.push_back({CM_SIGMA, i, 0, s_sigma + i});
@@ -502,11 +511,11 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
     hd.n_items = item;
     hd.proof_len = 32 * item;
     hd.n_challenges = n_squeeze;
-    hd.n_inst_cols = num_instance_columns;
-    hd.n_inst_q = I;
+    hd.n_inst_cols = num_instance_columns * m;  // instance-major "virtual" columns: the layout of lib.rs:76-82
+    hd.n_inst_q = I * m;
     hd.v_chal = S;
     hd.v_inst = S + n_squeeze;
-    hd.v_expected_h = S + n_squeeze + I;
+    hd.v_expected_h = S + n_squeeze + I * m;
     hd.n_vals = hd.v_expected_h + 1;
     for (auto& q : queries)
       if (q.eval_val == V_EXPECTED_H_TMP) q.eval_val = hd.v_expected_h;
@@ -520,22 +529,24 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
     hd.inst_max_rot = (u32)max_rot;
     hd.inst_min_rot_abs = (u32)(-(int64_t)min_rot);
     std::vector<InstQuery> instq;
-    for (auto& q : instance_queries) instq.push_back({q.first, (u32)(max_rot - q.second)});
+    for (u32 pi = 0; pi < m; pi++)
+      for (auto& q : instance_queries) instq.push_back({pi * num_instance_columns + q.first, (u32)(max_rot - q.second)});
 
     // ---------------- expressions (lib.rs:273-344)
     std::vector<PolyRange> polys;
     std::vector<PolyTerm> terms;
     std::vector<PolyVar> vars;
     std::vector<u32> polylist;
-    auto var_val = [&](u32 var) -> u32 {
-      if (var < A + F) return var;  // advice evals then fixed evals are contiguous proof scalars
-      if (var < A + F + I) return hd.v_inst + (var - A - F);
+    auto var_val = [&](u32 pi, u32 var) -> u32 {
+      if (var < A) return s_advice + pi * A + var;  // this instance's advice evals
+      if (var < A + F) return s_fixed + (var - A);
+      if (var < A + F + I) return hd.v_inst + pi * I + (var - A - F);
       H2V_REQUIRE(var < A + F + I + num_challenges, "polynomial variable index out of range");
       u32 sq = user_ch_sq[var - A - F - I];
       H2V_REQUIRE(sq != 0xFFFFFFFFu, "challenge is never squeezed");
       return hd.v_chal + sq;
     };
-    auto add_poly = [&](const Poly& p) -> u32 {
+    auto add_poly = [&](u32 pi, const Poly& p) -> u32 {
       H2V_REQUIRE(!p.terms.empty(), "empty polynomial (reference unwraps the first term)");
       PolyRange pr2;
       pr2.term_begin = (u32)terms.size();
@@ -544,7 +555,7 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
         PolyTerm pt;
         pt.coeff = c_coeff + t.first;
         pt.var_begin = (u32)vars.size();
-        for (auto& v : t.second) vars.push_back({var_val(v.first), v.second});
+        for (auto& v : t.second) vars.push_back({var_val(pi, v.first), v.second});
         pt.var_end = (u32)vars.size();
         terms.push_back(pt);
       }
@@ -553,52 +564,55 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
       return (u32)polys.size() - 1;
     };
     std::vector<ExprOp> eops;
-    for (auto& g_ : gates) eops.push_back({E_GATE, add_poly(g_), 0, 0, 0, 0});
     std::vector<PermCol> permcols;
-    if (n_sets) {
-      eops.push_back({E_PERM_FIRST, perm_eval(0, 0), 0, 0, 0, 0});
-      eops.push_back({E_PERM_LAST, perm_eval(n_sets - 1, 0), 0, 0, 0, 0});
-      for (u32 s = 1; s < n_sets; s++) eops.push_back({E_PERM_LINK, perm_eval(s, 0), perm_eval(s - 1, 2), 0, 0, 0});
-      for (u32 i = 0; i < n_perm; i++) {  // get_any_query_index(column, Rotation::cur()), vk.rs:413-455
-        u32 idx = perm_cols[i].first, typ = perm_cols[i].second, val = 0xFFFFFFFFu;
-        if (typ == 255) {
-          for (u32 q = 0; q < F && val == 0xFFFFFFFFu; q++)
-            if (fixed_queries[q].first == idx && fixed_queries[q].second == 0) val = s_fixed + q;
-        } else if (typ == 254) {
-          for (u32 q = 0; q < I && val == 0xFFFFFFFFu; q++)
-            if (instance_queries[q].first == idx && instance_queries[q].second == 0) val = hd.v_inst + q;
-        } else {
-          for (u32 q = 0; q < A && val == 0xFFFFFFFFu; q++)
-            if (advice_queries[q].col == idx && advice_queries[q].phase == typ && advice_queries[q].rot == 0) val = s_advice + q;
-        }
-        H2V_REQUIRE(val != 0xFFFFFFFFu, "permutation column has no query at the current rotation (reference panics)");
-        permcols.push_back({val, s_sigma + i});
-      }
-      for (u32 s = 0; s < n_sets; s++) {
-        u32 b = s * chunk_len, e = std::min(n_perm, b + chunk_len);
-        eops.push_back({E_PERM_PROD, perm_eval(s, 0), perm_eval(s, 1), b, e, add_const(delta.pow_u64((u64)s * chunk_len))});
-      }
-    }
     std::vector<LookupDesc> lks;
-    for (int pass = 0; pass < 2; pass++) {
-      auto& args = pass == 0 ? lookups : shuffles;
-      for (u32 a = 0; a < args.size(); a++) {
-        LookupDesc d;
-        memset(&d, 0, sizeof(d));
-        d.in_begin = (u32)polylist.size();
-        for (auto& p : args[a].in) polylist.push_back(add_poly(p));
-        d.in_end = d.tab_begin = (u32)polylist.size();
-        for (auto& p : args[a].tab) polylist.push_back(add_poly(p));
-        d.tab_end = (u32)polylist.size();
-        if (pass == 0) {
-          const u32 e = s_lookup + 5 * a;
-          d.v_prod = e; d.v_prod_next = e + 1; d.v_in = e + 2; d.v_in_inv = e + 3; d.v_tab = e + 4;
-        } else {
-          const u32 e = s_shuffle + 2 * a;
-          d.v_prod = e; d.v_prod_next = e + 1;
+    for (u32 pi = 0; pi < m; pi++) {  // lib.rs:273-344: gates, permutation, lookups, shuffles of instance pi, then the next instance
+      for (auto& g_ : gates) eops.push_back({E_GATE, add_poly(pi, g_), 0, 0, 0, 0});
+      if (n_sets) {
+        eops.push_back({E_PERM_FIRST, perm_eval(pi, 0, 0), 0, 0, 0, 0});
+        eops.push_back({E_PERM_LAST, perm_eval(pi, n_sets - 1, 0), 0, 0, 0, 0});
+        for (u32 s = 1; s < n_sets; s++) eops.push_back({E_PERM_LINK, perm_eval(pi, s, 0), perm_eval(pi, s - 1, 2), 0, 0, 0});
+        const u32 pc0 = (u32)permcols.size();
+        for (u32 i = 0; i < n_perm; i++) {  // get_any_query_index(column, Rotation::cur()), vk.rs:413-455
+          u32 idx = perm_cols[i].first, typ = perm_cols[i].second, val = 0xFFFFFFFFu;
+          if (typ == 255) {
+            for (u32 q = 0; q < F && val == 0xFFFFFFFFu; q++)
+              if (fixed_queries[q].first == idx && fixed_queries[q].second == 0) val = s_fixed + q;
+          } else if (typ == 254) {
+            for (u32 q = 0; q < I && val == 0xFFFFFFFFu; q++)
+              if (instance_queries[q].first == idx && instance_queries[q].second == 0) val = hd.v_inst + pi * I + q;
+          } else {
+            for (u32 q = 0; q < A && val == 0xFFFFFFFFu; q++)
+              if (advice_queries[q].col == idx && advice_queries[q].phase == typ && advice_queries[q].rot == 0) val = s_advice + pi * A + q;
+          }
+          H2V_REQUIRE(val != 0xFFFFFFFFu, "permutation column has no query at the current rotation (reference panics)");
+          permcols.push_back({val, s_sigma + i});
         }
-        lks.push_back(d);
-        eops.push_back({pass == 0 ? (u32)E_LOOKUP : (u32)E_SHUFFLE, (u32)lks.size() - 1, 0, 0, 0, 0});
+        for (u32 s = 0; s < n_sets; s++) {
+          u32 b = s * chunk_len, e = std::min(n_perm, b + chunk_len);
+          eops.push_back({E_PERM_PROD, perm_eval(pi, s, 0), perm_eval(pi, s, 1), pc0 + b, pc0 + e, add_const(delta.pow_u64((u64)s * chunk_len))});
+        }
+      }
+      for (int pass = 0; pass < 2; pass++) {
+        auto& args = pass == 0 ? lookups : shuffles;
+        for (u32 a = 0; a < args.size(); a++) {
+          LookupDesc d;
+          memset(&d, 0, sizeof(d));
+          d.in_begin = (u32)polylist.size();
+          for (auto& p : args[a].in) polylist.push_back(add_poly(pi, p));
+          d.in_end = d.tab_begin = (u32)polylist.size();
+          for (auto& p : args[a].tab) polylist.push_back(add_poly(pi, p));
+          d.tab_end = (u32)polylist.size();
+          if (pass == 0) {
+            const u32 e = s_lookup + 5 * (pi * L + a);
+            d.v_prod = e; d.v_prod_next = e + 1; d.v_in = e + 2; d.v_in_inv = e + 3; d.v_tab = e + 4;
+          } else {
+            const u32 e = s_shuffle + 2 * (pi * SH + a);
+            d.v_prod = e; d.v_prod_next = e + 1;
+          }
+          lks.push_back(d);
+          eops.push_back({pass == 0 ? (u32)E_LOOKUP : (u32)E_SHUFFLE, (u32)lks.size() - 1, 0, 0, 0, 0});
+        }
       }
     }
 
@@ -749,7 +763,7 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
     info.n_scalars = S;
     info.n_challenges = n_squeeze;
     info.proof_len = hd.proof_len;
-    info.n_inst_cols = num_instance_columns;
+    info.n_inst_cols = num_instance_columns * m;
     info.n_shared = hd.n_shared;
     info.n_mo = n_mo;
     return 0;

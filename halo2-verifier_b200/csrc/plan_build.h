@@ -21,8 +21,10 @@ struct PlanInfo {
   u32 q_left[32], q_right[32];
 };
 
+// circuit_instances: how many circuit instances one proof transcript carries (`instances.len()` of verify_proof; 1 in
+// every reference test)
 int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk, size_t vk_len, int vk_fmt, int multiopen,
-               int hash, std::vector<u8>& blob, PlanInfo& info, std::string& err);
+               int hash, std::vector<u8>& blob, PlanInfo& info, std::string& err, u32 circuit_instances = 1);
 
 // Miller-line tables of the G2 multiples [2^(c w)] Q used by the window-decomposed pairing check
 // (pairing_cta.cuh): pairs 0..W0-1 = right channel (Q = -G2, c = c0), then W1 pairs of the left

@@ -45,6 +45,14 @@ typedef struct h2v_ctx h2v_ctx;
  * parses both byte strings, compiles the device plan, uploads it to `device`. */
 int h2v_ctx_create(h2v_ctx** out, const uint8_t* params, size_t params_len, int params_format,
                    const uint8_t* vk, size_t vk_len, int vk_format, int multiopen, int hash, int device);
+/* Same for proofs that carry `circuit_instances` circuit instances in ONE transcript (`instances.len()` of the
+ * reference's verify_proof, lib.rs:63,92,117,134; h2v_ctx_create = 1): the per-instance commitments, evaluations,
+ * expressions and queries repeat in the reference's interleaving.  The instance scalars of a proof are then laid out
+ * instance-major (instance 0: column 0, column 1, ...; instance 1: ...), i.e. as circuit_instances x columns "columns":
+ * h2v_ctx_info reports that product as the column count and h2v_batch_set_columns takes that many lengths per proof. */
+int h2v_ctx_create_multi(h2v_ctx** out, const uint8_t* params, size_t params_len, int params_format,
+                         const uint8_t* vk, size_t vk_len, int vk_format,
+                         int multiopen, int hash, int device, uint32_t circuit_instances);
 /* Same from the `VALID_VK.bin` bundle the reference's tooling writes (serialize/examples/vector_mul.rs:374-393):
  * ParamsKZG::write (Processed form, 164 bytes) immediately followed by VerifyingKey::write(SerdeFormat::RawBytes). */
 int h2v_ctx_create_from_bundle(h2v_ctx** out, const uint8_t* bundle, size_t bundle_len, int multiopen, int hash, int device);

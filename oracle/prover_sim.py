@@ -137,20 +137,21 @@ def query_rotations(vk):
     return rots
 
 
-def proof_layout(vk, multiopen="shplonk"):
+def proof_layout(vk, multiopen="shplonk", m=1):
     """Item kinds ('P' compressed point / 'S' scalar) in transcript read order (lib.rs:86-253,
-    then shplonk.rs:198-200 or gwc.rs:72-74); second value = index of the first multiopen item."""
+    then shplonk.rs:198-200 or gwc.rs:72-74); second value = index of the first multiopen item.
+    m = circuit instances carried by the proof (`instances.len()`): the per-instance items repeat m times."""
     cs = vk.cs
     chunk = vk.cs_degree - 2
     n_sets = -(-len(cs.permutation_columns) // chunk) if cs.permutation_columns else 0
     items = []
     for phase in cs.phases():
-        items += ["P"] * sum(1 for p in cs.advice_column_phase if p == phase)
-    items += ["P"] * (2 * len(cs.lookups) + n_sets + len(cs.lookups) + len(cs.shuffles) + 1)
+        items += ["P"] * (m * sum(1 for p in cs.advice_column_phase if p == phase))
+    items += ["P"] * (m * (2 * len(cs.lookups) + n_sets + len(cs.lookups) + len(cs.shuffles)) + 1)
     items += ["P"] * vk.quotient_poly_degree
-    items += ["S"] * (len(cs.advice_queries) + len(cs.fixed_queries) + 1 + len(vk.permutation_commitments))
-    items += ["S"] * (3 * n_sets - 1 if n_sets else 0)
-    items += ["S"] * (5 * len(cs.lookups) + 2 * len(cs.shuffles))
+    items += ["S"] * (m * len(cs.advice_queries) + len(cs.fixed_queries) + 1 + len(vk.permutation_commitments))
+    items += ["S"] * (m * (3 * n_sets - 1 if n_sets else 0))
+    items += ["S"] * (m * (5 * len(cs.lookups) + 2 * len(cs.shuffles)))
     first_multiopen = len(items)
     if multiopen == "shplonk":
         items += ["P", "P"]
@@ -166,7 +167,7 @@ def random_instances(vk, rng, rows=10):
 
 def simulate_proof(params, vk, dlogs, s, instances, rng, multiopen="shplonk", hash_kind="blake2b"):
     """Returns accepting proof bytes for (params, vk, instances)."""
-    items, first_mo = proof_layout(vk, multiopen)
+    items, first_mo = proof_layout(vk, multiopen, len(instances))
     slot_dlogs = []
     body = bytearray()
     for kind in items[:first_mo]:
@@ -241,11 +242,11 @@ CORRUPTIONS = (
 )
 
 
-def corrupt(proof, vk, kind, rng, multiopen="shplonk"):
-    """Returns (corrupted proof, expected status)."""
+def corrupt(proof, vk, kind, rng, multiopen="shplonk", m=1):
+    """Returns (corrupted proof, expected status); m = circuit instances carried by the proof."""
     from verifier import CONSTRAINT_SYSTEM_FAILURE, OPENING, TRANSCRIPT
 
-    items, first_mo = proof_layout(vk, multiopen)
+    items, first_mo = proof_layout(vk, multiopen, m)
     b = bytearray(proof)
     pre_points = [i for i, k in enumerate(items[:first_mo]) if k == "P"]
     pre_scalars = [i for i, k in enumerate(items[:first_mo]) if k == "S"]

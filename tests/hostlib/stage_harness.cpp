@@ -11,6 +11,9 @@ extern "C" {
 int s_build(const u8* params, size_t pl, int pf, const u8* vk, size_t vl, int vf, int mo, int hash) {
   return build_plan(params, pl, pf, vk, vl, vf, mo, hash, g_blob, g_info, g_err);
 }
+int s_build_m(const u8* params, size_t pl, int pf, const u8* vk, size_t vl, int vf, int mo, int hash, u32 circuit_instances) {
+  return build_plan(params, pl, pf, vk, vl, vf, mo, hash, g_blob, g_info, g_err, circuit_instances);
+}
 const char* s_err() { return g_err.c_str(); }
 void s_info(u32* out) { memcpy(out, &g_info, 8 * sizeof(u32)); }
 // returns status; outputs canonical LE: challenges [C][32], right [P][32], shared [Sh][32], left [n_mo][32],

@@ -498,3 +498,36 @@ def test_verify_batches_sharded_world1(pkg):
         assert verdicts == [False, True]
         want = [orc.verify_proof(params, vk, inst, p, "gwc", "keccak").status for inst, p in zip(instances, bad)]
         assert status[0] + status[1] == want and status[0][3] == orc.CONSTRAINT_SYSTEM_FAILURE
+
+
+@pytest.mark.parametrize("shape,k,m,mo", [("mix", 6, 3, "shplonk"), ("vm", 8, 2, "gwc")])
+def test_multi_instance_proofs(pkg, shape, k, m, mo):
+    """Proofs carrying m circuit instances in one transcript (h2v_ctx_create_multi; `instances.len() = m` in the reference's
+    verify_proof): statuses, challenges, MSM scalars, per-proof and folded accumulators against the oracle, with one
+    corrupted proof and one proof whose LAST instance has a wrong public input."""
+    from workloads import setup
+
+    params, vk, dl, s = setup(shape, k)
+    rng = random.Random(f"gpu-multi-{shape}{k}{m}{mo}")
+    n = 5
+    insts = [[sim.random_instances(vk, rng, 6)[0] for _ in range(m)] for _ in range(n)]
+    proofs = [sim.simulate_proof(params, vk, dl, s, inst, rng, mo, "blake2b") for inst in insts]
+    proofs[1], _ = sim.corrupt(proofs[1], vk, "eval_flip", rng, mo, m)
+    if vk.cs.num_instance_columns:
+        insts[3] = [[list(c) for c in inst] for inst in insts[3]]
+        insts[3][-1][0][0] = (insts[3][-1][0][0] + 1) % bn.R
+    rs = [rng.randrange(1, bn.R) for _ in range(n)]
+    bv = pkg.BatchVerifier(pkg.ParamsKZG.from_bytes(params.to_bytes()), pkg.VerifyingKey.from_bytes(vk.to_bytes(F.RAW_BYTES), F.RAW_BYTES),
+                           mo, "blake2b", device=0, circuit_instances=m)
+    with bv:
+        assert bv.proof_len == len(proofs[0]) and bv.n_inst_cols == m * vk.cs.num_instance_columns
+        res = bv.verify_batch(proofs, insts, rlc_scalars=rs, want_challenges=True, want_accum=True, want_batch_accum=True, want_scalars=True)
+        want = [orc.verify_proof(params, vk, inst, p, mo, "blake2b") for inst, p in zip(insts, proofs)]
+        assert res.status == [w.status for w in want] and res.status[1] == 4 and res.status[0] == 0
+        C, nb = bv.n_challenges, bv.n_bases
+        for j, w in enumerate(want):
+            assert split32(res.challenges[32 * C * j:], C) == w.challenges
+            assert split32(res.msm_scalars[32 * nb * j:], nb) == oracle_scalars(vk, w, bv.n_points, bv.n_mo)
+            assert res.accum[128 * j: 128 * j + 128] == enc_point(w.L) + enc_point(w.R)
+        L, R_, ok = orc.accumulate(params, want, rs)
+        assert res.batch_accum == enc_point(L) + enc_point(R_) and not ok and not res.verdict

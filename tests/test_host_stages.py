@@ -165,6 +165,52 @@ def test_stages_match_oracle(stage, shape, k, mo, hk):
     _run_case(stage, shape, k, mo, hk, F.RAW_BYTES if mo == "shplonk" else F.PROCESSED, corruptions=(hk == "blake2b" and shape in ("vm", "mix")))
 
 
+@pytest.mark.parametrize("shape,k,m", [("vm", 8, 2), ("mix", 6, 3), ("sh", 8, 2)])
+@pytest.mark.parametrize("mo", ["shplonk", "gwc"])
+def test_stages_multi_instance_transcripts(stage, shape, k, m, mo):
+    """Proofs that carry m circuit instances in one transcript (`instances.len() = m`, lib.rs:63,92,117,134): the plan
+    compiler repeats the per-instance commitments, evaluations, expressions and queries in the reference's interleaving.
+    Statuses, challenges, MSM scalars and accumulators against the Python oracle, plus every corruption class."""
+    params, vk, dl, s = setup(shape, k)
+    rng = random.Random(f"multi-{shape}{k}{m}{mo}")
+    pb, vb = params.to_bytes(), vk.to_bytes(F.RAW_BYTES)
+    assert stage.s_build_m(pb, len(pb), 0, vb, len(vb), F.RAW_BYTES, 0 if mo == "shplonk" else 1, 0, m) == 0, stage.s_err()
+    info = (ctypes.c_uint32 * 8)()
+    stage.s_info(info)
+    _k, P, _S, C, plen, nic, nsh, nmo = list(info)
+    assert nic == m * vk.cs.num_instance_columns
+    insts = [sim.random_instances(vk, rng, 10)[0] for _ in range(m)]
+    proof = sim.simulate_proof(params, vk, dl, s, insts, rng, mo, "blake2b")
+    assert plen == len(proof) == 32 * len(sim.proof_layout(vk, mo, m)[0])
+
+    def call(proof, insts):
+        ib = b"".join(bn.fr_to_repr(v) for inst in insts for col in inst for v in col)  # instance-major, lib.rs:76-82
+        tot = sum(len(c) for inst in insts for c in inst)
+        ch = (ctypes.c_uint8 * (32 * C))(); rt = (ctypes.c_uint8 * (32 * P))(); sh = (ctypes.c_uint8 * (32 * nsh))()
+        lf = (ctypes.c_uint8 * (32 * nmo))(); LR = (ctypes.c_uint8 * 128)(); ok = ctypes.c_int(0)
+        st = stage.s_verify_one(proof, len(proof), ib, tot, None, -1, ch, rt, sh, lf, LR, ctypes.byref(ok))
+        g = lambda a, i: int.from_bytes(bytes(a[32 * i: 32 * i + 32]), "little")
+        return st, [g(ch, i) for i in range(C)], [g(rt, i) for i in range(P)] + [g(sh, i) for i in range(nsh)] + [g(lf, i) for i in range(nmo)], [g(LR, i) for i in range(4)]
+
+    st, ch, scalars, LR = call(proof, insts)
+    res = orc.verify_proof(params, vk, insts, proof, mo, "blake2b")
+    assert st == res.status == 0 and ch == res.challenges
+    assert scalars == oracle_scalars(vk, res, P, nmo)
+    assert (LR[0], LR[1]) == res.L and (LR[2], LR[3]) == res.R
+    for kind in sim.CORRUPTIONS:
+        bad, exp = sim.corrupt(proof, vk, kind, rng, mo, m)
+        assert orc.verify_proof(params, vk, insts, bad, mo, "blake2b").status == exp
+        assert call(bad, insts)[0] == exp, kind
+    if vk.cs.num_instance_columns:  # a wrong public input of the LAST instance
+        bad_insts = [[list(c) for c in inst] for inst in insts]
+        bad_insts[-1][0][0] = (bad_insts[-1][0][0] + 1) % bn.R
+        assert call(proof, bad_insts)[0] == orc.verify_proof(params, vk, bad_insts, proof, mo, "blake2b").status == 4
+    # the single-instance plan rejects / differs on the same bytes: the layouts are not interchangeable
+    assert stage.s_build(pb, len(pb), 0, vb, len(vb), F.RAW_BYTES, 0 if mo == "shplonk" else 1, 0) == 0
+    stage.s_info(info)
+    assert list(info)[4] != plen
+
+
 def test_stages_k18_lookup_heavy(stage):
     _run_case(stage, "k18", 18, "shplonk", "blake2b", F.RAW_BYTES, corruptions=False)
 
