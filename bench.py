@@ -122,6 +122,22 @@ def algorithmic_mm(bv, n, geom):
     return mm
 
 
+def plan_launch_sets(steps, fold_groups, n_ctx):
+    """How exactly `steps` batches are timed with `fold_groups` batches per launch set on `n_ctx` contexts.
+    Returns (G, G_rem, full, assign): `full` launch sets of G groups and, when G does not divide steps, ONE launch set
+    of the remaining G_rem groups, which the LAST context runs (the other contexts share the full sets); assign[i] =
+    context of launch set i.  A single context cannot hold two resident uploads: G shrinks to a divisor of steps."""
+    G = max(1, min(fold_groups, steps))
+    if n_ctx == 1:
+        while steps % G:
+            G -= 1
+    G_rem = steps % G
+    full = steps // G
+    n_full = n_ctx - 1 if G_rem else n_ctx
+    assign = [i % n_full for i in range(full)] + ([n_ctx - 1] if G_rem else [])
+    return G, G_rem, full, assign
+
+
 def bucket_sum_mm(bv, n, geom):
     """k_msm_bucket_sum alone: one mixed addition (7 MM + 4 S, counted as 11 MM) per bucket entry"""
     W0, W1 = geom["windows"] & 0xFFFF, geom["windows"] >> 16
@@ -171,13 +187,9 @@ def run_ours(args):
     gen_s = time.time() - t0
     # fold groups: G consecutive independent batches per set of kernel launches (own fold and own pairing check each;
     # at N > 1 group q is this rank's shard of global batch q); the packed upload alternates the two distinct batches
-    G = max(1, min(args.fold_groups, args.steps))
-    if n_ctx == 1:
-        while args.steps % G:
-            G -= 1
     # exactly `steps` batches are timed: steps // G launch sets of G groups, and, when G does not divide steps, ONE launch
     # set of the remaining groups, which the last context runs (the other contexts share the full sets)
-    G_rem = args.steps % G
+    G, G_rem, full, assign = plan_launch_sets(args.steps, args.fold_groups, n_ctx)
 
     def packed_groups(first, count):
         pr, ins = [], []
@@ -354,10 +366,7 @@ def run_ours(args):
         return [float(x) for x in t]
 
     W = max(args.warmup, 3)
-    full = args.steps // G  # launch sets of G batches each; a step is ONE batch of n proofs per GPU
-    runs = full + (1 if G_rem else 0)
-    n_full = n_ctx - 1 if G_rem else n_ctx  # contexts that run the full sets
-    assign = [i % n_full for i in range(full)] + ([n_ctx - 1] if G_rem else [])
+    runs = full + (1 if G_rem else 0)  # launch sets; a step is ONE batch of n proofs per GPU
     warm_assign = [ci for _ in range(W) for ci in range(n_ctx)]
     total = n * world * args.steps
     # ---------------- device-resident throughput (`value`)
