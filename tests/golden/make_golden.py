@@ -44,6 +44,29 @@ for name, shape, k, mo, hk, vkfmt in CASES:
     json.dump(out, open(os.path.join(HERE, name + ".json"), "w"), indent=0)
     print(name, [r.status for r in results], "folded_ok", ok)
 
+# ---- proofs carrying m = 3 circuit instances in one transcript (h2v_ctx_create_multi; `instances.len() = 3` in the reference)
+for name, shape, k, mo, hk, vkfmt, m in [("mix_k6_shplonk_blake2b_m3", "mix", 6, "shplonk", "blake2b", F.RAW_BYTES, 3)]:
+    params, vk, dl, s = setup(shape, k)
+    rng = random.Random("golden-" + name)
+    n = 3
+    instances = [[sim.random_instances(vk, rng, 4 + j)[0] for _ in range(m)] for j in range(n)]
+    proofs = [sim.simulate_proof(params, vk, dl, s, inst, rng, mo, hk) for inst in instances]
+    proofs[1], _ = sim.corrupt(proofs[1], vk, "eval_flip", rng, mo, m)
+    rs = [rng.randrange(1, bn.R) for _ in range(n)]
+    results = [orc.verify_proof(params, vk, inst, p, mo, hk) for inst, p in zip(instances, proofs)]
+    items, first_mo = sim.proof_layout(vk, mo, m)
+    n_points = items.count("P"); n_mo = len(items) - first_mo
+    L, Rr, ok = orc.accumulate(params, results, rs)
+    out = {"shape": shape, "k": k, "multiopen": mo, "hash": hk, "vk_format": vkfmt, "circuit_instances": m,
+           "params": params.to_bytes().hex(), "vk": vk.to_bytes(vkfmt).hex(),
+           "rlc_scalars": [hex(r) for r in rs], "folded": (enc_point(L) + enc_point(Rr)).hex(), "folded_ok": ok, "proofs": []}
+    for inst, p, res in zip(instances, proofs, results):  # "instances": [circuit instance][column][row]
+        out["proofs"].append({"proof": p.hex(), "instances": [[[hex(v) for v in col] for col in ci] for ci in inst], "status": res.status,
+                              "challenges": [hex(c) for c in res.challenges], "accum": (enc_point(res.L) + enc_point(res.R)).hex(),
+                              "msm_scalars": [hex(v) for v in oracle_scalars(vk, res, n_points, n_mo)]})
+    json.dump(out, open(os.path.join(HERE, name + ".json"), "w"), indent=0)
+    print(name, [r.status for r in results], "folded_ok", ok)
+
 # ---- honest proofs of the vector_mul circuit (oracle/honest_prover.py: real witness, real polynomials, k = 8 fixture SRS secret)
 import honest_prover as hp
 rng = random.Random("golden-honest")

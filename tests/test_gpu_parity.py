@@ -107,9 +107,13 @@ def test_golden_vectors(pkg):
         g = json.load(open(os.path.join(HERE, "golden", fn)))
         bv = pkg.BatchVerifier(pkg.ParamsKZG.from_bytes(bytes.fromhex(g["params"])),
                                pkg.VerifyingKey.from_bytes(bytes.fromhex(g["vk"]), pkg.SerdeFormat(g["vk_format"])),
-                               g["multiopen"], "keccak256" if g["hash"] == "keccak" else g["hash"], device=0)
+                               g["multiopen"], "keccak256" if g["hash"] == "keccak" else g["hash"], device=0,
+                               circuit_instances=g.get("circuit_instances", 1))
         proofs = [bytes.fromhex(e["proof"]) for e in g["proofs"]]
-        insts = [[[int(v, 16) for v in col] for col in e["instances"]] for e in g["proofs"]]
+        if "circuit_instances" in g:  # [circuit instance][column][row]
+            insts = [[[[int(v, 16) for v in col] for col in ci] for ci in e["instances"]] for e in g["proofs"]]
+        else:
+            insts = [[[int(v, 16) for v in col] for col in e["instances"]] for e in g["proofs"]]
         res = bv.verify_batch(proofs, insts, rlc_scalars=[int(r, 16) for r in g["rlc_scalars"]], want_challenges=True,
                               want_accum=True, want_batch_accum=True, want_scalars=True)
         C, nb = bv.n_challenges, bv.n_bases

@@ -145,6 +145,9 @@ def test_golden_vectors_reproduce():
         params = F.ParamsKZG.from_bytes(bytes.fromhex(g["params"]))
         vk = F.VerifyingKey.from_bytes(bytes.fromhex(g["vk"]), g["vk_format"])
         for e in g["proofs"]:
-            inst = [[[int(v, 16) for v in col] for col in e["instances"]]]
+            if "circuit_instances" in g:
+                inst = [[[int(v, 16) for v in col] for col in ci] for ci in e["instances"]]
+            else:
+                inst = [[[int(v, 16) for v in col] for col in e["instances"]]]
             res = orc.verify_proof(params, vk, inst, bytes.fromhex(e["proof"]), g["multiopen"], g["hash"])
             assert res.status == e["status"] and [hex(c) for c in res.challenges] == e["challenges"], fn
