@@ -892,11 +892,13 @@ static int find_query(const h2vo_vk* v, uint32_t idx, uint8_t typ) { /* get_any_
   return -1;
 }
 
+/* m = circuit instances carried by the proof (`instances.len()`, lib.rs:63,92,117,134); the instance columns are laid out
+ * instance-major (ncols = m x instance columns of the VK), everything per instance repeats in the reference's interleaving */
 static void verify_one(const h2vo_vk* v, const uint8_t* proof, size_t plen, const uint8_t* inst, const uint32_t* col_len, uint32_t ncols,
-                       int multiopen, int keccak, int check_pairing, result_t* res) {
+                       uint32_t m, int multiopen, int keccak, int check_pairing, result_t* res) {
   memset(res, 0, sizeof(*res));
   res->L.inf = res->R.inf = 1;
-  if (ncols != v->n_instance) { /* lib.rs:51-55 */
+  if (m == 0 || ncols != v->n_instance * m) { /* lib.rs:51-55 */
     res->status = ST_INVALID_INSTANCES;
     return;
   }
@@ -920,33 +922,34 @@ static void verify_one(const h2vo_vk* v, const uint8_t* proof, size_t plen, cons
   const uint32_t chunk = v->cs_degree - 2; /* permutation.rs:72 */
   const uint32_t n_sets = v->n_perm ? (v->n_perm + chunk - 1) / chunk : 0;
   const uint32_t n_h = v->cs_degree - 1;
-  const uint32_t n_pts_max = v->n_advice + 3 * v->n_lookups + n_sets + v->n_shuffles + 1 + n_h + 8;
+  const uint32_t n_pts_max = m * (v->n_advice + 3 * v->n_lookups + n_sets + v->n_shuffles) + 1 + n_h + 8;
   g1a* P = (g1a*)calloc(n_pts_max, sizeof(g1a));
   uint32_t np = 0;
 #define READ_POINT() (tr_read_point(&tr, &P[np]), (int)np++)
-  int* adv_slot = (int*)malloc(sizeof(int) * (v->n_advice + 1));
+  int* adv_slot = (int*)malloc(sizeof(int) * ((size_t)m * v->n_advice + 1)); /* [pi][column] */
   fe* user_chal = (fe*)calloc(v->n_challenges + 1, sizeof(fe));
   uint8_t max_phase = 0;
   for (uint32_t i = 0; i < v->n_advice; i++)
     if (v->advice_phase[i] > max_phase) max_phase = v->advice_phase[i];
   for (uint32_t ph = 0; ph <= max_phase; ph++) { /* lib.rs:91-109 */
-    for (uint32_t c = 0; c < v->n_advice; c++)
-      if (v->advice_phase[c] == ph) adv_slot[c] = READ_POINT();
+    for (uint32_t pi = 0; pi < m; pi++)
+      for (uint32_t c = 0; c < v->n_advice; c++)
+        if (v->advice_phase[c] == ph) adv_slot[(size_t)pi * v->n_advice + c] = READ_POINT();
     for (uint32_t c = 0; c < v->n_challenges; c++)
       if (v->challenge_phase[c] == ph) user_chal[c] = tr_squeeze(&tr);
   }
   const fe theta = tr_squeeze(&tr);
-  int* lk_in = (int*)malloc(sizeof(int) * (v->n_lookups + 1));
-  int* lk_tab = (int*)malloc(sizeof(int) * (v->n_lookups + 1));
-  int* lk_prod = (int*)malloc(sizeof(int) * (v->n_lookups + 1));
-  int* sh_prod = (int*)malloc(sizeof(int) * (v->n_shuffles + 1));
-  int* pm_slot = (int*)malloc(sizeof(int) * (n_sets + 1));
+  int* lk_in = (int*)malloc(sizeof(int) * ((size_t)m * v->n_lookups + 1)); /* all of these: [pi][index] */
+  int* lk_tab = (int*)malloc(sizeof(int) * ((size_t)m * v->n_lookups + 1));
+  int* lk_prod = (int*)malloc(sizeof(int) * ((size_t)m * v->n_lookups + 1));
+  int* sh_prod = (int*)malloc(sizeof(int) * ((size_t)m * v->n_shuffles + 1));
+  int* pm_slot = (int*)malloc(sizeof(int) * ((size_t)m * n_sets + 1));
   int* h_slot = (int*)malloc(sizeof(int) * (n_h + 1));
-  for (uint32_t i = 0; i < v->n_lookups; i++) lk_in[i] = READ_POINT(), lk_tab[i] = READ_POINT();
+  for (uint32_t i = 0; i < m * v->n_lookups; i++) lk_in[i] = READ_POINT(), lk_tab[i] = READ_POINT();
   const fe beta = tr_squeeze(&tr), gamma = tr_squeeze(&tr);
-  for (uint32_t i = 0; i < n_sets; i++) pm_slot[i] = READ_POINT();
-  for (uint32_t i = 0; i < v->n_lookups; i++) lk_prod[i] = READ_POINT();
-  for (uint32_t i = 0; i < v->n_shuffles; i++) sh_prod[i] = READ_POINT();
+  for (uint32_t i = 0; i < m * n_sets; i++) pm_slot[i] = READ_POINT();
+  for (uint32_t i = 0; i < m * v->n_lookups; i++) lk_prod[i] = READ_POINT();
+  for (uint32_t i = 0; i < m * v->n_shuffles; i++) sh_prod[i] = READ_POINT();
   const int random_slot = READ_POINT(); /* vanishing.rs:49-57 */
   const fe y = tr_squeeze(&tr);
   for (uint32_t i = 0; i < n_h; i++) h_slot[i] = READ_POINT(); /* vanishing.rs:61-73 */
@@ -962,40 +965,49 @@ static void verify_one(const h2vo_vk* v, const uint8_t* proof, size_t plen, cons
   }
   fe* lis = l_i_range(v, &x, &xn, -max_rot, (uint32_t)max_rot + max_len + (uint32_t)(-min_rot));
   const uint32_t nvars = v->n_aq + v->n_fixed + v->n_instance + v->n_challenges;
-  fe* vars = (fe*)calloc(nvars + 1, sizeof(fe)); /* advice | fixed | instance | challenges (vk.rs:490-500) */
-  fe *adv_ev = vars, *fix_ev = vars + v->n_aq, *ins_ev = fix_ev + v->n_fixed;
-  memcpy(ins_ev + v->n_instance, user_chal, sizeof(fe) * v->n_challenges);
-  for (uint32_t qi = 0; qi < v->n_instance; qi++) {
-    uint32_t cbeg = 0;
-    for (uint32_t c = 0; c < v->iq[qi].col && c < ncols; c++) cbeg += col_len[c];
-    const uint32_t clen = v->iq[qi].col < ncols ? col_len[v->iq[qi].col] : 0, off = (uint32_t)(max_rot - v->iq[qi].rot);
-    fe acc, t;
-    memset(&acc, 0, sizeof(acc));
-    for (uint32_t i = 0; i < clen; i++) {
-      fe_mul(&t, &ivals[cbeg + i], &lis[off + i], &FR);
-      fe_add(&acc, &acc, &t, &FR);
+  /* per instance: advice | fixed | instance | challenges (vk.rs:490-500); instance pi at vars + pi * nvars */
+  fe* vars = (fe*)calloc((size_t)m * nvars + 1, sizeof(fe));
+#define ADV_EV(pi) (vars + (size_t)(pi) * nvars)
+#define FIX_EV(pi) (ADV_EV(pi) + v->n_aq)
+#define INS_EV(pi) (FIX_EV(pi) + v->n_fixed)
+  for (uint32_t pi = 0; pi < m; pi++) {
+    memcpy(INS_EV(pi) + v->n_instance, user_chal, sizeof(fe) * v->n_challenges);
+    for (uint32_t qi = 0; qi < v->n_instance; qi++) {
+      const uint32_t col = pi * v->n_instance + v->iq[qi].col;
+      uint32_t cbeg = 0;
+      for (uint32_t c = 0; c < col && c < ncols; c++) cbeg += col_len[c];
+      const uint32_t clen = (v->iq[qi].col < v->n_instance && col < ncols) ? col_len[col] : 0, off = (uint32_t)(max_rot - v->iq[qi].rot);
+      fe acc, t;
+      memset(&acc, 0, sizeof(acc));
+      for (uint32_t i = 0; i < clen; i++) {
+        fe_mul(&t, &ivals[cbeg + i], &lis[off + i], &FR);
+        fe_add(&acc, &acc, &t, &FR);
+      }
+      INS_EV(pi)[qi] = acc;
     }
-    ins_ev[qi] = acc;
   }
   free(lis);
-  for (uint32_t i = 0; i < v->n_aq; i++) tr_read_scalar(&tr, &adv_ev[i]);
-  for (uint32_t i = 0; i < v->n_fixed; i++) tr_read_scalar(&tr, &fix_ev[i]);
+  for (uint32_t pi = 0; pi < m; pi++)
+    for (uint32_t i = 0; i < v->n_aq; i++) tr_read_scalar(&tr, &ADV_EV(pi)[i]);
+  for (uint32_t i = 0; i < v->n_fixed; i++) tr_read_scalar(&tr, &FIX_EV(0)[i]);
+  for (uint32_t pi = 1; pi < m; pi++) memcpy(FIX_EV(pi), FIX_EV(0), sizeof(fe) * v->n_fixed);
+  fe* fix_ev = FIX_EV(0);
   fe random_eval;
   tr_read_scalar(&tr, &random_eval);
   fe* sigma_ev = (fe*)calloc(v->n_perm + 1, sizeof(fe));
   for (uint32_t i = 0; i < v->n_perm; i++) tr_read_scalar(&tr, &sigma_ev[i]);
-  fe(*pm_ev)[3] = calloc(n_sets + 1, sizeof(*pm_ev)); /* eval, next, last (permutation.rs:105-131) */
-  for (uint32_t i = 0; i < n_sets; i++) {
-    tr_read_scalar(&tr, &pm_ev[i][0]);
-    tr_read_scalar(&tr, &pm_ev[i][1]);
-    if (i != n_sets - 1) tr_read_scalar(&tr, &pm_ev[i][2]);
+  fe(*pm_ev_all)[3] = calloc((size_t)m * n_sets + 1, sizeof(*pm_ev_all)); /* [pi][set]: eval, next, last (permutation.rs:105-131) */
+  for (uint32_t i = 0; i < m * n_sets; i++) {
+    tr_read_scalar(&tr, &pm_ev_all[i][0]);
+    tr_read_scalar(&tr, &pm_ev_all[i][1]);
+    if (i % n_sets != n_sets - 1) tr_read_scalar(&tr, &pm_ev_all[i][2]);
   }
-  fe(*lk_ev)[5] = calloc(v->n_lookups + 1, sizeof(*lk_ev)); /* product, product_next, input, input_inv, table */
-  for (uint32_t i = 0; i < v->n_lookups; i++)
-    for (int k = 0; k < 5; k++) tr_read_scalar(&tr, &lk_ev[i][k]);
-  fe(*sh_ev)[2] = calloc(v->n_shuffles + 1, sizeof(*sh_ev));
-  for (uint32_t i = 0; i < v->n_shuffles; i++)
-    for (int k = 0; k < 2; k++) tr_read_scalar(&tr, &sh_ev[i][k]);
+  fe(*lk_ev_all)[5] = calloc((size_t)m * v->n_lookups + 1, sizeof(*lk_ev_all)); /* product, product_next, input, input_inv, table */
+  for (uint32_t i = 0; i < m * v->n_lookups; i++)
+    for (int k = 0; k < 5; k++) tr_read_scalar(&tr, &lk_ev_all[i][k]);
+  fe(*sh_ev_all)[2] = calloc((size_t)m * v->n_shuffles + 1, sizeof(*sh_ev_all));
+  for (uint32_t i = 0; i < m * v->n_shuffles; i++)
+    for (int k = 0; k < 2; k++) tr_read_scalar(&tr, &sh_ev_all[i][k]);
   msm_t hmsm = {0, 0, 0}, left = {0, 0, 0}, right = {0, 0, 0};
   query_t* q = NULL;
   if (tr.failed) {
@@ -1026,9 +1038,14 @@ static void verify_one(const h2vo_vk* v, const uint8_t* proof, size_t plen, cons
     fe_mul(&h, &h, &y, &FR);       \
     fe_add(&h, &h, &(e), &FR);     \
   } while (0)
+    for (uint32_t pi = 0; pi < m && !panic; pi++) { /* lib.rs:273-344: all expressions of instance pi, then the next instance */
+    const fe *vars_pi = ADV_EV(pi), *adv_ev = ADV_EV(pi), *ins_ev = INS_EV(pi);
+    fe(*pm_ev)[3] = pm_ev_all + (size_t)pi * n_sets;
+    fe(*lk_ev)[5] = lk_ev_all + (size_t)pi * v->n_lookups;
+    fe(*sh_ev)[2] = sh_ev_all + (size_t)pi * v->n_shuffles;
     for (uint32_t g = 0; g < v->n_gates && !panic; g++) {
       fe e;
-      if (!eval_poly(v, v->gate_polys[g], vars, nvars, &e)) panic = 1;
+      if (!eval_poly(v, v->gate_polys[g], vars_pi, nvars, &e)) panic = 1;
       else FOLD(e);
     }
     if (n_sets && !panic) { /* permutation.rs:189-288 */
@@ -1081,10 +1098,10 @@ static void verify_one(const h2vo_vk* v, const uint8_t* proof, size_t plen, cons
       memset(&ctab, 0, sizeof(ctab));
       for (uint32_t j = 0; j < a->n && !panic; j++) {
         fe ev;
-        if (!eval_poly(v, a->in_polys[j], vars, nvars, &ev)) panic = 1;
+        if (!eval_poly(v, a->in_polys[j], vars_pi, nvars, &ev)) panic = 1;
         fe_mul(&cin, &cin, &theta, &FR);
         fe_add(&cin, &cin, &ev, &FR);
-        if (!eval_poly(v, a->tab_polys[j], vars, nvars, &ev)) panic = 1;
+        if (!eval_poly(v, a->tab_polys[j], vars_pi, nvars, &ev)) panic = 1;
         fe_mul(&ctab, &ctab, &theta, &FR);
         fe_add(&ctab, &ctab, &ev, &FR);
       }
@@ -1138,6 +1155,7 @@ static void verify_one(const h2vo_vk* v, const uint8_t* proof, size_t plen, cons
         FOLD(e);
       }
     }
+    } /* pi */
     fe xn_m1;
     fe_sub(&xn_m1, &xn, &one, &FR);
     if (panic || fe_is_zero(&xn_m1)) { /* vanishing.rs:100 unwrap */
@@ -1151,7 +1169,7 @@ static void verify_one(const h2vo_vk* v, const uint8_t* proof, size_t plen, cons
       msm_push(&hmsm, &one, &P[h_slot[i]]);
     }
     /* queries (lib.rs:349-414) */
-    const size_t qcap = v->n_aq + 3 * n_sets + 5 * v->n_lookups + 2 * v->n_shuffles + v->n_fixed + v->n_perm + 4;
+    const size_t qcap = (size_t)m * (v->n_aq + 3 * n_sets + 5 * v->n_lookups + 2 * v->n_shuffles) + v->n_fixed + v->n_perm + 4;
     q = (query_t*)calloc(qcap, sizeof(query_t));
     size_t nq = 0;
 #define ADDQ(id, ptr, rot, ev)                      \
@@ -1162,29 +1180,38 @@ static void verify_one(const h2vo_vk* v, const uint8_t* proof, size_t plen, cons
     q[nq].eval = (ev);                              \
     nq++;                                           \
   } while (0)
+    for (uint32_t pi = 0; pi < m; pi++) {
+    const fe* adv_ev = ADV_EV(pi);
+    const int *adv_slot_pi = adv_slot + (size_t)pi * v->n_advice, *pm_slot_pi = pm_slot + (size_t)pi * n_sets;
+    const int *lk_in_pi = lk_in + (size_t)pi * v->n_lookups, *lk_tab_pi = lk_tab + (size_t)pi * v->n_lookups;
+    const int *lk_prod_pi = lk_prod + (size_t)pi * v->n_lookups, *sh_prod_pi = sh_prod + (size_t)pi * v->n_shuffles;
+    fe(*pm_ev)[3] = pm_ev_all + (size_t)pi * n_sets;
+    fe(*lk_ev)[5] = lk_ev_all + (size_t)pi * v->n_lookups;
+    fe(*sh_ev)[2] = sh_ev_all + (size_t)pi * v->n_shuffles;
     for (uint32_t i = 0; i < v->n_aq; i++) {
       if (v->aq[i].col >= v->n_advice) {
         res->status = ST_PANIC;
         goto out;
       }
-      ADDQ(adv_slot[v->aq[i].col], &P[adv_slot[v->aq[i].col]], v->aq[i].rot, adv_ev[i]);
+      ADDQ(adv_slot_pi[v->aq[i].col], &P[adv_slot_pi[v->aq[i].col]], v->aq[i].rot, adv_ev[i]);
     }
     for (uint32_t s = 0; s < n_sets; s++) { /* permutation.rs:290-325 */
-      ADDQ(pm_slot[s], &P[pm_slot[s]], 0, pm_ev[s][0]);
-      ADDQ(pm_slot[s], &P[pm_slot[s]], 1, pm_ev[s][1]);
+      ADDQ(pm_slot_pi[s], &P[pm_slot_pi[s]], 0, pm_ev[s][0]);
+      ADDQ(pm_slot_pi[s], &P[pm_slot_pi[s]], 1, pm_ev[s][1]);
     }
-    for (uint32_t s = n_sets > 0 ? n_sets - 1 : 0; s-- > 0;) ADDQ(pm_slot[s], &P[pm_slot[s]], -(int32_t)(bf + 1), pm_ev[s][2]);
+    for (uint32_t s = n_sets > 0 ? n_sets - 1 : 0; s-- > 0;) ADDQ(pm_slot_pi[s], &P[pm_slot_pi[s]], -(int32_t)(bf + 1), pm_ev[s][2]);
     for (uint32_t i = 0; i < v->n_lookups; i++) { /* lookup.rs:232-271 */
-      ADDQ(lk_prod[i], &P[lk_prod[i]], 0, lk_ev[i][0]);
-      ADDQ(lk_in[i], &P[lk_in[i]], 0, lk_ev[i][2]);
-      ADDQ(lk_tab[i], &P[lk_tab[i]], 0, lk_ev[i][4]);
-      ADDQ(lk_in[i], &P[lk_in[i]], -1, lk_ev[i][3]);
-      ADDQ(lk_prod[i], &P[lk_prod[i]], 1, lk_ev[i][1]);
+      ADDQ(lk_prod_pi[i], &P[lk_prod_pi[i]], 0, lk_ev[i][0]);
+      ADDQ(lk_in_pi[i], &P[lk_in_pi[i]], 0, lk_ev[i][2]);
+      ADDQ(lk_tab_pi[i], &P[lk_tab_pi[i]], 0, lk_ev[i][4]);
+      ADDQ(lk_in_pi[i], &P[lk_in_pi[i]], -1, lk_ev[i][3]);
+      ADDQ(lk_prod_pi[i], &P[lk_prod_pi[i]], 1, lk_ev[i][1]);
     }
     for (uint32_t i = 0; i < v->n_shuffles; i++) { /* shuffle.rs:205-225 */
-      ADDQ(sh_prod[i], &P[sh_prod[i]], 0, sh_ev[i][0]);
-      ADDQ(sh_prod[i], &P[sh_prod[i]], 1, sh_ev[i][1]);
+      ADDQ(sh_prod_pi[i], &P[sh_prod_pi[i]], 0, sh_ev[i][0]);
+      ADDQ(sh_prod_pi[i], &P[sh_prod_pi[i]], 1, sh_ev[i][1]);
     }
+    } /* pi */
     for (uint32_t i = 0; i < v->n_fixed; i++) {
       if (v->fq[i].col >= v->n_fixed_commit) {
         res->status = ST_PANIC;
@@ -1209,15 +1236,22 @@ out:
   res->n_chal = tr.n_chal < 64 ? tr.n_chal : 64;
   memcpy(res->chal, tr.chal, sizeof(fe) * res->n_chal);
   free(tr.chal), free(ivals), free(P), free(adv_slot), free(user_chal), free(lk_in), free(lk_tab), free(lk_prod), free(sh_prod), free(pm_slot), free(h_slot);
-  free(vars), free(sigma_ev), free(pm_ev), free(lk_ev), free(sh_ev), free(hmsm.t), free(left.t), free(right.t), free(q);
+  free(vars), free(sigma_ev), free(pm_ev_all), free(lk_ev_all), free(sh_ev_all), free(hmsm.t), free(left.t), free(right.t), free(q);
 }
 
 /* ============================================================================ C API (ctypes) */
+int h2vo_verify_multi(const h2vo_vk* v, const uint8_t* proof, size_t plen, const uint8_t* inst, const uint32_t* col_len, uint32_t ncols, uint32_t m,
+                      int multiopen, int hash, int check_pairing, uint8_t* challenges, uint32_t* n_challenges, uint8_t* LR);
 /* one proof; col_len[ncols] scalars per instance column.  challenges: up to 64 x 32 B canonical; LR: 128 B affine L | R */
 int h2vo_verify(const h2vo_vk* v, const uint8_t* proof, size_t plen, const uint8_t* inst, const uint32_t* col_len, uint32_t ncols, int multiopen,
                 int hash, int check_pairing, uint8_t* challenges, uint32_t* n_challenges, uint8_t* LR) {
+  return h2vo_verify_multi(v, proof, plen, inst, col_len, ncols, 1, multiopen, hash, check_pairing, challenges, n_challenges, LR);
+}
+/* the same for a proof that carries m circuit instances: col_len[ncols], ncols = m x instance columns, instance-major */
+int h2vo_verify_multi(const h2vo_vk* v, const uint8_t* proof, size_t plen, const uint8_t* inst, const uint32_t* col_len, uint32_t ncols, uint32_t m,
+                      int multiopen, int hash, int check_pairing, uint8_t* challenges, uint32_t* n_challenges, uint8_t* LR) {
   result_t r;
-  verify_one(v, proof, plen, inst, col_len, ncols, multiopen, hash, check_pairing, &r);
+  verify_one(v, proof, plen, inst, col_len, ncols, m, multiopen, hash, check_pairing, &r);
   if (challenges)
     for (uint32_t i = 0; i < r.n_chal; i++) fe_to_repr(challenges + 32 * i, &r.chal[i], &FR);
   if (n_challenges) *n_challenges = r.n_chal;
@@ -1248,7 +1282,7 @@ static void* worker(void* arg) {
       r.L.inf = r.R.inf = 1;
     } else {
       for (uint32_t c = 0; c < j->ncols; c++) cl[c] = (uint32_t)(tot / j->ncols);
-      verify_one(j->v, j->proofs + j->poff[i], (size_t)(j->poff[i + 1] - j->poff[i]), j->inst + 32 * j->ioff[i], cl, j->ncols, j->multiopen, j->hash,
+      verify_one(j->v, j->proofs + j->poff[i], (size_t)(j->poff[i + 1] - j->poff[i]), j->inst + 32 * j->ioff[i], cl, j->ncols, 1, j->multiopen, j->hash,
                  j->check_pairing, &r);
     }
     j->status[i] = (uint8_t)r.status;

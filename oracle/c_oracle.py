@@ -29,6 +29,8 @@ def load():
     lib.h2vo_error.restype = ctypes.c_char_p
     lib.h2vo_verify.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, vp, ctypes.c_uint32, ctypes.c_int, ctypes.c_int,
                                 ctypes.c_int, vp, vp, vp]
+    lib.h2vo_verify_multi.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, vp, vp, vp]
     lib.h2vo_verify_many.argtypes = [vp, ctypes.c_uint32, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp,
                                      ctypes.c_uint32, ctypes.POINTER(ctypes.c_double)]
     lib.h2vo_fold.argtypes = [vp, ctypes.c_uint32, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int)]
@@ -69,6 +71,20 @@ class COracle:
         lr = ctypes.create_string_buffer(128)
         st = self.lib.h2vo_verify(self.h, proof, len(proof), inst, cl, len(instance_columns), _MO[multiopen], _HK[hash_kind],
                                   1 if check_pairing else 0, ch, ctypes.byref(nch), lr)
+        chal = [int.from_bytes(ch.raw[32 * i: 32 * i + 32], "little") for i in range(nch.value)]
+        return st, chal, lr.raw
+
+    def verify_multi(self, proof: bytes, instances, multiopen="shplonk", hash_kind="blake2b", check_pairing=True):
+        """A proof that carries len(instances) circuit instances (`instances`: [instance][column][row] ints, the
+        `instances` argument of the reference's verify_proof).  Returns (status, challenges, L|R bytes)."""
+        cols = [col for inst in instances for col in inst]
+        inst = b"".join(int(v).to_bytes(32, "little") for col in cols for v in col)
+        cl = (ctypes.c_uint32 * max(1, len(cols)))(*[len(c) for c in cols])
+        ch = ctypes.create_string_buffer(64 * 32)
+        nch = ctypes.c_uint32(0)
+        lr = ctypes.create_string_buffer(128)
+        st = self.lib.h2vo_verify_multi(self.h, proof, len(proof), inst, cl, len(cols), len(instances), _MO[multiopen], _HK[hash_kind],
+                                        1 if check_pairing else 0, ch, ctypes.byref(nch), lr)
         chal = [int.from_bytes(ch.raw[32 * i: 32 * i + 32], "little") for i in range(nch.value)]
         return st, chal, lr.raw
 

@@ -79,3 +79,38 @@ def test_c_oracle_k18_lookup_heavy(clib):
     want = orc.verify_proof(params, vk, instances[0], proofs[0])
     st, chal, lr = co.verify(proofs[0], instances[0][0])
     assert (st, chal, lr) == (want.status, want.challenges, enc_point(want.L) + enc_point(want.R)) and st == 0
+
+
+@pytest.mark.parametrize("shape,k,m", [("vm", 8, 2), ("mix", 6, 3), ("sh", 8, 2)])
+@pytest.mark.parametrize("mo", ["shplonk", "gwc"])
+def test_c_oracle_multi_instance_proofs(clib, shape, k, m, mo):
+    """Proofs that carry m circuit instances (`instances.len() = m`): the C restatement against the Python one on valid
+    proofs, every corruption class, and a wrong public input in the last instance."""
+    from workloads import setup
+
+    params, vk, dl, s = setup(shape, k)
+    rng = random.Random(f"c-multi-{shape}{k}{m}{mo}")
+    co = c_oracle.COracle(params.to_bytes(), 0, vk.to_bytes(1), 1)
+    insts = [sim.random_instances(vk, rng, 7)[0] for _ in range(m)]
+    proof = sim.simulate_proof(params, vk, dl, s, insts, rng, mo, "blake2b")
+    cases = [(proof, insts)] + [(sim.corrupt(proof, vk, kind, rng, mo, m)[0], insts) for kind in sim.CORRUPTIONS]
+    if vk.cs.num_instance_columns:
+        wrong = [[list(c) for c in inst] for inst in insts]
+        wrong[-1][0][0] = (wrong[-1][0][0] + 1) % bn.R
+        cases.append((proof, wrong))
+        cases.append((proof, insts[:-1]))  # one instance short: InvalidInstances for this m
+    for p, ins in cases:
+        want = orc.verify_proof(params, vk, ins, p, mo, "blake2b")
+        cols = [col for inst in ins for col in inst]
+        if len(ins) != m:  # the C entry point is told m; a missing instance shows up as a wrong column count
+            inst_b = b"".join(int(v).to_bytes(32, "little") for col in cols for v in col)
+            import ctypes
+            cl = (ctypes.c_uint32 * max(1, len(cols)))(*[len(c) for c in cols])
+            st = co.lib.h2vo_verify_multi(co.h, p, len(p), inst_b, cl, len(cols), m, 0 if mo == "shplonk" else 1, 0, 1, None, None, None)
+            assert st == orc.INVALID_INSTANCES
+            continue
+        st, chal, lr = co.verify_multi(p, ins, mo, "blake2b")
+        assert st == want.status and chal == want.challenges
+        if want.status in (orc.OK, orc.CONSTRAINT_SYSTEM_FAILURE):
+            assert lr == enc_point(want.L) + enc_point(want.R)
+    co.close()
