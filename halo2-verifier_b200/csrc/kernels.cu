@@ -1,17 +1,19 @@
 // CUDA kernels (sm_100a) and the C ABI of the batch verifier.  See include/h2v.h for the contract and
 // DESIGN.md for the data layout and per-kernel rooflines.
 //
-// Pipeline of one batch (all on the context's stream, no host round trip until the verdict):
+// Pipeline of one launch set = G fold groups of n proofs (G = 1: one batch), all on the context's stream and replayed as
+// one CUDA graph, no host round trip until the verdicts:
 //   k_init            instance-shape checks                                    lib.rs:51-55
 //   k_decompress      thread per (proof, point): sqrt + curve check            transcript/mod.rs:158-166
 //   k_transcript      thread per proof: Blake2b / Keccak replay -> challenges  lib.rs:66-253
 //   k_scalar          thread per proof: Lagrange, h(x), multi-open scalars     lib.rs:173-347, shplonk.rs / gwc.rs
-//   k_rlc_*           r_i expansion + suffix products c_j                      strategy.rs:125-136
+//   k_rlc_*           r_i expansion + suffix products c_j per fold group       strategy.rs:125-136
 //   k_shared_reduce   column sums of the shared-base scalars
-//   k_msm_*           one signed-digit Pippenger over every proof's points     arithmetic.rs:7-108, msm.rs:81-86
+//   k_msm_digits, k_scan_*, k_bucket_order, k_msm_scatter, k_msm_bucket_sum, k_msm_chunk_reduce, k_msm_window_reduce
+//                     one signed-digit Pippenger per fold group over its proofs' points   arithmetic.rs:7-108, msm.rs:81-86
 //   k_lines           per Miller iteration: product of the lines of every (channel, window) pair
 //   k_pairing_check   f = f^2 M_i, division-free final exponentiation test     msm.rs:185-203
-//   (k_finalize       explicit window combination -> affine (L, R): parity hook only)
+//   (k_pack_partial / k_sum_partials: shards of a multi-GPU batch; k_fold_accum: explicit (L, R), parity hook only)
 //   (k_pp_*           per-proof accumulators / pairings: parity hook and rejection attribution)
 #include <cuda_runtime.h>
 #include <stdio.h>
