@@ -1370,7 +1370,7 @@ int h2v_verify_batch(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint
                      const uint64_t* inst_off, const uint8_t* rlc_scalars, uint64_t seed, uint8_t* status, uint8_t* challenges,
                      uint8_t* accum, uint8_t* batch_accum) {
   int rc;
-  if ((rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, 0, n / (ctx->opt_fold_groups ? ctx->opt_fold_groups : 1))) != 0) return rc;
+  if ((rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, 0, n / (ctx && ctx->opt_fold_groups ? ctx->opt_fold_groups : 1))) != 0) return rc;
   if ((rc = run_impl(ctx, RUN_PAIRING | (batch_accum ? RUN_ACCUM : 0))) != 0) return rc;
   if ((rc = hooks_impl(ctx, challenges)) != 0) return rc;
   u32 verdict = 0;
