@@ -254,205 +254,228 @@ def prove(params, vk, pk, s, advice, instance, rng, hash_kind="blake2b", expect_
     """advice: [column][row] (at most `usable` rows, zero-padded), instance: [column][row].  Returns proof bytes.
     expect_honest = False: the assignment violates a constraint; the quotient is then no polynomial of the allowed
     degree (asserted) and the returned proof must be rejected."""
+    return prove_multi(params, vk, pk, s, [advice], [instance], rng, hash_kind, expect_honest)
+
+
+def prove_multi(params, vk, pk, s, advices, instances, rng, hash_kind="blake2b", expect_honest=True):
+    """One proof for m = len(advices) circuit instances of the same circuit (the `instances: &[&[&[Fr]]]` of the reference's
+    verify_proof with instances.len() = m, lib.rs:63,92,117,134): advice / lookup / permutation / shuffle polynomials per
+    instance, ONE random polynomial and ONE quotient over the y-fold of every instance's expressions, in the interleaving
+    the verifier reads.  advices[pi]: [column][row], instances[pi]: [column][row]."""
     dom, bf, usable, circ = pk["dom"], pk["bf"], pk["usable"], pk["circ"]
     cs, n = circ.cs, dom.n
+    M = len(advices)
+    assert M == len(instances) and M >= 1
     assert cs.num_challenges == 0 and max(cs.advice_column_phase, default=0) == 0, "single phase only"
     chunk = circ.cs_degree - 2
     ncols = len(cs.permutation_columns)
     n_sets = -(-ncols // chunk) if ncols else 0
     commit = lambda coeffs: bn.g1_mul_gen(_eval(coeffs, s))
     blind = lambda col: list(col) + [0] * (usable - len(col)) + [rng.randrange(R) for _ in range(n - usable)]
-    adv = [blind(col) for col in advice]
-    inst = [list(col) + [0] * (n - len(col)) for col in instance]  # lib.rs:204-217 evaluates exactly this polynomial
-    adv_c = [dom.lagrange_to_coeff(col) for col in adv]
-    inst_c = [dom.lagrange_to_coeff(col) for col in inst]
     omega_pow = [pow(dom.omega, j, R) for j in range(n)]
 
-    def column(idx, typ):
-        return pk["fixed"][idx] if typ == COL_FIXED else inst[idx] if typ == COL_INSTANCE else adv[idx]
-
-    # values of every query variable on the base domain: advice | fixed | instance (vk.rs:490-500)
     def rot_col(col, rot):
         return [col[(j + rot) % n] for j in range(n)]
 
-    var_rows = [rot_col(adv[c], r) for c, _p, r in cs.advice_queries] + [rot_col(pk["fixed"][c], r) for c, r in cs.fixed_queries] \
-        + [rot_col(inst[c], r) for c, r in cs.instance_queries]
+    I = []  # per-instance prover state
+    for advice, instance in zip(advices, instances):
+        st = {}
+        st["adv"] = [blind(col) for col in advice]
+        st["inst"] = [list(col) + [0] * (n - len(col)) for col in instance]  # lib.rs:204-217 evaluates exactly this polynomial
+        st["adv_c"] = [dom.lagrange_to_coeff(col) for col in st["adv"]]
+        st["inst_c"] = [dom.lagrange_to_coeff(col) for col in st["inst"]]
+        # values of every query variable on the base domain: advice | fixed | instance (vk.rs:490-500)
+        st["var_rows"] = [rot_col(st["adv"][c], r) for c, _p, r in cs.advice_queries] + [rot_col(pk["fixed"][c], r) for c, r in cs.fixed_queries] \
+            + [rot_col(st["inst"][c], r) for c, r in cs.instance_queries]
+        I.append(st)
 
-    def poly_rows(poly):
+    def column(st, idx, typ):
+        return pk["fixed"][idx] if typ == COL_FIXED else st["inst"][idx] if typ == COL_INSTANCE else st["adv"][idx]
+
+    def poly_rows(st, poly):
         out = [0] * n
         for coeff, vars_ in poly[1]:
             for j in range(n):
                 t = cs.coeff_vals[coeff]
                 for v, pw in vars_:
-                    t = t * pow(var_rows[v][j], pw, R) % R
+                    t = t * pow(st["var_rows"][v][j], pw, R) % R
                 out[j] = (out[j] + t) % R
         return out
 
     tr = TranscriptWrite(hash_kind)
     tr.common_scalar(vk.transcript_repr)
-    for col in instance:
-        for v in col:
-            tr.common_scalar(v)
-    for c in adv_c:
-        tr.write_point(commit(c))
+    for instance in instances:  # lib.rs:76-82
+        for col in instance:
+            for v in col:
+                tr.common_scalar(v)
+    for st in I:  # lib.rs:91-103
+        for c in st["adv_c"]:
+            tr.write_point(commit(c))
     theta = tr.squeeze_challenge()
 
-    def compress_rows(polys):
+    def compress_rows(st, polys):
         acc = [0] * n
         for p in polys:
-            rows_ = poly_rows(p)
+            rows_ = poly_rows(st, p)
             acc = [(a * theta + b) % R for a, b in zip(acc, rows_)]
         return acc
 
     # ---- lookup argument, permuted columns (definition of the protocol; verifier side: lookup.rs:159-230)
-    lookups = []
-    for inputs, tables in cs.lookups:
-        A, S = compress_rows(inputs), compress_rows(tables)
-        Ap = sorted(A[:usable])
-        left = {}
-        for v in S[:usable]:
-            left[v] = left.get(v, 0) + 1
-        Sp = [None] * usable
-        for i in range(usable):
-            if i == 0 or Ap[i] != Ap[i - 1]:
-                if left.get(Ap[i], 0) == 0:
-                    assert not expect_honest, "lookup input not in the table"
-                    left[Ap[i]] = left.get(Ap[i], 0) + 1  # dishonest prover: pretend
-                Sp[i] = Ap[i]
-                left[Ap[i]] -= 1
-        rest = [v for v, c in left.items() for _ in range(max(c, 0))]
-        for i in range(usable):
-            if Sp[i] is None:
-                Sp[i] = rest.pop() if rest else 0
-        Ap, Sp = blind(Ap), blind(Sp)
-        Ap_c, Sp_c = dom.lagrange_to_coeff(Ap), dom.lagrange_to_coeff(Sp)
-        tr.write_point(commit(Ap_c))
-        tr.write_point(commit(Sp_c))
-        lookups.append({"A": A, "S": S, "Ap": Ap, "Sp": Sp, "Ap_c": Ap_c, "Sp_c": Sp_c})
+    for st in I:
+        st["lookups"] = []
+        for inputs, tables in cs.lookups:
+            A, S = compress_rows(st, inputs), compress_rows(st, tables)
+            Ap = sorted(A[:usable])
+            left = {}
+            for v in S[:usable]:
+                left[v] = left.get(v, 0) + 1
+            Sp = [None] * usable
+            for i in range(usable):
+                if i == 0 or Ap[i] != Ap[i - 1]:
+                    if left.get(Ap[i], 0) == 0:
+                        assert not expect_honest, "lookup input not in the table"
+                        left[Ap[i]] = left.get(Ap[i], 0) + 1  # dishonest prover: pretend
+                    Sp[i] = Ap[i]
+                    left[Ap[i]] -= 1
+            rest = [v for v, c in left.items() for _ in range(max(c, 0))]
+            for i in range(usable):
+                if Sp[i] is None:
+                    Sp[i] = rest.pop() if rest else 0
+            Ap, Sp = blind(Ap), blind(Sp)
+            Ap_c, Sp_c = dom.lagrange_to_coeff(Ap), dom.lagrange_to_coeff(Sp)
+            tr.write_point(commit(Ap_c))
+            tr.write_point(commit(Sp_c))
+            st["lookups"].append({"A": A, "S": S, "Ap": Ap, "Sp": Sp, "Ap_c": Ap_c, "Sp_c": Sp_c})
     beta = tr.squeeze_challenge()
     gamma = tr.squeeze_challenge()
     # ---- permutation argument: chained grand products, `chunk` columns per set (verifier side: permutation.rs:189-288)
-    z, start = [], 1
-    for t in range(n_sets):
-        cols = list(range(t * chunk, min((t + 1) * chunk, ncols)))
-        zi = [0] * n
-        zi[0] = start
-        dens = [1] * usable
-        for c in cols:
-            colv = column(*cs.permutation_columns[c])
-            dens = [d * ((colv[j] + beta * pk["sigma"][c][j] + gamma) % R) % R for j, d in enumerate(dens)]
-        dens = bn.batch_invert_skip_zero(dens, R)
-        for j in range(usable):
-            num = 1
+    for st in I:
+        z, start = [], 1
+        for t in range(n_sets):
+            cols = list(range(t * chunk, min((t + 1) * chunk, ncols)))
+            zi = [0] * n
+            zi[0] = start
+            dens = [1] * usable
             for c in cols:
-                colv = column(*cs.permutation_columns[c])
-                num = num * ((colv[j] + beta * pow(bn.FR_DELTA, c, R) % R * omega_pow[j] + gamma) % R) % R
-            zi[j + 1] = zi[j] * num % R * dens[j] % R
-        start = zi[usable]
-        for j in range(usable + 1, n):
-            zi[j] = rng.randrange(R)
-        z.append(zi)
-    if n_sets and expect_honest:
-        assert start == 1, "grand product of an honest permutation must close to 1"
-    z_c = [dom.lagrange_to_coeff(zi) for zi in z]
-    for c in z_c:
-        tr.write_point(commit(c))
+                colv = column(st, *cs.permutation_columns[c])
+                dens = [d * ((colv[j] + beta * pk["sigma"][c][j] + gamma) % R) % R for j, d in enumerate(dens)]
+            dens = bn.batch_invert_skip_zero(dens, R)
+            for j in range(usable):
+                num = 1
+                for c in cols:
+                    colv = column(st, *cs.permutation_columns[c])
+                    num = num * ((colv[j] + beta * pow(bn.FR_DELTA, c, R) % R * omega_pow[j] + gamma) % R) % R
+                zi[j + 1] = zi[j] * num % R * dens[j] % R
+            start = zi[usable]
+            for j in range(usable + 1, n):
+                zi[j] = rng.randrange(R)
+            z.append(zi)
+        if n_sets and expect_honest:
+            assert start == 1, "grand product of an honest permutation must close to 1"
+        st["z_c"] = [dom.lagrange_to_coeff(zi) for zi in z]
+        for c in st["z_c"]:
+            tr.write_point(commit(c))
     # ---- lookup / shuffle grand products
-    for L in lookups:
-        zl = [0] * n
-        zl[0] = 1
-        dens = bn.batch_invert_skip_zero([((L["Ap"][j] + beta) % R) * ((L["Sp"][j] + gamma) % R) % R for j in range(usable)], R)
-        for j in range(usable):
-            zl[j + 1] = zl[j] * ((L["A"][j] + beta) % R) % R * ((L["S"][j] + gamma) % R) % R * dens[j] % R
-        for j in range(usable + 1, n):
-            zl[j] = rng.randrange(R)
-        L["Z"], L["Z_c"] = zl, dom.lagrange_to_coeff(zl)
-        tr.write_point(commit(L["Z_c"]))
-    shuffles = []
-    for inputs, shufs in cs.shuffles:
-        A, S = compress_rows(inputs), compress_rows(shufs)
-        zs = [0] * n
-        zs[0] = 1
-        dens = bn.batch_invert_skip_zero([(S[j] + gamma) % R for j in range(usable)], R)
-        for j in range(usable):
-            zs[j + 1] = zs[j] * ((A[j] + gamma) % R) % R * dens[j] % R
-        for j in range(usable + 1, n):
-            zs[j] = rng.randrange(R)
-        sh = {"A": A, "S": S, "Z": zs, "Z_c": dom.lagrange_to_coeff(zs)}
-        tr.write_point(commit(sh["Z_c"]))
-        shuffles.append(sh)
+    for st in I:
+        for L in st["lookups"]:
+            zl = [0] * n
+            zl[0] = 1
+            dens = bn.batch_invert_skip_zero([((L["Ap"][j] + beta) % R) * ((L["Sp"][j] + gamma) % R) % R for j in range(usable)], R)
+            for j in range(usable):
+                zl[j + 1] = zl[j] * ((L["A"][j] + beta) % R) % R * ((L["S"][j] + gamma) % R) % R * dens[j] % R
+            for j in range(usable + 1, n):
+                zl[j] = rng.randrange(R)
+            L["Z"], L["Z_c"] = zl, dom.lagrange_to_coeff(zl)
+            tr.write_point(commit(L["Z_c"]))
+    for st in I:
+        st["shuffles"] = []
+        for inputs, shufs in cs.shuffles:
+            A, S = compress_rows(st, inputs), compress_rows(st, shufs)
+            zs = [0] * n
+            zs[0] = 1
+            dens = bn.batch_invert_skip_zero([(S[j] + gamma) % R for j in range(usable)], R)
+            for j in range(usable):
+                zs[j + 1] = zs[j] * ((A[j] + gamma) % R) % R * dens[j] % R
+            for j in range(usable + 1, n):
+                zs[j] = rng.randrange(R)
+            sh = {"A": A, "S": S, "Z": zs, "Z_c": dom.lagrange_to_coeff(zs)}
+            tr.write_point(commit(sh["Z_c"]))
+            st["shuffles"].append(sh)
     rand_c = [rng.randrange(R) for _ in range(n)]  # vanishing.rs:49-57: random polynomial
     tr.write_point(commit(rand_c))
     y = tr.squeeze_challenge()
 
-    # ---- quotient: N(X) = fold_y(expressions)(X) on the extended coset, h = N / (X^n - 1)
+    # ---- quotient: N(X) = fold_y(expressions of every instance)(X) on the extended coset, h = N / (X^n - 1)
     E = dom.coeff_to_ext
-    adv_e, inst_e, fix_e = [E(c) for c in adv_c], [E(c) for c in inst_c], [E(c) for c in pk["fixed_c"]]
+    fix_e = [E(c) for c in pk["fixed_c"]]
     m = 1 << dom.ext_k
     x_e = [dom.shift * pow(dom.ext_omega, i, R) % R for i in range(m)]
-    var_e = [dom.rotate_ext(adv_e[c], r) for c, _p, r in cs.advice_queries] + [dom.rotate_ext(fix_e[c], r) for c, r in cs.fixed_queries] \
-        + [dom.rotate_ext(inst_e[c], r) for c, r in cs.instance_queries]
-
-    def poly_ext(poly):
-        out = [0] * m
-        for coeff, vars_ in poly[1]:
-            for i in range(m):
-                t = cs.coeff_vals[coeff]
-                for v, pw in vars_:
-                    t = t * pow(var_e[v][i], pw, R) % R
-                out[i] = (out[i] + t) % R
-        return out
-
-    def compress_ext(polys):
-        acc = [0] * m
-        for p in polys:
-            pe = poly_ext(p)
-            acc = [(a * theta + b) % R for a, b in zip(acc, pe)]
-        return acc
-
     lag = lambda rows_: E(dom.lagrange_to_coeff([1 if j in rows_ else 0 for j in range(n)]))
     l0_e, llast_e, lblind_e = lag({0}), lag({usable}), lag(set(range(usable + 1, n)))
     active_e = [(1 - llast_e[i] - lblind_e[i]) % R for i in range(m)]
-    exprs = [poly_ext(g) for g in cs.gates]  # vk.rs:478-512
-    if n_sets:  # permutation.rs:189-288
-        z_e = [E(c) for c in z_c]
-        sig_e = [E(c) for c in pk["sigma_c"]]
+    sig_e = [E(c) for c in pk["sigma_c"]] if n_sets else []
+    exprs = []
+    for st in I:  # lib.rs:273-344: every expression of instance pi, then the next instance
+        adv_e, inst_e = [E(c) for c in st["adv_c"]], [E(c) for c in st["inst_c"]]
+        var_e = [dom.rotate_ext(adv_e[c], r) for c, _p, r in cs.advice_queries] + [dom.rotate_ext(fix_e[c], r) for c, r in cs.fixed_queries] \
+            + [dom.rotate_ext(inst_e[c], r) for c, r in cs.instance_queries]
 
-        def col_ext(idx, typ):
-            return fix_e[idx] if typ == COL_FIXED else inst_e[idx] if typ == COL_INSTANCE else adv_e[idx]
+        def poly_ext(poly):
+            out = [0] * m
+            for coeff, vars_ in poly[1]:
+                for i in range(m):
+                    t = cs.coeff_vals[coeff]
+                    for v, pw in vars_:
+                        t = t * pow(var_e[v][i], pw, R) % R
+                    out[i] = (out[i] + t) % R
+            return out
 
-        exprs.append([l0_e[i] * ((1 - z_e[0][i]) % R) % R for i in range(m)])
-        exprs.append([llast_e[i] * ((z_e[-1][i] * z_e[-1][i] - z_e[-1][i]) % R) % R for i in range(m)])
-        for t in range(1, n_sets):
-            zl = dom.rotate_ext(z_e[t - 1], -(bf + 1))
-            exprs.append([l0_e[i] * ((z_e[t][i] - zl[i]) % R) % R for i in range(m)])
-        for t in range(n_sets):
-            cols = list(range(t * chunk, min((t + 1) * chunk, ncols)))
-            zn = dom.rotate_ext(z_e[t], 1)
-            left, right = list(zn), list(z_e[t])
-            for c in cols:
-                ce = col_ext(*cs.permutation_columns[c])
-                dp = pow(bn.FR_DELTA, c, R)
-                left = [left[i] * ((ce[i] + beta * sig_e[c][i] + gamma) % R) % R for i in range(m)]
-                right = [right[i] * ((ce[i] + beta * dp % R * x_e[i] + gamma) % R) % R for i in range(m)]
-            exprs.append([active_e[i] * ((left[i] - right[i]) % R) % R for i in range(m)])
-    for (inputs, tables), L in zip(cs.lookups, lookups):  # lookup.rs:159-230
-        Z, Ap, Sp = E(L["Z_c"]), E(L["Ap_c"]), E(L["Sp_c"])
-        Zn, Apm = dom.rotate_ext(Z, 1), dom.rotate_ext(Ap, -1)
-        Ae, Se = compress_ext(inputs), compress_ext(tables)
-        exprs.append([l0_e[i] * ((1 - Z[i]) % R) % R for i in range(m)])
-        exprs.append([llast_e[i] * ((Z[i] * Z[i] - Z[i]) % R) % R for i in range(m)])
-        exprs.append([active_e[i] * ((Zn[i] * ((Ap[i] + beta) % R) % R * ((Sp[i] + gamma) % R)
-                                     - Z[i] * ((Ae[i] + beta) % R) % R * ((Se[i] + gamma) % R)) % R) % R for i in range(m)])
-        exprs.append([l0_e[i] * ((Ap[i] - Sp[i]) % R) % R for i in range(m)])
-        exprs.append([active_e[i] * ((Ap[i] - Sp[i]) % R) % R * ((Ap[i] - Apm[i]) % R) % R for i in range(m)])
-    for (inputs, shufs), sh in zip(cs.shuffles, shuffles):  # shuffle.rs:148-203
-        Z = E(sh["Z_c"])
-        Zn = dom.rotate_ext(Z, 1)
-        Ae, Se = compress_ext(inputs), compress_ext(shufs)
-        exprs.append([l0_e[i] * ((1 - Z[i]) % R) % R for i in range(m)])
-        exprs.append([llast_e[i] * ((Z[i] * Z[i] - Z[i]) % R) % R for i in range(m)])
-        exprs.append([active_e[i] * ((Zn[i] * ((Se[i] + gamma) % R) - Z[i] * ((Ae[i] + gamma) % R)) % R) % R for i in range(m)])
+        def compress_ext(polys):
+            acc = [0] * m
+            for p in polys:
+                pe = poly_ext(p)
+                acc = [(a * theta + b) % R for a, b in zip(acc, pe)]
+            return acc
+
+        exprs += [poly_ext(g) for g in cs.gates]  # vk.rs:478-512
+        if n_sets:  # permutation.rs:189-288
+            z_e = [E(c) for c in st["z_c"]]
+
+            def col_ext(idx, typ):
+                return fix_e[idx] if typ == COL_FIXED else inst_e[idx] if typ == COL_INSTANCE else adv_e[idx]
+
+            exprs.append([l0_e[i] * ((1 - z_e[0][i]) % R) % R for i in range(m)])
+            exprs.append([llast_e[i] * ((z_e[-1][i] * z_e[-1][i] - z_e[-1][i]) % R) % R for i in range(m)])
+            for t in range(1, n_sets):
+                zl = dom.rotate_ext(z_e[t - 1], -(bf + 1))
+                exprs.append([l0_e[i] * ((z_e[t][i] - zl[i]) % R) % R for i in range(m)])
+            for t in range(n_sets):
+                cols = list(range(t * chunk, min((t + 1) * chunk, ncols)))
+                zn = dom.rotate_ext(z_e[t], 1)
+                left, right = list(zn), list(z_e[t])
+                for c in cols:
+                    ce = col_ext(*cs.permutation_columns[c])
+                    dp = pow(bn.FR_DELTA, c, R)
+                    left = [left[i] * ((ce[i] + beta * sig_e[c][i] + gamma) % R) % R for i in range(m)]
+                    right = [right[i] * ((ce[i] + beta * dp % R * x_e[i] + gamma) % R) % R for i in range(m)]
+                exprs.append([active_e[i] * ((left[i] - right[i]) % R) % R for i in range(m)])
+        for (inputs, tables), L in zip(cs.lookups, st["lookups"]):  # lookup.rs:159-230
+            Z, Ap, Sp = E(L["Z_c"]), E(L["Ap_c"]), E(L["Sp_c"])
+            Zn, Apm = dom.rotate_ext(Z, 1), dom.rotate_ext(Ap, -1)
+            Ae, Se = compress_ext(inputs), compress_ext(tables)
+            exprs.append([l0_e[i] * ((1 - Z[i]) % R) % R for i in range(m)])
+            exprs.append([llast_e[i] * ((Z[i] * Z[i] - Z[i]) % R) % R for i in range(m)])
+            exprs.append([active_e[i] * ((Zn[i] * ((Ap[i] + beta) % R) % R * ((Sp[i] + gamma) % R)
+                                         - Z[i] * ((Ae[i] + beta) % R) % R * ((Se[i] + gamma) % R)) % R) % R for i in range(m)])
+            exprs.append([l0_e[i] * ((Ap[i] - Sp[i]) % R) % R for i in range(m)])
+            exprs.append([active_e[i] * ((Ap[i] - Sp[i]) % R) % R * ((Ap[i] - Apm[i]) % R) % R for i in range(m)])
+        for (inputs, shufs), sh in zip(cs.shuffles, st["shuffles"]):  # shuffle.rs:148-203
+            Z = E(sh["Z_c"])
+            Zn = dom.rotate_ext(Z, 1)
+            Ae, Se = compress_ext(inputs), compress_ext(shufs)
+            exprs.append([l0_e[i] * ((1 - Z[i]) % R) % R for i in range(m)])
+            exprs.append([llast_e[i] * ((Z[i] * Z[i] - Z[i]) % R) % R for i in range(m)])
+            exprs.append([active_e[i] * ((Zn[i] * ((Se[i] + gamma) % R) - Z[i] * ((Ae[i] + gamma) % R)) % R) % R for i in range(m)])
     N = [0] * m
     for e in exprs:
         N = [(N[i] * y + e[i]) % R for i in range(m)]
@@ -468,65 +491,59 @@ def prove(params, vk, pk, s, advice, instance, rng, hash_kind="blake2b", expect_
     xn = pow(x, n, R)
     rot = lambda r: x * pow(dom.omega, r % n, R) % R
     ev = lambda coeffs, r=0: _eval(coeffs, rot(r))
-    for c, _p, r in cs.advice_queries:
-        tr.write_scalar(ev(adv_c[c], r))
+    for st in I:  # lib.rs:219-253
+        for c, _p, r in cs.advice_queries:
+            tr.write_scalar(ev(st["adv_c"][c], r))
     for c, r in cs.fixed_queries:
         tr.write_scalar(ev(pk["fixed_c"][c], r))
     tr.write_scalar(ev(rand_c))
     for c in pk["sigma_c"]:
         tr.write_scalar(ev(c))
-    for t in range(n_sets):
-        tr.write_scalar(ev(z_c[t]))
-        tr.write_scalar(ev(z_c[t], 1))
-        if t != n_sets - 1:
-            tr.write_scalar(ev(z_c[t], -(bf + 1)))
-    for L in lookups:  # product, product_next, permuted input, permuted input at omega^-1 x, permuted table
-        for coeffs, r in ((L["Z_c"], 0), (L["Z_c"], 1), (L["Ap_c"], 0), (L["Ap_c"], -1), (L["Sp_c"], 0)):
-            tr.write_scalar(ev(coeffs, r))
-    for sh in shuffles:
-        tr.write_scalar(ev(sh["Z_c"]))
-        tr.write_scalar(ev(sh["Z_c"], 1))
+    for st in I:
+        for t in range(n_sets):
+            tr.write_scalar(ev(st["z_c"][t]))
+            tr.write_scalar(ev(st["z_c"][t], 1))
+            if t != n_sets - 1:
+                tr.write_scalar(ev(st["z_c"][t], -(bf + 1)))
+    for st in I:
+        for L in st["lookups"]:  # product, product_next, permuted input, permuted input at omega^-1 x, permuted table
+            for coeffs, r in ((L["Z_c"], 0), (L["Z_c"], 1), (L["Ap_c"], 0), (L["Ap_c"], -1), (L["Sp_c"], 0)):
+                tr.write_scalar(ev(coeffs, r))
+    for st in I:
+        for sh in st["shuffles"]:
+            tr.write_scalar(ev(sh["Z_c"]))
+            tr.write_scalar(ev(sh["Z_c"], 1))
     # ---- SHPLONK opening of every query (shplonk.rs): polynomials by commitment identity, slots in transcript order
-    slot = {}
-    nxt = 0
-    for c in range(cs.num_advice_columns):
-        slot[("adv", c)] = nxt
-        nxt += 1
-    for li in range(len(lookups)):
-        slot[("lk_in", li)], slot[("lk_tab", li)] = nxt, nxt + 1
-        nxt += 2
-    for t in range(n_sets):
-        slot[("perm", t)] = nxt
-        nxt += 1
-    for li in range(len(lookups)):
-        slot[("lk_z", li)] = nxt
-        nxt += 1
-    for si in range(len(shuffles)):
-        slot[("sh_z", si)] = nxt
-        nxt += 1
-    slot["random"] = nxt
+    n_adv, n_lk, n_sh = cs.num_advice_columns, len(cs.lookups), len(cs.shuffles)
+    b_lk = M * n_adv
+    b_perm = b_lk + 2 * M * n_lk
+    b_lkz = b_perm + M * n_sets
+    b_shz = b_lkz + M * n_lk
+    slot_random = b_shz + M * n_sh
     polys, queries = {}, []
 
     def add_q(ident, coeffs, r):
         polys[ident] = coeffs
         queries.append(Query(ident, rot(r), _eval(coeffs, rot(r)), None, r))
 
-    for c, _p, r in cs.advice_queries:
-        add_q(("proof", slot[("adv", c)]), adv_c[c], r)
-    for t in range(n_sets):
-        add_q(("proof", slot[("perm", t)]), z_c[t], 0)
-        add_q(("proof", slot[("perm", t)]), z_c[t], 1)
-    for t in reversed(range(n_sets - 1)):
-        add_q(("proof", slot[("perm", t)]), z_c[t], -(bf + 1))
-    for li, L in enumerate(lookups):
-        add_q(("proof", slot[("lk_z", li)]), L["Z_c"], 0)
-        add_q(("proof", slot[("lk_in", li)]), L["Ap_c"], 0)
-        add_q(("proof", slot[("lk_tab", li)]), L["Sp_c"], 0)
-        add_q(("proof", slot[("lk_in", li)]), L["Ap_c"], -1)
-        add_q(("proof", slot[("lk_z", li)]), L["Z_c"], 1)
-    for si, sh in enumerate(shuffles):
-        add_q(("proof", slot[("sh_z", si)]), sh["Z_c"], 0)
-        add_q(("proof", slot[("sh_z", si)]), sh["Z_c"], 1)
+    for pi, st in enumerate(I):  # lib.rs:349-414
+        for c, _p, r in cs.advice_queries:
+            add_q(("proof", pi * n_adv + c), st["adv_c"][c], r)
+        for t in range(n_sets):
+            add_q(("proof", b_perm + pi * n_sets + t), st["z_c"][t], 0)
+            add_q(("proof", b_perm + pi * n_sets + t), st["z_c"][t], 1)
+        for t in reversed(range(n_sets - 1)):
+            add_q(("proof", b_perm + pi * n_sets + t), st["z_c"][t], -(bf + 1))
+        for li, L in enumerate(st["lookups"]):
+            s_in, s_tab, s_z = b_lk + 2 * (pi * n_lk + li), b_lk + 2 * (pi * n_lk + li) + 1, b_lkz + pi * n_lk + li
+            add_q(("proof", s_z), L["Z_c"], 0)
+            add_q(("proof", s_in), L["Ap_c"], 0)
+            add_q(("proof", s_tab), L["Sp_c"], 0)
+            add_q(("proof", s_in), L["Ap_c"], -1)
+            add_q(("proof", s_z), L["Z_c"], 1)
+        for si, sh in enumerate(st["shuffles"]):
+            add_q(("proof", b_shz + pi * n_sh + si), sh["Z_c"], 0)
+            add_q(("proof", b_shz + pi * n_sh + si), sh["Z_c"], 1)
     for c, r in cs.fixed_queries:
         add_q(("fixed", c), pk["fixed_c"][c], r)
     for t in range(ncols):
@@ -535,7 +552,7 @@ def prove(params, vk, pk, s, advice, instance, rng, hash_kind="blake2b", expect_
     for piece in reversed(h_pieces):
         hmsm_c = [(hmsm_c[i] * xn + piece[i]) % R for i in range(n)]
     add_q(("hmsm",), hmsm_c, 0)
-    add_q(("proof", slot["random"]), rand_c, 0)
+    add_q(("proof", slot_random), rand_c, 0)
     rotation_sets, super_points = _shplonk_sets(queries)
     yy = tr.squeeze_challenge()
     v = tr.squeeze_challenge()

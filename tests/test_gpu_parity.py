@@ -535,3 +535,30 @@ def test_multi_instance_proofs(pkg, shape, k, m, mo):
             assert res.accum[128 * j: 128 * j + 128] == enc_point(w.L) + enc_point(w.R)
         L, R_, ok = orc.accumulate(params, want, rs)
         assert res.batch_accum == enc_point(L) + enc_point(R_) and not ok and not res.verdict
+
+
+def test_honest_multi_instance_proof_through_the_c_abi(pkg):
+    """An honest proof for 3 circuit instances of the vector_mul circuit (oracle/honest_prover.prove_multi: real witnesses,
+    real polynomials) is accepted by the CUDA path; swapped public inputs and a cheat in one instance are rejected."""
+    import honest_prover as hp
+
+    rng = random.Random("gpu-honest-multi")
+    s = rng.randrange(1, bn.R)
+    params, vk, pk = hp.keygen_vm(6, s, 4)
+    m = 3
+    wit = [([rng.randrange(bn.R) for _ in range(4)], [rng.randrange(bn.R) for _ in range(4)]) for _ in range(m)]
+    asg = [hp.vm_assignment(l, r) for l, r in wit]
+    proof = hp.prove_multi(params, vk, pk, s, [a for a, _ in asg], [i for _, i in asg], rng)
+    insts = [i for _, i in asg]
+    asg_bad = list(asg)
+    asg_bad[2] = hp.vm_assignment(*wit[2], cheat_row=1)
+    bad = hp.prove_multi(params, vk, pk, s, [a for a, _ in asg_bad], [i for _, i in asg_bad], rng, expect_honest=False)
+    bv = pkg.BatchVerifier(pkg.ParamsKZG.from_bytes(params.to_bytes()), pkg.VerifyingKey.from_bytes(vk.to_bytes(F.RAW_BYTES), F.RAW_BYTES),
+                           "shplonk", "blake2b", device=0, circuit_instances=m)
+    with bv:
+        res = bv.verify_batch([proof, proof, bad], [insts, [insts[1], insts[0], insts[2]], [i for _, i in asg_bad]],
+                              want_challenges=True, want_accum=True)
+        assert res.status == [0, 4, 4]
+        w = orc.verify_proof(params, vk, insts, proof)
+        assert w.status == 0 and split32(res.challenges, bv.n_challenges) == w.challenges
+        assert res.accum[:128] == enc_point(w.L) + enc_point(w.R)

@@ -79,3 +79,75 @@ def test_honest_lookup_shuffle_circuit(built, hk):
         assert orc.verify_proof(params, vk, [ins], bad, "shplonk", hk).status == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
         assert co.verify(bad, ins, "shplonk", hk)[0] == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
     co.close()
+
+
+def _host_stage_status(params, vk, m, proof, instances, hk="blake2b"):
+    """status of the host build of the CUDA stages (plan compiled for m circuit instances per proof)"""
+    import ctypes
+
+    lib = ctypes.CDLL(os.path.join(HERE, "hostlib", "libstage.so"))
+    lib.s_err.restype = ctypes.c_char_p
+    pb, vb = params.to_bytes(), vk.to_bytes(F.RAW_BYTES)
+    assert lib.s_build_m(pb, len(pb), 0, vb, len(vb), F.RAW_BYTES, 0, 0 if hk == "blake2b" else 1, m) == 0, lib.s_err()
+    info = (ctypes.c_uint32 * 8)()
+    lib.s_info(info)
+    _k, P, _S, C, _plen, _nic, nsh, nmo = list(info)
+    cols = [col for inst in instances for col in inst]
+    ib = b"".join(bn.fr_to_repr(v) for col in cols for v in col)
+    cl = (ctypes.c_uint32 * max(1, len(cols)))(*[len(c) for c in cols])
+    ch = (ctypes.c_uint8 * (32 * C))(); rt = (ctypes.c_uint8 * (32 * P))(); sh = (ctypes.c_uint8 * (32 * nsh))()
+    lf = (ctypes.c_uint8 * (32 * nmo))(); LR = (ctypes.c_uint8 * 128)(); ok = ctypes.c_int(0)
+    return lib.s_verify_one(proof, len(proof), ib, sum(len(c) for c in cols), cl, len(cols), ch, rt, sh, lf, LR, ctypes.byref(ok))
+
+
+def test_honest_multi_instance_proofs(built):
+    """ONE proof for several circuit instances (`instances.len() = m`, lib.rs:63,92,117,134) from real witnesses: accepted by
+    the Python oracle, the C oracle and the host build of the CUDA stages; rejected when only ONE instance cheats, when a public
+    input of one instance is wrong, and when the instances' public inputs are swapped (per-instance index plumbing)."""
+    rng = random.Random("honest-multi")
+    s = rng.randrange(1, bn.R)
+    # vector_mul, 3 instances with different witnesses
+    params, vk, pk = hp.keygen_vm(6, s, 4)
+    co = c_oracle.COracle(params.to_bytes(1), 1, vk.to_bytes(1), 1)
+    m = 3
+    wit = [([rng.randrange(bn.R) for _ in range(4)], [rng.randrange(bn.R) for _ in range(4)]) for _ in range(m)]
+    asg = [hp.vm_assignment(l, r) for l, r in wit]
+    proof = hp.prove_multi(params, vk, pk, s, [a for a, _ in asg], [i for _, i in asg], rng)
+    insts = [i for _, i in asg]
+    res = orc.verify_proof(params, vk, insts, proof)
+    assert res.status == orc.OK
+    assert co.verify_multi(proof, insts) == (0, res.challenges, enc_point(res.L) + enc_point(res.R))
+    assert _host_stage_status(params, vk, m, proof, insts) == 0
+    swapped = [insts[1], insts[0], insts[2]]
+    wrong = [[list(c) for c in i] for i in insts]
+    wrong[2][0][1] = (wrong[2][0][1] + 1) % bn.R
+    for bad_insts in (swapped, wrong):
+        assert orc.verify_proof(params, vk, bad_insts, proof).status == orc.CONSTRAINT_SYSTEM_FAILURE
+        assert co.verify_multi(proof, bad_insts)[0] == orc.CONSTRAINT_SYSTEM_FAILURE
+        assert _host_stage_status(params, vk, m, proof, bad_insts) == orc.CONSTRAINT_SYSTEM_FAILURE
+    asg_bad = list(asg)
+    asg_bad[1] = hp.vm_assignment(*wit[1], cheat_row=2)  # only instance 1 violates the gate
+    bad = hp.prove_multi(params, vk, pk, s, [a for a, _ in asg_bad], [i for _, i in asg_bad], rng, expect_honest=False)
+    bad_insts = [i for _, i in asg_bad]
+    assert orc.verify_proof(params, vk, bad_insts, bad).status == orc.CONSTRAINT_SYSTEM_FAILURE
+    assert co.verify_multi(bad, bad_insts)[0] == orc.CONSTRAINT_SYSTEM_FAILURE
+    assert _host_stage_status(params, vk, m, bad, bad_insts) == orc.CONSTRAINT_SYSTEM_FAILURE
+    co.close()
+    # lookup + shuffle + rotated gate + permutation with a fixed column, 2 instances
+    circ = hp.lookup_shuffle_circuit(6, 16)
+    params, vk, pk = hp.keygen(circ, s)
+    co = c_oracle.COracle(params.to_bytes(1), 1, vk.to_bytes(1), 1)
+    a0, i0 = hp.lookup_shuffle_assignment(circ, 16, rng)
+    a1, i1 = hp.lookup_shuffle_assignment(circ, 16, rng)
+    proof = hp.prove_multi(params, vk, pk, s, [a0, a1], [i0, i1], rng)
+    res = orc.verify_proof(params, vk, [i0, i1], proof)
+    assert res.status == orc.OK
+    assert co.verify_multi(proof, [i0, i1]) == (0, res.challenges, enc_point(res.L) + enc_point(res.R))
+    assert _host_stage_status(params, vk, 2, proof, [i0, i1]) == 0
+    for cheat in ("lookup", "shuffle", "gate", "copy"):  # the SECOND instance cheats
+        a1b, i1b = hp.lookup_shuffle_assignment(circ, 16, rng, cheat)
+        bad = hp.prove_multi(params, vk, pk, s, [a0, a1b], [i0, i1b], rng, expect_honest=False)
+        assert orc.verify_proof(params, vk, [i0, i1b], bad).status == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
+        assert co.verify_multi(bad, [i0, i1b])[0] == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
+        assert _host_stage_status(params, vk, 2, bad, [i0, i1b]) == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
+    co.close()
