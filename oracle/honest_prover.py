@@ -250,14 +250,14 @@ def keygen_vm(k, s, rows, transcript_repr=0x1234567):
 
 
 # ---------------------------------------------------------------- prover
-def prove(params, vk, pk, s, advice, instance, rng, hash_kind="blake2b", expect_honest=True):
+def prove(params, vk, pk, s, advice, instance, rng, hash_kind="blake2b", expect_honest=True, multiopen="shplonk"):
     """advice: [column][row] (at most `usable` rows, zero-padded), instance: [column][row].  Returns proof bytes.
     expect_honest = False: the assignment violates a constraint; the quotient is then no polynomial of the allowed
-    degree (asserted) and the returned proof must be rejected."""
-    return prove_multi(params, vk, pk, s, [advice], [instance], rng, hash_kind, expect_honest)
+    degree (asserted) and the returned proof must be rejected.  multiopen: "shplonk" or "gwc" opening argument."""
+    return prove_multi(params, vk, pk, s, [advice], [instance], rng, hash_kind, expect_honest, multiopen)
 
 
-def prove_multi(params, vk, pk, s, advices, instances, rng, hash_kind="blake2b", expect_honest=True):
+def prove_multi(params, vk, pk, s, advices, instances, rng, hash_kind="blake2b", expect_honest=True, multiopen="shplonk"):
     """One proof for m = len(advices) circuit instances of the same circuit (the `instances: &[&[&[Fr]]]` of the reference's
     verify_proof with instances.len() = m, lib.rs:63,92,117,134): advice / lookup / permutation / shuffle polynomials per
     instance, ONE random polynomial and ONE quotient over the y-fold of every instance's expressions, in the interleaving
@@ -553,6 +553,26 @@ def prove_multi(params, vk, pk, s, advices, instances, rng, hash_kind="blake2b",
         hmsm_c = [(hmsm_c[i] * xn + piece[i]) % R for i in range(n)]
     add_q(("hmsm",), hmsm_c, 0)
     add_q(("proof", slot_random), rand_c, 0)
+    if multiopen == "gwc":
+        # GWC (gwc.rs:54-163): queries grouped by point in first-appearance order; per point z_i the witness
+        # W_i = [ sum_j v^j (P_j(X) - e_j) / (X - z_i) ](s) G, the powers of v restarting in every group
+        v = tr.squeeze_challenge()
+        groups = []
+        for q in queries:
+            for pt, qs in groups:
+                if pt == q.point:
+                    qs.append(q)
+                    break
+            else:
+                groups.append((q.point, [q]))
+        for z, qs in groups:
+            acc, pow_v = 0, 1
+            for q in qs:
+                acc = (acc + pow_v * ((_eval(polys[q.ident], s) - q.eval) % R)) % R
+                pow_v = pow_v * v % R
+            tr.write_point(bn.g1_mul_gen(acc * bn.fr_inv((s - z) % R) % R))
+        return bytes(tr.out)
+    assert multiopen == "shplonk"
     rotation_sets, super_points = _shplonk_sets(queries)
     yy = tr.squeeze_challenge()
     v = tr.squeeze_challenge()

@@ -562,3 +562,31 @@ def test_honest_multi_instance_proof_through_the_c_abi(pkg):
         w = orc.verify_proof(params, vk, insts, proof)
         assert w.status == 0 and split32(res.challenges, bv.n_challenges) == w.challenges
         assert res.accum[:128] == enc_point(w.L) + enc_point(w.R)
+
+
+def test_honest_gwc_proof_through_the_c_abi(pkg):
+    """Honest proofs opened with GWC (oracle/honest_prover, multiopen="gwc"): the lookup + shuffle + rotated-gate circuit and a
+    two-instance vector_mul proof through the CUDA path, with one cheating witness each."""
+    import honest_prover as hp
+
+    rng = random.Random("gpu-honest-gwc")
+    s = rng.randrange(1, bn.R)
+    circ = hp.lookup_shuffle_circuit(6, 16)
+    params, vk, pk = hp.keygen(circ, s)
+    adv, ins = hp.lookup_shuffle_assignment(circ, 16, rng)
+    good = hp.prove(params, vk, pk, s, adv, ins, rng, multiopen="gwc")
+    adv_b, ins_b = hp.lookup_shuffle_assignment(circ, 16, rng, "lookup")
+    bad = hp.prove(params, vk, pk, s, adv_b, ins_b, rng, expect_honest=False, multiopen="gwc")
+    with make_bv(pkg, params, vk, "gwc", "blake2b") as bv:
+        res = bv.verify_batch([good, bad], [ins, ins_b], want_accum=True)
+        w = orc.verify_proof(params, vk, [ins], good, "gwc")
+        assert res.status == [0, 4] and w.status == 0 and res.accum[:128] == enc_point(w.L) + enc_point(w.R)
+    params, vk, pk = hp.keygen_vm(6, s, 4)
+    wit = [([rng.randrange(bn.R) for _ in range(4)], [rng.randrange(bn.R) for _ in range(4)]) for _ in range(2)]
+    asg = [hp.vm_assignment(l, r) for l, r in wit]
+    proof = hp.prove_multi(params, vk, pk, s, [a for a, _ in asg], [i for _, i in asg], rng, multiopen="gwc")
+    insts = [i for _, i in asg]
+    bv = pkg.BatchVerifier(pkg.ParamsKZG.from_bytes(params.to_bytes()), pkg.VerifyingKey.from_bytes(vk.to_bytes(F.RAW_BYTES), F.RAW_BYTES),
+                           "gwc", "blake2b", device=0, circuit_instances=2)
+    with bv:
+        assert bv.verify_batch([proof, proof], [insts, insts[::-1]]).status == [0, 4]

@@ -151,3 +151,65 @@ def test_honest_multi_instance_proofs(built):
         assert co.verify_multi(bad, [i0, i1b])[0] == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
         assert _host_stage_status(params, vk, 2, bad, [i0, i1b]) == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
     co.close()
+
+
+def test_honest_proofs_with_the_gwc_opening(built):
+    """The honest prover with the GWC multi-open argument (gwc.rs:54-163): true evaluations, witnesses per distinct
+    point.  Accepted by the Python oracle, the C oracle and the host build of the CUDA stages (GWC plan); cheats rejected."""
+    import ctypes
+
+    rng = random.Random("honest-gwc")
+    s = rng.randrange(1, bn.R)
+    lib = ctypes.CDLL(os.path.join(HERE, "hostlib", "libstage.so"))
+    lib.s_err.restype = ctypes.c_char_p
+
+    def host_status(params, vk, m, proof, insts):
+        pb, vb = params.to_bytes(), vk.to_bytes(F.RAW_BYTES)
+        assert lib.s_build_m(pb, len(pb), 0, vb, len(vb), F.RAW_BYTES, 1, 0, m) == 0, lib.s_err()
+        info = (ctypes.c_uint32 * 8)()
+        lib.s_info(info)
+        _k, P, _S, C, plen, _nic, nsh, nmo = list(info)
+        assert plen == len(proof)
+        cols = [col for inst in insts for col in inst]
+        ib = b"".join(bn.fr_to_repr(v) for col in cols for v in col)
+        cl = (ctypes.c_uint32 * max(1, len(cols)))(*[len(c) for c in cols])
+        bufs = [(ctypes.c_uint8 * (32 * k_))() for k_ in (C, P, nsh, nmo)]
+        LR = (ctypes.c_uint8 * 128)(); ok = ctypes.c_int(0)
+        return lib.s_verify_one(proof, len(proof), ib, sum(len(c) for c in cols), cl, len(cols), *bufs, LR, ctypes.byref(ok))
+
+    # vector_mul: one instance, and two instances in one proof
+    params, vk, pk = hp.keygen_vm(6, s, 4)
+    co = c_oracle.COracle(params.to_bytes(1), 1, vk.to_bytes(1), 1)
+    wit = [([rng.randrange(bn.R) for _ in range(4)], [rng.randrange(bn.R) for _ in range(4)]) for _ in range(2)]
+    asg = [hp.vm_assignment(l, r) for l, r in wit]
+    for m in (1, 2):
+        proof = hp.prove_multi(params, vk, pk, s, [a for a, _ in asg[:m]], [i for _, i in asg[:m]], rng, multiopen="gwc")
+        insts = [i for _, i in asg[:m]]
+        res = orc.verify_proof(params, vk, insts, proof, "gwc")
+        assert res.status == orc.OK
+        assert co.verify_multi(proof, insts, "gwc") == (0, res.challenges, enc_point(res.L) + enc_point(res.R))
+        assert host_status(params, vk, m, proof, insts) == 0
+        wrong = [[list(c) for c in i] for i in insts]
+        wrong[-1][0][0] = (wrong[-1][0][0] + 1) % bn.R
+        assert orc.verify_proof(params, vk, wrong, proof, "gwc").status == orc.CONSTRAINT_SYSTEM_FAILURE
+        assert co.verify_multi(proof, wrong, "gwc")[0] == orc.CONSTRAINT_SYSTEM_FAILURE
+        assert host_status(params, vk, m, proof, wrong) == orc.CONSTRAINT_SYSTEM_FAILURE
+    bad_a, bad_i = hp.vm_assignment(*wit[0], cheat_row=3)
+    bad = hp.prove(params, vk, pk, s, bad_a, bad_i, rng, expect_honest=False, multiopen="gwc")
+    assert orc.verify_proof(params, vk, [bad_i], bad, "gwc").status == orc.CONSTRAINT_SYSTEM_FAILURE
+    assert co.verify_multi(bad, [bad_i], "gwc")[0] == orc.CONSTRAINT_SYSTEM_FAILURE
+    co.close()
+    # lookup + shuffle + rotated gate circuit
+    circ = hp.lookup_shuffle_circuit(6, 16)
+    params, vk, pk = hp.keygen(circ, s)
+    co = c_oracle.COracle(params.to_bytes(1), 1, vk.to_bytes(1), 1)
+    adv, ins = hp.lookup_shuffle_assignment(circ, 16, rng)
+    proof = hp.prove(params, vk, pk, s, adv, ins, rng, multiopen="gwc")
+    res = orc.verify_proof(params, vk, [ins], proof, "gwc")
+    assert res.status == orc.OK and co.verify_multi(proof, [ins], "gwc")[0] == 0 and host_status(params, vk, 1, proof, [ins]) == 0
+    for cheat in ("lookup", "shuffle", "gate", "copy"):
+        adv, ins = hp.lookup_shuffle_assignment(circ, 16, rng, cheat)
+        bad = hp.prove(params, vk, pk, s, adv, ins, rng, expect_honest=False, multiopen="gwc")
+        assert orc.verify_proof(params, vk, [ins], bad, "gwc").status == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
+        assert host_status(params, vk, 1, bad, [ins]) == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
+    co.close()
