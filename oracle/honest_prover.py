@@ -215,6 +215,41 @@ def lookup_shuffle_assignment(circ, rows, rng, cheat=None):
     return [a0, a1, a2], []
 
 
+def two_phase_circuit(k, rows):
+    """advice a (phase 0), b (phase 1), one user challenge c squeezed after the phase-0 commitments (lib.rs:91-109), fixed
+    selector q, instance column pub.  Variables: a b | q | pub | c  (challenges come last, vk.rs:490-500).
+    gate   q * (b - c * a)                b = c * a can only be assigned once c is known
+    gate   q * (b * b - c^2 * a^2)        a challenge variable with a power
+    permutation over (a, phase 0) and the instance column: a row j == public input row j"""
+    cs = ConstraintSystem()
+    cs.num_fixed_columns, cs.num_advice_columns, cs.num_instance_columns = 1, 2, 1
+    cs.num_selectors, cs.num_challenges = 0, 1
+    cs.advice_column_phase = [0, 1]
+    cs.challenge_phase = [0]
+    cs.num_advice_queries = [1, 1]
+    cs.advice_queries = [(0, 0, 0), (1, 1, 0)]
+    cs.fixed_queries = [(0, 0)]
+    cs.instance_queries = [(0, 0)]
+    cs.permutation_columns = [(0, 0), (0, COL_INSTANCE)]
+    A, B, Q, _PUB, CH = range(5)
+    cs.coeff_vals = [1, R - 1]
+    cs.gates = [(5, [(0, [(B, 1), (Q, 1)]), (1, [(A, 1), (CH, 1), (Q, 1)])]),
+                (5, [(0, [(B, 2), (Q, 1)]), (1, [(A, 2), (CH, 2), (Q, 1)])])]
+    return Circuit(k, cs, 4, [[1] * rows], [((0, j), (1, j)) for j in range(rows)])
+
+
+def two_phase_assignment(a_vals, cheat=False):
+    """Returns (advice as a function of the challenge list, instance): b = c * a is assigned in phase 1."""
+    def advice(challenges):
+        c = challenges[0]
+        b = [c * a % R for a in a_vals]
+        if cheat:
+            b[0] = (b[0] + 1) % R
+        return [list(a_vals), b]
+
+    return advice, [list(a_vals)]
+
+
 # ---------------------------------------------------------------- keygen
 def keygen(circ: Circuit, s, transcript_repr=0x1234567):
     cs, k = circ.cs, circ.k
@@ -266,7 +301,6 @@ def prove_multi(params, vk, pk, s, advices, instances, rng, hash_kind="blake2b",
     cs, n = circ.cs, dom.n
     M = len(advices)
     assert M == len(instances) and M >= 1
-    assert cs.num_challenges == 0 and max(cs.advice_column_phase, default=0) == 0, "single phase only"
     chunk = circ.cs_degree - 2
     ncols = len(cs.permutation_columns)
     n_sets = -(-ncols // chunk) if ncols else 0
@@ -278,15 +312,10 @@ def prove_multi(params, vk, pk, s, advices, instances, rng, hash_kind="blake2b",
         return [col[(j + rot) % n] for j in range(n)]
 
     I = []  # per-instance prover state
-    for advice, instance in zip(advices, instances):
-        st = {}
-        st["adv"] = [blind(col) for col in advice]
+    for instance in instances:
+        st = {"adv": [None] * cs.num_advice_columns, "adv_c": [None] * cs.num_advice_columns}
         st["inst"] = [list(col) + [0] * (n - len(col)) for col in instance]  # lib.rs:204-217 evaluates exactly this polynomial
-        st["adv_c"] = [dom.lagrange_to_coeff(col) for col in st["adv"]]
         st["inst_c"] = [dom.lagrange_to_coeff(col) for col in st["inst"]]
-        # values of every query variable on the base domain: advice | fixed | instance (vk.rs:490-500)
-        st["var_rows"] = [rot_col(st["adv"][c], r) for c, _p, r in cs.advice_queries] + [rot_col(pk["fixed"][c], r) for c, r in cs.fixed_queries] \
-            + [rot_col(st["inst"][c], r) for c, r in cs.instance_queries]
         I.append(st)
 
     def column(st, idx, typ):
@@ -308,9 +337,23 @@ def prove_multi(params, vk, pk, s, advices, instances, rng, hash_kind="blake2b",
         for col in instance:
             for v in col:
                 tr.common_scalar(v)
-    for st in I:  # lib.rs:91-103
-        for c in st["adv_c"]:
-            tr.write_point(commit(c))
+    # lib.rs:91-109: per phase, every instance's advice commitments of that phase, then the phase's challenges.  An
+    # advice assignment that depends on earlier challenges is given as a function of the challenge list.
+    challenges = [0] * cs.num_challenges
+    for phase in sorted(set(cs.advice_column_phase)):
+        for st, advice in zip(I, advices):
+            cols = advice(list(challenges)) if callable(advice) else advice
+            for c, ph in enumerate(cs.advice_column_phase):
+                if ph == phase:
+                    st["adv"][c] = blind(cols[c])
+                    st["adv_c"][c] = dom.lagrange_to_coeff(st["adv"][c])
+                    tr.write_point(commit(st["adv_c"][c]))
+        for ci, ph in enumerate(cs.challenge_phase):
+            if ph == phase:
+                challenges[ci] = tr.squeeze_challenge()
+    for st in I:  # values of every query variable on the base domain: advice | fixed | instance | challenges (vk.rs:490-500)
+        st["var_rows"] = [rot_col(st["adv"][c], r) for c, _p, r in cs.advice_queries] + [rot_col(pk["fixed"][c], r) for c, r in cs.fixed_queries] \
+            + [rot_col(st["inst"][c], r) for c, r in cs.instance_queries] + [[ch] * n for ch in challenges]
     theta = tr.squeeze_challenge()
 
     def compress_rows(st, polys):
@@ -418,7 +461,7 @@ def prove_multi(params, vk, pk, s, advices, instances, rng, hash_kind="blake2b",
     for st in I:  # lib.rs:273-344: every expression of instance pi, then the next instance
         adv_e, inst_e = [E(c) for c in st["adv_c"]], [E(c) for c in st["inst_c"]]
         var_e = [dom.rotate_ext(adv_e[c], r) for c, _p, r in cs.advice_queries] + [dom.rotate_ext(fix_e[c], r) for c, r in cs.fixed_queries] \
-            + [dom.rotate_ext(inst_e[c], r) for c, r in cs.instance_queries]
+            + [dom.rotate_ext(inst_e[c], r) for c, r in cs.instance_queries] + [[ch] * m for ch in challenges]
 
         def poly_ext(poly):
             out = [0] * m

@@ -213,3 +213,54 @@ def test_honest_proofs_with_the_gwc_opening(built):
         assert orc.verify_proof(params, vk, [ins], bad, "gwc").status == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
         assert host_status(params, vk, 1, bad, [ins]) == orc.CONSTRAINT_SYSTEM_FAILURE, cheat
     co.close()
+
+
+@pytest.mark.parametrize("mo", ["shplonk", "gwc"])
+def test_honest_two_phase_circuit_with_a_user_challenge(built, mo):
+    """Advice columns in two phases and a user challenge squeezed between them (lib.rs:91-109; challenge variables in gate
+    polynomials, vk.rs:490-500): the phase-1 column is assigned from the challenge.  Honest proofs (one and two circuit
+    instances) are accepted by the Python oracle, the C oracle and the host build of the CUDA stages; a phase-1 cheat and a
+    wrong public input are rejected."""
+    import ctypes
+
+    rng = random.Random("honest-phases-" + mo)
+    s = rng.randrange(1, bn.R)
+    circ = hp.two_phase_circuit(5, 6)
+    params, vk, pk = hp.keygen(circ, s)
+    co = c_oracle.COracle(params.to_bytes(1), 1, vk.to_bytes(1), 1)
+    lib = ctypes.CDLL(os.path.join(HERE, "hostlib", "libstage.so"))
+    lib.s_err.restype = ctypes.c_char_p
+
+    def host_status(m, proof, insts):
+        pb, vb = params.to_bytes(), vk.to_bytes(F.RAW_BYTES)
+        assert lib.s_build_m(pb, len(pb), 0, vb, len(vb), F.RAW_BYTES, 0 if mo == "shplonk" else 1, 0, m) == 0, lib.s_err()
+        info = (ctypes.c_uint32 * 8)()
+        lib.s_info(info)
+        _k, P, _S, C, plen, _nic, nsh, nmo = list(info)
+        assert plen == len(proof)
+        cols = [col for inst in insts for col in inst]
+        ib = b"".join(bn.fr_to_repr(v) for col in cols for v in col)
+        cl = (ctypes.c_uint32 * max(1, len(cols)))(*[len(c) for c in cols])
+        bufs = [(ctypes.c_uint8 * (32 * k_))() for k_ in (C, P, nsh, nmo)]
+        LR = (ctypes.c_uint8 * 128)(); ok = ctypes.c_int(0)
+        return lib.s_verify_one(proof, len(proof), ib, sum(len(c) for c in cols), cl, len(cols), *bufs, LR, ctypes.byref(ok))
+
+    asg = [hp.two_phase_assignment([rng.randrange(bn.R) for _ in range(6)]) for _ in range(2)]
+    for m in (1, 2):
+        advs, insts = [a for a, _ in asg[:m]], [i for _, i in asg[:m]]
+        proof = hp.prove_multi(params, vk, pk, s, advs, insts, rng, multiopen=mo)
+        res = orc.verify_proof(params, vk, insts, proof, mo)
+        assert res.status == orc.OK and len(res.trace["user_challenges"]) == 1
+        assert co.verify_multi(proof, insts, mo) == (0, res.challenges, enc_point(res.L) + enc_point(res.R))
+        assert host_status(m, proof, insts) == 0
+        wrong = [[list(c) for c in i] for i in insts]
+        wrong[-1][0][2] = (wrong[-1][0][2] + 1) % bn.R
+        assert orc.verify_proof(params, vk, wrong, proof, mo).status == orc.CONSTRAINT_SYSTEM_FAILURE
+        assert co.verify_multi(proof, wrong, mo)[0] == orc.CONSTRAINT_SYSTEM_FAILURE
+        assert host_status(m, proof, wrong) == orc.CONSTRAINT_SYSTEM_FAILURE
+    cheat_adv, cheat_inst = hp.two_phase_assignment(asg[0][1][0], cheat=True)
+    bad = hp.prove_multi(params, vk, pk, s, [cheat_adv], [cheat_inst], rng, expect_honest=False, multiopen=mo)
+    assert orc.verify_proof(params, vk, [cheat_inst], bad, mo).status == orc.CONSTRAINT_SYSTEM_FAILURE
+    assert co.verify_multi(bad, [cheat_inst], mo)[0] == orc.CONSTRAINT_SYSTEM_FAILURE
+    assert host_status(1, bad, [cheat_inst]) == orc.CONSTRAINT_SYSTEM_FAILURE
+    co.close()
