@@ -590,3 +590,24 @@ def test_honest_gwc_proof_through_the_c_abi(pkg):
                            "gwc", "blake2b", device=0, circuit_instances=2)
     with bv:
         assert bv.verify_batch([proof, proof], [insts, insts[::-1]]).status == [0, 4]
+
+
+def test_honest_two_phase_proof_through_the_c_abi(pkg):
+    """The two-phase circuit with a user challenge (oracle/honest_prover.two_phase_circuit): honest proof accepted, phase-1
+    cheat and wrong public input rejected by the CUDA path; challenges equal the oracle's."""
+    import honest_prover as hp
+
+    rng = random.Random("gpu-honest-phases")
+    s = rng.randrange(1, bn.R)
+    circ = hp.two_phase_circuit(5, 6)
+    params, vk, pk = hp.keygen(circ, s)
+    adv, ins = hp.two_phase_assignment([rng.randrange(bn.R) for _ in range(6)])
+    good = hp.prove_multi(params, vk, pk, s, [adv], [ins], rng)
+    adv_b, ins_b = hp.two_phase_assignment(ins[0], cheat=True)
+    bad = hp.prove_multi(params, vk, pk, s, [adv_b], [ins_b], rng, expect_honest=False)
+    wrong = [list(ins[0])]
+    wrong[0][1] = (wrong[0][1] + 1) % bn.R
+    with make_bv(pkg, params, vk, "shplonk", "blake2b") as bv:
+        res = bv.verify_batch([good, bad, good], [ins, ins_b, wrong], want_challenges=True)
+        w = orc.verify_proof(params, vk, [ins], good)
+        assert res.status == [0, 4, 4] and w.status == 0 and split32(res.challenges, bv.n_challenges) == w.challenges
