@@ -5,12 +5,18 @@ transcript) of the reference's vector_mul test-circuit shape at k = 10 (BASELINE
     python bench.py --gpus N --steps K --warmup W          this repo's CUDA path (one rank per GPU)
     python bench.py --impl reference ...                    CPU restatement of the reference algorithm
                                                             (oracle/), all host threads, rank 0 only
+    python bench.py --config 5 [--gpus N]                   ONE 65,536-proof global batch sharded over N GPUs (configs[4])
+    python bench.py --config 4                              the k = 18 lookup-heavy shape, batch 1024 (configs[3])
+    python bench.py --selfcheck ...                         additionally: the (sharded) path against the C oracle on the
+                                                            bench's own inputs, incl. a corrupted proof on a non-root rank
 
-A step = one complete batch verification (transcript replay, expression / multi-open scalars, one
-folded MSM, one pairing) of `--batch` proofs per GPU.  `value` times steps on inputs already resident
-in HBM (L2 flushed between steps); `e2e` times the C-ABI call `h2v_verify_batch` (N=1) or
-`h2v_accumulate_shard` + NCCL all-gather + `h2v_finalize` (N>1) from pinned host buffers, host<->device
-copies included.  Prints ONE JSON line on rank 0.
+A step = ONE launch set: `--fold-groups` complete, independent batch verifications (each: transcript replay,
+expression / multi-open scalars, one folded MSM, one pairing check, one verdict) of `--batch` proofs per GPU that
+share one set of kernel launches.  `value` times `--blocks` blocks of `--steps` steps on inputs already resident in
+HBM (L2 flushed between steps) and reports the median block; `e2e` times the C-ABI call a user makes
+(`h2v_verify_batch` at N=1, `h2v_verify_shard` at N>1) from pinned host buffers, host<->device copies included.
+At N>1 the one exchange step runs device-side over NVLink inside the CUDA graph (csrc/exchange.cuh); torch.distributed
+is plumbing (barriers, start-up handle exchange).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes
@@ -105,46 +111,57 @@ class PackedBatch:
         return (self.n, self.proofs.data_ptr(), self.poff.data_ptr(), self.inst.data_ptr(), self.ioff.data_ptr())
 
 
-def algorithmic_mm(bv, n, geom):
-    """Algorithmic 256-bit Montgomery multiplications per stage of one batch (DESIGN.md section 4);
-    1 MM = 136 32x32->64 multiply-adds (8-limb CIOS: 64 for a*b, 64 for m*p, 8 for m_i)."""
-    P, S = bv.n_points, bv.n_scalars
+def algorithmic_mm(bv, n, geom, rows=10):
+    """Algorithmic 256-bit Montgomery multiplications per stage of ONE batch of n proofs (DESIGN.md section 5);
+    1 MM = 136 32x32->64 multiply-adds (8-limb CIOS: 64 for a*b, 64 for m*p, 8 for m_i); a squaring counts as one MM.
+    The per-proof stages come from the plan itself (h2v_ctx_work_model walks the plan like scalar_stage does), the MSM and
+    pairing terms from the window geometry of the run."""
+    wm = bv.work_model(rows)
+    P = bv.n_points
     c0, c1 = geom["window_bits"] & 0xFFFF, geom["window_bits"] >> 16
     W0, W1 = geom["windows"] & 0xFFFF, geom["windows"] >> 16
-    t_right, t_left = n * P + bv.n_shared, n * bv.n_mo // 2  # half of the left multi-open slots carry scalar 0 (h1)
-    mm = {
-        "decompress": n * P * (250 + 38 + 16 + 9),  # sqrt by 5-bit sliding window (250 S + 38 M + 16 table) + curve check / conversions; a squaring counts as one MM
-        "transcript": n * (P * 2 + S + bv.n_challenges * 2),  # only Montgomery conversions; the hash is ALU work
-        "scalar": n * (10 + 310 + 3 * 12 + 40 * 4 + 160),  # x^n, one inversion, Lagrange, expressions, SHPLONK sets (VM shape)
+    left_live = bv.n_mo if getattr(bv, "multiopen", "shplonk") == "gwc" else bv.n_mo // 2  # SHPLONK: h1 has left scalar 0
+    t_right, t_left = n * P + bv.n_shared, n * left_live
+    return {
+        "decompress": n * P * wm["decompress_per_point"],
+        "transcript": n * wm["transcript"],
+        "scalar": n * wm["scalar"],
+        # fold coefficients (scalar x c_j per term) + bucket accumulation (mixed addition 7 M + 4 S) + bucket reduction (2 full additions per bucket)
         "rlc_msm": n * (P + bv.n_mo) * 2 + (W0 * t_right + W1 * t_left) * 11 + (W0 * (1 << (c0 - 1)) + W1 * (1 << (c1 - 1))) * 32,
-        "pairing": (65 * (W0 + W1) * 58 + 430 * 54),  # k_lines: line value (4) + product (54) per pair and step; check: ~430 Fq12 products
+        "pairing": 65 * (W0 + W1) * 58 + 430 * 54,  # k_lines: line value (4) + sparse product (54) per pair and step; check: ~430 Fq12 products
     }
-    return mm
-
-
-def plan_launch_sets(steps, fold_groups, n_ctx):
-    """How exactly `steps` batches are timed with `fold_groups` batches per launch set on `n_ctx` contexts.
-    Returns (G, G_rem, full, assign): `full` launch sets of G groups and, when G does not divide steps, ONE launch set
-    of the remaining G_rem groups, which the LAST context runs (the other contexts share the full sets); assign[i] =
-    context of launch set i.  A single context cannot hold two resident uploads: G shrinks to a divisor of steps."""
-    G = max(1, min(fold_groups, steps))
-    if n_ctx == 1:
-        while steps % G:
-            G -= 1
-    G_rem = steps % G
-    full = steps // G
-    n_full = n_ctx - 1 if G_rem else n_ctx
-    assign = [i % n_full for i in range(full)] + ([n_ctx - 1] if G_rem else [])
-    return G, G_rem, full, assign
 
 
 def bucket_sum_mm(bv, n, geom):
     """k_msm_bucket_sum alone: one mixed addition (7 MM + 4 S, counted as 11 MM) per bucket entry"""
     W0, W1 = geom["windows"] & 0xFFFF, geom["windows"] >> 16
-    return (W0 * (n * bv.n_points + bv.n_shared) + W1 * (n * bv.n_mo // 2)) * 11
+    left_live = bv.n_mo if getattr(bv, "multiopen", "shplonk") == "gwc" else bv.n_mo // 2
+    return (W0 * (n * bv.n_points + bv.n_shared) + W1 * (n * left_live)) * 11
+
+
+def plan_launch_sets(steps, n_ctx):
+    """A step is ONE launch set (fold_groups independent batches through one set of kernel launches on one context).
+    The `steps` launch sets of a timed block go round-robin over the contexts; launch set i is rooted at rank i mod N.
+    Returns assign[i] = context of launch set i (identical on every rank: the contexts of equal index form a channel and
+    must see the same sequence of launch sets)."""
+    return [i % n_ctx for i in range(steps)]
+
+
+CONFIGS = {
+    # BASELINE.json configs[1]: the headline
+    2: dict(shape="vm", k=10, batch=4096, multiopen="shplonk", scaling="weak",
+            name="BASELINE.json configs[1]: 4096-proof SHPLONK batches, vector_mul test-circuit shape, k=10"),
+    # configs[3]: lookup + permutation heavy
+    4: dict(shape="k18", k=18, batch=1024, multiopen="shplonk", scaling="weak",
+            name="BASELINE.json configs[3]: 1024-proof batches of the lookup+permutation-heavy shape (k=18, degree 5, 64 advice columns, 12,960-byte proofs)"),
+    # configs[4]: ONE 65,536-proof global batch sharded over the ranks
+    5: dict(shape="vm", k=10, batch=65536, multiopen="shplonk", scaling="strong",
+            name="BASELINE.json configs[4]: ONE 65,536-proof SHPLONK global batch sharded over the GPUs, partial accumulators gathered over NVLink, one final pairing"),
+}
 
 
 def run_ours(args):
+    import numpy as np
     import torch
     import __graft_entry__ as g
 
@@ -155,7 +172,7 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
     dist = None
-    if world > 1:
+    if world > 1:  # torch.distributed = plumbing only: barriers, the start-up exchange of window handles, max over ranks
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -163,10 +180,19 @@ def run_ours(args):
     from importlib import import_module
 
     synth = import_module("halo2_verifier_b200.synth")
+    sharding = import_module("halo2_verifier_b200.sharding")
     lib = pkg.load_library()
-    k, n = args.k, args.batch
+    cfg = CONFIGS[args.config]
+    k, shape = args.k, args.shape
+    strong = cfg["scaling"] == "strong"
+    if strong:  # one global batch per fold group, every rank holds 1 / world of it
+        assert args.batch % world == 0
+        n, G = args.batch // world, 1
+    else:
+        n, G = args.batch, max(1, args.fold_groups)
+    gcount, gbase = n * world, n * rank  # of ONE global batch
     s = srs_secret(k)
-    vk_bytes, shared_dlogs = synth.make_vk_bytes(args.shape, k)
+    vk_bytes, shared_dlogs = synth.make_vk_bytes(shape, k)
     params = pkg.ParamsKZG.from_bytes(synth.params_bytes_raw(k, s), pkg.SerdeFormat.RawBytes)
     vk = pkg.VerifyingKey.from_bytes(vk_bytes, pkg.SerdeFormat.RawBytes)
     n_ctx = max(1, args.streams)
@@ -178,18 +204,21 @@ def run_ours(args):
     blocking = n_ctx * world > max(1, (os.cpu_count() or 1) // 2)
     for b in bvs:
         lib.h2v_ctx_set_blocking_sync(b._ctx, 1 if blocking else 0)
-    # two distinct accepting batches per rank (seeded), alternated between steps
+    for ci, ctx in enumerate(bvs):
+        ctx.ci = ci
+    if world > 1:  # one exchange channel per context index (include/h2v.h): windows mapped once, at start-up
+        for ctx in bvs:
+            if not sharding.connect_channel(ctx, rank, world, max_groups=G):
+                raise SystemExit("the ranks cannot map each other's exchange windows (CUDA IPC / peer access): " + lib.h2v_last_error(ctx._ctx).decode())
+    # ---------------- inputs: two distinct accepting batches per rank (seeded), alternated between fold groups
     t0 = time.time()
+    n_dist = min(n, 4096)
     batches = []
     for b in range(2):
-        proofs, instances = synth.synthesize_shplonk_batch(bv, shared_dlogs, s, n, seed=(rank, b))
-        batches.append(PackedBatch(torch, proofs, instances))
+        proofs, instances = synth.synthesize_shplonk_batch(bv, shared_dlogs, s, n_dist, seed=(rank, b))
+        reps = -(-n // n_dist)
+        batches.append(PackedBatch(torch, (proofs * reps)[:n], (instances * reps)[:n]))
     gen_s = time.time() - t0
-    # fold groups: G consecutive independent batches per set of kernel launches (own fold and own pairing check each;
-    # at N > 1 group q is this rank's shard of global batch q); the packed upload alternates the two distinct batches
-    # exactly `steps` batches are timed: steps // G launch sets of G groups, and, when G does not divide steps, ONE launch
-    # set of the remaining groups, which the last context runs (the other contexts share the full sets)
-    G, G_rem, full, assign = plan_launch_sets(args.steps, args.fold_groups, n_ctx)
 
     def packed_groups(first, count):
         pr, ins = [], []
@@ -199,102 +228,41 @@ def run_ours(args):
         return PackedBatch(torch, pr, ins)
 
     gbatches = [packed_groups(b, G) for b in range(2)] if G > 1 else batches
-    rbatch = packed_groups(0, G_rem) if G_rem > 1 else batches[0]
-    gcount, gbase = n * world, n * rank
-    seed = 7
-    pbytes = int(lib.h2v_partial_bytes())
     chk = lambda ctx, rc: ctx._check(rc)
     ext_streams = [torch.cuda.ExternalStream(b.stream_handle(), device=torch.device("cuda", local)) for b in bvs]
-    # Per context: its own partial buffers and (N > 1) its own NCCL communicator, so that the batches in flight
-    # exchange their partials independently; each context is driven by one host thread whose current torch stream
-    # IS the context's stream, which orders shard kernels -> all-gather -> pairing check without extra events.
-    for ci, ctx in enumerate(bvs):
-        ctx.ci = ci
-        # partial / gathered buffers per group count in use: 1 (single batches: latency view) and G (throughput view)
-        ctx.cur_groups = 1
-        ctx.partial_by = {q: torch.zeros(q * pbytes, dtype=torch.uint8, device="cuda") for q in {1, G, max(1, G_rem)}}
-        ctx.gathered_by = {q: (torch.zeros(world * q * pbytes, dtype=torch.uint8, device="cuda") if world > 1 else None) for q in {1, G, max(1, G_rem)}}
-    comm_stream = torch.cuda.Stream(priority=-1) if world > 1 else None
-    comm_group = None
-    if world > 1:  # create the communicator (high-priority NCCL stream: the tiny gather must not queue behind compute) before any worker thread exists
-        opts = dist.ProcessGroupNCCL.Options()
-        opts.is_high_priority_stream = True
-        comm_group = dist.new_group(backend="nccl", pg_options=opts)
-        with torch.cuda.stream(comm_stream):
-            dist.all_gather_into_tensor(bvs[0].gathered_by[1], bvs[0].partial_by[1], group=comm_group)
-        torch.cuda.synchronize()
+    NULL = None
 
-    class Exchange:
-        """The one exchange step of a sharded batch: NCCL all-gather of the per-window partials.  All gathers of all
-        batches in flight go through ONE communicator in global step order, issued by one thread on one stream
-        (several communicators spinning on each other's peers can deadlock on the hardware work queues); the
-        contexts' streams are tied to it with CUDA events, so nothing waits on the host."""
+    def set_groups(ctx, pb):
+        if pb.n > n:
+            chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
 
-        def __init__(self, count):
-            self.ready = [threading.Event() for _ in range(count)]
-            self.done = [threading.Event() for _ in range(count)]
-            self.ev_ready = [None] * count
-            self.ev_done = [None] * count
-            self.slot = [None] * count
-            self.thread = threading.Thread(target=self.run, args=(count,))
-            self.thread.start()
-
-        def run(self, count):
-            torch.cuda.set_device(local)
-            with torch.cuda.stream(comm_stream):
-                for i in range(count):
-                    self.ready[i].wait()
-                    ctx = self.slot[i]
-                    comm_stream.wait_event(self.ev_ready[i])
-                    dist.all_gather_into_tensor(ctx.gathered_by[ctx.cur_groups], ctx.partial_by[ctx.cur_groups], group=comm_group)
-                    ev = torch.cuda.Event(blocking=blocking)
-                    ev.record(comm_stream)
-                    self.ev_done[i] = ev
-                    self.done[i].set()
-
-        def gather(self, ctx, i):
-            """called by the context's thread after it enqueued the shard's kernels on its stream"""
-            ev = torch.cuda.Event()
-            ev.record(ext_streams[ctx.ci])
-            self.ev_ready[i], self.slot[i] = ev, ctx
-            self.ready[i].set()
-            self.done[i].wait()
-            ext_streams[ctx.ci].wait_event(self.ev_done[i])
-            return self.ev_done[i]
-
-    xchg = [None]
-
-    def gather_and_finalize(ctx, i):
-        """NCCL all-gather of the partials over NVLink, then the single pairing check on rank 0."""
-        v = ctypes.c_int(1)
-        ev = xchg[0].gather(ctx, i)
-        if rank == i % world:  # every rank holds all partials after the all-gather: the ONE pairing check of global batch i runs on rank i mod N
-            chk(ctx, lib.h2v_finalize_groups(ctx._ctx, world, ctx.cur_groups, ctx.gathered_by[ctx.cur_groups].data_ptr(), None, ctypes.byref(v)))
+    def upload(ctx, pb):
+        set_groups(ctx, pb)
+        if world == 1:
+            chk(ctx, lib.h2v_batch_upload(ctx._ctx, *pb.args(), NULL, 0))
         else:
-            ev.synchronize()  # this context's buffers are reused by its next step
-        return v.value
+            chk(ctx, lib.h2v_batch_upload_shard(ctx._ctx, *pb.args(), NULL, 0, gbase, gcount))
 
-    def step_resident(ctx, i=0, flush=True):
+    def step_resident(ctx, i=0):
+        """one launch set on data resident in HBM; N > 1: through the device-side exchange, rooted at rank i mod N"""
         v = ctypes.c_int(0)
-        if flush and not os.environ.get("H2V_BENCH_DIAG_NOFLUSH"):  # (diagnosis only; reported numbers always flush)
+        if not os.environ.get("H2V_BENCH_DIAG_NOFLUSH"):  # (diagnosis only; reported numbers always flush)
             chk(ctx, lib.h2v_flush_l2(ctx._ctx, 256 << 20))
         if world == 1:
             chk(ctx, lib.h2v_batch_run(ctx._ctx, ctypes.byref(v)))
-            return v.value
-        chk(ctx, lib.h2v_batch_run_shard_async(ctx._ctx, ctx.partial_by[ctx.cur_groups].data_ptr()))  # enqueue only: the gather is event-ordered after it
-        return gather_and_finalize(ctx, i)
+        else:
+            chk(ctx, lib.h2v_batch_run_shard_exchange(ctx._ctx, i % world, NULL, ctypes.byref(v)))
+        return v.value
 
     def step_e2e(ctx, pb, i=0):
+        """the call a user makes: host buffers in, statuses out (fold randomness from the OS: seed 0, no scalars)"""
+        set_groups(ctx, pb)
         if world == 1:
-            if pb.n > n:
-                chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
-            chk(ctx, lib.h2v_verify_batch(ctx._ctx, *pb.args(), None, seed, pb.status.data_ptr(), None, None, None))
+            chk(ctx, lib.h2v_verify_batch(ctx._ctx, *pb.args(), NULL, 0, pb.status.data_ptr(), NULL, NULL, NULL))
             return int(pb.status.max()) == 0
-        ctx.cur_groups = pb.n // n
-        if pb.n > n:
-            chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
-        chk(ctx, lib.h2v_accumulate_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount, pb.status.data_ptr(), ctx.partial_by[ctx.cur_groups].data_ptr()))
-        return gather_and_finalize(ctx, i) == 1
+        v = ctypes.c_int(0)
+        chk(ctx, lib.h2v_verify_shard(ctx._ctx, *pb.args(), NULL, 0, gbase, gcount, i % world, pb.status.data_ptr(), NULL, ctypes.byref(v)))
+        return v.value == 1 and int(pb.status.max()) == 0
 
     def sync_all():
         torch.cuda.synchronize()
@@ -302,102 +270,94 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def upload(ctx, pb):
-        if world == 1:
-            if pb.n > n:
-                chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
-            chk(ctx, lib.h2v_batch_upload(ctx._ctx, *pb.args(), None, seed))
-        else:
-            ctx.cur_groups = pb.n // n
-            if pb.n > n:
-                chk(ctx, lib.h2v_batch_set_fold_groups(ctx._ctx, pb.n // n))
-            chk(ctx, lib.h2v_batch_upload_shard(ctx._ctx, *pb.args(), None, seed, gbase, gcount))
-
-    def timed(fn, count, ctxs, assign=None):
-        """count steps between barrier + synchronize on both sides; returns (results, seconds on the DEVICE clock:
-        CUDA events on the contexts' streams, first start -> last end; wall seconds)."""
-        sync_all()
-        ev0 = torch.cuda.Event(enable_timing=True)
-        ev0.record(ext_streams[0])
-        w0 = time.perf_counter()
-        res_ = run_steps(fn, count, ctxs, assign)
-        ends = []
-        for st in ext_streams[: len(ctxs)] + [torch.cuda.current_stream()] + ([comm_stream] if comm_stream is not None else []):
-            e = torch.cuda.Event(enable_timing=True)
-            e.record(st)
-            ends.append(e)
-        sync_all()
-        wall = time.perf_counter() - w0
-        return res_, max(ev0.elapsed_time(e) for e in ends) * 1e-3, wall
-
-    def run_steps(fn, count, ctxs, assign=None):
-        """count launch sets spread over the contexts (round-robin, or set i on context assign[i]); each context is
-        driven by its own host thread (ctypes releases the GIL), so batches of different contexts overlap on the device."""
+    def run_steps(fn, count, ctxs, before=None):
+        """`count` launch sets round-robin over the contexts; each context is driven by its own host thread (ctypes
+        releases the GIL), so the launch sets of different contexts overlap on the device.  `before` runs on the
+        main thread once every worker stands at the start line."""
         out = [None] * count
-        if world > 1:
-            xchg[0] = Exchange(count)
-        if assign is None:
-            assign = [i % len(ctxs) for i in range(count)]
+        assign = plan_launch_sets(count, len(ctxs))
+        start = threading.Barrier(len(ctxs) + 1)
+        errs = []
 
         def worker(ci):
             torch.cuda.set_device(local)
-            with torch.cuda.stream(ext_streams[ctxs[ci].ci]):
+            start.wait()
+            try:
                 for i in range(count):
                     if assign[i] == ci:
                         out[i] = fn(ctxs[ci], i)
-
-        if len(ctxs) == 1:
-            worker(0)
-            if world > 1:
-                xchg[0].thread.join()
-            return out
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
 
         ths = [threading.Thread(target=worker, args=(ci,)) for ci in range(len(ctxs))]
         [t.start() for t in ths]
+        if before is not None:
+            before()
+        start.wait()
         [t.join() for t in ths]
-        if world > 1:
-            xchg[0].thread.join()
+        if errs:
+            raise errs[0]
         return out
 
-    def reduce_max(*vals):
+    def timed_block(fn, count, ctxs):
+        """`count` launch sets between barrier + synchronize on both sides; returns (results, seconds on the DEVICE clock:
+        CUDA events on the contexts' streams, first start -> last end; seconds on the host clock)."""
+        sync_all()
+        ev0 = torch.cuda.Event(enable_timing=True)
+        w0 = [0.0]
+
+        def before():
+            ev0.record(ext_streams[ctxs[0].ci])
+            w0[0] = time.perf_counter()
+
+        res_ = run_steps(fn, count, ctxs, before)
+        ends = []
+        for c in ctxs:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(ext_streams[c.ci])
+            ends.append(e)
+        sync_all()
+        wall = time.perf_counter() - w0[0]
+        return res_, max(ev0.elapsed_time(e) for e in ends) * 1e-3, wall
+
+    def reduce_max(vals):
         t = torch.tensor(vals, dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(x) for x in t]
 
     W = max(args.warmup, 3)
-    runs = full + (1 if G_rem else 0)  # launch sets; a step is ONE batch of n proofs per GPU
-    warm_assign = [ci for _ in range(W) for ci in range(n_ctx)]
-    total = n * world * args.steps
-    # ---------------- device-resident throughput (`value`)
+    R = max(1, args.blocks)
+    steps = args.steps
+    proofs_per_step = n * G * world  # one launch set on every rank
+    # ---------------- one batch in flight: latency view (single batches, one context, spinning waits)
     upload(bv, batches[0])
     ok = run_steps(lambda ctx, i: step_resident(ctx, i), W, bvs[:1])
     assert all(v == 1 for v in ok), "warm-up batch was rejected"
-    geom = geom_tp = bv.msm_geometry()  # single batch (latency windows); geom_tp: the launch sets of the throughput view
+    geom = geom_tp = bv.msm_geometry()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = sum(b.launch_count() for b in bvs)
-    # one batch in flight: latency view (one host thread per rank: spinning waits)
     lib.h2v_ctx_set_blocking_sync(bv._ctx, 0)
-    res, dt1, _ = timed(lambda ctx, i: step_resident(ctx, i), args.steps, bvs[:1])
+    lat_steps = max(8, min(steps, 32))
+    res, dt1, _ = timed_block(lambda ctx, i: step_resident(ctx, i), lat_steps, bvs[:1])
     lib.h2v_ctx_set_blocking_sync(bv._ctx, 1 if blocking else 0)
     assert all(v == 1 for v in res), "a timed batch was rejected"
-    launches = sum(b.launch_count() for b in bvs) - launches0
-    dt = dt1
-    if n_ctx > 1 or G > 1:  # several independent batches in flight (fold groups per launch set x contexts): throughput view
-        for ci, ctx in enumerate(bvs):
-            upload(ctx, rbatch if (G_rem and ci == n_ctx - 1) else gbatches[ci % 2])
-        ok = run_steps(lambda ctx, i: step_resident(ctx, i), W * n_ctx, bvs, warm_assign)
-        assert all(v == 1 for v in ok), "warm-up batch was rejected"
-        geom_tp = bv.msm_geometry()
+    # ---------------- device-resident throughput (`value`): R timed blocks of `steps` launch sets, median block
+    for ci, ctx in enumerate(bvs):
+        upload(ctx, gbatches[ci % 2])
+    ok = run_steps(lambda ctx, i: step_resident(ctx, i), W * n_ctx, bvs)
+    assert all(v == 1 for v in ok), "warm-up launch set was rejected"
+    geom_tp = bv.msm_geometry()
+    block_dt = []
+    launches = 0
+    for _ in range(R):
         launches0 = sum(b.launch_count() for b in bvs)
-        res, dt, _ = timed(lambda ctx, i: step_resident(ctx, i), runs, bvs, assign)
-        assert all(v == 1 for v in res), "a timed batch was rejected"
+        res, dtb, _ = timed_block(lambda ctx, i: step_resident(ctx, i), steps, bvs)
+        assert all(v == 1 for v in res), "a timed launch set was rejected"
         launches = sum(b.launch_count() for b in bvs) - launches0
+        block_dt.append(dtb)
     clocks = sampler.summary()
-    if os.environ.get("H2V_BENCH_DIAG_TIMELINE") and rank == 0:  # (diagnosis only) per-block timeline of 2 steps per context
-        import numpy as np
-
+    if os.environ.get("H2V_BENCH_DIAG_TIMELINE") and rank == 0 and world == 1:  # (diagnosis only) per-block timeline of 3 sets per context
         cap = 1 << 20
         chk(bv, lib.h2v_debug_timeline_start(local, cap))
         run_steps(lambda ctx, i: step_resident(ctx, i), 3 * n_ctx, bvs)
@@ -405,132 +365,302 @@ def run_ours(args):
         cnt = ctypes.c_uint32(0)
         chk(bv, lib.h2v_debug_timeline_stop(local, buf.ctypes.data, cap, ctypes.byref(cnt)))
         np.save(os.environ["H2V_BENCH_DIAG_TIMELINE"], buf[: cnt.value * 8].reshape(-1, 8))
-    # the same CUDA-event stage timings, of the LAST batch of every context of the run with all batches in flight
-    inflight_acc = {}
-    for b in (bvs if os.environ.get("H2V_BENCH_DIAG_NOGRAPH") else []):  # (diagnosis only: needs direct launches)
-        for name, ms in b.timings().items():
-            inflight_acc.setdefault(name, []).append(ms)
-    stage_ms_in_flight = {k_: statistics.median(v) for k_, v in inflight_acc.items()}
-    # per-stage / per-kernel device times of a few serial single batches under graph replay, from the on-device block
-    # timeline (global nanosecond timer: first block start -> last block end of every kernel; no host in the loop)
-    import numpy as np
-
-    upload(bv, batches[0])
-    run_steps(lambda ctx, i_: step_resident(ctx, i_), 2, bvs[:1])
-    stage_acc, kern_acc = {}, {}
-    cap = 1 << 18
-    tlbuf = np.zeros(cap * 8, dtype=np.uint32)
-    for i in range(5):
-        chk(bv, lib.h2v_debug_timeline_start(local, cap))
-        run_steps(lambda ctx, i_: step_resident(ctx, i_), 1, bvs[:1])
-        cnt = ctypes.c_uint32(0)
-        chk(bv, lib.h2v_debug_timeline_stop(local, tlbuf.ctypes.data, cap, ctypes.byref(cnt)))
-        rec = tlbuf[: cnt.value * 8].reshape(-1, 8).astype(np.uint64)
-        kid, t0, t1 = rec[:, 0], rec[:, 4] | (rec[:, 5] << np.uint64(32)), rec[:, 6] | (rec[:, 7] << np.uint64(32))
-        span = {int(k_): (int(t0[kid == k_].min()), int(t1[kid == k_].max())) for k_ in np.unique(kid)}
-        if not all(k_ in span for k_ in range(1, 11)):
-            continue
-        ms = lambda a, b: (b - a) * 1e-6
-        for name, v in (("total", ms(span[1][0], span[10][1])), ("decompress", ms(*span[1])), ("transcript", ms(span[1][1], span[2][1])),
-                        ("scalar", ms(span[2][1], span[3][1])), ("rlc_msm", ms(span[3][1], span[8][1])), ("pairing", ms(span[8][1], span[10][1]))):
-            stage_acc.setdefault(name, []).append(v)
-        for name, k_ in (("k_decompress", 1), ("k_transcript", 2), ("k_scalar", 3), ("k_msm_bucket_sum", 6), ("k_msm_chunk_reduce", 7), ("k_lines", 9), ("k_pairing_check", 10)):
-            kern_acc.setdefault(name, []).append(ms(*span[k_]))
-    stage_ms = {k_: statistics.median(v) for k_, v in stage_acc.items()}
-    kern_ms = {k_: statistics.median(v) for k_, v in kern_acc.items()}
+    # ---------------- per-stage / per-kernel device times of serial single batches under graph replay, from the on-device
+    # block timeline (global nanosecond timer: first block start -> last block end of every kernel; no host in the loop)
+    stage_ms, kern_ms = {}, {}
+    if world == 1:
+        upload(bv, batches[0])
+        run_steps(lambda ctx, i_: step_resident(ctx, i_), 2, bvs[:1])
+        stage_acc, kern_acc = {}, {}
+        cap = 1 << 18
+        tlbuf = np.zeros(cap * 8, dtype=np.uint32)
+        for _ in range(5):
+            chk(bv, lib.h2v_debug_timeline_start(local, cap))
+            run_steps(lambda ctx, i_: step_resident(ctx, i_), 1, bvs[:1])
+            cnt = ctypes.c_uint32(0)
+            chk(bv, lib.h2v_debug_timeline_stop(local, tlbuf.ctypes.data, cap, ctypes.byref(cnt)))
+            rec = tlbuf[: cnt.value * 8].reshape(-1, 8).astype(np.uint64)
+            kid, t0_, t1_ = rec[:, 0], rec[:, 4] | (rec[:, 5] << np.uint64(32)), rec[:, 6] | (rec[:, 7] << np.uint64(32))
+            span = {int(k_): (int(t0_[kid == k_].min()), int(t1_[kid == k_].max())) for k_ in np.unique(kid)}
+            if not all(k_ in span for k_ in range(1, 11)):
+                continue
+            ms = lambda a, b: (b - a) * 1e-6
+            for name, v in (("total", ms(span[1][0], span[10][1])), ("decompress", ms(*span[1])), ("transcript", ms(span[1][1], span[2][1])),
+                            ("scalar", ms(span[2][1], span[3][1])), ("rlc_msm", ms(span[3][1], span[8][1])), ("pairing", ms(span[8][1], span[10][1]))):
+                stage_acc.setdefault(name, []).append(v)
+            for name, k_ in (("k_decompress", 1), ("k_transcript", 2), ("k_scalar", 3), ("k_msm_digits", 4), ("k_msm_scatter", 5), ("k_msm_bucket_sum", 6),
+                             ("k_msm_chunk_reduce", 7), ("k_msm_window_reduce", 8), ("k_lines", 9), ("k_pairing_check", 10)):
+                kern_acc.setdefault(name, []).append(ms(*span[k_]))
+        stage_ms = {k_: statistics.median(v) for k_, v in stage_acc.items()}
+        kern_ms = {k_: statistics.median(v) for k_, v in kern_acc.items()}
     # ---------------- end to end through the C ABI from pinned host memory
     run_steps(lambda ctx, i: step_e2e(ctx, batches[i % 2], i), W, bvs[:1])
     lat = []
 
-    def timed_e2e(ctx, i, pbs=batches):
+    def timed_e2e(ctx, i, pbs):
         a = time.perf_counter()
         okk = step_e2e(ctx, pbs[i % 2], i)
         lat.append(time.perf_counter() - a)
         return okk
 
     lib.h2v_ctx_set_blocking_sync(bv._ctx, 0)
-    res, _, dt_e2e1 = timed(timed_e2e, args.steps, bvs[:1])  # e2e is what the caller sees: host clock around the calls
+    res, _, dt_e2e1 = timed_block(lambda ctx, i: timed_e2e(ctx, i, batches), lat_steps, bvs[:1])  # e2e is what the caller sees: host clock around the calls
     lib.h2v_ctx_set_blocking_sync(bv._ctx, 1 if blocking else 0)
     assert all(res), "an end-to-end batch was rejected"
     p50 = statistics.median(lat) * 1e3
-    dt_e2e = dt_e2e1
-    if n_ctx > 1 or G > 1:
-        pick = lambda ctx, i: [rbatch, rbatch] if (G_rem and ctx.ci == n_ctx - 1) else gbatches
-        run_steps(lambda ctx, i: step_e2e(ctx, pick(ctx, i)[i % 2], i), W * n_ctx, bvs, warm_assign)
-        res, _, dt_e2e = timed(lambda ctx, i: timed_e2e(ctx, i, pick(ctx, i)), runs, bvs, assign)
-        assert all(res), "an end-to-end batch was rejected"
-    dt, dt1, dt_e2e, dt_e2e1 = reduce_max(dt, dt1, dt_e2e, dt_e2e1)
+    run_steps(lambda ctx, i: step_e2e(ctx, gbatches[i % 2], i), W * n_ctx, bvs)
+    block_e2e = []
+    for _ in range(R):
+        res, _, dte = timed_block(lambda ctx, i: timed_e2e(ctx, i, gbatches), steps, bvs)
+        assert all(res), "an end-to-end launch set was rejected"
+        block_e2e.append(dte)
+    red = reduce_max(block_dt + block_e2e + [dt1, dt_e2e1])  # every block: max over ranks
+    block_dt, block_e2e, dt1, dt_e2e1 = red[:R], red[R:2 * R], red[2 * R], red[2 * R + 1]
+    dt, dt_e2e = statistics.median(block_dt), statistics.median(block_e2e)
+
+    selfcheck = run_selfcheck(args, pkg, lib, torch, dist, synth, sharding, bv, batches[0], rank, world, n, gbase, gcount, synth.params_bytes_raw(k, s), vk_bytes) if args.selfcheck else None
 
     out = None
     if rank == 0:
-        mm = algorithmic_mm(bv, n, geom)  # one batch alone (the stage / kernel times below)
-        mm_tp = algorithmic_mm(bv, n, geom_tp)  # one batch of a launch set of the timed region
-        # dominant kernel group = the stage that carries the largest share of the algorithmic work (the one that bounds
-        # throughput with several batches in flight); every stage's own time / work / fraction is listed under "stages"
+        rows = 10
+        mm = algorithmic_mm(bv, n, geom, rows)  # one batch alone (the stage / kernel times below)
+        mm_tp = algorithmic_mm(bv, n, geom_tp, rows)  # one batch of a launch set of the timed region
         imad_peak = lib.h2v_calibrate_imad(local)
         slots = lambda m: m * IMAD_SLOTS_PER_MM
-        kern_mm = {"k_decompress": mm["decompress"], "k_msm_bucket_sum": bucket_sum_mm(bv, n, geom)}  # the two multiplier-bound kernels
-        dom = max(kern_mm, key=lambda k_: kern_mm[k_])
-        achieved = slots(kern_mm[dom]) / (kern_ms[dom] * 1e-3)
-        achieved_all = slots(sum(mm_tp.values())) / (dt / args.steps)
+        # whole timed step: the work of one launch set on this GPU (G batches) / the median block time per launch set
+        achieved_all = slots(sum(mm_tp.values()) * G) / (dt / steps)
+        if world > 1:  # the pairing checks of a global batch run once, on its root: 1 / world of them per rank
+            achieved_all = slots((sum(mm_tp.values()) - mm_tp["pairing"] * (1 - 1 / world)) * G) / (dt / steps)
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        eval_bytes = n * (bv.proof_len + 32 * bv.n_inst_cols * 10 + 64 * bv.n_points + 32 * (bv.n_scalars + bv.n_challenges))
+        pipe = {}
+        ppath = os.path.join(ROOT, "profiles", "ncu_pipe.json")  # sm__pipe_fmaheavy_cycles_active of the stage kernels from the committed ncu --set full capture
+        if os.path.exists(ppath):
+            pipe = json.load(open(ppath))
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")  # per-launch dram bytes of the stage kernels from one ncu --set full capture
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom)
+        kern_mm = {"k_decompress": mm["decompress"], "k_msm_bucket_sum": bucket_sum_mm(bv, n, geom), "k_scalar": mm["scalar"]}
+        roof = {"bound": "imad", "kernel": "whole timed step (every kernel of a launch set; no single kernel holds more than 40 % of it)",
+                "achieved": achieved_all / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s", "frac": achieved_all / imad_peak,
+                "mm_per_proof": sum(mm_tp.values()) / n, "traffic": None,
+                "note": "integer-multiply bound (no HBM/tensor roofline applies, DESIGN.md section 5): algorithmic 256-bit Montgomery multiplications (a squaring "
+                        "counted as one, so squaring-heavy kernels read up to 23 % high) x 272 IMAD issue slots (136 32x32->64 multiply-adds, lo + hi) of ALL stages of a "
+                        "launch set / the median timed block (CUDA events) per launch set; peak = 32-bit IMAD issue rate measured by the calibration kernel in this run. "
+                        "`kernels` / `stages`: one 4096-proof batch ALONE under graph replay, durations from the on-device global timer (first block start -> last block "
+                        "end, h2v_debug_timeline); `pipe_fmaheavy_pct` = sm__pipe_fmaheavy_cycles_active of that kernel in the committed ncu --set full capture"}
+        if kern_ms:
+            if os.path.exists(tpath):
+                roof["traffic"] = json.load(open(tpath)).get("k_decompress")
+            roof["kernels"] = {k_: {"ms_one_in_flight": round(kern_ms[k_], 4), "mm": int(kern_mm[k_]), "frac": slots(kern_mm[k_]) / (kern_ms[k_] * 1e-3) / imad_peak,
+                                    "pipe_fmaheavy_pct": pipe.get(k_)} for k_ in kern_mm if k_ in kern_ms}
+            roof["stages"] = {k_: {"ms_one_in_flight": round(stage_ms[k_], 4), "mm": int(mm[k_]), "frac": slots(mm[k_]) / (stage_ms[k_] * 1e-3) / imad_peak}
+                              for k_ in mm if k_ in stage_ms}
+        eval_bytes = n * (bv.proof_len + 32 * bv.n_inst_cols * rows + 64 * bv.n_points + 32 * (bv.n_scalars + bv.n_challenges))
         out = {
-            "metric": METRIC, "value": total / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic (trapdoor-simulated accepting proofs, seeded)",
-            "config": {"workload": f"{n} SHPLONK proofs per GPU, vector_mul test-circuit shape ('{args.shape}'), k={k}, Blake2b transcript, "
-                                   f"10 public inputs, 1,024-byte proofs; BASELINE.json configs[1]",
-                       "batch_per_gpu": n, "global_batch": n * world, "contexts_in_flight": n_ctx, "fold_groups_per_launch_set": G, "host_waits": "blocking" if blocking else "spinning",
-                       "step": f"one global batch of {n * world} proofs: {n} per GPU, per-window partials all-gathered, ONE pairing check",
-                       "in_flight_note": "a step is one complete 4096-proof batch (own fold coefficients, own pairing check, own verdict); `value`/`e2e` keep "
-                                         "`contexts_in_flight` x `fold_groups_per_launch_set` independent batches in flight: every context (CUDA stream + host thread) "
-                                         "runs `fold_groups_per_launch_set` batches per set of kernel launches (h2v_batch_set_fold_groups); `one_in_flight` times strictly serial single batches",
-                       "timing": "CUDA events on the contexts' streams (first start -> last end) between barrier + synchronize, max over ranks; "
-                                 "e2e on the host clock around the C-ABI calls",
+            "metric": METRIC, "value": proofs_per_step * steps / dt, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": W,
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+            "dtype": "u32x8 (256-bit Montgomery integers)",
+            "data": "synthetic (trapdoor-simulated accepting proofs, seeded; two distinct 4096-proof batches per rank, tiled where a shard is larger)",
+            "config": {"workload": f"{cfg['name']}; shape '{shape}', k={k}, Blake2b transcript, {rows} public inputs, {bv.proof_len}-byte proofs",
+                       "batch": args.batch, "proofs_per_gpu_and_batch": n, "global_batch": n * world,
+                       "step": f"one launch set = {G} independent global batch(es) of {n * world} proofs ({n} per GPU): every batch has its own fold coefficients, "
+                               f"its own MSM, its own pairing check and its own verdict; they share one set of kernel launches (h2v_batch_set_fold_groups)",
+                       "proofs_per_step": proofs_per_step, "fold_groups_per_launch_set": G, "contexts_in_flight": n_ctx,
+                       "timed_blocks": R, "block_ms": [round(x * 1e3, 3) for x in block_dt],
+                       "timing": f"{R} timed blocks of {steps} steps, each between barrier + synchronize on both sides; a block's time = CUDA events on the contexts' "
+                                 f"streams (first start -> last end), max over ranks; `value` = proofs of a block / MEDIAN block time; e2e on the host clock around the C-ABI calls",
+                       "host_waits": "blocking" if blocking else "spinning",
                        "l2": "flushed before every step (256 MiB overwrite on the step's stream, inside the timed region)",
-                       "parallelism": f"proof-sharded x{world}, NCCL all-gather of the per-window partial accumulators (12,320 B per rank and global batch), one pairing check per global batch (the checks of launch set i run on rank i mod N)"},
-            "e2e": {"value": total / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": batches[0].h2d_bytes, "d2h_bytes_per_step": batches[0].d2h_bytes,
-                    "ms_per_step": dt_e2e / args.steps * 1e3, "p50_latency_ms": p50},
-            "one_in_flight": {"value": total / dt1, "ms_per_step": dt1 / args.steps * 1e3, "e2e_value": total / dt_e2e1, "e2e_p50_latency_ms": p50},
+                       "fold_randomness": "OS entropy per upload (h2v.h: no scalars, no key, seed 0)",
+                       "parallelism": (f"proof-sharded x{world}: device-side exchange (csrc/exchange.cuh) - each rank's pack kernel stores its per-window partial accumulators "
+                                       f"(12,320 B per global batch) into the root's HBM window over NVLink, the root (rank i mod N for launch set i) sums them in place, runs the "
+                                       f"pairing check(s) and stores the verdicts into every rank's window; all inside the CUDA graph, no host or NCCL call per step")
+                       if world > 1 else "one GPU"},
+            "e2e": {"value": proofs_per_step * steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": gbatches[0].h2d_bytes, "d2h_bytes_per_step": gbatches[0].d2h_bytes,
+                    "ms_per_step": dt_e2e / steps * 1e3, "block_ms": [round(x * 1e3, 3) for x in block_e2e], "p50_latency_ms_one_batch": p50},
+            "one_in_flight": {"value": n * world * lat_steps / dt1, "ms_per_batch": dt1 / lat_steps * 1e3, "e2e_value": n * world * lat_steps / dt_e2e1,
+                              "e2e_p50_latency_ms": p50, "note": f"strictly serial single batches of {n * world} proofs on one context"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "stage_ms": {k_: round(v, 4) for k_, v in stage_ms.items()},
             "kernel_ms": {k_: round(v, 4) for k_, v in kern_ms.items()},
-            "stage_ms_all_in_flight": {k_: round(v, 4) for k_, v in stage_ms_in_flight.items()},
             "msm": {"window_bits": [geom_tp["window_bits"] & 0xFFFF, geom_tp["window_bits"] >> 16], "windows": [geom_tp["windows"] & 0xFFFF, geom_tp["windows"] >> 16],
                     "terms": geom_tp["terms"], "buckets": geom_tp["buckets"],
                     "one_in_flight": {"window_bits": [geom["window_bits"] & 0xFFFF, geom["window_bits"] >> 16], "buckets": geom["buckets"]}},
-            "roofline": {"bound": "imad", "kernel": dom, "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD/s",
-                         "frac": achieved / imad_peak, "traffic": traffic,
-                         "whole_step": {"achieved": achieved_all / 1e12, "frac": achieved_all / imad_peak, "mm_per_proof": sum(mm_tp.values()) / n},
-                         "kernels": {k_: {"ms_one_in_flight": round(kern_ms[k_], 4), "mm": int(kern_mm[k_]),
-                                          "frac": slots(kern_mm[k_]) / (kern_ms[k_] * 1e-3) / imad_peak} for k_ in kern_mm},
-                         "stages": {k_: {"ms_one_in_flight": round(stage_ms[k_], 4), "mm": int(mm[k_]),
-                                         "frac": slots(mm[k_]) / (stage_ms[k_] * 1e-3) / imad_peak} for k_ in mm if k_ in stage_ms},
-                         "note": "integer-multiply bound (no HBM/tensor roofline applies, DESIGN.md section 5): algorithmic 256-bit Montgomery "
-                                 "multiplications (a squaring counted as one) x 272 IMAD issue slots (136 32x32->64 multiply-adds, lo + hi) of the "
-                                 "kernel with the largest share of the work / its duration on the device's global timer (first block start -> last block end, h2v_debug_timeline) "
-                                 "in serial single batches under graph replay (in the timed region 64 batches overlap, so a kernel's own duration is not defined there); "
-                                 "peak = 32-bit IMAD issue rate measured by the calibration kernel in this run; `whole_step` = all stages / the timed step (CUDA events)"},
-            "roofline_hbm": {"bound": "hbm", "kernel": "transcript+scalar (evaluation loads)", "achieved": eval_bytes / ((stage_ms["transcript"] + stage_ms["scalar"]) * 1e-3) / 1e9,
-                             "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
-                             "frac": eval_bytes / ((stage_ms["transcript"] + stage_ms["scalar"]) * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+            "roofline": roof,
             "input_generation_s": round(gen_s, 2),
         }
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_from_batch(synth.params_bytes_raw(k, s), vk_bytes, batches[0], budget_s=args.cpu_budget)
+        if stage_ms:
+            t_eval = (stage_ms["transcript"] + stage_ms["scalar"]) * 1e-3
+            out["roofline_hbm"] = {"bound": "hbm", "kernel": "transcript+scalar (evaluation loads)", "achieved": eval_bytes / t_eval / 1e9, "peak": hbm_peak,
+                                   "peak_source": hbm_src, "unit": "GB/s", "frac": eval_bytes / t_eval / 1e9 / hbm_peak, "traffic": None}
+        if selfcheck is not None:
+            out["selfcheck"] = selfcheck
+    if world == 1 and args.config == 2 and not args.no_config3:
+        c3 = config3_leg(args, pkg, torch)
+        if out is not None:
+            out["config3_gwc_attribution"] = c3
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_from_batch(synth.params_bytes_raw(k, s), vk_bytes, batches[0], budget_s=args.cpu_budget)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     for b in bvs:
         b.close()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# --selfcheck: the sharded product path against the C oracle (checker only), on the bench's own inputs
+# ------------------------------------------------------------------------------------------------
+def run_selfcheck(args, pkg, lib, torch, dist, synth, sharding, bv, pb, rank, world, n, gbase, gcount, params_bytes, vk_bytes):
+    """(1) clean global batch with GLOBAL explicit coefficients: the folded (L, R) the root computed from the gathered
+    partials == the C oracle's fold of every proof's accumulators (so they are identical for every shard count);
+    (2) one corrupted proof on the LAST rank (not the root): every rank learns the rejection, the statuses of every
+    shard == the C oracle's per-proof verdicts."""
+    import random
+
+    import numpy as np
+
+    cores = max(1, (os.cpu_count() or 1) // world)
+    co = _load_c_oracle(params_bytes, vk_bytes)
+    proofs, insts = pb.src
+    rng = random.Random(20261018)
+    rs = [rng.randrange(1, R_MOD) for _ in range(gcount)]  # the same on every rank
+    root = 0
+    if world == 1:
+        res = bv.verify_batch(proofs, insts, rlc_scalars=rs, want_batch_accum=True)
+        ok, status, folded = res.verdict, res.status, res.batch_accum
+    else:
+        verdicts, status = bv.verify_shard(proofs, insts, gbase, gcount, root, rlc_scalars=rs)
+        ok = verdicts[0]
+        folded = bv.comm_last_batch_accum() if rank == root else None
+    assert ok and status == [0] * n, "selfcheck: clean batch rejected"
+    # C oracle: per-proof accumulators of this shard, folded with the global coefficients of the shard
+    proofs_np, inst_np = pb.proofs.numpy(), pb.inst.numpy()
+    poff, ioff = pb.poff.numpy().view(np.uint64), pb.ioff.numpy().view(np.uint64)
+    st, _, lr, _ = co.verify_many(proofs_np, poff, inst_np, ioff, n, "shplonk", "blake2b", False, cores, want_lr=True)
+    assert int(st.max()) == 0
+    tail = 1
+    for r_ in rs[gbase + n:]:
+        tail = tail * r_ % R_MOD
+    part, _ = co.fold(lr + bytes(128), rs[gbase:gbase + n] + [tail], [1] * n + [0])  # the dummy last entry carries the product of the later ranks' r_i
+    parts = sharding.all_gather_bytes(part, world)
+    match = None
+    if rank == root:
+        dec = lambda e: None if e == bytes(64) else (int.from_bytes(e[:32], "little"), int.from_bytes(e[32:], "little"))
+        enc = lambda p: bytes(64) if p is None else p[0].to_bytes(32, "little") + p[1].to_bytes(32, "little")
+        L = R_ = None
+        for p in parts:
+            L, R_ = synth.g1_add(L, dec(p[:64])), synth.g1_add(R_, dec(p[64:]))
+        match = folded == enc(L) + enc(R_)
+        assert match, "selfcheck: folded (L, R) differ from the C oracle's"
+    # corrupted proof on the last rank
+    bad_rank, j_bad = world - 1, 17 % n
+    bad = list(proofs)
+    if rank == bad_rank:
+        b = bytearray(bad[j_bad])
+        b[(bv.n_points - bv.n_mo) * 32 + 1] ^= 0x40  # an evaluation scalar: still canonical, wrong value
+        bad[j_bad] = bytes(b)
+    pbb = PackedBatch(torch, bad, insts)
+    if world == 1:
+        res = bv.verify_batch(bad, insts, rlc_scalars=rs)
+        ok2, status2 = res.verdict, res.status
+    else:
+        verdicts, status2 = bv.verify_shard(bad, insts, gbase, gcount, root, rlc_scalars=rs)
+        ok2 = verdicts[0]
+    st2, _, _, _ = co.verify_many(pbb.proofs.numpy(), pbb.poff.numpy().view(np.uint64), pbb.inst.numpy(), pbb.ioff.numpy().view(np.uint64), n,
+                                  "shplonk", "blake2b", True, cores)
+    assert not ok2, "selfcheck: the corrupted global batch was accepted"
+    assert status2 == [int(x) for x in st2], "selfcheck: statuses differ from the C oracle's"
+    assert (sum(1 for x in status2 if x) == 1 and status2[j_bad] == 4) if rank == bad_rank else not any(status2)
+    co.close()
+    flag = torch.ones(1, dtype=torch.int32, device="cuda")
+    if dist is not None:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    folded_hex = None
+    if rank == root:
+        import hashlib
+
+        folded_hex = hashlib.sha256(folded).hexdigest()
+    return {"ranks_ok": int(flag.item()) == 1, "global_batch": gcount, "folded_LR_equals_c_oracle": match, "folded_LR_sha256": folded_hex,
+            "corrupted_proof": {"rank": bad_rank, "index_in_shard": j_bad, "root": root, "global_verdict": "rejected", "statuses_equal_c_oracle": True},
+            "note": "explicit global fold coefficients (seeded) so that the folded (L, R) are comparable across shard counts; checker = oracle/c"}
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2]: GWC, 4096-proof batch, 1 % corrupted proofs -> the fold is rejected and attributed per proof
+# ------------------------------------------------------------------------------------------------
+def _gwc_gen_worker(job):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import random
+
+    import prover_sim as sim
+
+    shape, k, s, seed = job
+    params = sim.make_params(k, s)
+    vk, dl = sim.make_vk(shape, k)
+    rng = random.Random(seed)
+    inst = sim.random_instances(vk, rng, 10)
+    return inst[0], sim.simulate_proof(params, vk, dl, s, inst, rng, "gwc", "blake2b")
+
+
+def config3_leg(args, pkg, torch):
+    """Clean and 1 %-corrupted 4096-proof GWC batches end to end through h2v_verify_batch (host clock, median of 7);
+    statuses of the corrupted batch against the C oracle.  The GWC inputs come from the oracle's proof simulator
+    (64 distinct proofs, tiled) and its corruption injector: input generation and checking only, not the measured path."""
+    import random
+    from multiprocessing import get_context
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import formats as F
+    import prover_sim as sim
+
+    n, distinct, k, shape = 4096, 64, args.k, "vm"
+    s = srs_secret(k)
+    params = sim.make_params(k, s)
+    vk, _dl = sim.make_vk(shape, k)
+    with get_context("spawn").Pool(min(os.cpu_count() or 1, 16)) as pool:
+        items = pool.map(_gwc_gen_worker, [(shape, k, s, 3000003 + i) for i in range(distinct)])
+    proofs = [it[1] for it in items] * (n // distinct)
+    insts = [[[int(v).to_bytes(32, "little") for v in col] for col in it[0]] for it in items] * (n // distinct)
+    rng = random.Random(3)
+    idx = sorted(rng.sample(range(n), n // 100))
+    kinds = list(sim.CORRUPTIONS)
+    bad = list(proofs)
+    for t, i in enumerate(idx):
+        bad[i], _ = sim.corrupt(proofs[i], vk, kinds[t % len(kinds)], rng, "gwc")
+    pvk = pkg.VerifyingKey.from_bytes(vk.to_bytes(F.RAW_BYTES), pkg.SerdeFormat.RawBytes)
+    bv = pkg.BatchVerifier(pkg.ParamsKZG.from_bytes(params.to_bytes(F.RAW_BYTES), pkg.SerdeFormat.RawBytes), pvk, "gwc", "blake2b", device=0)
+    lib = bv.lib
+    clean, dirty = PackedBatch(torch, proofs, insts), PackedBatch(torch, bad, insts)
+
+    def timed(pb):
+        ts = []
+        for _ in range(9):
+            a = time.perf_counter()
+            bv._check(lib.h2v_verify_batch(bv._ctx, *pb.args(), None, 0, pb.status.data_ptr(), None, None, None))
+            ts.append(time.perf_counter() - a)
+        return statistics.median(ts[2:]) * 1e3
+
+    ms_clean = timed(clean)
+    assert int(clean.status.max()) == 0
+    ms_bad = timed(dirty)
+    att = bv.timings()
+    got = [int(x) for x in dirty.status]
+    co = _load_c_oracle(params.to_bytes(F.RAW_BYTES), vk.to_bytes(F.RAW_BYTES))
+    st, _, _, _ = co.verify_many(dirty.proofs.numpy(), dirty.poff.numpy().view(np.uint64), dirty.inst.numpy(), dirty.ioff.numpy().view(np.uint64), n,
+                                 "gwc", "blake2b", True, os.cpu_count() or 1)
+    co.close()
+    same = got == [int(x) for x in st]
+    assert same and [i for i, x in enumerate(got) if x] == idx, "config 3: statuses differ from the C oracle's"
+    bv.close()
+    return {"workload": "BASELINE.json configs[2]: 4096 GWC proofs (vector_mul shape, k=10, 1,056-byte proofs), h2v_verify_batch from pinned host buffers, median of 7",
+            "clean_ms": round(ms_clean, 3), "corrupted_1pct_ms": round(ms_bad, 3), "ratio": round(ms_bad / ms_clean, 3),
+            "clean_proofs_per_s": n / (ms_clean * 1e-3), "corrupted_1pct_proofs_per_s": n / (ms_bad * 1e-3),
+            "corrupted_proofs": len(idx), "statuses_equal_c_oracle": same, "last_call_ms": {k_: round(v, 3) for k_, v in att.items() if v}}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -642,26 +772,34 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=20, help="launch sets per timed block")
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--blocks", type=int, default=7, help="timed blocks of --steps steps; the median block is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--shape", default="vm")
-    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configuration (2 = configs[1], the headline)")
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--shape", default="")
+    ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--streams", type=int, default=int(os.environ.get("H2V_BENCH_STREAMS", "0")),
-                    help="contexts (CUDA stream + host thread each) per GPU; default 8 (4 from 8 GPUs on: 8 ranks share one host)")
+                    help="contexts (CUDA stream + host thread each) per GPU; default 4")
     ap.add_argument("--fold-groups", type=int, default=int(os.environ.get("H2V_BENCH_FOLD_GROUPS", "0")),
-                    help="independent batches (own fold + pairing check each) per set of kernel launches of a context; default 8 (16 from 8 GPUs on)")
+                    help="independent batches (own fold + pairing check each) per launch set of a context; default 16")
+    ap.add_argument("--selfcheck", action="store_true", help="also check the (sharded) path against the C oracle, incl. a corrupted proof on a non-root rank")
+    ap.add_argument("--no-config3", action="store_true", help="skip the GWC attribution leg (BASELINE.json configs[2]) of the N=1 line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--ref-proofs-per-core", type=int, default=64)
     args = ap.parse_args()
-    # 64 batches in flight per GPU either way.  From 8 ranks on, fewer host threads and fewer, larger exchanges per rank measured
-    # better on the shared host (N = 8: 47.7 M proofs/s with 4 x 16 against 37 - 42 M with 8 x 8; N = 1: equal)
+    cfg = CONFIGS[args.config]
+    args.batch = args.batch or cfg["batch"]
+    args.shape = args.shape or cfg["shape"]
+    args.k = args.k or cfg["k"]
+    # 64 batches in flight per GPU: 4 contexts x 16 fold groups (the driver's --steps 20 then spreads evenly over the contexts; fewer host
+    # threads and fewer, larger launch sets also measured better at 8 ranks on one host)
     if args.streams <= 0:
-        args.streams = 4 if args.gpus >= 8 else 8
+        args.streams = 4
     if args.fold_groups <= 0:
-        args.fold_groups = 16 if args.gpus >= 8 else 8
+        args.fold_groups = 16 if args.config == 2 else (8 if args.config == 4 else 1)
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
     sys.stdout.flush()
     if out is not None:

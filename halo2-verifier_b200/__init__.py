@@ -115,6 +115,17 @@ def load_library():
                                          ctypes.c_uint64, ctypes.c_uint64, u8p, u8p]
     lib.h2v_finalize.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u8p, ctypes.POINTER(ctypes.c_int)]
     lib.h2v_attribute_shard.argtypes = [ctypes.c_void_p, u8p]
+    lib.h2v_attribute_shard_groups.argtypes = [ctypes.c_void_p, u8p, ctypes.c_uint32, u8p]
+    lib.h2v_batch_set_rlc_key.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    lib.h2v_last_rlc_source.argtypes = [ctypes.c_void_p]
+    lib.h2v_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, u8p]
+    lib.h2v_comm_connect.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    lib.h2v_batch_run_shard_exchange.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, ctypes.POINTER(ctypes.c_int)]
+    lib.h2v_verify_shard.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64, ctypes.c_uint64,
+                                     ctypes.c_uint64, ctypes.c_uint32, u8p, u8p, ctypes.POINTER(ctypes.c_int)]
+    lib.h2v_comm_last_batch_accum.argtypes = [ctypes.c_void_p, u8p]
+    lib.h2v_ctx_cache_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.h2v_ctx_work_model.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
     lib.h2v_batch_upload.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64]
     lib.h2v_batch_upload_shard.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64,
                                            ctypes.c_uint64, ctypes.c_uint64]
@@ -145,7 +156,11 @@ EXPORTED_SYMBOLS = (
     "h2v_batch_set_columns", "h2v_batch_set_scalar_hook", "h2v_batch_set_shard_hint", "h2v_partial_bytes", "h2v_accumulate_shard", "h2v_finalize", "h2v_attribute_shard",
     "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync", "h2v_ctx_set_graphs", "h2v_ctx_create_multi", "h2v_batch_set_fold_groups", "h2v_last_group_verdicts", "h2v_finalize_groups", "h2v_debug_timeline_start", "h2v_debug_timeline_stop",
     "h2v_last_msm_geometry", "h2v_selftest_field", "h2v_calibrate_imad",
+    "h2v_attribute_shard_groups", "h2v_batch_set_rlc_key", "h2v_last_rlc_source", "h2v_comm_init", "h2v_comm_connect",
+    "h2v_batch_run_shard_exchange", "h2v_verify_shard", "h2v_comm_last_batch_accum", "h2v_ctx_cache_stats", "h2v_ctx_work_model",
 )
+
+COMM_HANDLE_BYTES = 128
 
 
 @dataclass
@@ -245,6 +260,7 @@ class BatchVerifier:
         self.lib = load_library()
         self._ctx = ctypes.c_void_p()
         self.circuit_instances = int(circuit_instances)
+        self.multiopen, self.transcript = multiopen, transcript
         rc = self.lib.h2v_ctx_create_multi(ctypes.byref(self._ctx), params.data, len(params.data), int(params.format), vk.data,
                                            len(vk.data), int(vk.format), _MULTIOPEN[multiopen], _HASH[transcript], int(device),
                                            self.circuit_instances)
@@ -307,16 +323,38 @@ class BatchVerifier:
             keep = [a, b]
         return pbytes, poff, ibytes, ioff, keep
 
-    def verify_batch(self, proofs: Sequence[bytes], instances, rlc_scalars: Optional[Sequence[int]] = None, seed=0,
-                     want_challenges=False, want_accum=False, want_batch_accum=False, want_scalars=False, fold_groups=1) -> BatchResult:
+    def _fold_randomness(self, rlc_scalars, seed, key):
+        """Fold randomness of the next upload (include/h2v.h): explicit scalars (parity hook) > `key` (32 secret bytes) >
+        `seed` (a non-zero test seed: public, reproducible) > None: the library draws a fresh key from the OS, which is
+        what the reference does (strategy.rs:129) and what production callers want.  Returns (scalar bytes, seed)."""
+        if rlc_scalars is not None:
+            return b"".join(int(r).to_bytes(32, "little") for r in rlc_scalars), 0
+        if key is not None:
+            if len(key) != 32:
+                raise ValueError("the fold key is 32 bytes")
+            self._check(self.lib.h2v_batch_set_rlc_key(self._ctx, bytes(key)))
+            return None, 0
+        if seed is None:
+            return None, 0
+        if int(seed) == 0:
+            raise ValueError("seed 0 is reserved (the C ABI reads it as 'draw from the OS'): pass seed=None for OS entropy")
+        return None, int(seed)
+
+    def rlc_source(self):
+        """of the last upload: 'scalars' | 'seed' | 'key' | 'os'"""
+        return ("scalars", "seed", "key", "os")[self.lib.h2v_last_rlc_source(self._ctx)]
+
+    def verify_batch(self, proofs: Sequence[bytes], instances, rlc_scalars: Optional[Sequence[int]] = None, seed=None,
+                     want_challenges=False, want_accum=False, want_batch_accum=False, want_scalars=False, fold_groups=1, key=None) -> BatchResult:
         """`fold_groups` = G: the proofs are G consecutive independent batches of len(proofs) / G proofs (own fold, own
-        pairing check) that share every kernel launch; `group_verdicts` holds their G batch verdicts."""
+        pairing check) that share every kernel launch; `group_verdicts` holds their G batch verdicts.
+        Fold randomness: OS entropy unless `rlc_scalars` / `key` / `seed` say otherwise (_fold_randomness)."""
         n = len(proofs)
         assert n == len(instances) and n > 0
         if fold_groups > 1:
             self._check(self.lib.h2v_batch_set_fold_groups(self._ctx, int(fold_groups)))
         pbytes, poff, ibytes, ioff, keep = self._pack(proofs, instances)
-        rlc = b"".join(int(r).to_bytes(32, "little") for r in rlc_scalars) if rlc_scalars is not None else None
+        rlc, seed = self._fold_randomness(rlc_scalars, seed, key)
         status = (ctypes.c_uint8 * n)()
         ch = ctypes.create_string_buffer(32 * n * self.n_challenges) if want_challenges else None
         acc = ctypes.create_string_buffer(128 * n) if want_accum else None
@@ -331,41 +369,104 @@ class BatchVerifier:
         return BatchResult(st, all(s == 0 for s in st), ch.raw if ch else None, acc.raw if acc else None,
                            bacc.raw if bacc else None, sc.raw if sc else None, [bool(v) for v in gv[:ng]])
 
-    def accumulate_shard(self, proofs, instances, global_base, global_count, rlc_scalars=None, seed=0, shard_hint=0, fold_groups=1):
+    def accumulate_shard(self, proofs, instances, global_base, global_count, rlc_scalars=None, seed=None, shard_hint=0, fold_groups=1, key=None,
+                         partial_out=None):
         """Returns (statuses, partial): `partial` is the opaque H2V_PARTIAL_BYTES blob of this shard's
-        per-window bucket sums.  `shard_hint` = size of the largest shard of the global batch when the
+        per-window bucket sums (bytes; or None when `partial_out`, a device or host pointer, receives it).
+        `shard_hint` = size of the largest shard of the global batch when the
         shards are not all of the same size (every rank must use the same window geometry)."""
         n = len(proofs)
         pbytes, poff, ibytes, ioff, keep = self._pack(proofs, instances)
-        rlc = b"".join(int(r).to_bytes(32, "little") for r in rlc_scalars) if rlc_scalars is not None else None
+        rlc, seed = self._fold_randomness(rlc_scalars, seed, key)
         status = (ctypes.c_uint8 * n)()
-        partial = ctypes.create_string_buffer(self.lib.h2v_partial_bytes() * max(1, int(fold_groups)))
+        partial = ctypes.create_string_buffer(self.lib.h2v_partial_bytes() * max(1, int(fold_groups))) if partial_out is None else None
         if fold_groups > 1:  # group q = this rank's shard of global batch q; rlc_scalars: fold_groups x global_count values
             self._check(self.lib.h2v_batch_set_fold_groups(self._ctx, int(fold_groups)))
         if shard_hint:
             self._check(self.lib.h2v_batch_set_shard_hint(self._ctx, int(shard_hint)))
         self._check(self.lib.h2v_accumulate_shard(self._ctx, n, pbytes, poff, ibytes, ioff, rlc, seed, global_base,
-                                                  global_count, status, partial))
-        return list(status), partial.raw
+                                                  global_count, status, partial if partial_out is None else ctypes.c_void_p(int(partial_out))))
+        return list(status), (partial.raw if partial is not None else None)
 
-    def finalize(self, partials: Sequence[bytes], want_batch_accum=True):
+    # ---- device-side exchange (include/h2v.h "device-side exchange of sharded batches")
+    def comm_init(self, rank, world, max_groups=1) -> bytes:
+        """allocates this context's exchange window; returns the opaque handle to ship to every rank"""
+        h = ctypes.create_string_buffer(COMM_HANDLE_BYTES)
+        self._check(self.lib.h2v_comm_init(self._ctx, int(rank), int(world), int(max_groups), h))
+        self.comm_rank, self.comm_world, self.comm_ready = int(rank), int(world), False
+        return h.raw
+
+    def comm_connect(self, handles: Sequence[bytes]):
+        """handles of all ranks' contexts of this channel, rank order (own included)"""
+        self._check(self.lib.h2v_comm_connect(self._ctx, b"".join(handles)))
+        self.comm_ready = True
+
+    def verify_shard(self, proofs, instances, global_base, global_count, root, rlc_scalars=None, seed=None, key=None, shard_hint=0, fold_groups=1):
+        """This rank's part of a sharded batch through the device-side exchange: returns (group verdicts, statuses of
+        this shard); rejected groups are attributed per proof inside the shard."""
+        n = len(proofs)
+        pbytes, poff, ibytes, ioff, keep = self._pack(proofs, instances)
+        rlc, seed = self._fold_randomness(rlc_scalars, seed, key)
+        status = (ctypes.c_uint8 * n)()
+        G = max(1, int(fold_groups))
+        gv = (ctypes.c_uint8 * G)()
+        verdict = ctypes.c_int(0)
+        if G > 1:
+            self._check(self.lib.h2v_batch_set_fold_groups(self._ctx, G))
+        if shard_hint:
+            self._check(self.lib.h2v_batch_set_shard_hint(self._ctx, int(shard_hint)))
+        self._check(self.lib.h2v_verify_shard(self._ctx, n, pbytes, poff, ibytes, ioff, rlc, seed, global_base, global_count, int(root),
+                                              status, gv, ctypes.byref(verdict)))
+        return [bool(v) for v in gv], list(status)
+
+    def comm_last_batch_accum(self) -> bytes:
+        out = ctypes.create_string_buffer(128)
+        self._check(self.lib.h2v_comm_last_batch_accum(self._ctx, out))
+        return out.raw
+
+    def work_model(self, instance_rows):
+        """algorithmic Montgomery multiplications per proof of this plan (include/h2v.h h2v_ctx_work_model)"""
+        out = (ctypes.c_double * 4)()
+        self._check(self.lib.h2v_ctx_work_model(self._ctx, int(instance_rows), out))
+        return dict(zip(("scalar", "transcript", "decompress_per_point", "instance_scalars"), list(out)))
+
+    def cache_stats(self):
+        out = (ctypes.c_uint64 * 2)()
+        self._check(self.lib.h2v_ctx_cache_stats(self._ctx, out))
+        return {"lines_builds": int(out[0]), "graph_captures": int(out[1])}
+
+    def finalize(self, partials, want_batch_accum=True, n_partials=None):
+        """partials: list of blobs, or (with n_partials) the address of n_partials consecutive blobs in host or device memory"""
+        if n_partials is not None:
+            bacc = ctypes.create_string_buffer(128) if want_batch_accum else None
+            verdict = ctypes.c_int(0)
+            self._check(self.lib.h2v_finalize(self._ctx, int(n_partials), ctypes.c_void_p(int(partials)), bacc, ctypes.byref(verdict)))
+            return bool(verdict.value), (bacc.raw if bacc is not None else None)
         buf = b"".join(partials)
         bacc = ctypes.create_string_buffer(128) if want_batch_accum else None
         verdict = ctypes.c_int(0)
         self._check(self.lib.h2v_finalize(self._ctx, len(partials), buf, bacc, ctypes.byref(verdict)))
         return bool(verdict.value), (bacc.raw if bacc is not None else None)
 
-    def finalize_groups(self, partials: Sequence[bytes], fold_groups):
-        """partials: one accumulate_shard(..., fold_groups=G) output per rank; returns the G batch verdicts"""
-        buf = b"".join(partials)
+    def finalize_groups(self, partials, fold_groups, n_partials=None):
+        """partials: one accumulate_shard(..., fold_groups=G) output per rank (or, with n_partials, the address of the
+        ranks' outputs concatenated in host or device memory); returns the G batch verdicts"""
         gv = (ctypes.c_uint8 * int(fold_groups))()
         verdict = ctypes.c_int(0)
-        self._check(self.lib.h2v_finalize_groups(self._ctx, len(partials), int(fold_groups), buf, gv, ctypes.byref(verdict)))
+        if n_partials is not None:
+            self._check(self.lib.h2v_finalize_groups(self._ctx, int(n_partials), int(fold_groups), ctypes.c_void_p(int(partials)), gv, ctypes.byref(verdict)))
+        else:
+            self._check(self.lib.h2v_finalize_groups(self._ctx, len(partials), int(fold_groups), b"".join(partials), gv, ctypes.byref(verdict)))
         return [bool(v) for v in gv]
 
-    def attribute_shard(self, status):
+    def attribute_shard(self, status, group_verdicts=None):
+        """per-proof re-check of the shard last processed; with `group_verdicts` only inside the rejected fold groups"""
         arr = (ctypes.c_uint8 * len(status))(*status)
-        self._check(self.lib.h2v_attribute_shard(self._ctx, arr))
+        if group_verdicts is not None:
+            gv = (ctypes.c_uint8 * len(group_verdicts))(*[1 if v else 0 for v in group_verdicts])
+            self._check(self.lib.h2v_attribute_shard_groups(self._ctx, gv, len(group_verdicts), arr))
+        else:
+            self._check(self.lib.h2v_attribute_shard(self._ctx, arr))
         return list(arr)
 
     def timings(self):
@@ -402,9 +503,11 @@ def verify_proof(params: ParamsKZG, vk: VerifyingKey, proof: bytes, instances, m
 
 
 def verify_proofs_batch(params: ParamsKZG, vk: VerifyingKey, proofs: Sequence[bytes], instances, multiopen="shplonk",
-                        transcript="blake2b", device=0, rlc_scalars=None, seed=0) -> List[Optional[Error]]:
+                        transcript="blake2b", device=0, rlc_scalars=None, seed=None) -> List[Optional[Error]]:
     """Batch entry point: one folded pairing check for the whole batch (AccumulatorStrategy,
     strategy.rs:125-140), per-proof attribution when the fold is rejected.  Returns one entry per
-    proof: None (accepted) or the plonk Error the reference's verify_proof would have returned."""
+    proof: None (accepted) or the plonk Error the reference's verify_proof would have returned.
+    The fold coefficients come from OS entropy, as in the reference (strategy.rs:129), unless `rlc_scalars` or a
+    non-zero test `seed` is given (parity hooks: public coefficients are not sound against an adversarial prover)."""
     with BatchVerifier(params, vk, multiopen, transcript, device) as bv:
         return bv.verify_batch(proofs, instances, rlc_scalars, seed).errors()

@@ -16,8 +16,11 @@
 //   (k_pack_partial / k_sum_partials: shards of a multi-GPU batch; k_fold_accum: explicit (L, R), parity hook only)
 //   (k_pp_*           per-proof accumulators / pairings: parity hook and rejection attribution)
 #include <cuda_runtime.h>
+#include <errno.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/random.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -31,6 +34,7 @@
 #include "pairing_warp.cuh"
 #include "timeline.cuh"
 #include "pairing_cta.cuh"
+#include "exchange.cuh"
 
 using namespace h2v;
 
@@ -137,10 +141,11 @@ __global__ void __launch_bounds__(64, H2V_SCALAR_MINB) k_scalar(PlanView pv, u32
   }
 }
 
-__global__ void k_rlc_expand(u64 count, u64 seed, const u8* bytes, Fr* r) {
+// fold randomness r_i: caller-supplied bytes (parity hook), a 64-bit test seed (parity hook), or the secret per-batch key
+__global__ void k_rlc_expand(u64 count, u64 seed, const u8* bytes, bool keyed, RlcKey key, Fr* r) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  r[i] = bytes ? Fr::from_canonical(Fr::load_le(bytes + 32 * i)) : rlc_scalar_from_seed(seed, i);
+  r[i] = bytes ? Fr::from_canonical(Fr::load_le(bytes + 32 * i)) : keyed ? rlc_scalar_from_key(key, i) : rlc_scalar_from_seed(seed, i);
 }
 
 // c_j = prod_{i > j} r_i over the GLOBAL batch; one block, chunked suffix scan through shared memory.
@@ -510,6 +515,7 @@ struct PartialHeader {
 static constexpr u32 H2V_PARTIAL_MAGIC = 0x50563248u;
 static_assert(sizeof(PartialHeader) == 32 && sizeof(G1Jac) == 96, "partial layout");
 static_assert(sizeof(PartialHeader) + 128 * sizeof(G1Jac) == H2V_PARTIAL_BYTES, "H2V_PARTIAL_BYTES");
+static_assert(XCH_PARTIAL_BYTES == H2V_PARTIAL_BYTES, "exchange.cuh partial size");
 
 __global__ void k_pack_partial(u32 cbits, u32 windows, u32 npts, const G1Jac* wsums, u8* out) {
   pdl_prologue();
@@ -525,16 +531,30 @@ __global__ void k_pack_partial(u32 cbits, u32 windows, u32 npts, const G1Jac* ws
   for (u32 i = t; i < H2V_PARTIAL_BYTES / 4 - 8; i += gridDim.x * blockDim.x) o[8 + i] = i < npts * 24 ? src[i] : 0u;
 }
 
-// window-wise sum of the shards' partials (thread per window); flags a geometry mismatch in *err
-// (fold groups: block q sums group q; the partials are rank-major, [rank][group])
-__global__ void __launch_bounds__(128) k_sum_partials(u32 n_partials, u32 cbits, u32 windows, u32 npts, const u8* partials, G1Jac* out, u32* err) {
+// window-wise sum of the shards' partials (thread per window).  *err: bit 0 = a wait timed out, bit 1 = geometry mismatch
+// (fold groups: block q sums group q; partial (rank, group) lives at partials + rank * rank_stride + group * H2V_PARTIAL_BYTES).
+// Exchange mode (dyn != null, exchange.cuh): the partials sit in this rank's window, stored there by the peers' pack
+// kernels over NVLink; thread r first waits for rank r's sequence number of this launch set.
+__global__ void __launch_bounds__(128) k_sum_partials(u32 n_partials, u32 cbits, u32 windows, u32 npts, const u8* partials, size_t rank_stride, G1Jac* out,
+                                                      u32* err, const XDyn* dyn, const u64* arrive) {
   const u32 wi = threadIdx.x;
-  const size_t rank_stride = (size_t)gridDim.x * H2V_PARTIAL_BYTES;
   partials += (size_t)blockIdx.x * H2V_PARTIAL_BYTES;
   out += (size_t)blockIdx.x * npts;
+  if (dyn) {  // block-uniform
+    __shared__ u32 timed_out;
+    if (wi == 0) timed_out = 0;
+    __syncthreads();
+    if (wi < n_partials && !spin_until_ge(arrive + wi, dyn->seq, dyn->timeout_ns)) atomicOr(&timed_out, 1u);
+    __syncthreads();
+    if (timed_out) {  // never sum half-delivered data: the host turns the flag into an error, the verdicts are void
+      if (wi == 0) atomicOr(err, 1u);
+      if (wi < npts) out[wi] = G1Jac::identity();
+      return;
+    }
+  }
   if (wi < n_partials) {
     const PartialHeader* h = (const PartialHeader*)(partials + (size_t)wi * rank_stride);
-    if (h->magic != H2V_PARTIAL_MAGIC || h->cbits != cbits || h->windows != windows || h->n_pts != npts) atomicOr(err, 1u);
+    if (h->magic != H2V_PARTIAL_MAGIC || h->cbits != cbits || h->windows != windows || h->n_pts != npts) atomicOr(err, 2u);
   }
   if (wi >= npts) return;
   G1Jac acc = G1Jac::identity();
@@ -695,7 +715,7 @@ __global__ void k_imad(u32 iters, u32* out) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static std::string g_create_error;
+static thread_local std::string g_create_error;  // per host thread: contexts may be created concurrently
 
 struct DevBuf {
   void* p = nullptr;
@@ -717,7 +737,7 @@ struct DevBuf {
 };
 
 struct h2v_ctx {
-  int device = 0;
+  int device = -1;  // -1 until a device was selected (h2v_ctx_destroy then frees host state only)
   cudaStream_t stream = nullptr;
   cudaStream_t stream_aux = nullptr;  // the fold-coefficient scan runs beside the per-proof stages
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done = nullptr;
@@ -744,21 +764,49 @@ struct h2v_ctx {
   std::vector<u32> h_verdicts;  // per fold group, of the last run
   bool verdicts_on_device = false;  // d_verdict holds the group verdicts of the batch in this context's buffers
   u32 opt_shard_hint = 0;   // geometry as for a shard of this many proofs (common to all ranks)
-  u64 lines_key = ~0ull;    // window geometry the prepared G2 lines in d_lines belong to
+  bool opt_has_key = false;  // next upload: fold randomness expanded from this 256-bit key (h2v_batch_set_rlc_key)
+  RlcKey opt_key{};
+  u32 rlc_source = 0;  // of the last upload: 0 caller scalars, 1 test seed, 2 caller key, 3 key drawn from the OS
+  // prepared G2 window lines, one slot per window geometry (small LRU: a service alternating batch shapes on one
+  // context must not rebuild ~5,000 lines on the host at every call)
+  struct LinesSlot {
+    u64 key = ~0ull, used = 0;
+    DevBuf buf;
+  } lines[4];
+  int lines_cur = -1;       // slot of the current geometry
+  u64 lines_builds = 0;     // host rebuilds so far (h2v_ctx_cache_stats)
+  u64 use_clock = 0;        // LRU clock of both caches
   // CUDA graphs: the ~20 kernels of a batch are captured once per (mode, shape, buffers) and replayed with one launch
   bool use_graphs = true;
   bool use_pdl = false;  // programmatic dependent launch between the kernels of a batch (pdl_prologue)
   bool capturing = false;
   bool stages_timed = false;  // ev[1..5] of the last run are valid (direct launches only)
   struct GraphSlot {
-    u64 key = 0;
+    u64 key = 0, used = 0;
     u64 kernels = 0;
     cudaGraphExec_t exec = nullptr;
-  } graphs[8];
+  } graphs[16];             // LRU over (entry point, batch shape, buffers): alternating shapes replay, never recapture
+  u64 graph_captures = 0;   // captures so far (h2v_ctx_cache_stats)
+  // device-side exchange of sharded batches (exchange.cuh)
+  struct Comm {
+    bool ready = false;
+    XLayout lay{};
+    u8* window = nullptr;             // this context's window (cudaMalloc, exported through CUDA IPC)
+    std::vector<u8*> peers;           // every rank's window as mapped here (own window at [rank])
+    std::vector<void*> opened;        // cudaIpcOpenMemHandle mappings to close
+    u8** d_peers = nullptr;
+    XDyn* d_dyn = nullptr;
+    u32* d_done = nullptr;
+    XDyn* h_dyn = nullptr;            // pinned ring of per-launch parameters
+    u32 ring = 0;
+    u64 seq = 0;                      // launch sets run on this channel so far
+    u64 timeout_ns = 30ull * 1000000000ull;
+  } comm;
   // device buffers
   DevBuf d_plan, d_proofs, d_proof_off, d_inst, d_inst_off, d_ncols, d_col_len, d_pts, d_bad, d_status, d_vals, d_scratch, d_right,
       d_shared, d_left, d_rlc_bytes, d_r, d_coef, d_shared_sum, d_dig, d_hist, d_off, d_cursor, d_order, d_sorted, d_buckets, d_wsums,
-      d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush, d_lines, d_M, d_partial_out, d_wsums_fin, d_tiles;
+      d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush, d_M, d_partial_out, d_wsums_fin, d_tiles;
+  const G2Line* d_lines() const { return lines_cur >= 0 ? lines[lines_cur].buf.as<G2Line>() : nullptr; }
   std::vector<u32> h_status;
   PlanView pv() const { return PlanView{d_plan.as<u8>()}; }
 };
@@ -778,6 +826,21 @@ struct h2v_ctx {
   } while (0)
 
 static inline u32 cdiv(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
+
+// `len` bytes from the kernel's CSPRNG; 0 on success
+static int os_entropy(void* out, size_t len) {
+  u8* p = (u8*)out;
+  while (len) {
+    const ssize_t got = getrandom(p, len, 0);
+    if (got < 0) {
+      if (errno == EINTR) continue;
+      return -1;
+    }
+    p += got;
+    len -= (size_t)got;
+  }
+  return 0;
+}
 
 // kernel launch with (pdl) or without the programmatic-stream-serialization attribute
 template <class... KArgs, class... Args>
@@ -888,24 +951,39 @@ static constexpr int LINES_GROUPS = 8;
 static u64 lines_key_of(const MsmGeom& g) { return (u64)g.c[0] | (u64)g.W[0] << 8 | (u64)g.c[1] << 16 | (u64)g.W[1] << 24; }
 
 // Prepared Miller lines of [2^(c w)] Q for the current window geometry (host: G2Prepared-style
-// preparation, once per geometry; cached in the context).
+// preparation, once per geometry; the last few geometries stay cached in the context).
 static int ensure_lines(h2v_ctx* ctx) {
   const MsmGeom& g = ctx->geom;
   const u64 key = lines_key_of(g);
-  if (ctx->lines_key == key) return 0;
+  ctx->use_clock++;
+  int victim = 0;
+  for (int i = 0; i < 4; i++) {
+    if (ctx->lines[i].key == key) {
+      ctx->lines[i].used = ctx->use_clock;
+      ctx->lines_cur = i;
+      return 0;
+    }
+    if (ctx->lines[i].used < ctx->lines[victim].used) victim = i;
+  }
   if (g.W[0] + g.W[1] > 128) {
     ctx->err = "window geometry exceeds 128 (channel, window) pairs";
     return -1;
   }
   std::vector<u8> tab;
   build_window_lines(ctx->info, g.c[0], g.W[0], g.c[1], g.W[1], tab);
-  CKC(ctx->d_lines.ensure(tab.size()));
+  h2v_ctx::LinesSlot& sl = ctx->lines[victim];
+  CKC(ctx_sync(ctx));  // the victim's lines may still be read by queued work
+  sl.key = ~0ull;
+  CKC(sl.buf.ensure(tab.size()));
   CKC(ctx->d_M.ensure(sizeof(E12) * H2V_ATE_ITERS));
   CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128));
   CKC(ctx->d_partial_out.ensure(H2V_PARTIAL_BYTES));
-  CKC(cudaMemcpyAsync(ctx->d_lines.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CKC(cudaMemcpyAsync(sl.buf.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
   CKC(ctx_sync(ctx));
-  ctx->lines_key = key;
+  sl.key = key;
+  sl.used = ctx->use_clock;
+  ctx->lines_cur = victim;
+  ctx->lines_builds++;
   return 0;
 }
 
@@ -913,22 +991,58 @@ static int ensure_lines(h2v_ctx* ctx) {
 static int launch_pairing(h2v_ctx* ctx, const G1Jac* wsums, u32 groups) {
   const MsmGeom& g = ctx->geom;
   cudaStream_t s = ctx->stream;
-  KLAUNCH((k_lines<LINES_GROUPS>), dim3(H2V_ATE_ITERS, groups), 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s, LinesArgs{g.W[0] + g.W[1]}, wsums, ctx->d_lines.as<G2Line>(),
+  KLAUNCH((k_lines<LINES_GROUPS>), dim3(H2V_ATE_ITERS, groups), 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s, LinesArgs{g.W[0] + g.W[1]}, wsums, ctx->d_lines(),
                                                                                        ctx->d_M.as<E12>());
   KLAUNCH(k_pairing_check, groups, 128, 0, s, ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>());
   return 0;
 }
 
-// verdicts of all fold groups of the last run -> ctx->h_verdicts; *all = every group accepted (waits for the stream)
-static int read_verdicts(h2v_ctx* ctx, u32* all) {
+// verdicts of all fold groups of the last run -> ctx->h_verdicts; *all = every group accepted (waits for the stream).
+// xchg: the run went through the device-side exchange; its two error words follow the verdicts.
+static int read_verdicts(h2v_ctx* ctx, u32* all, bool xchg = false) {
   const u32 G = ctx->geom.G ? ctx->geom.G : 1;
-  ctx->h_verdicts.assign(G, 0);
-  CKC(cudaMemcpyAsync(ctx->h_verdicts.data(), ctx->d_verdict.p, 4 * (size_t)G, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->h_verdicts.assign(G + 2, 0);
+  CKC(cudaMemcpyAsync(ctx->h_verdicts.data(), ctx->d_verdict.p, 4 * (size_t)(G + (xchg ? 2 : 0)), cudaMemcpyDeviceToHost, ctx->stream));
   CKC(ctx_sync(ctx));
+  const u32 e_local = ctx->h_verdicts[G], e_root = ctx->h_verdicts[G + 1];
+  ctx->h_verdicts.resize(G);
+  if (xchg && ((e_local | e_root) & 1)) {
+    ctx->err = "sharded exchange timed out: a peer never delivered its partial accumulators or the verdicts (a rank died, or the ranks disagree on the launch-set order)";
+    return -3;
+  }
+  if (xchg && ((e_local | e_root) & 2)) {
+    ctx->err = "partial accumulators were produced with different window geometries (use h2v_batch_set_shard_hint)";
+    return -1;
+  }
   u32 a = 1;
   for (u32 v : ctx->h_verdicts) a &= v ? 1u : 0u;
   *all = a;
   return 0;
+}
+
+// ---- exchange windows (exchange.cuh): export / connect / release
+struct CommHandle {  // H2V_COMM_HANDLE_BYTES, shipped between the ranks by the caller (plumbing: 128 bytes per context)
+  u32 magic, rank, world, max_groups;
+  u64 pid, ptr, bytes;
+  int device, rsv;
+  cudaIpcMemHandle_t ipc;
+  u8 pad[H2V_COMM_HANDLE_BYTES - 48 - sizeof(cudaIpcMemHandle_t)];
+};
+static_assert(sizeof(CommHandle) == H2V_COMM_HANDLE_BYTES, "comm handle size");
+static constexpr u32 H2V_COMM_MAGIC = 0x58563248u;
+static constexpr u32 XDYN_RING = 64;
+
+static void comm_release(h2v_ctx* ctx) {
+  h2v_ctx::Comm& cm = ctx->comm;
+  for (void* p : cm.opened) cudaIpcCloseMemHandle(p);
+  cm.opened.clear();
+  cm.peers.clear();
+  if (cm.window) cudaFree(cm.window);
+  if (cm.d_peers) cudaFree(cm.d_peers);
+  if (cm.d_dyn) cudaFree(cm.d_dyn);
+  if (cm.d_done) cudaFree(cm.d_done);
+  if (cm.h_dyn) cudaFreeHost(cm.h_dyn);
+  cm = h2v_ctx::Comm{};
 }
 
 extern "C" {
@@ -950,22 +1064,22 @@ int h2v_ctx_create_multi(h2v_ctx** out, const uint8_t* params, size_t params_len
   std::string err;
   if (build_plan(params, params_len, params_format, vk, vk_len, vk_format, multiopen, hash, ctx->blob, ctx->info, err, circuit_instances) != 0) {
     g_create_error = err;
-    delete ctx;
+    h2v_ctx_destroy(ctx);
     return -1;
   }
   memcpy(&ctx->hd, ctx->blob.data(), sizeof(PlanHeader));
-  ctx->device = device;
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || device < 0 || device >= count) {
     g_create_error = std::string("no usable CUDA device (this library has no CPU fallback): ") +
                      (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
-    delete ctx;
+    h2v_ctx_destroy(ctx);  // device still -1: nothing was created on a device
     return -2;
   }
+  ctx->device = device;
   auto fail = [&](const char* what, cudaError_t ce) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
-    delete ctx;
+    h2v_ctx_destroy(ctx);  // frees whatever streams / events / buffers exist so far
     return -2;
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
@@ -1000,6 +1114,10 @@ int h2v_ctx_create_from_bundle(h2v_ctx** out, const uint8_t* bundle, size_t bund
 
 void h2v_ctx_destroy(h2v_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->device < 0) {  // failed before any device object existed
+    delete ctx;
+    return;
+  }
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->stream_aux) cudaStreamSynchronize(ctx->stream_aux);
@@ -1008,7 +1126,8 @@ void h2v_ctx_destroy(h2v_ctx* ctx) {
                     &ctx->d_rlc_bytes, &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off,
                     &ctx->d_cursor, &ctx->d_order, &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict,
                     &ctx->d_partials, &ctx->d_partials_msm, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal, &ctx->d_flush,
-                    &ctx->d_lines, &ctx->d_M, &ctx->d_partial_out, &ctx->d_wsums_fin, &ctx->d_tiles};
+                    &ctx->lines[0].buf, &ctx->lines[1].buf, &ctx->lines[2].buf, &ctx->lines[3].buf, &ctx->d_M, &ctx->d_partial_out, &ctx->d_wsums_fin, &ctx->d_tiles};
+  comm_release(ctx);
   for (auto& gsl : ctx->graphs)
     if (gsl.exec) cudaGraphExecDestroy(gsl.exec);
   for (DevBuf* b : bufs)
@@ -1036,6 +1155,86 @@ int h2v_ctx_info(const h2v_ctx* ctx, uint32_t* out8) {
   return 0;
 }
 
+// Algorithmic work of scalar_stage (stages.cuh) for one proof of this plan, in Montgomery multiplications (a squaring
+// counts as one): the same walk over the plan as the kernel, counting instead of multiplying.  Feeds the roofline of
+// bench.py, so that the model follows the circuit instead of being fitted to one shape.
+static double pow_cost(u64 e) {  // square-and-multiply, as Fp::pow_u64
+  double c = 0;
+  for (; e > 1; e >>= 1) c += 1 + (e & 1);
+  return c;
+}
+static double scalar_stage_mm(const std::vector<u8>& blob, u32 rows) {
+  PlanView pv{blob.data()};
+  const PlanHeader& hd = pv.h();
+  const RotSet* sets = pv.sec<RotSet>(hd.off_sets);
+  auto poly = [&](u32 pid) {
+    const PolyRange pr = pv.sec<PolyRange>(hd.off_polys)[pid];
+    const PolyTerm* terms = pv.sec<PolyTerm>(hd.off_terms);
+    const PolyVar* vars = pv.sec<PolyVar>(hd.off_vars);
+    double c = 0;
+    for (u32 t = pr.term_begin; t < pr.term_end; t++)
+      for (u32 v = terms[t].var_begin; v < terms[t].var_end; v++) c += 1 + pow_cost(vars[v].pow);
+    return c;
+  };
+  auto compress = [&](u32 b, u32 e) {
+    const u32* list = pv.sec<u32>(hd.off_polylist);
+    double c = 0;
+    for (u32 i = b; i < e; i++) c += 1 + poly(list[i]);
+    return c;
+  };
+  double mm = hd.k + 1;  // x^n, common
+  if (hd.multiopen == MO_SHPLONK) mm += hd.n_rot + (sets[0].diff_end - sets[0].diff_begin);
+  const u32 nl = hd.blinding + 2;
+  const u32 li = hd.n_inst_q ? hd.inst_max_rot + rows + hd.inst_min_rot_abs : 0;
+  mm += 3 + nl + pow_cost(hd.inst_max_rot) + 2.0 * li;  // prefix products
+  mm += 252 + 57;                                       // the one Fermat inversion (5-bit sliding window)
+  mm += 5.0 * li + 2.0 * rows * hd.n_inst_q;            // instance Lagrange walk + inner products (from_canonical + multiply)
+  mm += 4.0 * nl + 4;                                   // l_last / l_blind / l_0, the three unbatched inverses
+  const ExprOp* eops = pv.sec<ExprOp>(hd.off_exprops);
+  const LookupDesc* lks = pv.sec<LookupDesc>(hd.off_lookups);
+  for (u32 o = 0; o < hd.n_exprops; o++) {
+    const ExprOp& e = eops[o];
+    switch (e.kind) {
+      case E_GATE: mm += 1 + poly(e.a); break;
+      case E_PERM_FIRST: mm += 2; break;
+      case E_PERM_LAST: mm += 3; break;
+      case E_PERM_LINK: mm += 2; break;
+      case E_PERM_PROD: mm += 4.0 * (e.d - e.c) + 4; break;
+      case E_LOOKUP: mm += 16 + compress(lks[e.a].in_begin, lks[e.a].in_end) + compress(lks[e.a].tab_begin, lks[e.a].tab_end); break;
+      default: mm += 9 + compress(lks[e.a].in_begin, lks[e.a].in_end) + compress(lks[e.a].tab_begin, lks[e.a].tab_end); break;
+    }
+  }
+  mm += 1;  // h / (x^n - 1)
+  if (hd.multiopen == MO_SHPLONK) {
+    const SetCommit* sc = pv.sec<SetCommit>(hd.off_setcms);
+    for (u32 si = 0; si < hd.n_sets; si++) {
+      const RotSet& S = sets[si];
+      const u32 m = S.pt_end - S.pt_begin;
+      mm += si == 0 ? m : (S.diff_end - S.diff_begin) + 1;
+      mm += (m - 1) + (double)m * m + 1 + 1;  // x^-(m-1), Lagrange basis at u, coef_set, v power
+      for (u32 c = S.cm_begin; c < S.cm_end; c++) mm += m + 3 + (sc[c].kind == CM_HMSM ? hd.n_h : 0);
+    }
+  } else {
+    const GwcPoint* gp = pv.sec<GwcPoint>(hd.off_gwcpts);
+    const GwcQuery* gq = pv.sec<GwcQuery>(hd.off_gwcq);
+    for (u32 p = 0; p < hd.n_gwc_points; p++) {
+      mm += 4;
+      for (u32 q = gp[p].q_begin; q < gp[p].q_end; q++) mm += 3 + (gq[q].kind == CM_HMSM ? hd.n_h : 0);
+    }
+  }
+  return mm;
+}
+
+extern "C" int h2v_ctx_work_model(const h2v_ctx* ctx, uint32_t instance_rows, double* out4) {
+  if (!ctx || !out4) return -1;
+  const PlanHeader& hd = ctx->hd;
+  out4[0] = scalar_stage_mm(ctx->blob, instance_rows);                        // k_scalar
+  out4[1] = 2.0 * hd.n_points + hd.n_scalars + 2.0 * hd.n_challenges;         // k_transcript: Montgomery conversions only (the hash is ALU work)
+  out4[2] = 250 + 38 + 16 + 9;                                                // k_decompress per point: sqrt window chain + curve check + conversions
+  out4[3] = (double)hd.n_inst_cols * instance_rows;                           // instance scalars per proof
+  return 0;
+}
+
 int h2v_batch_set_columns(h2v_ctx* ctx, const uint32_t* inst_ncols, const uint32_t* inst_col_len) {
   if (!ctx) return -1;
   ctx->opt_ncols = inst_ncols;
@@ -1053,6 +1252,14 @@ int h2v_last_group_verdicts(const h2v_ctx* ctx, uint8_t* out, uint32_t capacity)
   for (u32 i = 0; i < G && i < capacity; i++) out[i] = ctx->h_verdicts[i] ? 1 : 0;
   return (int)G;
 }
+
+int h2v_batch_set_rlc_key(h2v_ctx* ctx, const uint8_t* key32) {
+  if (!ctx || !key32) return -1;
+  memcpy(ctx->opt_key.w, key32, 32);
+  ctx->opt_has_key = true;
+  return 0;
+}
+int h2v_last_rlc_source(const h2v_ctx* ctx) { return ctx ? (int)ctx->rlc_source : -1; }
 
 int h2v_batch_set_shard_hint(h2v_ctx* ctx, uint32_t max_shard_proofs) {
   if (!ctx) return -1;
@@ -1083,6 +1290,25 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
     ctx->err = "offset arrays must start at 0";
     return -1;
   }
+  // The offset arrays are caller data: a decreasing offset or an oversized proof would become an out-of-bounds device
+  // read (the kernels index with 32-bit per-proof lengths), so they are validated here.
+  for (u32 j = 0; j < n; j++) {
+    if (proof_off[j + 1] < proof_off[j] || inst_off[j + 1] < inst_off[j] || proof_off[j + 1] - proof_off[j] > 0x7FFFFFFFull ||
+        inst_off[j + 1] - inst_off[j] > 0x03FFFFFFull) {
+      ctx->err = "offset arrays must be non-decreasing with per-proof sizes below 2^31 bytes / 2^26 scalars";
+      return -1;
+    }
+  }
+  {
+    // 32-bit index spaces of the kernels: term ids carry the sign in bit 31 (k_msm_scatter), k_decompress indexes
+    // (proof, point) pairs and the per-proof arrays with 32-bit products
+    const u64 terms = (u64)n * (hd.n_points + hd.n_mo) + (u64)hd.n_shared * groups;
+    const u64 widest = std::max<u64>(std::max<u64>(hd.n_points, hd.n_vals), hd.n_points + hd.n_shared + hd.n_mo);
+    if (terms >= (1ull << 31) || (u64)n * widest >= (1ull << 32)) {
+      ctx->err = "batch too large for the 32-bit index space of the MSM (split it into several uploads)";
+      return -1;
+    }
+  }
   // scratch rows for the instance Lagrange range = max column length + rotation margins
   u32 max_len = 0;
   if (ctx->opt_col_len) {
@@ -1091,6 +1317,10 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
     for (u32 j = 0; j < n; j++) max_len = std::max<u32>(max_len, (u32)((inst_off[j + 1] - inst_off[j]) / hd.n_inst_cols));
   }
   ctx->scratch_rows = hd.inst_max_rot + max_len + hd.inst_min_rot_abs + 1;
+  if ((u64)n * ctx->scratch_rows * 32 > (16ull << 30)) {  // instance columns longer than 2^k are rejected per proof; this bounds the allocation
+    ctx->err = "instance columns too long for this batch size (Lagrange scratch would exceed 16 GiB)";
+    return -1;
+  }
   ctx->n = n;
   ctx->gbase = gbase;
   ctx->gcount = gcount;
@@ -1117,6 +1347,7 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   CKC(ctx->d_left.ensure(32 * (size_t)n * hd.n_mo));
   CKC(ctx->d_r.ensure(32 * (size_t)gcount * groups));
   CKC(ctx->d_partial_out.ensure((size_t)H2V_PARTIAL_BYTES * groups));
+  CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
   CKC(ctx->d_coef.ensure(32 * (size_t)n));
   CKC(ctx->d_shared_sum.ensure(32 * (size_t)hd.n_shared * g.G));
   CKC(ctx->d_dig.ensure(2 * (size_t)g.G * g.T * g.Wmax));
@@ -1153,7 +1384,29 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
     CKC(ctx->d_rlc_bytes.ensure(32 * (size_t)n_r));
     CKC(cudaMemcpyAsync(ctx->d_rlc_bytes.p, rlc, 32 * (size_t)n_r, cudaMemcpyHostToDevice, s));
   }
-  k_rlc_expand<<<cdiv(n_r, 128), 128, 0, s>>>(n_r, seed, rlc ? ctx->d_rlc_bytes.as<u8>() : nullptr, ctx->d_r.as<Fr>());
+  // Fold randomness (reference strategy.rs:129 draws every r_i from the OS): explicit scalars and the 64-bit seed are
+  // parity / test hooks; otherwise the r_i are expanded from a 256-bit secret key, the caller's (sharded batches: one
+  // fresh key broadcast to every rank) or one drawn from the OS for this batch.
+  RlcKey key{};
+  bool keyed = false;
+  if (rlc) {
+    ctx->rlc_source = 0;
+  } else if (ctx->opt_has_key) {
+    key = ctx->opt_key;
+    keyed = true;
+    ctx->rlc_source = 2;
+  } else if (seed != 0) {
+    ctx->rlc_source = 1;
+  } else {
+    if (os_entropy(&key, sizeof(key)) != 0) {
+      ctx->err = "no OS entropy for the fold coefficients (getrandom failed)";
+      return -2;
+    }
+    keyed = true;
+    ctx->rlc_source = 3;
+  }
+  ctx->opt_has_key = false;
+  k_rlc_expand<<<cdiv(n_r, 128), 128, 0, s>>>(n_r, seed, rlc ? ctx->d_rlc_bytes.as<u8>() : nullptr, keyed, key, ctx->d_r.as<Fr>());
   LAUNCH_CHECK();
   return 0;
 }
@@ -1161,7 +1414,7 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
 // every kernel of the batch.  mode bits: RUN_PAIRING = batch pairing check -> d_verdict; RUN_ACCUM = explicit
 // window combination -> affine (L, R) bytes in d_acc_bytes (parity hook); RUN_PARTIAL = pack the window
 // sums into d_partial_out (sharded batches)
-enum : int { RUN_PAIRING = 1, RUN_ACCUM = 2, RUN_PARTIAL = 4 };
+enum : int { RUN_PAIRING = 1, RUN_ACCUM = 2, RUN_PARTIAL = 4, RUN_XCHG = 8, RUN_ROOT = 16 };
 static int enqueue_batch(h2v_ctx* ctx, int mode) {
   const PlanHeader& hd = ctx->hd;
   const u32 n = ctx->n;
@@ -1224,6 +1477,23 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   if (mode & RUN_PARTIAL) {
     KLAUNCH(k_pack_partial, dim3(8, g.G), 256, 0, s, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, g.W[0] + g.W[1], ctx->d_wsums.as<G1Jac>(), ctx->d_partial_out.as<u8>());
   }
+  if (mode & RUN_XCHG) {
+    // The one exchange step of a sharded batch, device side (exchange.cuh): partials -> the root's window over NVLink;
+    // root: wait for all ranks, sum in place, pairing checks, verdicts -> every rank's window; every rank: wait for them.
+    h2v_ctx::Comm& cm = ctx->comm;
+    const u32 cb = g.c[0] | g.c[1] << 16, wd = g.W[0] | g.W[1] << 16, npts = g.W[0] + g.W[1];
+    u32* vd = ctx->d_verdict.as<u32>();
+    CKC(cudaMemsetAsync(vd + g.G, 0, 8, s));  // error words of this launch set
+    KLAUNCH(k_pack_partial_x, g.G, 256, 0, s, cb, wd, npts, ctx->d_wsums.as<G1Jac>(), cm.d_dyn, cm.d_peers, cm.lay, cm.d_done);
+    if (mode & RUN_ROOT) {
+      KLAUNCH_P(false, k_sum_partials, g.G, 128, 0, s, cm.lay.world, cb, wd, npts, cm.window + cm.lay.partials_off(), (size_t)cm.lay.max_groups * H2V_PARTIAL_BYTES,
+                ctx->d_wsums_fin.as<G1Jac>(), vd + g.G, cm.d_dyn, (const u64*)(cm.window + cm.lay.arrive_off()));
+      int prc = launch_pairing(ctx, ctx->d_wsums_fin.as<G1Jac>(), g.G);
+      if (prc) return prc;
+      KLAUNCH_P(false, k_bcast_verdict, 1, 256, 0, s, cm.d_dyn, cm.d_peers, cm.lay, g.G, vd, vd + g.G);
+    }
+    KLAUNCH_P(false, k_wait_verdict, 1, 64, 0, s, cm.d_dyn, cm.window, cm.lay, g.G, vd);
+  }
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[5], s));
   if (mode & RUN_ACCUM) {
     FoldArgs fa{{g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {g.wbase[0], g.wbase[1]}};
@@ -1254,9 +1524,11 @@ static u64 graph_key(const h2v_ctx* ctx, int mode) {
   const DevBuf* bufs[] = {&ctx->d_plan, &ctx->d_proofs, &ctx->d_proof_off, &ctx->d_inst, &ctx->d_inst_off, &ctx->d_ncols, &ctx->d_col_len,
                           &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
                           &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off, &ctx->d_cursor, &ctx->d_order,
-                          &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict, &ctx->d_partials_msm, &ctx->d_lines,
-                          &ctx->d_M, &ctx->d_partial_out, &ctx->d_tiles};
+                          &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict, &ctx->d_partials_msm,
+                          &ctx->d_M, &ctx->d_partial_out, &ctx->d_tiles, &ctx->d_wsums_fin};
   for (const DevBuf* b : bufs) mix((u64)(size_t)b->p);
+  mix((u64)(size_t)ctx->d_lines());
+  mix((u64)(size_t)ctx->comm.window);
   return h | 1;
 }
 
@@ -1274,11 +1546,20 @@ static int run_impl(h2v_ctx* ctx, int mode) {
     ctx->ran = true;
     return 0;
   }
-  h2v_ctx::GraphSlot& gs = ctx->graphs[mode & 7];
   const u64 key = graph_key(ctx, mode);
-  if (!gs.exec || gs.key != key) {
+  ctx->use_clock++;
+  h2v_ctx::GraphSlot* hit = nullptr;
+  h2v_ctx::GraphSlot* victim = &ctx->graphs[0];
+  for (auto& sl : ctx->graphs) {
+    if (sl.exec && sl.key == key) hit = &sl;
+    if (!sl.exec ? victim->exec != nullptr : (victim->exec && sl.used < victim->used)) victim = &sl;
+  }
+  h2v_ctx::GraphSlot& gs = hit ? *hit : *victim;
+  gs.used = ctx->use_clock;
+  if (!hit) {
     if (gs.exec) cudaGraphExecDestroy(gs.exec);
     gs.exec = nullptr;
+    gs.key = 0;
     const u64 before = ctx->launches;
     CKC(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     ctx->capturing = true;
@@ -1297,6 +1578,7 @@ static int run_impl(h2v_ctx* ctx, int mode) {
     cudaGraphDestroy(graph);
     CKC(ie);
     gs.key = key;
+    ctx->graph_captures++;
   }
   CKC(cudaEventRecord(ctx->ev[0], s));
   CKC(cudaGraphLaunch(gs.exec, s));
@@ -1401,11 +1683,21 @@ static int finalize_impl(h2v_ctx* ctx, u32 n_partials, u32 groups, const u8* par
   if (!ctx || !partials || !n_partials || n_partials > 128 || !groups || groups > 1024 || (batch_accum && groups != 1)) return -1;
   CKC(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  CKC(ctx->d_partials.ensure((size_t)H2V_PARTIAL_BYTES * n_partials * groups));
-  CKC(cudaMemcpyAsync(ctx->d_partials.p, partials, (size_t)H2V_PARTIAL_BYTES * n_partials * groups, cudaMemcpyDefault, s));
+  // partials already in this device's memory (e.g. the output of a gather) are summed in place
+  const u8* d_parts = nullptr;
+  {
+    cudaPointerAttributes pa{};
+    if (cudaPointerGetAttributes(&pa, partials) == cudaSuccess && pa.type == cudaMemoryTypeDevice && pa.device == ctx->device) d_parts = partials;
+    (void)cudaGetLastError();
+  }
+  if (!d_parts) {
+    CKC(ctx->d_partials.ensure((size_t)H2V_PARTIAL_BYTES * n_partials * groups));
+    CKC(cudaMemcpyAsync(ctx->d_partials.p, partials, (size_t)H2V_PARTIAL_BYTES * n_partials * groups, cudaMemcpyDefault, s));
+    d_parts = ctx->d_partials.as<u8>();
+  }
   if (ctx->n == 0) {  // a context that has not processed a shard itself: take the geometry from the first partial
     PartialHeader h;
-    CKC(cudaMemcpyAsync(&h, ctx->d_partials.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CKC(cudaMemcpyAsync(&h, d_parts, sizeof(h), cudaMemcpyDeviceToHost, s));
     CKC(ctx_sync(ctx));
     MsmGeom& g = ctx->geom;
     g = MsmGeom{};
@@ -1430,8 +1722,8 @@ static int finalize_impl(h2v_ctx* ctx, u32 n_partials, u32 groups, const u8* par
   CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
   CKC(cudaMemsetAsync(ctx->d_verdict.p, 0, 4 * (size_t)groups + 16, s));
   ctx->verdicts_on_device = false;  // d_verdict now belongs to the global batches being finalized
-  k_sum_partials<<<groups, 128, 0, s>>>(n_partials, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, npts, ctx->d_partials.as<u8>(), ctx->d_wsums_fin.as<G1Jac>(),
-                                        ctx->d_verdict.as<u32>() + groups);
+  k_sum_partials<<<groups, 128, 0, s>>>(n_partials, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, npts, d_parts, (size_t)groups * H2V_PARTIAL_BYTES,
+                                        ctx->d_wsums_fin.as<G1Jac>(), ctx->d_verdict.as<u32>() + groups, nullptr, nullptr);
   LAUNCH_CHECK();
   int prc = launch_pairing(ctx, ctx->d_wsums_fin.as<G1Jac>(), groups);
   if (prc) return prc;
@@ -1469,6 +1761,170 @@ int h2v_attribute_shard(h2v_ctx* ctx, uint8_t* status) {
   int rc;
   if ((rc = per_proof_impl(ctx, true, nullptr)) != 0) return rc;
   return download_status(ctx, status);
+}
+
+int h2v_attribute_shard_groups(h2v_ctx* ctx, const uint8_t* group_verdicts, uint32_t groups, uint8_t* status) {
+  if (!ctx || !ctx->ran || !group_verdicts || groups != ctx->geom.G) return -1;
+  CKC(cudaSetDevice(ctx->device));
+  std::vector<u32> v(groups);
+  for (u32 q = 0; q < groups; q++) v[q] = group_verdicts[q] ? 1u : 0u;
+  CKC(ctx->d_verdict.ensure(4 * (size_t)groups + 16));
+  CKC(cudaMemcpyAsync(ctx->d_verdict.p, v.data(), 4 * (size_t)groups, cudaMemcpyHostToDevice, ctx->stream));
+  CKC(ctx_sync(ctx));  // v is a stack buffer
+  ctx->verdicts_on_device = true;  // per_proof_impl skips the proofs of accepted groups
+  int rc;
+  if ((rc = per_proof_impl(ctx, true, nullptr)) != 0) return rc;
+  return download_status(ctx, status);
+}
+
+// ---- device-side exchange (exchange.cuh) ---------------------------------------------------------
+int h2v_comm_init(h2v_ctx* ctx, uint32_t rank, uint32_t world, uint32_t max_groups, uint8_t* handle_out) {
+  if (!ctx || !handle_out || world == 0 || world > XCH_MAX_RANKS || rank >= world || max_groups == 0 || max_groups > 1024) {
+    if (ctx) ctx->err = "h2v_comm_init: bad arguments (world <= 128, max_groups <= 1024)";
+    return -1;
+  }
+  CKC(cudaSetDevice(ctx->device));
+  CKC(ctx_sync(ctx));
+  comm_release(ctx);
+  for (auto& gsl : ctx->graphs) gsl.key = 0;  // graphs captured with the old window
+  h2v_ctx::Comm& cm = ctx->comm;
+  cm.lay = XLayout{rank, world, max_groups, 0};
+  const size_t bytes = cm.lay.bytes();
+  CKC(cudaMalloc((void**)&cm.window, bytes));
+  CKC(cudaMemset(cm.window, 0, bytes));
+  CKC(cudaMalloc((void**)&cm.d_peers, sizeof(u8*) * world));
+  CKC(cudaMalloc((void**)&cm.d_dyn, sizeof(XDyn)));
+  CKC(cudaMalloc((void**)&cm.d_done, 4));
+  CKC(cudaMemset(cm.d_done, 0, 4));
+  CKC(cudaMallocHost((void**)&cm.h_dyn, sizeof(XDyn) * XDYN_RING));
+  if (const char* t = getenv("H2V_COMM_TIMEOUT_MS")) {
+    const long ms = atol(t);
+    if (ms > 0) cm.timeout_ns = (u64)ms * 1000000ull;
+  }
+  CommHandle h{};
+  h.magic = H2V_COMM_MAGIC;
+  h.rank = rank;
+  h.world = world;
+  h.max_groups = max_groups;
+  h.pid = (u64)getpid();
+  h.ptr = (u64)(size_t)cm.window;
+  h.bytes = bytes;
+  h.device = ctx->device;
+  CKC(cudaIpcGetMemHandle(&h.ipc, cm.window));
+  memcpy(handle_out, &h, sizeof(h));
+  CKC(cudaDeviceSynchronize());
+  return 0;
+}
+
+int h2v_comm_connect(h2v_ctx* ctx, const uint8_t* handles) {
+  if (!ctx || !handles || !ctx->comm.window) {
+    if (ctx) ctx->err = "h2v_comm_connect: call h2v_comm_init first";
+    return -1;
+  }
+  CKC(cudaSetDevice(ctx->device));
+  h2v_ctx::Comm& cm = ctx->comm;
+  const XLayout& lay = cm.lay;
+  cm.peers.assign(lay.world, nullptr);
+  for (u32 r = 0; r < lay.world; r++) {
+    CommHandle h;
+    memcpy(&h, handles + (size_t)r * H2V_COMM_HANDLE_BYTES, sizeof(h));
+    if (h.magic != H2V_COMM_MAGIC || h.rank != r || h.world != lay.world || h.max_groups != lay.max_groups || h.bytes != lay.bytes()) {
+      ctx->err = "h2v_comm_connect: handle " + std::to_string(r) + " does not belong to this job (rank order, world size and max_groups must agree on every rank)";
+      return -1;
+    }
+    if (r == lay.rank) {
+      cm.peers[r] = cm.window;
+    } else if (h.pid == (u64)getpid()) {  // a peer context of this very process (tests, single-process multi-GPU)
+      if (h.device != ctx->device) {
+        int can = 0;
+        CKC(cudaDeviceCanAccessPeer(&can, ctx->device, h.device));
+        if (!can) {
+          ctx->err = "h2v_comm_connect: no peer access between devices " + std::to_string(ctx->device) + " and " + std::to_string(h.device);
+          return -2;
+        }
+        const cudaError_t pe = cudaDeviceEnablePeerAccess(h.device, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CKC(pe);
+        (void)cudaGetLastError();
+      }
+      cm.peers[r] = (u8*)(size_t)h.ptr;
+    } else {
+      void* p = nullptr;
+      const cudaError_t oe = cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess);
+      if (oe != cudaSuccess) {
+        (void)cudaGetLastError();
+        ctx->err = std::string("h2v_comm_connect: cudaIpcOpenMemHandle of rank ") + std::to_string(r) + "'s window failed (" + cudaGetErrorString(oe) +
+                   "): the ranks must be processes of one node with NVLink / PCIe peer access; otherwise exchange the partials with h2v_accumulate_shard + a gather + h2v_finalize";
+        return -2;
+      }
+      cm.opened.push_back(p);
+      cm.peers[r] = (u8*)p;
+    }
+  }
+  CKC(cudaMemcpy(cm.d_peers, cm.peers.data(), sizeof(u8*) * lay.world, cudaMemcpyHostToDevice));
+  cm.seq = 0;
+  cm.ready = true;
+  return 0;
+}
+
+// one launch set through the exchange; `status` != null: attribution inside rejected groups + status download
+static int exchange_run(h2v_ctx* ctx, u32 root, u8* group_verdicts, int* verdict, bool e2e, u8* status) {
+  h2v_ctx::Comm& cm = ctx->comm;
+  if (!cm.ready || root >= cm.lay.world || ctx->n == 0 || ctx->geom.G > cm.lay.max_groups) {
+    ctx->err = "sharded exchange: the context needs h2v_comm_init + h2v_comm_connect, an uploaded shard, root < world and fold groups <= max_groups";
+    return -1;
+  }
+  CKC(cudaSetDevice(ctx->device));
+  XDyn* d = &cm.h_dyn[cm.ring++ % XDYN_RING];
+  d->seq = ++cm.seq;
+  d->root = root;
+  d->rsv = 0;
+  d->timeout_ns = cm.timeout_ns;
+  CKC(cudaMemcpyAsync(cm.d_dyn, d, sizeof(XDyn), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = run_impl(ctx, RUN_XCHG | (root == cm.lay.rank ? RUN_ROOT : 0));
+  if (rc) return rc;
+  u32 all = 0;
+  if ((rc = read_verdicts(ctx, &all, true)) != 0) return rc;
+  ctx->verdicts_on_device = true;  // d_verdict holds the verdicts of this rank's groups: attribution skips accepted groups
+  if (group_verdicts)
+    for (u32 q = 0; q < ctx->geom.G; q++) group_verdicts[q] = ctx->h_verdicts[q] ? 1 : 0;
+  if (verdict) *verdict = (int)all;
+  if (e2e) {
+    if (!all && (rc = per_proof_impl(ctx, true, nullptr)) != 0) return rc;
+    return download_status(ctx, status);
+  }
+  return 0;
+}
+
+int h2v_batch_run_shard_exchange(h2v_ctx* ctx, uint32_t root, uint8_t* group_verdicts, int* verdict) {
+  if (!ctx) return -1;
+  return exchange_run(ctx, root, group_verdicts, verdict, false, nullptr);
+}
+
+int h2v_verify_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off, const uint8_t* instances,
+                     const uint64_t* inst_off, const uint8_t* rlc_scalars, uint64_t seed, uint64_t global_base, uint64_t global_count,
+                     uint32_t root, uint8_t* status, uint8_t* group_verdicts, int* verdict) {
+  int rc;
+  if ((rc = upload_impl(ctx, n, proofs, proof_off, instances, inst_off, rlc_scalars, seed, global_base, global_count)) != 0) return rc;
+  return exchange_run(ctx, root, group_verdicts, verdict, true, status);
+}
+
+int h2v_comm_last_batch_accum(h2v_ctx* ctx, uint8_t* batch_accum) {
+  if (!ctx || !batch_accum || !ctx->comm.ready || ctx->geom.G != 1) return -1;
+  CKC(cudaSetDevice(ctx->device));
+  const MsmGeom& g = ctx->geom;
+  FoldArgs fa{{g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {0, g.W[0]}};
+  k_fold_accum<<<1, 32, 0, ctx->stream>>>(fa, ctx->d_wsums_fin.as<G1Jac>(), ctx->d_acc_bytes.as<u8>());
+  LAUNCH_CHECK();
+  CKC(cudaMemcpyAsync(batch_accum, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(ctx_sync(ctx));
+  return 0;
+}
+
+int h2v_ctx_cache_stats(const h2v_ctx* ctx, uint64_t* out2) {
+  if (!ctx || !out2) return -1;
+  out2[0] = ctx->lines_builds;
+  out2[1] = ctx->graph_captures;
+  return 0;
 }
 
 int h2v_batch_upload(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off, const uint8_t* instances,
@@ -1575,8 +2031,8 @@ int h2v_debug_timeline_stop(int device, void* out, uint32_t capacity, uint32_t* 
 int h2v_ctx_set_graphs(h2v_ctx* ctx, int on) {
   if (!ctx) return -1;
   ctx->use_graphs = (on & 1) != 0;
-  ctx->use_pdl = (on & 2) == 0;  // diagnosis: bit 1 switches programmatic dependent launch off
-  for (auto& gsl : ctx->graphs) gsl.key = 0;
+  ctx->use_pdl = (on & 2) != 0;  // bit 1 switches programmatic dependent launch ON (default off)
+  for (auto& gsl : ctx->graphs) gsl.key = 0;  // (the captured graphs embed the launch attributes)
   return 0;
 }
 

@@ -428,4 +428,22 @@ H2V_HDN inline Fr rlc_scalar_from_seed(u64 seed, u64 i) {
   return Fr::from_uniform(d);
 }
 
+// The production path: r_i = from_uniform(Blake2b-512(personal "Halo2-Transcript", "h2v-rlk" | key[32] | i_le64)) with a
+// 256-bit SECRET key drawn from the OS per batch (the reference draws every r_i from the OS, strategy.rs:129; the
+// soundness of the fold needs coefficients the prover cannot predict).  The 64-bit-seed variant above is a parity / test hook.
+struct RlcKey {
+  u32 w[8];
+};
+H2V_HDN inline Fr rlc_scalar_from_key(const RlcKey& key, u64 i) {
+  Blake2b b;
+  b.init_halo2();
+  const char* tag = "h2v-rlk";
+  for (int t = 0; t < 7; t++) b.update_byte((u8)tag[t]);
+  for (int t = 0; t < 32; t++) b.update_byte((u8)(key.w[t >> 2] >> (8 * (t & 3))));
+  for (int t = 0; t < 8; t++) b.update_byte((u8)(i >> (8 * t)));
+  u8 d[64];
+  b.digest(d);
+  return Fr::from_uniform(d);
+}
+
 }  // namespace h2v

@@ -36,7 +36,11 @@ extern "C" {
 #define H2V_TRANSCRIPT 2                 /* Error::Transcript: any read before the multi-open part fails */
 #define H2V_OPENING 3                    /* Error::Opening: lib.rs:420-424 (h1/h2 or W_i unreadable) */
 #define H2V_CONSTRAINT_SYSTEM_FAILURE 4  /* strategy.rs:164-176: pairing check fails */
-#define H2V_WOULD_PANIC 5                /* reference unwraps None: vanishing.rs:100, shplonk.rs:215 */
+#define H2V_WOULD_PANIC 5                /* reference unwraps None: vanishing.rs:100 (x^n = 1), shplonk.rs:215 (z_diff = 0).
+                                          * One deviation: the evaluation challenge x = 0 is also reported as H2V_WOULD_PANIC although the
+                                          * reference would not panic on it (the Lagrange-basis shortcut used here divides by x; the
+                                          * reference's l_i_range, poly/domain.rs:187-212, does not).  x is a transcript hash output, so
+                                          * the case has probability 2^-254 and cannot be steered by a prover. */
 
 typedef struct h2v_ctx h2v_ctx;
 
@@ -84,6 +88,20 @@ int h2v_verify_batch(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint
                      const uint8_t* instances, const uint64_t* inst_off, const uint8_t* rlc_scalars,
                      uint64_t seed, uint8_t* status, uint8_t* challenges, uint8_t* accum,
                      uint8_t* batch_accum);
+
+/* Fold randomness (reference strategy.rs:129: the accumulator is scaled by Fr::random(OsRng) before every proof; the
+ * soundness of the batch check rests on r_i the prover cannot predict).  Precedence for a batch:
+ *   rlc_scalars != NULL            the caller's r_i                                   (parity hook: bit-exact accumulators)
+ *   h2v_batch_set_rlc_key(key)     r_i = Blake2b-512("h2v-rlk" | key | i) mod r, key = 32 SECRET bytes; one-shot option for
+ *                                  the next upload.  Sharded batches: draw one fresh key per global batch and give it to
+ *                                  every rank (the c_j are then defined globally, independent of the shard count)
+ *   seed != 0                      r_i = Blake2b-512("h2v-rlc" | seed | i) mod r      (test hook: public, reproducible)
+ *   otherwise (NULL, no key, 0)    the library draws a fresh 256-bit key from the OS (getrandom) for this upload; a shard
+ *                                  drawing its own key is sound too (its proofs get unpredictable coefficients), only the
+ *                                  folded (L, R) then depend on the sharding
+ * h2v_last_rlc_source: 0 caller scalars, 1 test seed, 2 caller key, 3 OS entropy (of the last upload). */
+int h2v_batch_set_rlc_key(h2v_ctx* ctx, const uint8_t* key32);
+int h2v_last_rlc_source(const h2v_ctx* ctx);
 
 /* Optional ragged instance layout for the NEXT batch call: inst_ncols[n] = columns supplied per proof
  * (a mismatch with the VK gives H2V_INVALID_INSTANCES, lib.rs:51-55) and inst_col_len[n * columns]
@@ -139,6 +157,42 @@ int h2v_finalize(h2v_ctx* ctx, uint32_t n_partials, const uint8_t* partials, uin
  * context; proofs that fail get H2V_CONSTRAINT_SYSTEM_FAILURE in status (n bytes, in/out). */
 int h2v_attribute_shard(h2v_ctx* ctx, uint8_t* status);
 
+/* Same for a launch set with fold groups: only the proofs of groups whose verdict (group_verdicts[q] = 0) was a
+ * rejection are re-checked; `groups` must equal the fold groups of the shard last processed by this context. */
+int h2v_attribute_shard_groups(h2v_ctx* ctx, const uint8_t* group_verdicts, uint32_t groups, uint8_t* status);
+
+/* ---- device-side exchange of sharded batches (one process per GPU of one node; NVLink peer memory) ------------
+ * The product path of SURVEY.md 8e / north_star "the 8 partial accumulators are gathered for the single final pairing":
+ * every rank's context owns a window in its HBM which the peers map through CUDA IPC.  A launch set then runs WITHOUT
+ * the host or a library collective in its data path, as part of the captured CUDA graph: the kernel that packs a
+ * shard's per-window sums stores them into the ROOT rank's window over NVLink and publishes a sequence number; the
+ * root's summing kernel waits for all ranks, adds the partials in place, runs the pairing check of every fold group and
+ * stores the verdicts into every rank's window; every rank's last kernel waits for them (a gather to the root plus a
+ * verdict broadcast, not an all-gather).  The contexts that share a window set form a CHANNEL: every rank must run the
+ * same sequence of launch sets on it, with the same `root` per launch set (e.g. launch set i on rank i mod world, which
+ * spreads the pairing checks).  Several channels (contexts) per rank run independently.  Every device-side wait is bounded
+ * (H2V_COMM_TIMEOUT_MS, default 30000): a missing peer yields return code -3, never a hung GPU or an "accepted".
+ *   h2v_comm_init     allocates the window for `world` ranks and up to `max_groups` fold groups per launch set; writes an
+ *                     opaque handle (H2V_COMM_HANDLE_BYTES) that the caller ships to every rank (plumbing: e.g. one
+ *                     torch.distributed all_gather of 128 bytes per context at start-up)
+ *   h2v_comm_connect  handles: world x H2V_COMM_HANDLE_BYTES in rank order (own handle included)
+ *   h2v_batch_run_shard_exchange   on a shard resident in HBM (h2v_batch_upload_shard): the launch set described above;
+ *                     group_verdicts: G bytes out (may be NULL), verdict: AND of them
+ *   h2v_verify_shard  the end-to-end call of a rank: upload of its shard (arguments as h2v_accumulate_shard), the launch
+ *                     set, per-proof attribution inside the rejected groups of this rank's shard (poly/strategy.rs:26-30),
+ *                     status download.  Reference: AccumulatorStrategy::process per proof + finalize (strategy.rs:125-140)
+ *                     with the MSM split over the ranks.
+ *   h2v_comm_last_batch_accum      root only, one fold group: the folded affine (L, R) of the last launch set, 2 x 64 B
+ *                     (parity hook: identical for every shard count when the fold randomness is defined globally) */
+#define H2V_COMM_HANDLE_BYTES 128
+int h2v_comm_init(h2v_ctx* ctx, uint32_t rank, uint32_t world, uint32_t max_groups, uint8_t* handle_out);
+int h2v_comm_connect(h2v_ctx* ctx, const uint8_t* handles);
+int h2v_batch_run_shard_exchange(h2v_ctx* ctx, uint32_t root, uint8_t* group_verdicts, int* verdict);
+int h2v_verify_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off, const uint8_t* instances,
+                     const uint64_t* inst_off, const uint8_t* rlc_scalars, uint64_t seed, uint64_t global_base,
+                     uint64_t global_count, uint32_t root, uint8_t* status, uint8_t* group_verdicts, int* verdict);
+int h2v_comm_last_batch_accum(h2v_ctx* ctx, uint8_t* batch_accum);
+
 /* ---- staged execution for measurement (bench.py): upload, run (device-resident), download ---- */
 int h2v_batch_upload(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off,
                      const uint8_t* instances, const uint64_t* inst_off, const uint8_t* rlc_scalars,
@@ -168,16 +222,25 @@ void* h2v_ctx_stream(const h2v_ctx* ctx);
 /* host waits of this context: 0 (default) spin on the stream (lowest latency), 1 block on an event (use when many
  * contexts share few host cores, e.g. several batches in flight on every GPU of a box) */
 int h2v_ctx_set_blocking_sync(h2v_ctx* ctx, int blocking);
-/* CUDA graphs (default 1): the kernels of a batch are captured once per (entry point, batch shape, buffers) and
+/* CUDA graphs (bit 0, default 1): the kernels of a batch are captured once per (entry point, batch shape, buffers) and
  * replayed with ONE launch per batch, which removes ~40 driver calls per batch from the host threads (with many
- * batches in flight those calls, serialised by the driver, bounded the throughput).  0 = direct launches with a CUDA
- * event after every stage: required for the per-stage values of h2v_last_timings (a replay only yields the total). */
+ * batches in flight those calls, serialised by the driver, bounded the throughput).  The context keeps the last 16
+ * graphs and the prepared window lines of the last 4 MSM geometries, so a service that alternates batch shapes replays.
+ * Bit 0 = 0: direct launches with a CUDA event after every stage: required for the per-stage values of
+ * h2v_last_timings (a replay only yields the total).  Bit 1 (default 0): programmatic dependent launch between the
+ * kernels of a batch (measured: no gain, kept for diagnosis). */
 int h2v_ctx_set_graphs(h2v_ctx* ctx, int on);
+/* out[0] = host rebuilds of prepared window lines, out[1] = graph captures, since the context was created */
+int h2v_ctx_cache_stats(const h2v_ctx* ctx, uint64_t* out2);
 /* diagnostics: per-block timeline of the per-proof and MSM kernels on `device` (all contexts).  start allocates a
  * log of `capacity` records and switches recording on; stop switches it off and copies up to `capacity` 32-byte
  * records {u32 kernel id, block, SM, context tag; u64 start_ns, end_ns} (global nanosecond timer) into `out`. */
 int h2v_debug_timeline_start(int device, uint32_t capacity);
 int h2v_debug_timeline_stop(int device, void* out, uint32_t capacity, uint32_t* count);
+/* Algorithmic work model of this plan (bench.py roofline), per proof with `instance_rows` values per instance column:
+ * out[0] Montgomery multiplications of the scalar stage (a walk over the plan that counts what scalar_stage multiplies),
+ * out[1] of the transcript stage (Montgomery conversions), out[2] of one point decompression, out[3] instance scalars. */
+int h2v_ctx_work_model(const h2v_ctx* ctx, uint32_t instance_rows, double* out4);
 /* MSM geometry of the last run: out[0] window bits, [1] windows, [2] terms, [3] buckets */
 int h2v_last_msm_geometry(const h2v_ctx* ctx, uint32_t* out4);
 

@@ -114,6 +114,87 @@ def test_two_rank_sharded_fold_equals_whole_batch():
     assert all(p.exitcode == 0 for p in procs)
 
 
+def _rank_product_logic(rank, world, port, q):
+    """sharding.verify_batch_sharded itself (library-gather path + fresh fold key + root-only gather + verdict broadcast +
+    local attribution) over gloo, with a stand-in for the C-ABI surface whose folding is done by the oracle"""
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import ctypes
+    import random
+
+    import bn254 as bn
+    import prover_sim as sim
+    import verifier as orc
+    from workloads import enc_point, make_batch
+    import __graft_entry__ as g
+
+    g.load_package()
+    sharding = __import__("importlib").import_module("halo2_verifier_b200.sharding")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 7  # uneven shards: 4 + 3
+    params, vk, instances, proofs, rng = make_batch("vm", 8, n, "shplonk", "blake2b", seed=23)
+    dec = lambda e: None if e == bytes(64) else (int.from_bytes(e[:32], "little"), int.from_bytes(e[32:], "little"))
+
+    class FakeBV:
+        comm_ready = False
+
+        class lib:
+            h2v_partial_bytes = staticmethod(lambda: 128)
+
+        def __init__(self):
+            self.keys = []
+
+        def accumulate_shard(self, proofs, insts, lo, n_glob, rlc_scalars=None, seed=None, shard_hint=0, fold_groups=1, key=None, partial_out=None):
+            assert rlc_scalars is None and seed is None and key is not None and len(key) == 32  # the default: a fresh global key
+            self.keys.append(key)
+            kr = random.Random(key)
+            rs = [kr.randrange(1, bn.R) for _ in range(n_glob)]
+            self.res = [orc.verify_proof(params, vk, i, p, check_pairing=False) for i, p in zip(insts, proofs)]
+            self.args = (proofs, insts)
+            cs = orc.rlc_coefficients(rs)[lo:lo + len(proofs)]
+            L = R_ = None
+            for w, c in zip(self.res, cs):
+                if w.status == orc.OK:
+                    L, R_ = bn.g1_add(L, bn.g1_mul(w.L, c)), bn.g1_add(R_, bn.g1_mul(w.R, c))
+            ctypes.memmove(partial_out, enc_point(L) + enc_point(R_), 128)
+            return [w.status for w in self.res], None
+
+        def finalize(self, ptr, want_batch_accum=False, n_partials=None):
+            blob = ctypes.string_at(ptr, 128 * n_partials)
+            L = R_ = None
+            for r in range(n_partials):
+                L, R_ = bn.g1_add(L, dec(blob[128 * r:128 * r + 64])), bn.g1_add(R_, dec(blob[128 * r + 64:128 * r + 128]))
+            return bn.pairing_check([(L, params.s_g2), (R_, bn.g2_neg(params.g2))]), None
+
+        def attribute_shard(self, status, group_verdicts=None):
+            return [orc.verify_proof(params, vk, i, p).status for p, i in zip(*self.args)]
+
+    bv = FakeBV()
+    ok_clean, st_clean = sharding.verify_batch_sharded(bv, proofs, instances, rank, world, root=1)
+    bad = list(proofs)
+    bad[5], _ = sim.corrupt(proofs[5], vk, "eval_flip", rng)  # lives on rank 1; root is rank 0
+    ok_bad, st_bad = sharding.verify_batch_sharded(bv, bad, instances, rank, world, root=0)
+    keys = sharding.all_gather_bytes(b"".join(bv.keys), world)
+    lo, hi = sharding.shard_range(n, rank, world)
+    want = [4 if j == 5 else 0 for j in range(lo, hi)]
+    q.put((rank, ok_clean and st_clean == [0] * (hi - lo), (not ok_bad) and st_bad == want, keys[0] == keys[1] and bv.keys[0] != bv.keys[1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_product_sharding_logic():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_rank_product_logic, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = sorted(q.get(timeout=600) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert got == [(0, True, True, True), (1, True, True, True)], got
+    assert all(p.exitcode == 0 for p in procs)
+
+
 def test_shard_range_partition():
     sys.path.insert(0, ROOT)
     import __graft_entry__ as g
