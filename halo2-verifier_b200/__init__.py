@@ -120,6 +120,7 @@ def load_library():
     lib.h2v_last_rlc_source.argtypes = [ctypes.c_void_p]
     lib.h2v_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, u8p]
     lib.h2v_comm_connect.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    lib.h2v_comm_set_timeout_ms.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
     lib.h2v_batch_run_shard_exchange.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, ctypes.POINTER(ctypes.c_int)]
     lib.h2v_verify_shard.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64, ctypes.c_uint64,
                                      ctypes.c_uint64, ctypes.c_uint32, u8p, u8p, ctypes.POINTER(ctypes.c_int)]
@@ -156,7 +157,7 @@ EXPORTED_SYMBOLS = (
     "h2v_batch_set_columns", "h2v_batch_set_scalar_hook", "h2v_batch_set_shard_hint", "h2v_partial_bytes", "h2v_accumulate_shard", "h2v_finalize", "h2v_attribute_shard",
     "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync", "h2v_ctx_set_graphs", "h2v_ctx_create_multi", "h2v_batch_set_fold_groups", "h2v_last_group_verdicts", "h2v_finalize_groups", "h2v_debug_timeline_start", "h2v_debug_timeline_stop",
     "h2v_last_msm_geometry", "h2v_selftest_field", "h2v_calibrate_imad",
-    "h2v_attribute_shard_groups", "h2v_batch_set_rlc_key", "h2v_last_rlc_source", "h2v_comm_init", "h2v_comm_connect",
+    "h2v_attribute_shard_groups", "h2v_batch_set_rlc_key", "h2v_last_rlc_source", "h2v_comm_init", "h2v_comm_connect", "h2v_comm_set_timeout_ms",
     "h2v_batch_run_shard_exchange", "h2v_verify_shard", "h2v_comm_last_batch_accum", "h2v_ctx_cache_stats", "h2v_ctx_work_model",
 )
 

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_bcast_verdict(const XDyn* __restrict__ 
 }
 
 // Every rank: waits for the verdicts of this launch set in its own window and copies them next to the batch
-// (out[0..groups) verdicts, out[groups] = wait timed out, out[groups + 1] = root's status word).
+// (out[0..groups) verdicts, out[groups] |= 4 when the wait timed out, out[groups + 1] = root's status word).
 __global__ void __launch_bounds__(64) k_wait_verdict(const XDyn* __restrict__ dyn, const u8* __restrict__ window, XLayout lay, u32 groups, u32* out) {
   __shared__ u32 ok;
   if (threadIdx.x == 0) ok = spin_until_ge(&((const XHeader*)window)->vseq, dyn->seq, dyn->timeout_ns) ? 1u : 0u;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(64) k_wait_verdict(const XDyn* __restrict__ dy
   const u32* vd = (const u32*)(window + lay.verdict_off());
   for (u32 g = threadIdx.x; g < groups; g += 64) out[g] = ok ? ld_relaxed_sys(vd + g) : 0u;
   if (threadIdx.x == 0) {
-    if (!ok) atomicOr(out + groups, 1u);
+    if (!ok) atomicOr(out + groups, 4u);  // bit 2: the verdicts never arrived (bit 0: a partial never arrived, k_sum_partials)
     out[groups + 1] = ok ? ld_relaxed_sys(vd + lay.max_groups) : 0u;
   }
 }

@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <sys/random.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -717,18 +718,61 @@ __global__ void k_imad(u32 iters, u32* out) {
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_create_error;  // per host thread: contexts may be created concurrently
 
+// Device buffers grow on demand.  Growth uses the stream-ordered allocator on the context's stream: cudaFree would wait
+// for the whole device, i.e. also for another context's kernel that is waiting for a peer (exchange.cuh), which can close
+// a cycle between two GPUs; cudaFreeAsync only orders after this context's own work.
 struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaStream_t* st = nullptr;  // the owning context's stream (set at context creation)
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) {
+      cudaError_t fe = st ? cudaFreeAsync(p, *st) : cudaFree(p);
+      if (fe != cudaSuccess) return fe;
+    }
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = st ? cudaMallocAsync(&p, want, *st) : cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) {
+      if (st) cudaFreeAsync(p, *st);
+      else cudaFree(p);
+    }
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return (T*)p;
+  }
+};
+
+// Pinned host staging for everything the library reads back on the data path (verdicts, statuses): a device-to-host copy
+// into PAGEABLE memory keeps the calling thread inside the CUDA call until the stream reaches it - i.e., with the
+// device-side exchange, until a peer rank delivered - and another thread's cudaStreamBeginCapture waits for that call
+// (see ctx_sync).
+struct HostBuf {
   void* p = nullptr;
   size_t cap = 0;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) cudaFreeHost(p);
     p = nullptr;
     cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
   }
   template <class T>
   T* as() const {
@@ -761,7 +805,7 @@ struct h2v_ctx {
   MsmGeom geom{};
   bool ran = false;
   u32 opt_fold_groups = 0;  // next upload: that many consecutive independent fold groups (h2v_batch_set_fold_groups)
-  std::vector<u32> h_verdicts;  // per fold group, of the last run
+  std::vector<u32> h_verdicts;  // per fold group, of the last run (copied out of h_verd)
   bool verdicts_on_device = false;  // d_verdict holds the group verdicts of the batch in this context's buffers
   u32 opt_shard_hint = 0;   // geometry as for a shard of this many proofs (common to all ranks)
   bool opt_has_key = false;  // next upload: fold randomness expanded from this 256-bit key (h2v_batch_set_rlc_key)
@@ -807,7 +851,13 @@ struct h2v_ctx {
       d_shared, d_left, d_rlc_bytes, d_r, d_coef, d_shared_sum, d_dig, d_hist, d_off, d_cursor, d_order, d_sorted, d_buckets, d_wsums,
       d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush, d_M, d_partial_out, d_wsums_fin, d_tiles;
   const G2Line* d_lines() const { return lines_cur >= 0 ? lines[lines_cur].buf.as<G2Line>() : nullptr; }
-  std::vector<u32> h_status;
+  std::vector<DevBuf*> all_bufs() {
+    return {&d_plan, &d_proofs, &d_proof_off, &d_inst, &d_inst_off, &d_ncols, &d_col_len, &d_pts, &d_bad, &d_status, &d_vals, &d_scratch, &d_right,
+            &d_shared, &d_left, &d_rlc_bytes, &d_r, &d_coef, &d_shared_sum, &d_dig, &d_hist, &d_off, &d_cursor, &d_order, &d_sorted, &d_buckets, &d_wsums,
+            &d_acc_bytes, &d_verdict, &d_partials, &d_partials_msm, &d_pp_prod, &d_pp_lr, &d_pp_bytes, &d_hook, &d_chal, &d_flush, &d_M, &d_partial_out,
+            &d_wsums_fin, &d_tiles, &lines[0].buf, &lines[1].buf, &lines[2].buf, &lines[3].buf};
+  }
+  HostBuf h_status, h_verd;  // pinned staging of the per-proof statuses / the group verdicts + error words
   PlanView pv() const { return PlanView{d_plan.as<u8>()}; }
 };
 
@@ -826,6 +876,18 @@ struct h2v_ctx {
   } while (0)
 
 static inline u32 cdiv(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
+
+// H2V_TRACE=1: host-side timestamps of the steps of a call on stderr (diagnosis of stalls between contexts)
+static bool trace_on() {
+  static const bool on = getenv("H2V_TRACE") != nullptr;
+  return on;
+}
+static void trace(const h2v_ctx* ctx, const char* what) {
+  if (!trace_on()) return;
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  fprintf(stderr, "[h2v %p %ld.%06ld] %s\n", (const void*)ctx, (long)(ts.tv_sec % 1000), ts.tv_nsec / 1000, what);
+}
 
 // `len` bytes from the kernel's CSPRNG; 0 on success
 static int os_entropy(void* out, size_t len) {
@@ -867,6 +929,10 @@ static cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 bl
 // Host wait for everything queued on the context's stream.  Default: cudaStreamSynchronize (spins: lowest latency).
 // With many contexts per host (several batches in flight on several GPUs) the spinning threads starve the cores, so
 // a context can be switched to a blocking wait on an event (h2v_ctx_set_blocking_sync).
+// (Everything the data path reads back lands in PINNED staging, HostBuf: a device-to-host copy into pageable memory
+// keeps the caller inside the CUDA call until the stream gets there, and - measured on B200, tools/exchange_diag.py with
+// H2V_TRACE - cudaStreamBeginCapture of another thread does not return while such a call is pending.  With the
+// device-side exchange the stream may be waiting for a peer rank, so that stalled two contexts against each other.)
 static cudaError_t ctx_sync(h2v_ctx* ctx) {
   if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->stream);
   cudaError_t e = cudaEventRecord(ctx->ev_done, ctx->stream);
@@ -1001,13 +1067,20 @@ static int launch_pairing(h2v_ctx* ctx, const G1Jac* wsums, u32 groups) {
 // xchg: the run went through the device-side exchange; its two error words follow the verdicts.
 static int read_verdicts(h2v_ctx* ctx, u32* all, bool xchg = false) {
   const u32 G = ctx->geom.G ? ctx->geom.G : 1;
-  ctx->h_verdicts.assign(G + 2, 0);
-  CKC(cudaMemcpyAsync(ctx->h_verdicts.data(), ctx->d_verdict.p, 4 * (size_t)(G + (xchg ? 2 : 0)), cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(ctx->h_verd.ensure(4 * (size_t)(G + 2)));
+  u32* hv = ctx->h_verd.as<u32>();
+  hv[G] = hv[G + 1] = 0;
+  CKC(cudaMemcpyAsync(hv, ctx->d_verdict.p, 4 * (size_t)(G + (xchg ? 2 : 0)), cudaMemcpyDeviceToHost, ctx->stream));
   CKC(ctx_sync(ctx));
+  ctx->h_verdicts.assign(hv, hv + G + 2);
   const u32 e_local = ctx->h_verdicts[G], e_root = ctx->h_verdicts[G + 1];
   ctx->h_verdicts.resize(G);
-  if (xchg && ((e_local | e_root) & 1)) {
-    ctx->err = "sharded exchange timed out: a peer never delivered its partial accumulators or the verdicts (a rank died, or the ranks disagree on the launch-set order)";
+  if (xchg && ((e_local | e_root) & 5)) {
+    ctx->err = std::string("sharded exchange timed out: ") +
+               ((e_local & 1) ? "this rank is the root and a peer's partial accumulators never arrived"
+                : (e_root & 1) ? "the root reports that a peer's partial accumulators never arrived"
+                               : "the root's verdicts never arrived") +
+               " (a rank died, or the ranks disagree on the launch-set order of this channel)";
     return -3;
   }
   if (xchg && ((e_local | e_root) & 2)) {
@@ -1018,6 +1091,48 @@ static int read_verdicts(h2v_ctx* ctx, u32* all, bool xchg = false) {
   for (u32 v : ctx->h_verdicts) a &= v ? 1u : 0u;
   *all = a;
   return 0;
+}
+
+// CUDA loads kernels lazily, and loading one may wait for the device to drain.  With the device-side exchange a context
+// can sit in a kernel that waits for a PEER (exchange.cuh) while another context of this process launches a kernel for
+// the first time: that load would wait for the waiting kernel, whose peer may be stuck the same way on its side.  So
+// every kernel of the library is loaded when a context is created (querying a function's attributes loads it).
+static cudaError_t preload_kernels() {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaSuccess;
+#define H2V_PRELOAD(k) \
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, k)
+  H2V_PRELOAD(k_init);
+  H2V_PRELOAD(k_decompress);
+  H2V_PRELOAD(k_transcript<Blake2b>);
+  H2V_PRELOAD(k_transcript<Keccak256>);
+  H2V_PRELOAD(k_scalar);
+  H2V_PRELOAD(k_rlc_expand);
+  H2V_PRELOAD(k_rlc_scan);
+  H2V_PRELOAD(k_shared_reduce);
+  H2V_PRELOAD(k_msm_digits);
+  H2V_PRELOAD(k_scan_tiles);
+  H2V_PRELOAD(k_scan_apply);
+  H2V_PRELOAD(k_bucket_order);
+  H2V_PRELOAD(k_msm_scatter);
+  H2V_PRELOAD(k_msm_bucket_sum);
+  H2V_PRELOAD(k_msm_chunk_reduce);
+  H2V_PRELOAD(k_msm_window_reduce);
+  H2V_PRELOAD(k_fold_accum);
+  H2V_PRELOAD(k_pack_partial);
+  H2V_PRELOAD(k_sum_partials);
+  H2V_PRELOAD(k_pp_mul);
+  H2V_PRELOAD(k_pp_reduce);
+  H2V_PRELOAD(k_pp_pairing);
+  H2V_PRELOAD(k_gather_scalars);
+  H2V_PRELOAD(k_gather_challenges);
+  H2V_PRELOAD(k_lines<LINES_GROUPS>);
+  H2V_PRELOAD(k_pairing_check);
+  H2V_PRELOAD(k_pack_partial_x);
+  H2V_PRELOAD(k_bcast_verdict);
+  H2V_PRELOAD(k_wait_verdict);
+#undef H2V_PRELOAD
+  return e;
 }
 
 // ---- exchange windows (exchange.cuh): export / connect / release
@@ -1084,6 +1199,13 @@ int h2v_ctx_create_multi(h2v_ctx** out, const uint8_t* params, size_t params_len
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  for (DevBuf* b : ctx->all_bufs()) b->st = &ctx->stream;
+  {  // keep freed blocks in the stream-ordered pool instead of returning them to the OS at every synchronisation
+    cudaMemPool_t pool;
+    uint64_t keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    (void)cudaGetLastError();
+  }
   if ((e = cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
@@ -1092,11 +1214,13 @@ int h2v_ctx_create_multi(h2v_ctx** out, const uint8_t* params, size_t params_len
   for (auto& ev : ctx->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = ctx->d_plan.ensure(ctx->blob.size())) != cudaSuccess) return fail("cudaMalloc(plan)", e);
-  if ((e = cudaMemcpy(ctx->d_plan.p, ctx->blob.data(), ctx->blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+  if ((e = cudaMemcpyAsync(ctx->d_plan.p, ctx->blob.data(), ctx->blob.size(), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
     return fail("cudaMemcpy(plan)", e);
   if ((e = ctx->d_acc_bytes.ensure(128)) != cudaSuccess || (e = ctx->d_verdict.ensure(16)) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaFuncSetAttribute(k_lines<LINES_GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k_lines_smem<LINES_GROUPS>())) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_lines)", e);
+  if ((e = preload_kernels()) != cudaSuccess) return fail("loading the kernels", e);
   *out = ctx;
   return 0;
 }
@@ -1121,17 +1245,13 @@ void h2v_ctx_destroy(h2v_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->stream_aux) cudaStreamSynchronize(ctx->stream_aux);
-  DevBuf* bufs[] = {&ctx->d_plan, &ctx->d_proofs, &ctx->d_proof_off, &ctx->d_inst, &ctx->d_inst_off, &ctx->d_ncols, &ctx->d_col_len,
-                    &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
-                    &ctx->d_rlc_bytes, &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off,
-                    &ctx->d_cursor, &ctx->d_order, &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict,
-                    &ctx->d_partials, &ctx->d_partials_msm, &ctx->d_pp_prod, &ctx->d_pp_lr, &ctx->d_pp_bytes, &ctx->d_hook, &ctx->d_chal, &ctx->d_flush,
-                    &ctx->lines[0].buf, &ctx->lines[1].buf, &ctx->lines[2].buf, &ctx->lines[3].buf, &ctx->d_M, &ctx->d_partial_out, &ctx->d_wsums_fin, &ctx->d_tiles};
   comm_release(ctx);
   for (auto& gsl : ctx->graphs)
     if (gsl.exec) cudaGraphExecDestroy(gsl.exec);
-  for (DevBuf* b : bufs)
-    if (b->p) cudaFree(b->p);
+  for (DevBuf* b : ctx->all_bufs()) b->release();
+  ctx->h_status.release();
+  ctx->h_verd.release();
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);  // the stream-ordered frees
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -1333,6 +1453,7 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
     int lrc = ensure_lines(ctx);
     if (lrc) return lrc;
   }
+  trace(ctx, "lines ready");
   CKC(ctx->d_proofs.ensure(pbytes + 64));
   CKC(ctx->d_proof_off.ensure(8 * (size_t)(n + 1)));
   CKC(ctx->d_inst.ensure(32 * iscal + 64));
@@ -1408,6 +1529,7 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   ctx->opt_has_key = false;
   k_rlc_expand<<<cdiv(n_r, 128), 128, 0, s>>>(n_r, seed, rlc ? ctx->d_rlc_bytes.as<u8>() : nullptr, keyed, key, ctx->d_r.as<Fr>());
   LAUNCH_CHECK();
+  trace(ctx, "upload enqueued");
   return 0;
 }
 
@@ -1557,6 +1679,7 @@ static int run_impl(h2v_ctx* ctx, int mode) {
   h2v_ctx::GraphSlot& gs = hit ? *hit : *victim;
   gs.used = ctx->use_clock;
   if (!hit) {
+    trace(ctx, "graph capture begins");
     if (gs.exec) cudaGraphExecDestroy(gs.exec);
     gs.exec = nullptr;
     gs.key = 0;
@@ -1579,10 +1702,12 @@ static int run_impl(h2v_ctx* ctx, int mode) {
     CKC(ie);
     gs.key = key;
     ctx->graph_captures++;
+    trace(ctx, "graph instantiated");
   }
   CKC(cudaEventRecord(ctx->ev[0], s));
   CKC(cudaGraphLaunch(gs.exec, s));
   CKC(cudaEventRecord(ctx->ev[6], s));
+  trace(ctx, "graph launched");
   ctx->launches += gs.kernels;
   ctx->stages_timed = false;
   ctx->verdicts_on_device = (mode & RUN_PAIRING) != 0;
@@ -1618,11 +1743,12 @@ static int per_proof_impl(h2v_ctx* ctx, bool pairing, u8* accum_host) {
 }
 
 static int download_status(h2v_ctx* ctx, u8* status) {
-  ctx->h_status.resize(ctx->n);
-  CKC(cudaMemcpyAsync(ctx->h_status.data(), ctx->d_status.p, 4 * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CKC(ctx->h_status.ensure(4 * (size_t)ctx->n));
+  const u32* hs = ctx->h_status.as<u32>();
+  CKC(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, 4 * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
   CKC(ctx_sync(ctx));
   if (status)
-    for (u32 j = 0; j < ctx->n; j++) status[j] = (u8)ctx->h_status[j];
+    for (u32 j = 0; j < ctx->n; j++) status[j] = (u8)hs[j];
   return 0;
 }
 
@@ -1733,8 +1859,9 @@ static int finalize_impl(h2v_ctx* ctx, u32 n_partials, u32 groups, const u8* par
     LAUNCH_CHECK();
     CKC(cudaMemcpyAsync(batch_accum, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, s));
   }
-  std::vector<u32> v(groups + 1, 0);
-  CKC(cudaMemcpyAsync(v.data(), ctx->d_verdict.p, 4 * (size_t)(groups + 1), cudaMemcpyDeviceToHost, s));
+  CKC(ctx->h_verd.ensure(4 * (size_t)(groups + 2)));
+  const u32* v = ctx->h_verd.as<u32>();
+  CKC(cudaMemcpyAsync(ctx->h_verd.p, ctx->d_verdict.p, 4 * (size_t)(groups + 1), cudaMemcpyDeviceToHost, s));
   CKC(ctx_sync(ctx));
   if (v[groups]) {
     ctx->err = "partial accumulators were produced with different window geometries (use h2v_batch_set_shard_hint)";
@@ -1816,6 +1943,12 @@ int h2v_comm_init(h2v_ctx* ctx, uint32_t rank, uint32_t world, uint32_t max_grou
   return 0;
 }
 
+int h2v_comm_set_timeout_ms(h2v_ctx* ctx, uint32_t ms) {
+  if (!ctx || !ms) return -1;
+  ctx->comm.timeout_ns = (u64)ms * 1000000ull;
+  return 0;
+}
+
 int h2v_comm_connect(h2v_ctx* ctx, const uint8_t* handles) {
   if (!ctx || !handles || !ctx->comm.window) {
     if (ctx) ctx->err = "h2v_comm_connect: call h2v_comm_init first";
@@ -1883,7 +2016,9 @@ static int exchange_run(h2v_ctx* ctx, u32 root, u8* group_verdicts, int* verdict
   int rc = run_impl(ctx, RUN_XCHG | (root == cm.lay.rank ? RUN_ROOT : 0));
   if (rc) return rc;
   u32 all = 0;
-  if ((rc = read_verdicts(ctx, &all, true)) != 0) return rc;
+  rc = read_verdicts(ctx, &all, true);
+  trace(ctx, rc ? "exchange FAILED" : "verdicts read");
+  if (rc) return rc;
   ctx->verdicts_on_device = true;  // d_verdict holds the verdicts of this rank's groups: attribution skips accepted groups
   if (group_verdicts)
     for (u32 q = 0; q < ctx->geom.G; q++) group_verdicts[q] = ctx->h_verdicts[q] ? 1 : 0;

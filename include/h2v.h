@@ -187,6 +187,8 @@ int h2v_attribute_shard_groups(h2v_ctx* ctx, const uint8_t* group_verdicts, uint
 #define H2V_COMM_HANDLE_BYTES 128
 int h2v_comm_init(h2v_ctx* ctx, uint32_t rank, uint32_t world, uint32_t max_groups, uint8_t* handle_out);
 int h2v_comm_connect(h2v_ctx* ctx, const uint8_t* handles);
+/* bound of every device-side wait of this context's launch sets from now on (default 30 s, or H2V_COMM_TIMEOUT_MS at h2v_comm_init) */
+int h2v_comm_set_timeout_ms(h2v_ctx* ctx, uint32_t ms);
 int h2v_batch_run_shard_exchange(h2v_ctx* ctx, uint32_t root, uint8_t* group_verdicts, int* verdict);
 int h2v_verify_shard(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint64_t* proof_off, const uint8_t* instances,
                      const uint64_t* inst_off, const uint8_t* rlc_scalars, uint64_t seed, uint64_t global_base,
