@@ -167,4 +167,55 @@ H2V_HDN inline bool g1_decompress(const u8* b, G1Affine& out) {
   return true;
 }
 
+#if defined(__CUDACC__)
+// Fully inlined variants for the serial chains (window combination, conversion to affine): device only.
+__device__ __forceinline__ Fq fq_inv_inl(const Fq& a) {  // a^(p-2), plain square-and-multiply kept in registers
+  Fq acc = Fq::one();
+#pragma unroll 1
+  for (int i = 253; i >= 0; i--) {
+    acc = Fq::mul(acc, acc);
+    u32 limb;  // bit i of p - 2
+    switch (i >> 5) {
+      case 0: limb = FqP::mod(0) - 2; break;
+      case 1: limb = FqP::mod(1); break;
+      case 2: limb = FqP::mod(2); break;
+      case 3: limb = FqP::mod(3); break;
+      case 4: limb = FqP::mod(4); break;
+      case 5: limb = FqP::mod(5); break;
+      case 6: limb = FqP::mod(6); break;
+      default: limb = FqP::mod(7); break;
+    }
+    if ((limb >> (i & 31)) & 1) acc = Fq::mul(acc, a);
+  }
+  return acc;
+}
+// Jacobian doubling with everything inlined (serial window combination: ~255 dependent doublings)
+__device__ __forceinline__ void g1_double_inl(G1Jac& p) {
+  if (p.Z.is_zero()) return;
+  Fq A = Fq::mul(p.X, p.X);
+  Fq B = Fq::mul(p.Y, p.Y);
+  Fq C = Fq::mul(B, B);
+  Fq t = p.X + B;
+  Fq D = (Fq::mul(t, t) - A - C).dbl();
+  Fq E = A.dbl() + A;
+  Fq F = Fq::mul(E, E);
+  Fq Z3 = Fq::mul(p.Y, p.Z).dbl();
+  p.X = F - D.dbl();
+  p.Y = Fq::mul(E, D - p.X) - C.dbl().dbl().dbl();
+  p.Z = Z3;
+}
+__device__ __forceinline__ bool g1_to_affine_inl(const G1Jac& p, G1Affine& out) {
+  if (p.Z.is_zero()) {
+    out.x = Fq::zero();
+    out.y = Fq::zero();
+    return false;
+  }
+  Fq zi = fq_inv_inl(p.Z);
+  Fq zi2 = Fq::mul(zi, zi);
+  out.x = Fq::mul(p.X, zi2);
+  out.y = Fq::mul(Fq::mul(p.Y, zi2), zi);
+  return true;
+}
+#endif
+
 }  // namespace h2v

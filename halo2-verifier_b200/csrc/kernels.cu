@@ -32,7 +32,6 @@
 #include "plan_build.h"
 #include "stages.cuh"
 #include "tower.cuh"
-#include "pairing_warp.cuh"
 #include "timeline.cuh"
 #include "pairing_cta.cuh"
 #include "exchange.cuh"
@@ -149,14 +148,18 @@ __global__ void k_rlc_expand(u64 count, u64 seed, const u8* bytes, bool keyed, R
   r[i] = bytes ? Fr::from_canonical(Fr::load_le(bytes + 32 * i)) : keyed ? rlc_scalar_from_key(key, i) : rlc_scalar_from_seed(seed, i);
 }
 
-// c_j = prod_{i > j} r_i over the GLOBAL batch; one block, chunked suffix scan through shared memory.
+// c_j = prod_{i > j} r_i over the GLOBAL batch; one block per scan, chunked suffix scan through shared memory.
 static constexpr u32 RLC_NT = 256;
-// (fold groups: block g scans the `count` coefficients of its own global batch, r + g * count, and writes the n of
-// this rank's shard of it, coef + g * n)
-__global__ void __launch_bounds__(RLC_NT) k_rlc_scan(const Fr* r, u64 count, u64 base, u32 n, Fr* coef) {
+// Block b scans `count` coefficients starting at r + (b / subs) * group_stride + offset + (b % subs) * count and writes
+// those with index in [base, base + n) to coef + b * n.
+//   fold groups (subs = 1, group_stride = count, offset = 0): block g scans the coefficients of its own global batch and
+//     writes the n of this rank's shard of it
+//   attribution (count = n = m, base = 0, subs = sub-batches per fold group, offset = gbase): block b scans the m
+//     coefficients of sub-batch b % subs of fold group b / subs: the fold restarts inside every sub-batch
+__global__ void __launch_bounds__(RLC_NT) k_rlc_scan(const Fr* r, u64 count, u64 base, u32 n, Fr* coef, u32 subs, u64 group_stride, u64 offset) {
   pdl_prologue();
   __shared__ Fr sh[RLC_NT];
-  r += (size_t)blockIdx.x * count;
+  r += (size_t)(blockIdx.x / subs) * group_stride + offset + (size_t)(blockIdx.x % subs) * count;
   coef += (size_t)blockIdx.x * n;
   const u32 t = threadIdx.x;
   const u64 m = (count + RLC_NT - 1) / RLC_NT;
@@ -228,7 +231,7 @@ __device__ __forceinline__ const G1Affine& msm_point(const MsmGeom& g, u32 t, co
 
 // signed c-bit digits of every term's scalar (already multiplied by c_j) + bucket histogram
 __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, const Fr* left, const Fr* coef, const Fr* shared_sum,
-                                                    const G1Affine* shared_pts, int16_t* dig, u32* hist) {
+                                                    const G1Affine* shared_pts, int16_t* dig, u32* hist, const u32* parent_verdict, u32 parent_size) {
   pdl_prologue();
   TlScope tl_(4, right);
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -237,6 +240,11 @@ __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, 
   const u32 nP = g.n * g.P, nL = g.n * g.n_mo;
   Fr k;
   u32 ch = 0;
+  if (parent_verdict && parent_verdict[(u32)(((u64)grp * g.n) / parent_size)]) {  // sub-batch of an accepted fold group: nothing to re-check
+    ch = g.channel_of_term(tl);
+    for (u32 w = 0; w < g.W[ch]; w++) dig[(size_t)t * g.Wmax + w] = 0;
+    return;
+  }
   if (tl < nP) {
     const u32 j = grp * g.n + tl % g.n;
     k = (right[(size_t)(tl / g.n) * g.N + j] * coef[j]).to_canonical();
@@ -617,27 +625,93 @@ __global__ void __launch_bounds__(128) k_pp_reduce(PlanView pv, u32 n, const G1J
   }
 }
 
-// warp per proof: DualMSM::check of its own accumulators (SingleStrategy semantics, strategy.rs:164-176)
-static constexpr int PP_WARPS = 4;
-__global__ void __launch_bounds__(32 * PP_WARPS) k_pp_pairing(PlanView pv, u32 n, const G1Jac* lr, u32* status, const u32* gverdict, u32 gsize) {
-  __shared__ G1Affine aff[PP_WARPS][2];
-  __shared__ bool skip[PP_WARPS][2];
-  __shared__ W12 pool[PP_WARPS][H2V_WPOOL];
-  __shared__ WScratch ws[PP_WARPS];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const u32 j = blockIdx.x * PP_WARPS + wid;
-  if (j >= n) return;
-  if (status[j] != ST_OK || (gverdict && gverdict[j / gsize])) return;  // warp-uniform
-  if (lane < 2) {
-    G1Affine a;
-    const bool id = !g1_to_affine_inl(lr[(size_t)lane * n + j], a);  // lane 0: left, lane 1: right
-    aff[wid][lane] = a;
-    skip[wid][lane] = id;
+// ---- attribution of a rejected fold (reference contract poly/strategy.rs:26-30: "re-process the proofs separately")
+// Level 1 re-folds the rejected group in sub-batches of ATTR_SUB proofs through the bucket MSM (the fold restarts inside
+// every sub-batch, so each is an AccumulatorStrategy run of its own) and checks every sub-batch with one 2-pair
+// pairing; level 2 forms the accumulators of the proofs of rejected sub-batches only and checks each proof alone
+// (SingleStrategy semantics, strategy.rs:164-176).  With 1 % bad proofs level 2 sees ~15 % of the batch.
+static constexpr u32 ATTR_SUB = 16;
+
+// explicit window combination of a sub-batch: thread per (sub-batch, channel), acc = sum_w 2^(c w) S_w  (the batch path
+// avoids this serial chain through bilinearity; here 128 windows per sub-batch would cost far more line products)
+__global__ void __launch_bounds__(64) k_window_combine(u32 groups, FoldArgs fa, const G1Jac* __restrict__ wsums, G1Jac* __restrict__ pairs) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * groups) return;
+  const u32 grp = t >> 1, ch = t & 1;  // ch 0 = right, 1 = left: the pair order of the unit lines
+  const G1Jac* ws = wsums + (size_t)grp * (fa.W[0] + fa.W[1]) + fa.wbase[ch];
+  G1Jac acc = G1Jac::identity();
+  for (u32 w = fa.W[ch]; w-- > 0;) {
+    for (u32 i = 0; i < fa.c[ch]; i++) g1_double_inl(acc);
+    acc = g1_add(acc, ws[w]);
   }
-  __syncwarp();
+  pairs[t] = acc;
+}
+
+// suspects [base, base + cap) of the compacted list are processed per pass
+__device__ __forceinline__ u32 chunk_count(u32 count, u32 base, u32 cap) { return count > base ? (count - base < cap ? count - base : cap) : 0u; }
+
+// suspects = proofs that passed every earlier stage and sit in a rejected sub-batch (sub_verdict == null: in a rejected
+// fold group; gverdict == null too: every proof): compacted list + count
+__global__ void __launch_bounds__(128) k_pp_suspects(u32 n, const u32* status, const u32* sub_verdict, u32 sub_size, const u32* gverdict, u32 gsize,
+                                                     u32* list, u32* count) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  if (status[j] != ST_OK) return;
+  if (gverdict && gverdict[j / gsize]) return;
+  if (sub_verdict && sub_verdict[j / sub_size]) return;
+  list[atomicAdd(count, 1u)] = j;
+}
+
+// thread per (base, suspect): unscaled scalar * point, plain double-and-add -> prod[base][slot]
+__global__ void __launch_bounds__(128) k_pp_mul_list(PlanView pv, u32 n, const G1Affine* pts, const Fr* right, const Fr* shared, const Fr* left,
+                                                     const u32* list, const u32* count, u32 base, u32 cap, G1Jac* out) {
   const PlanHeader& hd = pv.h();
-  const bool ok = w_pairing_check2(aff[wid], skip[wid], pv.sec<G2Line>(hd.off_lines0), pv.sec<G2Line>(hd.off_lines1), pool[wid], &ws[wid], lane);
-  if (lane == 0 && !ok) status[j] = ST_CONSTRAINT_SYSTEM_FAILURE;
+  const u32 nb = hd.n_points + hd.n_shared + hd.n_mo;
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 cnt = chunk_count(*count, base, cap);
+  if (t >= nb * cnt) return;
+  const u32 slot = t % cnt, b = t / cnt, j = list[base + slot];
+  G1Jac r = G1Jac::identity();
+  Fr k;
+  const G1Affine* p;
+  if (b < hd.n_points) {
+    k = right[(size_t)b * n + j];
+    p = &pts[(size_t)b * n + j];
+  } else if (b < hd.n_points + hd.n_shared) {
+    k = shared[(size_t)(b - hd.n_points) * n + j];
+    p = &pv.sec<G1Affine>(hd.off_shared_pts)[b - hd.n_points];
+  } else {
+    const u32 q = b - hd.n_points - hd.n_shared;
+    k = left[(size_t)q * n + j];
+    p = &pts[(size_t)(hd.n_points - hd.n_mo + q) * n + j];
+  }
+  if (!k.is_zero() && !(p->x.is_zero() && p->y.is_zero())) {
+    k = k.to_canonical();
+    r = g1_mul_canonical(*p, k.l);
+  }
+  out[(size_t)b * cap + slot] = r;
+}
+
+// thread per (channel, suspect): sum of the per-base products -> pairs[slot][0] = R_j, pairs[slot][1] = L_j
+__global__ void __launch_bounds__(128) k_pp_reduce_list(PlanView pv, const u32* count, u32 base, u32 cap, const G1Jac* prod, G1Jac* pairs) {
+  const PlanHeader& hd = pv.h();
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 cnt = chunk_count(*count, base, cap);
+  if (t >= 2 * cnt) return;
+  const u32 slot = t >> 1, ch = t & 1;  // ch 0 = right, 1 = left
+  G1Jac acc = G1Jac::identity();
+  const u32 b0 = ch == 1 ? hd.n_points + hd.n_shared : 0;
+  const u32 b1 = ch == 1 ? hd.n_points + hd.n_shared + hd.n_mo : hd.n_points + hd.n_shared;
+  for (u32 b = b0; b < b1; b++) acc = g1_add(acc, prod[(size_t)b * cap + slot]);
+  pairs[t] = acc;
+}
+
+// verdicts of the suspects' own checks -> statuses
+__global__ void __launch_bounds__(128) k_pp_status(const u32* list, const u32* count, u32 base, u32 cap, const u32* verdict, u32* status) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 cnt = chunk_count(*count, base, cap);
+  if (t >= cnt) return;
+  if (!verdict[t]) status[list[base + t]] = ST_CONSTRAINT_SYSTEM_FAILURE;
 }
 
 __global__ void k_gather_scalars(PlanView pv, u32 n, const Fr* right, const Fr* shared, const Fr* left, u8* out) {
@@ -847,15 +921,24 @@ struct h2v_ctx {
     u64 timeout_ns = 30ull * 1000000000ull;
   } comm;
   // device buffers
+  // buffers of one MSM run (k_shared_reduce .. k_msm_window_reduce): `mb` for the batch itself, `ab` for the regrouped MSM of the
+  // attribution path (sub-batches of a rejected fold group, attribute_impl), which must not move the buffers the batch graph captured
+  struct MsmBufs {
+    DevBuf coef, shared_sum, dig, hist, off, cursor, order, sorted, buckets, wsums, partials_msm, tiles;
+  } mb, ab;
   DevBuf d_plan, d_proofs, d_proof_off, d_inst, d_inst_off, d_ncols, d_col_len, d_pts, d_bad, d_status, d_vals, d_scratch, d_right,
-      d_shared, d_left, d_rlc_bytes, d_r, d_coef, d_shared_sum, d_dig, d_hist, d_off, d_cursor, d_order, d_sorted, d_buckets, d_wsums,
-      d_acc_bytes, d_verdict, d_partials, d_partials_msm, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush, d_M, d_partial_out, d_wsums_fin, d_tiles;
+      d_shared, d_left, d_rlc_bytes, d_r, d_acc_bytes, d_verdict, d_partials, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush, d_M, d_partial_out,
+      d_wsums_fin, d_sub_pairs, d_sub_verdict, d_sub_M;
   const G2Line* d_lines() const { return lines_cur >= 0 ? lines[lines_cur].buf.as<G2Line>() : nullptr; }
   std::vector<DevBuf*> all_bufs() {
-    return {&d_plan, &d_proofs, &d_proof_off, &d_inst, &d_inst_off, &d_ncols, &d_col_len, &d_pts, &d_bad, &d_status, &d_vals, &d_scratch, &d_right,
-            &d_shared, &d_left, &d_rlc_bytes, &d_r, &d_coef, &d_shared_sum, &d_dig, &d_hist, &d_off, &d_cursor, &d_order, &d_sorted, &d_buckets, &d_wsums,
-            &d_acc_bytes, &d_verdict, &d_partials, &d_partials_msm, &d_pp_prod, &d_pp_lr, &d_pp_bytes, &d_hook, &d_chal, &d_flush, &d_M, &d_partial_out,
-            &d_wsums_fin, &d_tiles, &lines[0].buf, &lines[1].buf, &lines[2].buf, &lines[3].buf};
+    std::vector<DevBuf*> v = {&d_plan, &d_proofs, &d_proof_off, &d_inst, &d_inst_off, &d_ncols, &d_col_len, &d_pts, &d_bad, &d_status, &d_vals, &d_scratch,
+                              &d_right, &d_shared, &d_left, &d_rlc_bytes, &d_r, &d_acc_bytes, &d_verdict, &d_partials, &d_pp_prod, &d_pp_lr, &d_pp_bytes,
+                              &d_hook, &d_chal, &d_flush, &d_M, &d_partial_out, &d_wsums_fin, &d_sub_pairs, &d_sub_verdict, &d_sub_M,
+                              &lines[0].buf, &lines[1].buf, &lines[2].buf, &lines[3].buf};
+    for (MsmBufs* m : {&mb, &ab})
+      for (DevBuf* d : {&m->coef, &m->shared_sum, &m->dig, &m->hist, &m->off, &m->cursor, &m->order, &m->sorted, &m->buckets, &m->wsums, &m->partials_msm, &m->tiles})
+        v.push_back(d);
+    return v;
   }
   HostBuf h_status, h_verd;  // pinned staging of the per-proof statuses / the group verdicts + error words
   PlanView pv() const { return PlanView{d_plan.as<u8>()}; }
@@ -1018,18 +1101,18 @@ static u64 lines_key_of(const MsmGeom& g) { return (u64)g.c[0] | (u64)g.W[0] << 
 
 // Prepared Miller lines of [2^(c w)] Q for the current window geometry (host: G2Prepared-style
 // preparation, once per geometry; the last few geometries stay cached in the context).
-static int ensure_lines(h2v_ctx* ctx) {
-  const MsmGeom& g = ctx->geom;
+static int ensure_lines(h2v_ctx* ctx, const MsmGeom& g, int* slot_out) {
   const u64 key = lines_key_of(g);
   ctx->use_clock++;
-  int victim = 0;
+  int victim = -1;
   for (int i = 0; i < 4; i++) {
     if (ctx->lines[i].key == key) {
       ctx->lines[i].used = ctx->use_clock;
-      ctx->lines_cur = i;
+      *slot_out = i;
       return 0;
     }
-    if (ctx->lines[i].used < ctx->lines[victim].used) victim = i;
+    if (i == ctx->lines_cur && slot_out != &ctx->lines_cur) continue;  // never evict the batch's own geometry for an auxiliary one
+    if (victim < 0 || ctx->lines[i].used < ctx->lines[victim].used) victim = i;
   }
   if (g.W[0] + g.W[1] > 128) {
     ctx->err = "window geometry exceeds 128 (channel, window) pairs";
@@ -1048,18 +1131,29 @@ static int ensure_lines(h2v_ctx* ctx) {
   CKC(ctx_sync(ctx));
   sl.key = key;
   sl.used = ctx->use_clock;
-  ctx->lines_cur = victim;
+  *slot_out = victim;
   ctx->lines_builds++;
   return 0;
 }
+static int ensure_lines(h2v_ctx* ctx) { return ensure_lines(ctx, ctx->geom, &ctx->lines_cur); }
 
-// the batch pairing check over `wsums` (W0 + W1 Jacobian window sums) -> d_verdict[0]
+// the batch pairing check over `wsums` (W0 + W1 Jacobian window sums per group) -> d_verdict[group]
 static int launch_pairing(h2v_ctx* ctx, const G1Jac* wsums, u32 groups) {
   const MsmGeom& g = ctx->geom;
   cudaStream_t s = ctx->stream;
+  const PairSkip none{nullptr, nullptr, 1, 0};
   KLAUNCH((k_lines<LINES_GROUPS>), dim3(H2V_ATE_ITERS, groups), 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s, LinesArgs{g.W[0] + g.W[1]}, wsums, ctx->d_lines(),
-                                                                                       ctx->d_M.as<E12>());
-  KLAUNCH(k_pairing_check, groups, 128, 0, s, ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>());
+                                                                                       ctx->d_M.as<E12>(), none);
+  KLAUNCH(k_pairing_check, groups, 128, 0, s, ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>(), none);
+  return 0;
+}
+
+// Attribution: `count` independent 2-pair checks e(pairs[i][1], [s]G2) e(pairs[i][0], -G2) == 1 (pairs: right | left accumulator,
+// Jacobian) -> verdict[i]; groups for which sk says "skip" keep their verdict word.  M: E12[count][H2V_ATE_ITERS] scratch.
+static int launch_pair_checks(h2v_ctx* ctx, const G1Jac* pairs, u32 count, const G2Line* unit_lines, E12* M, u32* verdict, PairSkip sk) {
+  cudaStream_t s = ctx->stream;
+  KLAUNCH_P(false, (k_lines<2>), dim3(H2V_ATE_ITERS, count), 128, k_lines_smem<2>(), s, LinesArgs{2}, pairs, unit_lines, M, sk);
+  KLAUNCH_P(false, k_pairing_check, count, 128, 0, s, M, verdict, sk);
   return 0;
 }
 
@@ -1123,7 +1217,12 @@ static cudaError_t preload_kernels() {
   H2V_PRELOAD(k_sum_partials);
   H2V_PRELOAD(k_pp_mul);
   H2V_PRELOAD(k_pp_reduce);
-  H2V_PRELOAD(k_pp_pairing);
+  H2V_PRELOAD(k_window_combine);
+  H2V_PRELOAD(k_pp_suspects);
+  H2V_PRELOAD(k_pp_mul_list);
+  H2V_PRELOAD(k_pp_reduce_list);
+  H2V_PRELOAD(k_pp_status);
+  H2V_PRELOAD(k_lines<2>);
   H2V_PRELOAD(k_gather_scalars);
   H2V_PRELOAD(k_gather_challenges);
   H2V_PRELOAD(k_lines<LINES_GROUPS>);
@@ -1393,6 +1492,48 @@ int h2v_batch_set_scalar_hook(h2v_ctx* ctx, uint8_t* msm_scalars) {
   return 0;
 }
 
+// The MSM of G fold groups (geometry g) over the per-proof arrays of the current upload: column sums of the shared-base
+// scalars, signed digits + histogram, bucket offsets, size-ordered buckets, counting sort, bucket sums, bucket reduction
+// -> B.wsums[G][W0 + W1].  B.coef (the fold coefficients) and a zeroed B.hist must be ready on stream s.
+// parent_verdict != null (attribution): group q of g is a sub-batch of fold group q * g.n / parent_size of the batch
+// and is skipped (no bucket entries) when that group's batch check accepted.
+static int enqueue_msm(h2v_ctx* ctx, const MsmGeom& g, h2v_ctx::MsmBufs& B, cudaStream_t s, const u32* parent_verdict, u32 parent_size) {
+  const PlanHeader& hd = ctx->hd;
+  PlanView pv = ctx->pv();
+  const u32 nb = g.nb() * g.G;
+  if (hd.n_shared)
+    KLAUNCH(k_shared_reduce, dim3(hd.n_shared, g.G), 256, 0, s, g.n, g.N, (u32)hd.n_shared, ctx->d_shared.as<Fr>(), B.coef.as<Fr>(), B.shared_sum.as<Fr>());
+  KLAUNCH(k_msm_digits, cdiv((u64)g.G * g.T, 128), 128, 0, s, g, ctx->d_right.as<Fr>(), ctx->d_left.as<Fr>(), B.coef.as<Fr>(), B.shared_sum.as<Fr>(),
+          pv.sec<G1Affine>(hd.off_shared_pts), B.dig.as<int16_t>(), B.hist.as<u32>(), parent_verdict, parent_size);
+  const u32 n_tiles = cdiv(nb, SCAN_TILE);
+  KLAUNCH(k_scan_tiles, n_tiles, SCAN_NT, 0, s, B.hist.as<u32>(), nb, B.off.as<u32>(), B.tiles.as<u32>(), B.hist.as<u32>() + nb);
+  KLAUNCH(k_scan_apply, n_tiles, SCAN_NT, 0, s, nb, n_tiles, B.tiles.as<u32>(), B.off.as<u32>(), B.cursor.as<u32>());
+  KLAUNCH(k_bucket_order, n_tiles, SCAN_NT, 0, s, nb, B.hist.as<u32>(), B.hist.as<u32>() + nb, B.hist.as<u32>() + nb + SIZE_BINS, B.order.as<u32>());
+  KLAUNCH(k_msm_scatter, std::min<u32>(cdiv((u64)g.G * g.T * g.Wmax, 256), 148 * 16), 256, 0, s, g, B.dig.as<int16_t>(), B.cursor.as<u32>(), B.sorted.as<u32>());
+  KLAUNCH(k_msm_bucket_sum, cdiv(nb, 128), 128, 0, s, g, nb, B.off.as<u32>(), B.order.as<u32>(), B.sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
+          pv.sec<G1Affine>(hd.off_shared_pts), B.buckets.as<G1Jac>());
+  KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, B.buckets.as<G1Jac>(), B.partials_msm.as<G1Jac>());
+  KLAUNCH(k_msm_window_reduce, (g.W[0] + g.W[1]) * g.G, 128, 0, s, g, B.partials_msm.as<G1Jac>(), B.wsums.as<G1Jac>());
+  return 0;
+}
+
+static cudaError_t ensure_msm_bufs(const MsmGeom& g, h2v_ctx::MsmBufs& B, u32 n_shared) {
+  const size_t nb = (size_t)g.nb() * g.G;
+  cudaError_t e;
+  if ((e = B.coef.ensure(32 * (size_t)g.N)) != cudaSuccess) return e;
+  if ((e = B.shared_sum.ensure(32 * (size_t)n_shared * g.G + 32)) != cudaSuccess) return e;
+  if ((e = B.dig.ensure(2 * (size_t)g.G * g.T * g.Wmax)) != cudaSuccess) return e;
+  if ((e = B.hist.ensure(4 * (nb + 2 * SIZE_BINS))) != cudaSuccess) return e;
+  if ((e = B.order.ensure(4 * nb)) != cudaSuccess) return e;
+  if ((e = B.off.ensure(4 * (nb + 1))) != cudaSuccess) return e;
+  if ((e = B.cursor.ensure(4 * nb)) != cudaSuccess) return e;
+  if ((e = B.tiles.ensure(4 * (nb / 1024 + 2))) != cudaSuccess) return e;
+  if ((e = B.sorted.ensure(4 * (size_t)g.G * g.T * g.Wmax)) != cudaSuccess) return e;
+  if ((e = B.buckets.ensure(sizeof(G1Jac) * nb)) != cudaSuccess) return e;
+  if ((e = B.wsums.ensure(sizeof(G1Jac) * (size_t)(g.W[0] + g.W[1]) * g.G)) != cudaSuccess) return e;
+  return B.partials_msm.ensure(sizeof(G1Jac) * (nb / g.m));
+}
+
 static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_off, const u8* instances, const u64* inst_off,
                        const u8* rlc, u64 seed, u64 gbase, u64 gcount) {
   if (!ctx) return -1;
@@ -1469,20 +1610,9 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   CKC(ctx->d_r.ensure(32 * (size_t)gcount * groups));
   CKC(ctx->d_partial_out.ensure((size_t)H2V_PARTIAL_BYTES * groups));
   CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
-  CKC(ctx->d_coef.ensure(32 * (size_t)n));
-  CKC(ctx->d_shared_sum.ensure(32 * (size_t)hd.n_shared * g.G));
-  CKC(ctx->d_dig.ensure(2 * (size_t)g.G * g.T * g.Wmax));
+  CKC(ensure_msm_bufs(g, ctx->mb, hd.n_shared));
   CKC(ctx->d_M.ensure(sizeof(E12) * H2V_ATE_ITERS * (size_t)g.G));
   CKC(ctx->d_verdict.ensure(4 * (size_t)g.G + 16));
-  CKC(ctx->d_hist.ensure(4 * ((size_t)nb + 2 * SIZE_BINS)));
-  CKC(ctx->d_order.ensure(4 * (size_t)nb));
-  CKC(ctx->d_off.ensure(4 * (size_t)(nb + 1)));
-  CKC(ctx->d_cursor.ensure(4 * (size_t)nb));
-  CKC(ctx->d_tiles.ensure(4 * (size_t)(nb / 1024 + 2)));
-  CKC(ctx->d_sorted.ensure(4 * (size_t)g.G * g.T * g.Wmax));
-  CKC(ctx->d_buckets.ensure(sizeof(G1Jac) * (size_t)nb));
-  CKC(ctx->d_wsums.ensure(sizeof(G1Jac) * (size_t)(g.W[0] + g.W[1]) * g.G));
-  CKC(ctx->d_partials_msm.ensure(sizeof(G1Jac) * (size_t)(nb / g.m)));
   cudaStream_t s = ctx->stream;
   CKC(cudaMemcpyAsync(ctx->d_proofs.p, proofs, pbytes, cudaMemcpyHostToDevice, s));
   CKC(cudaMemcpyAsync(ctx->d_proof_off.p, proof_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, s));
@@ -1552,8 +1682,8 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   // c_j = prod_{i>j} r_i depends only on the coefficients: scanned on the auxiliary stream while the proofs are parsed
   CKC(cudaEventRecord(ctx->ev_fork, s));
   CKC(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_fork, 0));
-  CKC(cudaMemsetAsync(ctx->d_hist.p, 0, 4 * ((size_t)nb + 2 * SIZE_BINS), ctx->stream_aux));  // bucket histogram | size histogram | size cursors
-  KLAUNCH_P(false, k_rlc_scan, g.G, RLC_NT, 0, ctx->stream_aux, ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, g.n, ctx->d_coef.as<Fr>());
+  CKC(cudaMemsetAsync(ctx->mb.hist.p, 0, 4 * ((size_t)nb + 2 * SIZE_BINS), ctx->stream_aux));  // bucket histogram | size histogram | size cursors
+  KLAUNCH_P(false, k_rlc_scan, g.G, RLC_NT, 0, ctx->stream_aux, ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, g.n, ctx->mb.coef.as<Fr>(), 1u, ctx->gcount, (u64)0);
   CKC(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
   KLAUNCH(k_init, cdiv(n, 128), 128, 0, s, pv, n, ctx->d_inst_off.as<u64>(), ctx->has_ncols ? ctx->d_ncols.as<u32>() : nullptr,
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
@@ -1576,28 +1706,17 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
                                       ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_status.as<u32>());
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[3], s));
   CKC(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-  if (hd.n_shared)
-    KLAUNCH(k_shared_reduce, dim3(hd.n_shared, g.G), 256, 0, s, g.n, g.N, (u32)hd.n_shared, ctx->d_shared.as<Fr>(), ctx->d_coef.as<Fr>(), ctx->d_shared_sum.as<Fr>());
-  KLAUNCH(k_msm_digits, cdiv((u64)g.G * g.T, 128), 128, 0, s, g, ctx->d_right.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_coef.as<Fr>(),
-                                              ctx->d_shared_sum.as<Fr>(), pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_dig.as<int16_t>(),
-                                              ctx->d_hist.as<u32>());
-  const u32 n_tiles = cdiv(nb, SCAN_TILE);
-  KLAUNCH(k_scan_tiles, n_tiles, SCAN_NT, 0, s, ctx->d_hist.as<u32>(), nb, ctx->d_off.as<u32>(), ctx->d_tiles.as<u32>(), ctx->d_hist.as<u32>() + nb);
-  KLAUNCH(k_scan_apply, n_tiles, SCAN_NT, 0, s, nb, n_tiles, ctx->d_tiles.as<u32>(), ctx->d_off.as<u32>(), ctx->d_cursor.as<u32>());
-  KLAUNCH(k_bucket_order, n_tiles, SCAN_NT, 0, s, nb, ctx->d_hist.as<u32>(), ctx->d_hist.as<u32>() + nb, ctx->d_hist.as<u32>() + nb + SIZE_BINS,
-                                          ctx->d_order.as<u32>());
-  KLAUNCH(k_msm_scatter, std::min<u32>(cdiv((u64)g.G * g.T * g.Wmax, 256), 148 * 16), 256, 0, s, g, ctx->d_dig.as<int16_t>(), ctx->d_cursor.as<u32>(), ctx->d_sorted.as<u32>());
-  KLAUNCH(k_msm_bucket_sum, cdiv(nb, 128), 128, 0, s, g, nb, ctx->d_off.as<u32>(), ctx->d_order.as<u32>(), ctx->d_sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
-                                                 pv.sec<G1Affine>(hd.off_shared_pts), ctx->d_buckets.as<G1Jac>());
-  KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, ctx->d_buckets.as<G1Jac>(), ctx->d_partials_msm.as<G1Jac>());
-  KLAUNCH(k_msm_window_reduce, (g.W[0] + g.W[1]) * g.G, 128, 0, s, g, ctx->d_partials_msm.as<G1Jac>(), ctx->d_wsums.as<G1Jac>());
+  {
+    int mrc = enqueue_msm(ctx, g, ctx->mb, s, nullptr, 0);
+    if (mrc) return mrc;
+  }
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[4], s));
   if (mode & RUN_PAIRING) {
-    int prc = launch_pairing(ctx, ctx->d_wsums.as<G1Jac>(), g.G);
+    int prc = launch_pairing(ctx, ctx->mb.wsums.as<G1Jac>(), g.G);
     if (prc) return prc;
   }
   if (mode & RUN_PARTIAL) {
-    KLAUNCH(k_pack_partial, dim3(8, g.G), 256, 0, s, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, g.W[0] + g.W[1], ctx->d_wsums.as<G1Jac>(), ctx->d_partial_out.as<u8>());
+    KLAUNCH(k_pack_partial, dim3(8, g.G), 256, 0, s, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, g.W[0] + g.W[1], ctx->mb.wsums.as<G1Jac>(), ctx->d_partial_out.as<u8>());
   }
   if (mode & RUN_XCHG) {
     // The one exchange step of a sharded batch, device side (exchange.cuh): partials -> the root's window over NVLink;
@@ -1606,7 +1725,7 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
     const u32 cb = g.c[0] | g.c[1] << 16, wd = g.W[0] | g.W[1] << 16, npts = g.W[0] + g.W[1];
     u32* vd = ctx->d_verdict.as<u32>();
     CKC(cudaMemsetAsync(vd + g.G, 0, 8, s));  // error words of this launch set
-    KLAUNCH(k_pack_partial_x, g.G, 256, 0, s, cb, wd, npts, ctx->d_wsums.as<G1Jac>(), cm.d_dyn, cm.d_peers, cm.lay, cm.d_done);
+    KLAUNCH(k_pack_partial_x, g.G, 256, 0, s, cb, wd, npts, ctx->mb.wsums.as<G1Jac>(), cm.d_dyn, cm.d_peers, cm.lay, cm.d_done);
     if (mode & RUN_ROOT) {
       KLAUNCH_P(false, k_sum_partials, g.G, 128, 0, s, cm.lay.world, cb, wd, npts, cm.window + cm.lay.partials_off(), (size_t)cm.lay.max_groups * H2V_PARTIAL_BYTES,
                 ctx->d_wsums_fin.as<G1Jac>(), vd + g.G, cm.d_dyn, (const u64*)(cm.window + cm.lay.arrive_off()));
@@ -1619,7 +1738,7 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[5], s));
   if (mode & RUN_ACCUM) {
     FoldArgs fa{{g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {g.wbase[0], g.wbase[1]}};
-    KLAUNCH(k_fold_accum, 1, 32, 0, s, fa, ctx->d_wsums.as<G1Jac>(), ctx->d_acc_bytes.as<u8>());
+    KLAUNCH(k_fold_accum, 1, 32, 0, s, fa, ctx->mb.wsums.as<G1Jac>(), ctx->d_acc_bytes.as<u8>());
   }
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[6], s));
   return 0;
@@ -1645,9 +1764,9 @@ static u64 graph_key(const h2v_ctx* ctx, int mode) {
   mix((u64)g.G | (u64)g.N << 32);
   const DevBuf* bufs[] = {&ctx->d_plan, &ctx->d_proofs, &ctx->d_proof_off, &ctx->d_inst, &ctx->d_inst_off, &ctx->d_ncols, &ctx->d_col_len,
                           &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
-                          &ctx->d_r, &ctx->d_coef, &ctx->d_shared_sum, &ctx->d_dig, &ctx->d_hist, &ctx->d_off, &ctx->d_cursor, &ctx->d_order,
-                          &ctx->d_sorted, &ctx->d_buckets, &ctx->d_wsums, &ctx->d_acc_bytes, &ctx->d_verdict, &ctx->d_partials_msm,
-                          &ctx->d_M, &ctx->d_partial_out, &ctx->d_tiles, &ctx->d_wsums_fin};
+                          &ctx->d_r, &ctx->mb.coef, &ctx->mb.shared_sum, &ctx->mb.dig, &ctx->mb.hist, &ctx->mb.off, &ctx->mb.cursor, &ctx->mb.order,
+                          &ctx->mb.sorted, &ctx->mb.buckets, &ctx->mb.wsums, &ctx->d_acc_bytes, &ctx->d_verdict, &ctx->mb.partials_msm,
+                          &ctx->d_M, &ctx->d_partial_out, &ctx->mb.tiles, &ctx->d_wsums_fin};
   for (const DevBuf* b : bufs) mix((u64)(size_t)b->p);
   mix((u64)(size_t)ctx->d_lines());
   mix((u64)(size_t)ctx->comm.window);
@@ -1715,7 +1834,9 @@ static int run_impl(h2v_ctx* ctx, int mode) {
   return 0;
 }
 
-static int per_proof_impl(h2v_ctx* ctx, bool pairing, u8* accum_host) {
+// parity hook: per-proof affine accumulators (L_j, R_j) of EVERY proof of the upload (reference: the DualMSM a SingleStrategy
+// run would evaluate, msm.rs:81-95)
+static int per_proof_accum(h2v_ctx* ctx, u8* accum_host) {
   CKC(cudaSetDevice(ctx->device));
   const PlanHeader& hd = ctx->hd;
   const u32 n = ctx->n;
@@ -1724,20 +1845,92 @@ static int per_proof_impl(h2v_ctx* ctx, bool pairing, u8* accum_host) {
   const u32 nbases = hd.n_points + hd.n_shared + hd.n_mo;
   CKC(ctx->d_pp_prod.ensure(sizeof(G1Jac) * (size_t)n * nbases));
   CKC(ctx->d_pp_lr.ensure(sizeof(G1Jac) * (size_t)2 * n));
-  if (accum_host) CKC(ctx->d_pp_bytes.ensure(128 * (size_t)n));
-  // attribution only inside the fold groups whose batch check rejected (all proofs when the accumulators are wanted)
-  const u32* gv = (!accum_host && ctx->verdicts_on_device && ctx->geom.G > 1 && ctx->geom.G * ctx->geom.n == n) ? ctx->d_verdict.as<u32>() : nullptr;
+  CKC(ctx->d_pp_bytes.ensure(128 * (size_t)n));
   k_pp_mul<<<cdiv((u64)n * nbases, 128), 128, 0, s>>>(pv, n, ctx->d_pts.as<G1Affine>(), ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(),
-                                                       ctx->d_left.as<Fr>(), ctx->d_status.as<u32>(), ctx->d_pp_prod.as<G1Jac>(), gv, ctx->geom.n);
+                                                       ctx->d_left.as<Fr>(), ctx->d_status.as<u32>(), ctx->d_pp_prod.as<G1Jac>(), nullptr, ctx->geom.n);
   LAUNCH_CHECK();
-  k_pp_reduce<<<cdiv(2 * (u64)n, 128), 128, 0, s>>>(pv, n, ctx->d_pp_prod.as<G1Jac>(), ctx->d_pp_lr.as<G1Jac>(),
-                                                    accum_host ? ctx->d_pp_bytes.as<u8>() : nullptr);
+  k_pp_reduce<<<cdiv(2 * (u64)n, 128), 128, 0, s>>>(pv, n, ctx->d_pp_prod.as<G1Jac>(), ctx->d_pp_lr.as<G1Jac>(), ctx->d_pp_bytes.as<u8>());
   LAUNCH_CHECK();
-  if (pairing) {
-    k_pp_pairing<<<cdiv(n, PP_WARPS), 32 * PP_WARPS, 0, s>>>(pv, n, ctx->d_pp_lr.as<G1Jac>(), ctx->d_status.as<u32>(), gv, ctx->geom.n);
-    LAUNCH_CHECK();
+  CKC(cudaMemcpyAsync(accum_host, ctx->d_pp_bytes.p, 128 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+// Rejection attribution on the shard last processed by this context (see ATTR_SUB above): statuses of the proofs whose
+// own check fails become ST_CONSTRAINT_SYSTEM_FAILURE.  With fold groups and the group verdicts on the device only the
+// rejected groups are looked at.
+static int attribute_impl(h2v_ctx* ctx) {
+  CKC(cudaSetDevice(ctx->device));
+  const PlanHeader& hd = ctx->hd;
+  const u32 N = ctx->n;
+  const MsmGeom& g = ctx->geom;
+  cudaStream_t s = ctx->stream;
+  PlanView pv = ctx->pv();
+  const u32* gv = (ctx->verdicts_on_device && g.G > 1 && g.G * g.n == N) ? ctx->d_verdict.as<u32>() : nullptr;
+  const u32 nbases = hd.n_points + hd.n_shared + hd.n_mo;
+  static constexpr u32 CHUNK = 1024;  // checks per pass: bounds the Miller scratch (E12[CHUNK][65] = 115 MB)
+  MsmGeom unit{};
+  unit.c[0] = unit.c[1] = 1;
+  unit.W[0] = unit.W[1] = 1;
+  int unit_slot = -1;
+  {
+    int lrc = ensure_lines(ctx, unit, &unit_slot);  // lines of -G2 (pair 0, right) and [s]G2 (pair 1, left)
+    if (lrc) return lrc;
   }
-  if (accum_host) CKC(cudaMemcpyAsync(accum_host, ctx->d_pp_bytes.p, 128 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  const G2Line* unit_lines = ctx->lines[unit_slot].buf.as<G2Line>();
+  CKC(ctx->d_sub_M.ensure(sizeof(E12) * H2V_ATE_ITERS * (size_t)CHUNK));
+  CKC(ctx->d_pp_lr.ensure(sizeof(G1Jac) * (size_t)2 * CHUNK));
+  CKC(ctx->d_pp_prod.ensure(sizeof(G1Jac) * (size_t)CHUNK * nbases));
+  CKC(ctx->d_sub_pairs.ensure(4 * ((size_t)N + 8) + 4 * (size_t)CHUNK));  // suspect list | count | verdicts of a pass
+  u32* list = ctx->d_sub_pairs.as<u32>();
+  u32* count = list + N;
+  u32* pass_verdict = count + 8;
+  const u32* sub_verdict = nullptr;
+  u32 sub_size = 1;
+  // ---- level 1: sub-batches of ATTR_SUB proofs through the bucket MSM, one 2-pair check each
+  if (g.n >= 4 * ATTR_SUB && g.n % ATTR_SUB == 0) {
+    const u32 subs = g.n / ATTR_SUB, SG = N / ATTR_SUB;
+    MsmGeom sg = choose_geom(ATTR_SUB, hd, 0, SG);
+    CKC(ensure_msm_bufs(sg, ctx->ab, hd.n_shared));
+    CKC(ctx->d_sub_verdict.ensure(4 * (size_t)SG + sizeof(G1Jac) * 2 * (size_t)SG + 64));
+    u32* sv = ctx->d_sub_verdict.as<u32>();
+    G1Jac* sub_pairs = (G1Jac*)(((size_t)(sv + SG) + 15) & ~(size_t)15);
+    CKC(cudaMemsetAsync(ctx->ab.hist.p, 0, 4 * ((size_t)sg.nb() * sg.G + 2 * SIZE_BINS), s));
+    CKC(cudaMemsetAsync(sv, 1, 4 * (size_t)SG, s));  // non-zero = accepted: sub-batches of accepted groups are never checked
+    KLAUNCH_P(false, k_rlc_scan, SG, RLC_NT, 0, s, ctx->d_r.as<Fr>(), (u64)ATTR_SUB, (u64)0, ATTR_SUB, ctx->ab.coef.as<Fr>(), subs, ctx->gcount, ctx->gbase);
+    {
+      const bool pdl = ctx->use_pdl;
+      ctx->use_pdl = false;
+      int mrc = enqueue_msm(ctx, sg, ctx->ab, s, gv, g.n);
+      ctx->use_pdl = pdl;
+      if (mrc) return mrc;
+    }
+    FoldArgs fa{{sg.W[0], sg.W[1]}, {sg.c[0], sg.c[1]}, {sg.wbase[0], sg.wbase[1]}};
+    KLAUNCH_P(false, k_window_combine, cdiv(2 * (u64)SG, 64), 64, 0, s, SG, fa, ctx->ab.wsums.as<G1Jac>(), sub_pairs);
+    for (u32 base = 0; base < SG; base += CHUNK) {
+      const u32 cnt = std::min(CHUNK, SG - base);
+      int prc = launch_pair_checks(ctx, sub_pairs + 2 * (size_t)base, cnt, unit_lines, ctx->d_sub_M.as<E12>(), sv + base, PairSkip{gv, nullptr, subs, base});
+      if (prc) return prc;
+    }
+    sub_verdict = sv;
+    sub_size = ATTR_SUB;
+  }
+  // ---- level 2: every suspect proof alone
+  CKC(cudaMemsetAsync(count, 0, 4, s));
+  KLAUNCH_P(false, k_pp_suspects, cdiv(N, 128), 128, 0, s, N, ctx->d_status.as<u32>(), sub_verdict, sub_size, gv, g.n, list, count);
+  CKC(ctx->h_verd.ensure(4 * 1040));
+  u32* h_count = ctx->h_verd.as<u32>() + 1030;
+  CKC(cudaMemcpyAsync(h_count, count, 4, cudaMemcpyDeviceToHost, s));
+  CKC(ctx_sync(ctx));
+  const u32 total = *h_count;
+  for (u32 base = 0; base < total; base += CHUNK) {
+    const u32 cnt = std::min(CHUNK, total - base);
+    KLAUNCH_P(false, k_pp_mul_list, cdiv((u64)cnt * nbases, 128), 128, 0, s, pv, N, ctx->d_pts.as<G1Affine>(), ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(),
+              ctx->d_left.as<Fr>(), list, count, base, CHUNK, ctx->d_pp_prod.as<G1Jac>());
+    KLAUNCH_P(false, k_pp_reduce_list, cdiv(2 * (u64)cnt, 128), 128, 0, s, pv, count, base, CHUNK, ctx->d_pp_prod.as<G1Jac>(), ctx->d_pp_lr.as<G1Jac>());
+    int prc = launch_pair_checks(ctx, ctx->d_pp_lr.as<G1Jac>(), cnt, unit_lines, ctx->d_sub_M.as<E12>(), pass_verdict, PairSkip{nullptr, count, 1, base});
+    if (prc) return prc;
+    KLAUNCH_P(false, k_pp_status, cdiv(cnt, 128), 128, 0, s, list, count, base, CHUNK, pass_verdict, ctx->d_status.as<u32>());
+  }
   CKC(cudaEventRecord(ctx->ev[6], s));
   return 0;
 }
@@ -1784,9 +1977,8 @@ int h2v_verify_batch(h2v_ctx* ctx, uint32_t n, const uint8_t* proofs, const uint
   u32 verdict = 0;
   if (batch_accum) CKC(cudaMemcpyAsync(batch_accum, ctx->d_acc_bytes.p, 128, cudaMemcpyDeviceToHost, ctx->stream));
   if ((rc = read_verdicts(ctx, &verdict)) != 0) return rc;
-  if (!verdict || accum) {  // per-proof accumulators: parity hook, or attribution of a rejected batch
-    if ((rc = per_proof_impl(ctx, !verdict, accum)) != 0) return rc;
-  }
+  if (accum && (rc = per_proof_accum(ctx, accum)) != 0) return rc;  // parity hook
+  if (!verdict && (rc = attribute_impl(ctx)) != 0) return rc;      // rejected fold: poly/strategy.rs:26-30
   return download_status(ctx, status);
 }
 
@@ -1886,7 +2078,7 @@ int h2v_finalize_groups(h2v_ctx* ctx, uint32_t n_partials, uint32_t groups, cons
 int h2v_attribute_shard(h2v_ctx* ctx, uint8_t* status) {
   if (!ctx || !ctx->ran) return -1;
   int rc;
-  if ((rc = per_proof_impl(ctx, true, nullptr)) != 0) return rc;
+  if ((rc = attribute_impl(ctx)) != 0) return rc;
   return download_status(ctx, status);
 }
 
@@ -1898,9 +2090,9 @@ int h2v_attribute_shard_groups(h2v_ctx* ctx, const uint8_t* group_verdicts, uint
   CKC(ctx->d_verdict.ensure(4 * (size_t)groups + 16));
   CKC(cudaMemcpyAsync(ctx->d_verdict.p, v.data(), 4 * (size_t)groups, cudaMemcpyHostToDevice, ctx->stream));
   CKC(ctx_sync(ctx));  // v is a stack buffer
-  ctx->verdicts_on_device = true;  // per_proof_impl skips the proofs of accepted groups
+  ctx->verdicts_on_device = true;  // attribute_impl skips the proofs of accepted groups
   int rc;
-  if ((rc = per_proof_impl(ctx, true, nullptr)) != 0) return rc;
+  if ((rc = attribute_impl(ctx)) != 0) return rc;
   return download_status(ctx, status);
 }
 
@@ -2024,7 +2216,7 @@ static int exchange_run(h2v_ctx* ctx, u32 root, u8* group_verdicts, int* verdict
     for (u32 q = 0; q < ctx->geom.G; q++) group_verdicts[q] = ctx->h_verdicts[q] ? 1 : 0;
   if (verdict) *verdict = (int)all;
   if (e2e) {
-    if (!all && (rc = per_proof_impl(ctx, true, nullptr)) != 0) return rc;
+    if (!all && (rc = attribute_impl(ctx)) != 0) return rc;
     return download_status(ctx, status);
   }
   return 0;

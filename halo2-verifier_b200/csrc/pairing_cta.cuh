@@ -244,6 +244,17 @@ __device__ __noinline__ void g_pow_u(const Grp& g, E12* dst, const E12* x) {  //
 struct LinesArgs {
   u32 n_pairs;  // (channel, window) pairs = window sums; pair p uses lines[p * H2V_ATE_LINES ..]
 };
+// Which of the launched check groups are live (attribution runs many small checks and most of them are not needed):
+// group index i = base + block index; skipped when `count` is given and i >= *count, or when flags[i / div] != 0.
+struct PairSkip {
+  const u32* flags;
+  const u32* count;
+  u32 div, base;
+  __device__ __forceinline__ bool skip(u32 blk) const {
+    const u32 i = base + blk;
+    return (count && i >= *count) || (flags && flags[i / div] != 0);
+  }
+};
 struct LinesSmem {  // dynamic shared memory layout of k_lines<GROUPS>
   LinTables lt;
   Fq Y[128], XZ[128], Z3[128];
@@ -251,9 +262,10 @@ struct LinesSmem {  // dynamic shared memory layout of k_lines<GROUPS>
 };
 template <int GROUPS>
 __global__ void __launch_bounds__(64 * GROUPS) k_lines(LinesArgs la, const G1Jac* __restrict__ wsums, const G2Line* __restrict__ lines,
-                                                       E12* __restrict__ M) {
+                                                       E12* __restrict__ M, PairSkip sk) {
   asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch, see pdl_prologue() in kernels.cu
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (sk.skip(blockIdx.y)) return;
   ::TlScope tl_(9, M);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LinesSmem* sm = (LinesSmem*)smem_raw;
@@ -301,9 +313,10 @@ constexpr size_t k_lines_smem() {
 }
 
 // ---- k_pairing_check: Miller accumulation over the prepared iteration products + final check
-__global__ void __launch_bounds__(128) k_pairing_check(const E12* __restrict__ M, u32* verdict) {
+__global__ void __launch_bounds__(128) k_pairing_check(const E12* __restrict__ M, u32* verdict, PairSkip sk) {
   asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch, see pdl_prologue() in kernels.cu
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (sk.skip(blockIdx.x)) return;
   ::TlScope tl_(10, M);
   __shared__ LinTables lt;
   __shared__ E12 slot[12];
