@@ -1860,6 +1860,7 @@ static int per_proof_accum(h2v_ctx* ctx, u8* accum_host) {
 // rejected groups are looked at.
 static int attribute_impl(h2v_ctx* ctx) {
   CKC(cudaSetDevice(ctx->device));
+  trace(ctx, "attr: begins");
   const PlanHeader& hd = ctx->hd;
   const u32 N = ctx->n;
   const MsmGeom& g = ctx->geom;
@@ -1887,16 +1888,18 @@ static int attribute_impl(h2v_ctx* ctx) {
   const u32* sub_verdict = nullptr;
   u32 sub_size = 1;
   // ---- level 1: sub-batches of ATTR_SUB proofs through the bucket MSM, one 2-pair check each
-  if (g.n >= 4 * ATTR_SUB && g.n % ATTR_SUB == 0) {
-    const u32 subs = g.n / ATTR_SUB, SG = N / ATTR_SUB;
-    MsmGeom sg = choose_geom(ATTR_SUB, hd, 0, SG);
+  u32 msub = ATTR_SUB;
+  if (const char* e = getenv("H2V_ATTR_SUB")) msub = (u32)atoi(e);  // (tuning: 0 = no sub-batch level)
+  if (msub >= 2 && g.n >= 4 * msub && g.n % msub == 0) {
+    const u32 subs = g.n / msub, SG = N / msub;
+    MsmGeom sg = choose_geom(msub, hd, 0, SG);
     CKC(ensure_msm_bufs(sg, ctx->ab, hd.n_shared));
     CKC(ctx->d_sub_verdict.ensure(4 * (size_t)SG + sizeof(G1Jac) * 2 * (size_t)SG + 64));
     u32* sv = ctx->d_sub_verdict.as<u32>();
     G1Jac* sub_pairs = (G1Jac*)(((size_t)(sv + SG) + 15) & ~(size_t)15);
     CKC(cudaMemsetAsync(ctx->ab.hist.p, 0, 4 * ((size_t)sg.nb() * sg.G + 2 * SIZE_BINS), s));
     CKC(cudaMemsetAsync(sv, 1, 4 * (size_t)SG, s));  // non-zero = accepted: sub-batches of accepted groups are never checked
-    KLAUNCH_P(false, k_rlc_scan, SG, RLC_NT, 0, s, ctx->d_r.as<Fr>(), (u64)ATTR_SUB, (u64)0, ATTR_SUB, ctx->ab.coef.as<Fr>(), subs, ctx->gcount, ctx->gbase);
+    KLAUNCH_P(false, k_rlc_scan, SG, RLC_NT, 0, s, ctx->d_r.as<Fr>(), (u64)msub, (u64)0, msub, ctx->ab.coef.as<Fr>(), subs, ctx->gcount, ctx->gbase);
     {
       const bool pdl = ctx->use_pdl;
       ctx->use_pdl = false;
@@ -1904,15 +1907,17 @@ static int attribute_impl(h2v_ctx* ctx) {
       ctx->use_pdl = pdl;
       if (mrc) return mrc;
     }
+    if (trace_on()) { ctx_sync(ctx); trace(ctx, "attr: sub-batch msm done"); }
     FoldArgs fa{{sg.W[0], sg.W[1]}, {sg.c[0], sg.c[1]}, {sg.wbase[0], sg.wbase[1]}};
     KLAUNCH_P(false, k_window_combine, cdiv(2 * (u64)SG, 64), 64, 0, s, SG, fa, ctx->ab.wsums.as<G1Jac>(), sub_pairs);
+    if (trace_on()) { ctx_sync(ctx); trace(ctx, "attr: window combine done"); }
     for (u32 base = 0; base < SG; base += CHUNK) {
       const u32 cnt = std::min(CHUNK, SG - base);
       int prc = launch_pair_checks(ctx, sub_pairs + 2 * (size_t)base, cnt, unit_lines, ctx->d_sub_M.as<E12>(), sv + base, PairSkip{gv, nullptr, subs, base});
       if (prc) return prc;
     }
     sub_verdict = sv;
-    sub_size = ATTR_SUB;
+    sub_size = msub;
   }
   // ---- level 2: every suspect proof alone
   CKC(cudaMemsetAsync(count, 0, 4, s));
@@ -1922,13 +1927,16 @@ static int attribute_impl(h2v_ctx* ctx) {
   CKC(cudaMemcpyAsync(h_count, count, 4, cudaMemcpyDeviceToHost, s));
   CKC(ctx_sync(ctx));
   const u32 total = *h_count;
+  if (trace_on()) { char b[64]; snprintf(b, sizeof b, "attr: level 1 done, %u suspects", total); trace(ctx, b); }
   for (u32 base = 0; base < total; base += CHUNK) {
     const u32 cnt = std::min(CHUNK, total - base);
     KLAUNCH_P(false, k_pp_mul_list, cdiv((u64)cnt * nbases, 128), 128, 0, s, pv, N, ctx->d_pts.as<G1Affine>(), ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(),
               ctx->d_left.as<Fr>(), list, count, base, CHUNK, ctx->d_pp_prod.as<G1Jac>());
     KLAUNCH_P(false, k_pp_reduce_list, cdiv(2 * (u64)cnt, 128), 128, 0, s, pv, count, base, CHUNK, ctx->d_pp_prod.as<G1Jac>(), ctx->d_pp_lr.as<G1Jac>());
+    if (trace_on()) { ctx_sync(ctx); trace(ctx, "attr: suspects' accumulators done"); }
     int prc = launch_pair_checks(ctx, ctx->d_pp_lr.as<G1Jac>(), cnt, unit_lines, ctx->d_sub_M.as<E12>(), pass_verdict, PairSkip{nullptr, count, 1, base});
     if (prc) return prc;
+    if (trace_on()) { ctx_sync(ctx); trace(ctx, "attr: suspects' checks done"); }
     KLAUNCH_P(false, k_pp_status, cdiv(cnt, 128), 128, 0, s, list, count, base, CHUNK, pass_verdict, ctx->d_status.as<u32>());
   }
   CKC(cudaEventRecord(ctx->ev[6], s));

@@ -98,6 +98,51 @@ H2V_HD Fq lin_row(const uint16_t* start, const uint16_t* terms, int row, const F
   return lin_reduce(acc);
 }
 
+// ---- the latency-critical variant of the linear map (k_pairing_check: one 128-thread group walks ~435 dependent Fq12
+// products): every row of FULL is split over 2-3 consecutive threads of one warp, and a thread's terms (H2V_LIN_FAST_CAP
+// packed 16-bit terms + a meta word, pairing_lin.inc) stay in REGISTERS for the whole kernel, so that a product's map is a
+// fully unrolled run of independent shared-memory loads and multiply-adds instead of a table walk.
+static constexpr int FAST_W = H2V_LIN_FAST_CAP / 2;  // term words per thread
+struct FastTerms {
+  u32 w[FAST_W];
+  u32 meta;  // row | lead << 8 | followers << 16; row 255 = idle thread
+  H2V_HD int row() const { return (int)(meta & 0xFF); }
+  H2V_HD bool lead() const { return ((meta >> 8) & 1) != 0; }
+  H2V_HD int followers() const { return (int)(meta >> 16); }
+};
+static constexpr int FAST_MAX_FOLLOWERS = H2V_LIN_FAST_MAX_FOLLOWERS;
+// partial column accumulators of one thread's terms
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void lds_fq(u32 (&v)[8], u32 saddr) {  // explicit shared-memory loads: through a generic pointer they became LD
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%8];\n\tld.shared.v4.u32 {%4, %5, %6, %7}, [%8 + 16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(saddr));
+}
+#endif
+H2V_HD void fast_partial(u64* acc, const FastTerms& ft, const Fq* src) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = 0;
+#if defined(__CUDA_ARCH__)
+  const u32 sbase = (u32)__cvta_generic_to_shared(src);
+#endif
+#pragma unroll
+  for (int k = 0; k < FAST_W; k++) {
+    const u32 tt = ft.w[k];
+    const u32 c0 = (tt >> 8) & 0xFF, c1 = tt >> 24;
+#if defined(__CUDA_ARCH__)
+    u32 v0[8], v1[8];
+    lds_fq(v0, sbase + (tt & 0xFF) * 32u);
+    lds_fq(v1, sbase + ((tt >> 16) & 0xFF) * 32u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] += (u64)c0 * v0[i] + (u64)c1 * v1[i];
+#else
+    const Fq v0 = src[tt & 0xFF], v1 = src[(tt >> 16) & 0xFF];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] += (u64)c0 * v0.l[i] + (u64)c1 * v1.l[i];
+#endif
+  }
+}
+
 // ---- per-lane phases (host/device; the device wrappers below add the barriers)
 // products: pr[lane] = a[lane] * b[lane], pr[54 + lane] = p - pr[lane]
 H2V_HD void e12_mul_p1(Fq* pr, const E12* a, const E12* b, int lane) {
@@ -206,6 +251,35 @@ __device__ __forceinline__ void g_mul(const Grp& g, E12* dst, const E12* a, cons
   }
   g.sync();
 }
+// fast group (128 threads): products by lanes 0..53, then the register-resident split map with shuffle combination
+__device__ const u32 g_lin_fast[H2V_LIN_FAST_THREADS * (FAST_W + 1)] = H2V_LIN_FAST_INIT;
+__device__ __forceinline__ FastTerms fast_terms_of(int t) {
+  FastTerms ft;
+#pragma unroll
+  for (int k = 0; k < FAST_W; k++) ft.w[k] = g_lin_fast[t * (FAST_W + 1) + k];
+  ft.meta = g_lin_fast[t * (FAST_W + 1) + FAST_W];
+  return ft;
+}
+__device__ __forceinline__ void gf_mul(const Grp& g, const FastTerms& ft, E12* dst, const E12* a, const E12* b) {  // dst may alias a, b
+  if (g.lane < E12_N) e12_mul_p1(g.scr, a, b, g.lane);
+  g.sync();
+  u64 acc[8], sum[8];
+  fast_partial(acc, ft, g.scr);
+#pragma unroll
+  for (int i = 0; i < 8; i++) sum[i] = acc[i];
+  const int fol = ft.followers();
+#pragma unroll
+  for (int f = 1; f <= FAST_MAX_FOLLOWERS; f++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const u64 o = __shfl_down_sync(0xFFFFFFFFu, acc[i], f);
+      if (f <= fol) sum[i] += o;
+    }
+  }
+  if (ft.lead()) dst->e[ft.row()] = lin_reduce(sum);
+  g.sync();
+}
+
 __device__ __forceinline__ void g_expand(const Grp& g, E12* dst) {  // from base coordinates in scr[0..11]
   g.sync();
   if (g.lane < E12_N) e12_expand_p(dst, g.scr, g.lt, g.lane);
@@ -237,6 +311,16 @@ __device__ __noinline__ void g_pow_u(const Grp& g, E12* dst, const E12* x) {  //
   for (int i = 61; i >= 0; i--) {
     g_mul(g, dst, dst, dst);
     if ((H2V_BN_U >> i) & 1) g_mul(g, dst, dst, x);
+  }
+}
+
+// (inlined: as a separate function its FastTerms argument would live in local memory and the scratch pointer would be generic)
+__device__ __forceinline__ void gf_pow_u(const Grp& g, const FastTerms& ft, E12* dst, const E12* x) {  // dst != x
+  g_copy(g, dst, x);
+#pragma unroll 1
+  for (int i = 61; i >= 0; i--) {
+    gf_mul(g, ft, dst, dst, dst);
+    if ((H2V_BN_U >> i) & 1) gf_mul(g, ft, dst, dst, x);
   }
 }
 
@@ -313,7 +397,7 @@ constexpr size_t k_lines_smem() {
 }
 
 // ---- k_pairing_check: Miller accumulation over the prepared iteration products + final check
-__global__ void __launch_bounds__(128) k_pairing_check(const E12* __restrict__ M, u32* verdict, PairSkip sk) {
+__global__ void __launch_bounds__(128, 1) k_pairing_check(const E12* __restrict__ M, u32* verdict, PairSkip sk) {
   asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch, see pdl_prologue() in kernels.cu
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (sk.skip(blockIdx.x)) return;
@@ -321,62 +405,62 @@ __global__ void __launch_bounds__(128) k_pairing_check(const E12* __restrict__ M
   __shared__ LinTables lt;
   __shared__ E12 slot[12];
   __shared__ Fq scr[2 * E12_N];
-  __shared__ u64 part[E12_N * 8];
   const int t = threadIdx.x;
   M += (size_t)blockIdx.x * H2V_ATE_ITERS;  // one block per fold group
   verdict += blockIdx.x;
   for (int i = t; i < (int)(sizeof(LinTables) / 2); i += 128) ((uint16_t*)&lt)[i] = ((const uint16_t*)&g_lin_tables)[i];
   __syncthreads();
-  Grp g{t, 1, &lt, scr, 128, part};
+  Grp g{t, 1, &lt, scr, 128, nullptr};
+  const FastTerms ft = fast_terms_of(t);
   E12 *f = &slot[0], *tt = &slot[1], *fu = &slot[2], *fu2 = &slot[3], *fu3 = &slot[4], *a = &slot[5], *b = &slot[6], *y0 = &slot[7],
       *T0 = &slot[8], *T1 = &slot[9], *N = &slot[10], *m = &slot[11];
   g_copy(g, f, &M[0]);
 #pragma unroll 1
   for (int it = 1; it < H2V_ATE_ITERS; it++) {
     g_copy(g, m, &M[it]);
-    if (it < 64) g_mul(g, f, f, f);
-    g_mul(g, f, f, m);
+    if (it < 64) gf_mul(g, ft, f, f, f);
+    gf_mul(g, ft, f, f, m);
   }
   // t = f^(p^2 + 1); the easy factor p^6 - 1 is replaced by the conjugation test at the end
   g_frob2(g, a, f);
-  g_mul(g, tt, a, f);
-  g_pow_u(g, fu, tt);
-  g_pow_u(g, fu2, fu);
-  g_pow_u(g, fu3, fu2);
+  gf_mul(g, ft, tt, a, f);
+  gf_pow_u(g, ft, fu, tt);
+  gf_pow_u(g, ft, fu2, fu);
+  gf_pow_u(g, ft, fu3, fu2);
   // numerator: y0 = t^p t^(p^2) t^(p^3), y2 = (t^(u^2))^(p^2);  N = y0 y2^6
   g_frob(g, a, tt);
   g_frob2(g, b, tt);
-  g_mul(g, y0, a, b);
+  gf_mul(g, ft, y0, a, b);
   g_frob(g, a, b);
-  g_mul(g, y0, y0, a);
+  gf_mul(g, ft, y0, y0, a);
   g_frob2(g, a, fu2);
-  g_mul(g, a, a, a);        // y2^2
-  g_mul(g, b, a, a);        // y2^4
-  g_mul(g, b, b, a);        // y2^6
-  g_mul(g, N, y0, b);
+  gf_mul(g, ft, a, a, a);        // y2^2
+  gf_mul(g, ft, b, a, a);        // y2^4
+  gf_mul(g, ft, b, b, a);        // y2^6
+  gf_mul(g, ft, N, y0, b);
   // denominator (positive powers of the inverted terms): Y1 = t, Y3 = (t^u)^p, Y4 = t^u (t^(u^2))^p, Y5 = t^(u^2),
   // Y6 = t^(u^3) (t^(u^3))^p;  D = Y1^2 Y3^12 Y4^18 Y5^30 Y6^36 by the Scott et al. vector chain
   g_frob(g, a, fu3);
-  g_mul(g, a, fu3, a);      // Y6
-  g_mul(g, T0, a, a);       // Y6^2
+  gf_mul(g, ft, a, fu3, a);      // Y6
+  gf_mul(g, ft, T0, a, a);       // Y6^2
   g_frob(g, a, fu2);
-  g_mul(g, a, fu, a);       // Y4
-  g_mul(g, T0, T0, a);
-  g_mul(g, T0, T0, fu2);    // T0 = Y6^2 Y4 Y5
+  gf_mul(g, ft, a, fu, a);       // Y4
+  gf_mul(g, ft, T0, T0, a);
+  gf_mul(g, ft, T0, T0, fu2);    // T0 = Y6^2 Y4 Y5
   g_frob(g, a, fu);         // Y3
-  g_mul(g, T1, a, fu2);
-  g_mul(g, T1, T1, T0);     // T1 = Y3 Y5 T0
-  g_mul(g, T1, T1, T1);
-  g_mul(g, T1, T1, T0);
-  g_mul(g, T1, T1, T1);     // T1 = (T1^2 T0)^2
-  g_mul(g, T0, T1, tt);     // T0 = T1 Y1
-  g_mul(g, T0, T0, T0);
-  g_mul(g, T0, T0, T1);     // D = T0^2 T1
+  gf_mul(g, ft, T1, a, fu2);
+  gf_mul(g, ft, T1, T1, T0);     // T1 = Y3 Y5 T0
+  gf_mul(g, ft, T1, T1, T1);
+  gf_mul(g, ft, T1, T1, T0);
+  gf_mul(g, ft, T1, T1, T1);     // T1 = (T1^2 T0)^2
+  gf_mul(g, ft, T0, T1, tt);     // T0 = T1 Y1
+  gf_mul(g, ft, T0, T0, T0);
+  gf_mul(g, ft, T0, T0, T1);     // D = T0^2 T1
   // accept  <=>  conj(N) D == N conj(D)
   g_conj(g, a, N);
-  g_mul(g, a, a, T0);
+  gf_mul(g, ft, a, a, T0);
   g_conj(g, b, T0);
-  g_mul(g, b, N, b);
+  gf_mul(g, ft, b, N, b);
   bool ok = true;
   if (t < E12_NB) ok = a->e[e12_base_slot(t)] == b->e[e12_base_slot(t)];
   ok = __syncthreads_and(ok);

@@ -87,11 +87,39 @@ static Fq12 load_fq12(const u32* c) {  // 12 canonical Fq: a[i].c0, a[i].c1
 static void store_fq12(const Fq12& f, u32* out) {
   for (int i = 0; i < 6; i++) { Fq a = f.a[i].c0.to_canonical(), b = f.a[i].c1.to_canonical(); memcpy(out + 16 * i, a.l, 32); memcpy(out + 16 * i + 8, b.l, 32); }
 }
-// op: 0 mul, 1 conj, 2 frob, 3 frob2, 4 pow_u
+// the 128-thread split of the linear map (gf_mul of pairing_cta.cuh), threads emulated: per-thread partial column
+// accumulators, the row's lead thread adds its followers' and reduces
+static const u32 h_lin_fast[H2V_LIN_FAST_THREADS * (FAST_W + 1)] = H2V_LIN_FAST_INIT;
+static void fast_mul(HostEngine& he, E12* dst, const E12* a, const E12* b) {
+  for (int l = 0; l < E12_N; l++) e12_mul_p1(he.scr, a, b, l);
+  static u64 part[H2V_LIN_FAST_THREADS][8];
+  FastTerms ft[H2V_LIN_FAST_THREADS];
+  for (int t = 0; t < H2V_LIN_FAST_THREADS; t++) {
+    for (int k = 0; k < FAST_W; k++) ft[t].w[k] = h_lin_fast[t * (FAST_W + 1) + k];
+    ft[t].meta = h_lin_fast[t * (FAST_W + 1) + FAST_W];
+    fast_partial(part[t], ft[t], he.scr);
+  }
+  int rows_done = 0;
+  for (int t = 0; t < H2V_LIN_FAST_THREADS; t++) {
+    if (!ft[t].lead()) continue;
+    u64 sum[8];
+    for (int i = 0; i < 8; i++) sum[i] = part[t][i];
+    // followers sit in the same warp, right behind the lead (the device combines them with __shfl_down_sync)
+    if (ft[t].followers() > FAST_MAX_FOLLOWERS || (t % 32) + ft[t].followers() > 31) { memset(dst, 0xff, sizeof(E12)); return; }
+    for (int f = 1; f <= ft[t].followers(); f++) {
+      if (ft[t + f].lead() || ft[t + f].row() != ft[t].row()) { memset(dst, 0xff, sizeof(E12)); return; }
+      for (int i = 0; i < 8; i++) sum[i] += part[t + f][i];
+    }
+    dst->e[ft[t].row()] = lin_reduce(sum);
+    rows_done++;
+  }
+  if (rows_done != E12_N) memset(dst, 0xff, sizeof(E12));
+}
+// op: 0 mul, 1 conj, 2 frob, 3 frob2, 4 pow_u, 5 mul through the 128-thread split map
 void t_e12_op(int op, const u32* a, const u32* b, u32* out) {
   HostEngine he; E12 x, y, z;
   he.from_fq12(&x, load_fq12(a)); he.from_fq12(&y, load_fq12(b));
-  switch (op) { case 0: he.mul(&z, &x, &y); break; case 1: he.conj(&z, &x); break; case 2: he.frob(&z, &x); break; case 3: he.frob2(&z, &x); break; default: he.pow_u(&z, &x); }
+  switch (op) { case 0: he.mul(&z, &x, &y); break; case 5: fast_mul(he, &z, &x, &y); break; case 1: he.conj(&z, &x); break; case 2: he.frob(&z, &x); break; case 3: he.frob2(&z, &x); break; default: he.pow_u(&z, &x); }
   // the expanded form must be self-consistent: re-expanding the base coordinates reproduces it
   E12 chk; he.from_fq12(&chk, he.to_fq12(&z));
   for (int l = 0; l < E12_N; l++) if (chk.e[l] != z.e[l]) { memset(out, 0xff, 12 * 32); return; }

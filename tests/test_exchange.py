@@ -48,7 +48,7 @@ def run_ranks(fns):
 def test_exchange_two_contexts_one_gpu(pkg):
     """gather to the root + verdict broadcast inside the graphs; folded (L, R) == oracle; rejected batch attributed
     on the non-root rank; roots alternate; fold groups; graph replay (no recapture after the first of each kind)"""
-    os.environ.setdefault("H2V_COMM_TIMEOUT_MS", "20000")
+    os.environ.setdefault("H2V_COMM_TIMEOUT_MS", "5000")
     n, world = 64, 2
     per = n // world
     params, vk, instances, proofs, rng = make_batch("vm", 10, n, "shplonk", "blake2b", seed=61)

@@ -250,6 +250,7 @@ def test_e12_engine_matches_oracle_tower(prim):
     cases = [(rnd12(), rnd12()) for _ in range(12)] + [(edge, edge), (bn.F12_ONE, rnd12()), (rnd12(), tuple((0, 0) for _ in range(6)))]
     for x, y in cases:
         prim.t_e12_op(0, F12L(x), F12L(y), out); assert F12I(out) == bn.f12_mul(x, y)
+        prim.t_e12_op(5, F12L(x), F12L(y), out); assert F12I(out) == bn.f12_mul(x, y)  # the 128-thread split of the map (k_pairing_check)
         prim.t_e12_op(1, F12L(x), F12L(y), out); assert F12I(out) == bn.f12_conj(x)
         prim.t_e12_op(2, F12L(x), F12L(y), out); assert F12I(out) == bn.f12_frob(x)
         prim.t_e12_op(3, F12L(x), F12L(y), out); assert F12I(out) == bn.f12_frob2(x)

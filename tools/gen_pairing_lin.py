@@ -85,12 +85,59 @@ def emit(name, M, out):
     out.append(f"#define H2V_LIN_{name}_TERMS_INIT {{{', '.join(map(str, terms))}}}")
 
 
+def emit_fast(M, out, threads=128):
+    """FULL for the latency-critical 128-thread group (k_pairing_check): every row is split over 2-3 CONSECUTIVE threads of
+    one warp, each thread keeps its <= `cap` terms in registers for the whole kernel, partial column accumulators are
+    combined with warp shuffles.  Per thread: cap packed terms (index | coefficient << 8), then a meta word
+    row | lead << 8 | followers << 16 (lead = first thread of its row: adds the partials of its `followers` next lanes and
+    reduces; row 255 = idle thread)."""
+    n_src = M.shape[1]
+    rows = []
+    for row in M:
+        pos = [(j, int(c)) for j, c in enumerate(row) if c > 0]
+        neg = [(j + n_src, int(-c)) for j, c in enumerate(row) if c < 0]
+        rows.append([j | (c << 8) for j, c in pos + neg])
+    best = None
+    for cap in range(8, 40):
+        slots, ok = [], True
+        for r, terms in enumerate(rows):
+            k = -(-len(terms) // cap)
+            if k > 4:
+                ok = False
+                break
+            if (len(slots) % 32) + k > 32:  # the threads of a row share a warp
+                slots += [None] * (32 - len(slots) % 32)
+            per = -(-len(terms) // k)
+            for i in range(k):
+                slots.append((r, i == 0, k - 1 if i == 0 else 0, terms[i * per:(i + 1) * per]))
+        if ok and len(slots) <= threads:
+            best = (cap, slots)
+            break
+    cap, slots = best
+    slots += [None] * (threads - len(slots))
+    words = []
+    for sl in slots:
+        if sl is None:
+            words += [0] * (cap // 2 + cap % 2) + [255]
+            continue
+        r, lead, fol, terms = sl
+        terms = terms + [0] * (cap + cap % 2 - len(terms))
+        words += [terms[i] | (terms[i + 1] << 16) for i in range(0, len(terms), 2)]
+        words.append(r | (int(lead) << 8) | (fol << 16))
+    out.append(f"// FAST: FULL split over {threads} threads, <= {cap} register-resident terms per thread ({sum(1 for x in slots if x)} busy threads)")
+    out.append(f"#define H2V_LIN_FAST_CAP {cap + cap % 2}")
+    out.append(f"#define H2V_LIN_FAST_THREADS {threads}")
+    out.append(f"#define H2V_LIN_FAST_MAX_FOLLOWERS {max(sl[2] for sl in slots if sl)}")
+    out.append(f"#define H2V_LIN_FAST_INIT {{{', '.join(map(str, words))}}}")
+
+
 def main():
     EXP, INT, FULL = build()
     out = ["// generated by tools/gen_pairing_lin.py -- do not edit"]
     emit("EXP", EXP, out)
     emit("INT", INT, out)
     emit("FULL", FULL, out)
+    emit_fast(FULL, out)
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "halo2-verifier_b200", "csrc", "pairing_lin.inc")
     open(path, "w").write("\n".join(out) + "\n")
     print("wrote", os.path.normpath(path))
