@@ -66,7 +66,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.3)
 
     def summary(self):
         self.stop_flag.set()
@@ -340,8 +340,11 @@ def run_ours(args):
     ok = run_steps(lambda ctx, i: step_resident(ctx, i), W, bvs[:1])
     assert all(v == 1 for v in ok), "warm-up batch was rejected"
     geom = geom_tp = bv.msm_geometry()
-    sampler = ClockSampler(local)
-    sampler.start()
+    # clocks DURING the timed region: rank 0 samples its own GPU, a few times per second (every rank polling nvidia-smi ten
+    # times per second measurably disturbed the timed blocks at N = 8: the query takes driver locks and host cores)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
     lib.h2v_ctx_set_blocking_sync(bv._ctx, 0)
     lat_steps = max(8, min(steps, 32))
     res, dt1, _ = timed_block(lambda ctx, i: step_resident(ctx, i), lat_steps, bvs[:1])
@@ -361,7 +364,7 @@ def run_ours(args):
         assert all(v == 1 for v in res), "a timed launch set was rejected"
         launches = sum(b.launch_count() for b in bvs) - launches0
         block_dt.append(dtb)
-    clocks = sampler.summary()
+    clocks = sampler.summary() if sampler is not None else None
     if os.environ.get("H2V_BENCH_DIAG_TIMELINE") and rank == 0 and world == 1:  # (diagnosis only) per-block timeline of 3 sets per context
         cap = 1 << 20
         chk(bv, lib.h2v_debug_timeline_start(local, cap))
