@@ -706,8 +706,13 @@ def cpu_baseline_from_batch(params_bytes, vk_bytes, pb, budget_s=12.0):
     rate, _ = _cpu_rate(co, proofs_np, poff, inst_np, ioff, n0, cores)
     n1 = int(max(n0, min(pb.n, rate * budget_s)))
     rate, secs = _cpu_rate(co, proofs_np, poff, inst_np, ioff, n1, cores)
+    # latency of ONE verify_proof on one core (the shape of BASELINE.json configs[0]; the exact k = 8 fixture case: tools/config1_cpu_latency.py)
+    one = []
+    for _ in range(200):
+        _, s1, _, _ = co.verify_many(proofs_np, poff, inst_np, ioff, 1, "shplonk", "blake2b", True, 1)
+        one.append(s1 * 1e3)
     co.close()
-    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "single_verify_proof_p50_ms_one_core": round(statistics.median(one), 4),
             "sample": f"first {n1} proofs of the timed 4096-proof batch, {secs:.1f} s on {cores} threads; " + CPU_KIND_NOTE}
 
 

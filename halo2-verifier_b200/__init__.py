@@ -126,6 +126,7 @@ def load_library():
                                      ctypes.c_uint64, ctypes.c_uint32, u8p, u8p, ctypes.POINTER(ctypes.c_int)]
     lib.h2v_comm_last_batch_accum.argtypes = [ctypes.c_void_p, u8p]
     lib.h2v_ctx_cache_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.h2v_ctx_vk_lint.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.h2v_ctx_work_model.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
     lib.h2v_batch_upload.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64]
     lib.h2v_batch_upload_shard.argtypes = [ctypes.c_void_p, ctypes.c_uint32, u8p, u64p, u8p, u64p, u8p, ctypes.c_uint64,
@@ -158,7 +159,7 @@ EXPORTED_SYMBOLS = (
     "h2v_batch_upload", "h2v_batch_upload_shard", "h2v_batch_run", "h2v_batch_run_shard", "h2v_batch_run_shard_async", "h2v_flush_l2", "h2v_batch_download", "h2v_last_timings", "h2v_launch_count", "h2v_ctx_stream", "h2v_ctx_set_blocking_sync", "h2v_ctx_set_graphs", "h2v_ctx_create_multi", "h2v_batch_set_fold_groups", "h2v_last_group_verdicts", "h2v_finalize_groups", "h2v_debug_timeline_start", "h2v_debug_timeline_stop",
     "h2v_last_msm_geometry", "h2v_selftest_field", "h2v_calibrate_imad",
     "h2v_attribute_shard_groups", "h2v_batch_set_rlc_key", "h2v_last_rlc_source", "h2v_comm_init", "h2v_comm_connect", "h2v_comm_set_timeout_ms",
-    "h2v_batch_run_shard_exchange", "h2v_verify_shard", "h2v_comm_last_batch_accum", "h2v_ctx_cache_stats", "h2v_ctx_work_model",
+    "h2v_batch_run_shard_exchange", "h2v_verify_shard", "h2v_comm_last_batch_accum", "h2v_ctx_cache_stats", "h2v_ctx_work_model", "h2v_ctx_vk_lint",
 )
 
 COMM_HANDLE_BYTES = 128
@@ -424,6 +425,12 @@ class BatchVerifier:
         out = ctypes.create_string_buffer(128)
         self._check(self.lib.h2v_comm_last_batch_accum(self._ctx, out))
         return out.raw
+
+    def vk_lint(self) -> List[str]:
+        """places where this VK may have been mangled by the reference's own write/read asymmetry (include/h2v.h)"""
+        buf = ctypes.create_string_buffer(1 << 16)
+        n = self.lib.h2v_ctx_vk_lint(self._ctx, buf, len(buf))
+        return [l for l in buf.value.decode().split("\n") if l][:max(n, 0)]
 
     def work_model(self, instance_rows):
         """algorithmic Montgomery multiplications per proof of this plan (include/h2v.h h2v_ctx_work_model)"""

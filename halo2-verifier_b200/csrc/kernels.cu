@@ -16,6 +16,7 @@
 //   (k_pack_partial / k_sum_partials: shards of a multi-GPU batch; k_fold_accum: explicit (L, R), parity hook only)
 //   (k_pp_*           per-proof accumulators / pairings: parity hook and rejection attribution)
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <errno.h>
 #include <stdio.h>
 #include <string.h>
@@ -960,6 +961,13 @@ struct h2v_ctx {
 
 static inline u32 cdiv(u64 a, u32 b) { return (u32)((a + b - 1) / b); }
 
+// NVTX ranges around the host side of every stage (header-only NVTX 3: a no-op unless a profiler is attached).  Under
+// graph replay the stage ranges are seen at capture time; the replay itself shows as "h2v:launch_set".
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 // H2V_TRACE=1: host-side timestamps of the steps of a call on stderr (diagnosis of stalls between contexts)
 static bool trace_on() {
   static const bool on = getenv("H2V_TRACE") != nullptr;
@@ -1454,6 +1462,18 @@ extern "C" int h2v_ctx_work_model(const h2v_ctx* ctx, uint32_t instance_rows, do
   return 0;
 }
 
+int h2v_ctx_vk_lint(const h2v_ctx* ctx, char* report, size_t capacity) {
+  if (!ctx) return -1;
+  std::string all;
+  for (const std::string& f : ctx->info.lint) all += f + "\n";
+  if (report && capacity) {
+    const size_t k = std::min(capacity - 1, all.size());
+    memcpy(report, all.data(), k);
+    report[k] = 0;
+  }
+  return (int)ctx->info.lint.size();
+}
+
 int h2v_batch_set_columns(h2v_ctx* ctx, const uint32_t* inst_ncols, const uint32_t* inst_col_len) {
   if (!ctx) return -1;
   ctx->opt_ncols = inst_ncols;
@@ -1537,6 +1557,7 @@ static cudaError_t ensure_msm_bufs(const MsmGeom& g, h2v_ctx::MsmBufs& B, u32 n_
 static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_off, const u8* instances, const u64* inst_off,
                        const u8* rlc, u64 seed, u64 gbase, u64 gcount) {
   if (!ctx) return -1;
+  NvtxRange nv_("h2v:upload");
   ctx->ran = false;
   const u32 groups = ctx->opt_fold_groups ? ctx->opt_fold_groups : 1;  // gbase / gcount describe ONE fold group (global batch)
   ctx->opt_fold_groups = 0;
@@ -1685,13 +1706,16 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   CKC(cudaMemsetAsync(ctx->mb.hist.p, 0, 4 * ((size_t)nb + 2 * SIZE_BINS), ctx->stream_aux));  // bucket histogram | size histogram | size cursors
   KLAUNCH_P(false, k_rlc_scan, g.G, RLC_NT, 0, ctx->stream_aux, ctx->d_r.as<Fr>(), ctx->gcount, ctx->gbase, g.n, ctx->mb.coef.as<Fr>(), 1u, ctx->gcount, (u64)0);
   CKC(cudaEventRecord(ctx->ev_join, ctx->stream_aux));
+  nvtxRangePushA("h2v:decompress");
   KLAUNCH(k_init, cdiv(n, 128), 128, 0, s, pv, n, ctx->d_inst_off.as<u64>(), ctx->has_ncols ? ctx->d_ncols.as<u32>() : nullptr,
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
   // (one-warp blocks were measured for the two multiplier-bound kernels: no change, 0.300 ms / 0.364 ms alone.  A single
   // batch is 2.6 warps of decompression per SM sub-partition: the quantisation to 3 bounds the kernel at ~86 % of the pipe.)
   KLAUNCH(k_decompress, cdiv((u64)n * hd.n_points, 128), 128, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(),
                                                                 ctx->d_pts.as<G1Affine>(), ctx->d_bad.as<u32>());
+  nvtxRangePop();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[1], s));
+  nvtxRangePushA("h2v:transcript");
   if (hd.hash == HASH_BLAKE2B)
     KLAUNCH((k_transcript<Blake2b>), cdiv(n, 64), 64, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
                                                      ctx->d_inst_off.as<u64>(), ctx->d_pts.as<G1Affine>(), ctx->d_vals.as<Fr>(),
@@ -1700,18 +1724,23 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
     KLAUNCH((k_transcript<Keccak256>), cdiv(n, 64), 64, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
                                                        ctx->d_inst_off.as<u64>(), ctx->d_pts.as<G1Affine>(), ctx->d_vals.as<Fr>(),
                                                        ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
+  nvtxRangePop();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[2], s));
+  nvtxRangePushA("h2v:scalar");
   KLAUNCH(k_scalar, cdiv(n, 64), 64, 0, s, pv, n, ctx->d_inst.as<u8>(), ctx->d_inst_off.as<u64>(),
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_vals.as<Fr>(), ctx->d_scratch.as<Fr>(),
                                       ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_status.as<u32>());
+  nvtxRangePop();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[3], s));
   CKC(cudaStreamWaitEvent(s, ctx->ev_join, 0));
   {
+    NvtxRange nv_("h2v:msm");
     int mrc = enqueue_msm(ctx, g, ctx->mb, s, nullptr, 0);
     if (mrc) return mrc;
   }
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[4], s));
   if (mode & RUN_PAIRING) {
+    NvtxRange nv_("h2v:pairing");
     int prc = launch_pairing(ctx, ctx->mb.wsums.as<G1Jac>(), g.G);
     if (prc) return prc;
   }
@@ -1719,6 +1748,7 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
     KLAUNCH(k_pack_partial, dim3(8, g.G), 256, 0, s, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, g.W[0] + g.W[1], ctx->mb.wsums.as<G1Jac>(), ctx->d_partial_out.as<u8>());
   }
   if (mode & RUN_XCHG) {
+    NvtxRange nv_("h2v:exchange");
     // The one exchange step of a sharded batch, device side (exchange.cuh): partials -> the root's window over NVLink;
     // root: wait for all ranks, sum in place, pairing checks, verdicts -> every rank's window; every rank: wait for them.
     h2v_ctx::Comm& cm = ctx->comm;
@@ -1777,6 +1807,7 @@ static u64 graph_key(const h2v_ctx* ctx, int mode) {
 // off (per-stage event timings wanted), the direct launches.
 static int run_impl(h2v_ctx* ctx, int mode) {
   if (!ctx || ctx->n == 0) return -1;
+  NvtxRange nv_("h2v:launch_set");
   CKC(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   if (!ctx->use_graphs) {
@@ -1859,6 +1890,7 @@ static int per_proof_accum(h2v_ctx* ctx, u8* accum_host) {
 // own check fails become ST_CONSTRAINT_SYSTEM_FAILURE.  With fold groups and the group verdicts on the device only the
 // rejected groups are looked at.
 static int attribute_impl(h2v_ctx* ctx) {
+  NvtxRange nv_("h2v:attribution");
   CKC(cudaSetDevice(ctx->device));
   trace(ctx, "attr: begins");
   const PlanHeader& hd = ctx->hd;

@@ -214,6 +214,12 @@ u32 append(std::vector<u8>& blob, const std::vector<T>& v) {
 // queries repeat per instance in the reference's interleaving; fixed columns, sigma, the random polynomial and h are shared.
 int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vkb, size_t vk_len, int vk_fmt,
                int multiopen, int hash, std::vector<u8>& blob, PlanInfo& info, std::string& err, u32 m) {
+  // write emits len() of the instance / fixed query lists but read takes exactly one query per column
+  // (plonk/vk.rs:243-251 vs 310-322): with more queries than columns everything after them is read misaligned
+  static const char* const query_hint =
+      "VerifyingKey::write emits every instance / fixed query but ::read takes one per column (plonk/vk.rs:243-251 vs 310-322): "
+      "a constraint system that queries an instance or fixed column at more than one rotation does not survive its own write/read round trip";
+  bool in_vk = false;
   try {
     H2V_REQUIRE(m >= 1 && m <= 16, "circuit instances per proof out of range (1..16)");
     H2V_REQUIRE(multiopen == MO_SHPLONK || multiopen == MO_GWC, "unknown multiopen scheme");
@@ -230,6 +236,7 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
 
     // ---------------- verifying key (vk.rs:76-115)
     Rd r(vkb, vk_len);
+    in_vk = true;
     const u32 k = r.u32_();
     H2V_REQUIRE(!r.fail && k >= 1 && k <= 28, "vk: k out of range");
     H2V_REQUIRE(k == pk, "params.k != vk.k");
@@ -303,6 +310,11 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
           a.in.push_back(read_poly(r));
           a.tab.push_back(read_poly(r));
         }
+        if (m > 1)  // the reference's write emits all inputs, then all tables (lookup.rs:42-47, shuffle.rs:76-81)
+          info.lint.push_back(std::string(pass == 0 ? "lookup " : "shuffle ") + std::to_string(i) + " has " + std::to_string(m) +
+                              " expression pairs: VerifyingKey::write emits [inputs..., tables...] but VerifyingKey::read takes (input, table) pairs interleaved (" +
+                              (pass == 0 ? "plonk/lookup.rs:42-47 vs 58-61" : "plonk/shuffle.rs:76-81 vs 92-95") +
+                              "); this plan follows `read`, so bytes that came from `write` pair the wrong expressions");
         (pass == 0 ? lookups : shuffles).push_back(a);
       }
     }
@@ -314,6 +326,20 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
       H2V_REQUIRE(r.take((size_t)num_selectors * ((((size_t)1 << k) + 7) / 8)), "truncated selectors");
     Fr transcript_repr = read_fr(r, vk_fmt);
     H2V_REQUIRE(!r.fail, "truncated vk");
+    {
+      // symptoms of that misalignment that survive as a "successful" parse: a column queried twice among the first
+      // `columns` entries, bytes left over after transcript_repr (a failed parse gets the hint appended to its message)
+      auto dup = [](const std::vector<std::pair<u32, int32_t>>& q) {
+        for (size_t a = 0; a < q.size(); a++)
+          for (size_t b = a + 1; b < q.size(); b++)
+            if (q[a].first == q[b].first) return true;
+        return false;
+      };
+      if (dup(instance_queries) || dup(fixed_queries))
+        info.lint.push_back(std::string("an instance / fixed column appears twice among the per-column queries: ") + query_hint);
+      if (r.pos < vk_len) info.lint.push_back(std::to_string(vk_len - r.pos) + " bytes follow transcript_repr: " + query_hint);
+    }
+    in_vk = false;
 
     // ---------------- validation of what verify_proof would index
     const u32 A = (u32)advice_queries.size(), F = (u32)fixed_queries.size(), I = (u32)instance_queries.size();
@@ -769,6 +795,7 @@ int build_plan(const u8* params, size_t params_len, int params_fmt, const u8* vk
     return 0;
   } catch (const Err& e) {
     err = e.msg;
+    if (in_vk) err += std::string(" (if these bytes came from VerifyingKey::write: ") + query_hint + ")";
     return -1;
   }
 }

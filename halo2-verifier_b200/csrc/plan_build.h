@@ -19,6 +19,9 @@ struct PlanInfo {
   // G2 arguments of the pairing check as raw Montgomery limbs (x.c0 | x.c1 | y.c0 | y.c1):
   // q_left = [s]G2 (pairs with the left accumulator), q_right = -G2   (msm.rs:186-199)
   u32 q_left[32], q_right[32];
+  // VK lint (h2v_ctx_vk_lint): places where the reference's own VerifyingKey::write and ::read disagree, so that bytes
+  // produced by `write` would be read into a DIFFERENT constraint system than the one written
+  std::vector<std::string> lint;
 };
 
 // circuit_instances: how many circuit instances one proof transcript carries (`instances.len()` of verify_proof; 1 in

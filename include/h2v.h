@@ -67,6 +67,15 @@ const char* h2v_last_error(const h2v_ctx* ctx);
  * instance columns, shared MSM bases (fixed | sigma | G), multi-open points */
 int h2v_ctx_info(const h2v_ctx* ctx, uint32_t* out8);
 
+/* VK lint.  The reference's VerifyingKey::write and ::read disagree in three places: lookups and
+ * shuffles with more than one expression pair are written [inputs..., tables...] but read as interleaved pairs
+ * (plonk/lookup.rs:42-47 vs 58-61, plonk/shuffle.rs:76-81 vs 92-95), and `write` emits every instance / fixed query while
+ * `read` takes exactly one per column (plonk/vk.rs:243-251 vs 310-322).  This library parses what `read` reads, i.e. it
+ * builds the constraint system the reference's verifier would verify against; bytes that came out of `write` for such a
+ * circuit describe a different one.  The lint reports every place of the VK of this context where that can have happened
+ * (one line per finding, NUL-terminated, truncated to `capacity`); returns the number of findings. */
+int h2v_ctx_vk_lint(const h2v_ctx* ctx, char* report, size_t capacity);
+
 /* verify_proof with SingleStrategy (lib.rs:33-46, strategy.rs:164-176) for one proof.
  * instances: n_inst 32-byte little-endian canonical Fr values, columns concatenated. */
 int h2v_verify_proof(h2v_ctx* ctx, const uint8_t* proof, size_t proof_len, const uint8_t* instances,

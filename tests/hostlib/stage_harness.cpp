@@ -9,12 +9,17 @@ using namespace h2v;
 static std::vector<u8> g_blob; static PlanInfo g_info; static std::string g_err;
 extern "C" {
 int s_build(const u8* params, size_t pl, int pf, const u8* vk, size_t vl, int vf, int mo, int hash) {
+  g_info.lint.clear();
   return build_plan(params, pl, pf, vk, vl, vf, mo, hash, g_blob, g_info, g_err);
 }
 int s_build_m(const u8* params, size_t pl, int pf, const u8* vk, size_t vl, int vf, int mo, int hash, u32 circuit_instances) {
+  g_info.lint.clear();
   return build_plan(params, pl, pf, vk, vl, vf, mo, hash, g_blob, g_info, g_err, circuit_instances);
 }
 const char* s_err() { return g_err.c_str(); }
+// VK lint findings of the last successful s_build (PlanInfo::lint), newline-separated
+static std::string g_lint;
+const char* s_lint() { g_lint.clear(); for (auto& f : g_info.lint) g_lint += f + "\n"; return g_lint.c_str(); }
 void s_info(u32* out) { memcpy(out, &g_info, 8 * sizeof(u32)); }
 // returns status; outputs canonical LE: challenges [C][32], right [P][32], shared [Sh][32], left [n_mo][32],
 // L,R affine canonical x|y (zeros = identity) and verdict of the pairing in *pair_ok

@@ -233,6 +233,25 @@ def test_plan_compiler_rejects_malformed_vk(stage):
     assert stage.s_build(p10, len(p10), 0, vb, len(vb), 1, 0, 0) != 0  # params.k != vk.k
 
 
+def test_vk_lint_reports_the_reference_write_read_asymmetries(stage):
+    """lookups with several expression pairs (write: inputs then tables; read: interleaved,
+    plonk/lookup.rs:42-61) and query lists longer than the column counts (plonk/vk.rs:243-251 vs 310-322) are reported, a
+    VK without them is clean."""
+    stage.s_lint.restype = ctypes.c_char_p
+    params, vk, _dl, _s = setup("vm", 8)
+    pb, vb = params.to_bytes(), vk.to_bytes(F.RAW_BYTES)
+    assert stage.s_build(pb, len(pb), 0, vb, len(vb), 1, 0, 0) == 0 and stage.s_lint() == b""
+    vb2 = vb + b"\x00" * 12  # what a longer fixed-query list leaves behind after a misaligned but "successful" read
+    assert stage.s_build(pb, len(pb), 0, vb2, len(vb2), 1, 0, 0) == 0
+    assert b"12 bytes follow transcript_repr" in stage.s_lint() and b"vk.rs:243-251" in stage.s_lint()
+    params, vk, _dl, _s = setup("k18", 18)  # 8 lookups with 2 expression pairs each
+    pb, vb = params.to_bytes(), vk.to_bytes(F.RAW_BYTES)
+    assert stage.s_build(pb, len(pb), 0, vb, len(vb), 1, 0, 0) == 0
+    lint = stage.s_lint().decode().splitlines()
+    assert len(lint) == 8 and all("expression pairs" in l and "lookup.rs:42-47 vs 58-61" in l for l in lint)
+    assert stage.s_build(pb, len(pb), 0, vb[:-40], len(vb) - 40, 1, 0, 0) != 0 and b"VerifyingKey::write" in stage.s_err()
+
+
 # ---- cooperative Fq12 engine (pairing_cta.cuh), lanes emulated on the host
 def F12L(x):
     return (ctypes.c_uint32 * 96)(*sum([[(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)] for c in x for v in c], []))
