@@ -597,6 +597,80 @@ struct alignas(16) Fp {  // 16-byte alignment: element loads / stores vectorise 
     e[0] -= 2;  // neither modulus has low limb < 2
     return pow_limbs(e);
   }
+  // The same inverse (it is unique, so the result is bit-identical to inv()) by the binary extended Euclid in Kaliski's
+  // Montgomery-inverse form: shifts, additions and subtractions on 256-bit integers instead of ~310 dependent Montgomery
+  // multiplications.  On the GPU that is ~35 k ALU instructions off the multiply pipe instead of ~55 k on it, and a
+  // several times shorter dependent chain: it is what bounds the latency of the scalar stage (one inversion per proof).
+  // Written without data-dependent branches inside an iteration so that the lanes of a warp stay converged; the
+  // iteration COUNT is data dependent (254..508, then 512 - k doublings): a warp runs as long as its slowest lane.
+  //   phase 1: u = p, v = a, r = 0, s = 1; while v > 0: halve the even one of (u, v) - or the larger one minus the
+  //            smaller when both are odd - and double the cofactor of the other; ends with r = -a^-1 2^k mod p
+  //   phase 2: a^-1 2^k  ->  a^-1 2^512 = (aR)^-1 R^2 by 512 - k modular doublings.   inv_bin(0) = 0.
+  H2V_HDN Fp inv_bin() const {
+    u32 u[8], v[8], r[8], s[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      u[i] = P::mod(i);
+      v[i] = l[i];
+      r[i] = 0;
+      s[i] = 0;
+    }
+    s[0] = 1;
+    if (is_zero()) return zero();
+    u32 k = 0;
+    for (;;) {
+      u32 nz = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) nz |= v[i];
+      if (!nz) break;
+      u32 d[8], e[8];
+      sub_raw(d, u, v);
+      const u32 gt = sub_raw(e, v, u);  // borrow of v - u: u > v (u == v, the last step, goes to side B: v becomes 0)
+      const bool u_even = !(u[0] & 1), v_even = !(v[0] & 1);
+      // side A touches (u, s doubles, r grows), side B touches (v, r doubles, s grows)
+      const bool side_a = u_even || (!v_even && gt);
+      const bool subtract = !u_even && !v_even;  // both odd: the larger one minus the smaller one
+      u32 x[8], g[8];                            // x: the value to halve; g: cofactor sum r + s
+#pragma unroll
+      for (int i = 0; i < 8; i++) x[i] = side_a ? (subtract ? d[i] : u[i]) : (subtract ? e[i] : v[i]);
+      add_raw(g, r, s);  // r, s <= 2p - 1 < 2^255: no carry
+#pragma unroll
+      for (int i = 0; i < 7; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+      x[7] >>= 1;
+      u32 grow[8], dbl[8];  // the cofactor that takes the sum (or stays), the one that doubles
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        grow[i] = subtract ? g[i] : (side_a ? r[i] : s[i]);
+        dbl[i] = side_a ? s[i] : r[i];
+      }
+#pragma unroll
+      for (int i = 7; i > 0; i--) dbl[i] = (dbl[i] << 1) | (dbl[i - 1] >> 31);
+      dbl[0] <<= 1;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (side_a) {
+          u[i] = x[i];
+          r[i] = grow[i];
+          s[i] = dbl[i];
+        } else {
+          v[i] = x[i];
+          s[i] = grow[i];
+          r[i] = dbl[i];
+        }
+      }
+      k++;
+    }
+    Fp m, out;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      m.l[i] = P::mod(i);
+      out.l[i] = r[i];
+    }
+    out.cond_sub_mod();                 // r < 2p
+    sub_raw(out.l, m.l, out.l);         // a^-1 2^k = p - r   (r != 0 since gcd(a, p) = 1)
+    for (u32 i = k; i < 512; i++) out = out.dbl();
+    return out;
+  }
 };
 
 typedef Fp<FqP> Fq;

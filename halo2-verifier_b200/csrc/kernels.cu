@@ -1414,7 +1414,7 @@ static double scalar_stage_mm(const std::vector<u8>& blob, u32 rows) {
   const u32 nl = hd.blinding + 2;
   const u32 li = hd.n_inst_q ? hd.inst_max_rot + rows + hd.inst_min_rot_abs : 0;
   mm += 3 + nl + pow_cost(hd.inst_max_rot) + 2.0 * li;  // prefix products
-  mm += 252 + 57;                                       // the one Fermat inversion (5-bit sliding window)
+  // (the one inversion per proof runs as a binary Euclid on the ALU pipe, Fp::inv_bin: no Montgomery multiplications)
   mm += 5.0 * li + 2.0 * rows * hd.n_inst_q;            // instance Lagrange walk + inner products (from_canonical + multiply)
   mm += 4.0 * nl + 4;                                   // l_last / l_blind / l_0, the three unbatched inverses
   const ExprOp* eops = pv.sec<ExprOp>(hd.off_exprops);

@@ -5,16 +5,16 @@
 #include <string.h>
 using namespace h2v;
 extern "C" {
-// op: 0 mul, 1 add, 2 sub, 3 inv, 4 to_canonical, 5 from_canonical, 6 sqrt-candidate ; field: 0 Fq, 1 Fr
+// op: 0 mul, 1 add, 2 sub, 3 inv, 4 to_canonical, 5 from_canonical, 6 sqrt-candidate, 7 inv by the binary Euclid ; field: 0 Fq, 1 Fr
 void t_field(int field, int op, const u32* a, const u32* b, u32* out) {
   if (field == 0) {
     Fq x, y, r; memcpy(x.l, a, 32); memcpy(y.l, b, 32);
-    switch (op) { case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.inv(); break;
+    switch (op) { case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.inv(); break; case 7: r = x.inv_bin(); break;
       case 4: r = x.to_canonical(); break; case 5: r = Fq::from_canonical(x); break; default: r = fq_sqrt_candidate(x); }
     memcpy(out, r.l, 32);
   } else {
     Fr x, y, r; memcpy(x.l, a, 32); memcpy(y.l, b, 32);
-    switch (op) { case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.inv(); break;
+    switch (op) { case 0: r = x * y; break; case 1: r = x + y; break; case 2: r = x - y; break; case 3: r = x.inv(); break; case 7: r = x.inv_bin(); break;
       case 4: r = x.to_canonical(); break; default: r = Fr::from_canonical(x); }
     memcpy(out, r.l, 32);
   }

@@ -62,6 +62,13 @@ def test_montgomery_fields(prim):
             x = rng.randrange(1, mod)
             out = (ctypes.c_uint32 * 8)()
             prim.t_field(field, 3, L(x * M % mod), L(0), out); assert I(out) == pow(x, -1, mod) * M % mod
+        # the binary-Euclid Montgomery inverse used by the scalar stage: the same element as Fermat's, on random and edge inputs
+        for t in range(300):
+            x = [1, 2, mod - 1, mod - 2, (mod + 1) // 2, 1 << 253, (1 << 253) - 1, 3][t] if t < 8 else rng.randrange(1, mod)
+            out = (ctypes.c_uint32 * 8)()
+            prim.t_field(field, 7, L(x * M % mod), L(0), out); assert I(out) == pow(x, -1, mod) * M % mod, hex(x)
+        out = (ctypes.c_uint32 * 8)()
+        prim.t_field(field, 7, L(0), L(0), out); assert I(out) == 0
     for _ in range(10):
         d = rng.randbytes(64)
         out = (ctypes.c_uint32 * 8)()
