@@ -411,12 +411,14 @@ def test_graph_replay_equals_direct_launches(pkg):
     bad[2], _ = sim.corrupt(proofs[2], vk, list(sim.CORRUPTIONS)[0], rng, "shplonk")
     with make_bv(pkg, params, vk, "shplonk", "blake2b") as bv:
         runs = {}
-        for graphs in (True, False, True):
-            bv.set_graphs(graphs)
+        # mode word of h2v_ctx_set_graphs: bit 0 = graph replay, bit 1 = programmatic dependent launch (default off)
+        for mode in (1, 0, 1, 3, 2):
+            graphs = bool(mode & 1)
+            bv._check(bv.lib.h2v_ctx_set_graphs(bv._ctx, mode))
             for name, pr, n in (("all", proofs, 9), ("bad", bad, 9), ("short", proofs, 5), ("all2", proofs, 9)):
                 res = bv.verify_batch(pr[:n], [i[0] for i in instances[:n]], rlc_scalars=rs[:n], want_challenges=True, want_accum=True, want_batch_accum=True)
                 got = (res.verdict, tuple(res.status), bytes(res.challenges), bytes(res.accum), bytes(res.batch_accum))
-                assert runs.setdefault(name, got) == got, (name, graphs)
+                assert runs.setdefault(name, got) == got, (name, mode)
                 t = bv.timings()
                 assert t["total"] > 0 and (t["scalar"] > 0) == (not graphs)
         assert runs["all"][0] and not runs["bad"][0] and runs["bad"][1][2] != 0 and runs["all"] == runs["all2"]
