@@ -187,7 +187,9 @@ def run_ours(args):
     strong = cfg["scaling"] == "strong"
     if strong:  # one global batch per fold group, every rank holds 1 / world of it
         assert args.batch % world == 0
-        n, G = args.batch // world, 1
+        n = args.batch // world
+        # small shards (8 GPUs: 8192 proofs) do not fill a GPU: several global batches then share a launch set
+        G = args.fold_groups if args.fold_groups > 1 else max(1, min(8, 32768 // n))
     else:
         n, G = args.batch, max(1, args.fold_groups)
     gcount, gbase = n * world, n * rank  # of ONE global batch
@@ -813,7 +815,7 @@ def main():
     if args.streams <= 0:
         args.streams = 4
     if args.fold_groups <= 0:
-        args.fold_groups = 16 if args.config == 2 else (8 if args.config == 4 else 1)
+        args.fold_groups = 16 if args.config == 2 else (8 if args.config == 4 else 0)
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
     sys.stdout.flush()
     if out is not None:
