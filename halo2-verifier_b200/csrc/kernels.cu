@@ -40,8 +40,10 @@
 using namespace h2v;
 
 // Minimum resident blocks per SM of the latency-bound per-proof kernels (a register cap).  Measured on B200 with
-// 16 batches in flight: capping k_scalar at 128 / 96 / 64 and k_transcript at 80 / 64 registers spills almost
-// nothing but leaves the throughput unchanged (5.0 M proofs/s) and costs 5-10 % of their solo latency: left uncapped.
+// 16 batches in flight (round 1): capping k_scalar at 128 / 96 / 64 and k_transcript at 80 / 64 registers spills almost
+// nothing but leaves the throughput unchanged (5.0 M proofs/s) and costs 5-10 % of their solo latency; measured again in
+// round 2 with 4 contexts x 16 fold groups (k_transcript 128 registers, k_scalar 128): 6.08 M against 6.13 M proofs/s
+// uncapped.  Left uncapped.
 #ifndef H2V_TRANSCRIPT_MINB
 #define H2V_TRANSCRIPT_MINB 1
 #endif
@@ -89,19 +91,21 @@ __global__ void k_init(PlanView pv, u32 n, const u64* inst_off, const u32* ncols
 __global__ void __launch_bounds__(128) k_decompress(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, G1Affine* pts, u32* bad) {
   pdl_prologue();
   TlScope tl_(1, pts);
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   const PlanHeader& hd = pv.h();
-  if (t >= n * hd.n_points) return;
-  const u32 j = t % n, slot = t / n;
-  const u64 off = proof_off[j];
-  const u32 len = (u32)(proof_off[j + 1] - off);
-  G1Affine p;
-  if (!decompress_stage(pv, proofs + off, len, slot, p)) {
-    p.x = Fq::zero();
-    p.y = Fq::zero();
-    atomicMin(&bad[j], pv.sec<u32>(hd.off_pt_item)[slot]);
+  // grid-stride: the grid may be capped below the work (wide_grid) so that this multiplier-bound kernel leaves block
+  // slots on every SM to the latency-bound kernels of the other contexts in flight
+  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < n * hd.n_points; t += gridDim.x * blockDim.x) {
+    const u32 j = t % n, slot = t / n;
+    const u64 off = proof_off[j];
+    const u32 len = (u32)(proof_off[j + 1] - off);
+    G1Affine p;
+    if (!decompress_stage(pv, proofs + off, len, slot, p)) {
+      p.x = Fq::zero();
+      p.y = Fq::zero();
+      atomicMin(&bad[j], pv.sec<u32>(hd.off_pt_item)[slot]);
+    }
+    pts[t] = p;
   }
-  pts[t] = p;
 }
 
 template <class H>
@@ -425,16 +429,16 @@ __global__ void __launch_bounds__(128) k_msm_bucket_sum(MsmGeom g, u32 nb, const
                                                         const G1Affine* pts, const G1Affine* shared_pts, G1Jac* buckets) {
   pdl_prologue();
   TlScope tl_(6, pts);
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nb) return;
-  const u32 b = order[t];
-  G1Jac acc = G1Jac::identity();
-  const u32 e0 = off[b], e1 = off[b + 1];
-  for (u32 e = e0; e < e1; e++) {
-    const u32 ent = sorted[e];
-    acc = g1_add_mixed(acc, msm_point(g, ent & 0x7FFFFFFFu, pts, shared_pts), (ent >> 31) != 0);
+  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < nb; t += gridDim.x * blockDim.x) {  // grid-stride, see k_decompress
+    const u32 b = order[t];
+    G1Jac acc = G1Jac::identity();
+    const u32 e0 = off[b], e1 = off[b + 1];
+    for (u32 e = e0; e < e1; e++) {
+      const u32 ent = sorted[e];
+      acc = g1_add_mixed(acc, msm_point(g, ent & 0x7FFFFFFFu, pts, shared_pts), (ent >> 31) != 0);
+    }
+    buckets[b] = acc;
   }
-  buckets[b] = acc;
 }
 
 __device__ G1Jac g1_mul_small(const G1Jac& p, u32 k) {
@@ -978,6 +982,21 @@ static void trace(const h2v_ctx* ctx, const char* what) {
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
   fprintf(stderr, "[h2v %p %ld.%06ld] %s\n", (const void*)ctx, (long)(ts.tv_sec % 1000), ts.tv_nsec / 1000, what);
+}
+
+// Grid of a multiplier-bound kernel (k_decompress, k_msm_bucket_sum): at most H2V_WIDE_BLOCKS_PER_SM blocks per SM (0 = one
+// block per 128 work items, the uncapped grid).  See the comment in k_decompress.
+static u32 wide_grid(u64 items, u32 dflt_per_sm) {
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  static const int env = getenv("H2V_WIDE_BLOCKS_PER_SM") ? atoi(getenv("H2V_WIDE_BLOCKS_PER_SM")) : -1;
+  const u32 per_sm = env >= 0 ? (u32)env : dflt_per_sm;
+  const u32 full = cdiv(items, 128);
+  return per_sm ? std::min<u32>(full, (u32)sms * per_sm) : full;
 }
 
 // `len` bytes from the kernel's CSPRNG; 0 on success
@@ -1530,7 +1549,7 @@ static int enqueue_msm(h2v_ctx* ctx, const MsmGeom& g, h2v_ctx::MsmBufs& B, cuda
   KLAUNCH(k_scan_apply, n_tiles, SCAN_NT, 0, s, nb, n_tiles, B.tiles.as<u32>(), B.off.as<u32>(), B.cursor.as<u32>());
   KLAUNCH(k_bucket_order, n_tiles, SCAN_NT, 0, s, nb, B.hist.as<u32>(), B.hist.as<u32>() + nb, B.hist.as<u32>() + nb + SIZE_BINS, B.order.as<u32>());
   KLAUNCH(k_msm_scatter, std::min<u32>(cdiv((u64)g.G * g.T * g.Wmax, 256), 148 * 16), 256, 0, s, g, B.dig.as<int16_t>(), B.cursor.as<u32>(), B.sorted.as<u32>());
-  KLAUNCH(k_msm_bucket_sum, cdiv(nb, 128), 128, 0, s, g, nb, B.off.as<u32>(), B.order.as<u32>(), B.sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
+  KLAUNCH(k_msm_bucket_sum, wide_grid(nb, 0), 128, 0, s, g, nb, B.off.as<u32>(), B.order.as<u32>(), B.sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
           pv.sec<G1Affine>(hd.off_shared_pts), B.buckets.as<G1Jac>());
   KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, B.buckets.as<G1Jac>(), B.partials_msm.as<G1Jac>());
   KLAUNCH(k_msm_window_reduce, (g.W[0] + g.W[1]) * g.G, 128, 0, s, g, B.partials_msm.as<G1Jac>(), B.wsums.as<G1Jac>());
@@ -1711,7 +1730,7 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
   // (one-warp blocks were measured for the two multiplier-bound kernels: no change, 0.300 ms / 0.364 ms alone.  A single
   // batch is 2.6 warps of decompression per SM sub-partition: the quantisation to 3 bounds the kernel at ~86 % of the pipe.)
-  KLAUNCH(k_decompress, cdiv((u64)n * hd.n_points, 128), 128, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(),
+  KLAUNCH(k_decompress, wide_grid((u64)n * hd.n_points, 0), 128, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(),
                                                                 ctx->d_pts.as<G1Affine>(), ctx->d_bad.as<u32>());
   nvtxRangePop();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[1], s));
