@@ -522,6 +522,34 @@ __global__ void __launch_bounds__(32) k_fold_accum(FoldArgs fa, const G1Jac* win
   store_affine_bytes(a, id, acc_bytes + 64 * (t == 0 ? 1 : 0));
 }
 
+// Partial window combination before the pairing: the windows of a channel are combined in runs of `run` consecutive
+// windows, T_v = sum_{i < run} 2^(c i) S_(run v + i)  ((run - 1) c dependent doublings, thread per (fold group, run)), and
+// the pairing check then pairs T_v with the prepared lines of [2^(c run v)] Q.  With run = 4 the line products of
+// k_lines - the stage's dominant cost: shared-memory bound Fq12 products, one per (pair, Miller line) - drop by 4x for
+// ~40 doublings of latency; the full combination (one point per channel) would put ~260 dependent doublings in front of
+// the pairing, no combination costs 53 pairs x 102 lines.
+struct GroupArgs {
+  u32 W[2], c[2], wbase[2];  // window sums per channel (in)
+  u32 P[2], pbase[2];        // pairs per channel (out)
+  u32 run;
+};
+__global__ void __launch_bounds__(64) k_window_group(GroupArgs ga, u32 groups, const G1Jac* __restrict__ wsums, G1Jac* __restrict__ out) {
+  pdl_prologue();
+  const u32 np = ga.P[0] + ga.P[1];
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= groups * np) return;
+  const u32 grp = t / np, p = t % np;
+  const u32 ch = p >= ga.pbase[1] ? 1u : 0u, v = p - ga.pbase[ch];
+  const G1Jac* ws = wsums + (size_t)grp * (ga.W[0] + ga.W[1]) + ga.wbase[ch];
+  const u32 w0 = v * ga.run, w1 = w0 + ga.run < ga.W[ch] ? w0 + ga.run : ga.W[ch];
+  G1Jac acc = ws[w1 - 1];
+  for (u32 w = w1 - 1; w-- > w0;) {
+    for (u32 i = 0; i < ga.c[ch]; i++) g1_double_inl(acc);
+    acc = g1_add(acc, ws[w]);
+  }
+  out[t] = acc;
+}
+
 // ---- partial accumulators of a shard: header + the Jacobian window sums (Montgomery limbs)
 struct PartialHeader {
   u32 magic, cbits, windows, n_pts, rsv[4];
@@ -933,12 +961,12 @@ struct h2v_ctx {
   } mb, ab;
   DevBuf d_plan, d_proofs, d_proof_off, d_inst, d_inst_off, d_ncols, d_col_len, d_pts, d_bad, d_status, d_vals, d_scratch, d_right,
       d_shared, d_left, d_rlc_bytes, d_r, d_acc_bytes, d_verdict, d_partials, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush, d_M, d_partial_out,
-      d_wsums_fin, d_sub_pairs, d_sub_verdict, d_sub_M;
+      d_wsums_fin, d_sub_pairs, d_sub_verdict, d_sub_M, d_gsums;
   const G2Line* d_lines() const { return lines_cur >= 0 ? lines[lines_cur].buf.as<G2Line>() : nullptr; }
   std::vector<DevBuf*> all_bufs() {
     std::vector<DevBuf*> v = {&d_plan, &d_proofs, &d_proof_off, &d_inst, &d_inst_off, &d_ncols, &d_col_len, &d_pts, &d_bad, &d_status, &d_vals, &d_scratch,
                               &d_right, &d_shared, &d_left, &d_rlc_bytes, &d_r, &d_acc_bytes, &d_verdict, &d_partials, &d_pp_prod, &d_pp_lr, &d_pp_bytes,
-                              &d_hook, &d_chal, &d_flush, &d_M, &d_partial_out, &d_wsums_fin, &d_sub_pairs, &d_sub_verdict, &d_sub_M,
+                              &d_hook, &d_chal, &d_flush, &d_M, &d_partial_out, &d_wsums_fin, &d_sub_pairs, &d_sub_verdict, &d_sub_M, &d_gsums,
                               &lines[0].buf, &lines[1].buf, &lines[2].buf, &lines[3].buf};
     for (MsmBufs* m : {&mb, &ab})
       for (DevBuf* d : {&m->coef, &m->shared_sum, &m->dig, &m->hist, &m->off, &m->cursor, &m->order, &m->sorted, &m->buckets, &m->wsums, &m->partials_msm, &m->tiles})
@@ -1124,7 +1152,28 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom, u32 groups =
 
 static constexpr int LINES_GROUPS = 8;
 
-static u64 lines_key_of(const MsmGeom& g) { return (u64)g.c[0] | (u64)g.W[0] << 8 | (u64)g.c[1] << 16 | (u64)g.W[1] << 24; }
+// Run length of the partial window combination (k_window_group).  Measured on B200 (4096-proof VM batches): one batch alone
+// 2.57 ms with runs of 1 or 2, 2.62 with 4, 2.77 with 8 (the doubling chain sits on the critical path); 4 x 16 batches in
+// flight 6.15 / 6.27 / 6.33 / 6.42 M proofs/s (the line products are throughput).  Hence 2 for a single batch, 8 for launch
+// sets of several fold groups; H2V_LINE_RUN / H2V_LINE_RUN_GROUPS override (1 = pair every window).
+static u32 line_run(u32 groups) {
+  static const int e1 = getenv("H2V_LINE_RUN") ? atoi(getenv("H2V_LINE_RUN")) : 0;
+  static const int eg = getenv("H2V_LINE_RUN_GROUPS") ? atoi(getenv("H2V_LINE_RUN_GROUPS")) : 0;
+  const int v = groups > 1 ? (eg ? eg : e1 ? e1 : 8) : (e1 ? e1 : 2);
+  return (u32)(v >= 1 && v <= 64 ? v : 2);
+}
+// the (channel, run) pairs the pairing check sees for the window geometry of g: c' = c * run, P = ceil(W / run)
+static MsmGeom pair_geom(const MsmGeom& g, u32 groups) {
+  MsmGeom q{};
+  const u32 run = line_run(groups);
+  for (int ch = 0; ch < 2; ch++) {
+    q.c[ch] = g.c[ch] * run;
+    q.W[ch] = (g.W[ch] + run - 1) / run;
+  }
+  q.wbase[1] = q.W[0];
+  return q;
+}
+static u64 lines_key_of(const MsmGeom& g) { return (u64)g.c[0] | (u64)g.W[0] << 12 | (u64)g.c[1] << 24 | (u64)g.W[1] << 36; }
 
 // Prepared Miller lines of [2^(c w)] Q for the current window geometry (host: G2Prepared-style
 // preparation, once per geometry; the last few geometries stay cached in the context).
@@ -1162,14 +1211,22 @@ static int ensure_lines(h2v_ctx* ctx, const MsmGeom& g, int* slot_out) {
   ctx->lines_builds++;
   return 0;
 }
-static int ensure_lines(h2v_ctx* ctx) { return ensure_lines(ctx, ctx->geom, &ctx->lines_cur); }
+static int ensure_lines(h2v_ctx* ctx, u32 groups) { return ensure_lines(ctx, pair_geom(ctx->geom, groups), &ctx->lines_cur); }
 
 // the batch pairing check over `wsums` (W0 + W1 Jacobian window sums per group) -> d_verdict[group]
 static int launch_pairing(h2v_ctx* ctx, const G1Jac* wsums, u32 groups) {
   const MsmGeom& g = ctx->geom;
+  const MsmGeom q = pair_geom(g, groups);
   cudaStream_t s = ctx->stream;
   const PairSkip none{nullptr, nullptr, 1, 0};
-  KLAUNCH((k_lines<LINES_GROUPS>), dim3(H2V_ATE_ITERS, groups), 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s, LinesArgs{g.W[0] + g.W[1]}, wsums, ctx->d_lines(),
+  const u32 np = q.W[0] + q.W[1];
+  const G1Jac* pairs = wsums;
+  if (line_run(groups) > 1) {
+    GroupArgs ga{{g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {0, g.W[0]}, {q.W[0], q.W[1]}, {0, q.W[0]}, line_run(groups)};
+    KLAUNCH(k_window_group, cdiv((u64)groups * np, 64), 64, 0, s, ga, groups, wsums, ctx->d_gsums.as<G1Jac>());
+    pairs = ctx->d_gsums.as<G1Jac>();
+  }
+  KLAUNCH((k_lines<LINES_GROUPS>), dim3(H2V_ATE_ITERS, groups), 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s, LinesArgs{np}, pairs, ctx->d_lines(),
                                                                                        ctx->d_M.as<E12>(), none);
   KLAUNCH(k_pairing_check, groups, 128, 0, s, ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>(), none);
   return 0;
@@ -1240,6 +1297,7 @@ static cudaError_t preload_kernels() {
   H2V_PRELOAD(k_msm_chunk_reduce);
   H2V_PRELOAD(k_msm_window_reduce);
   H2V_PRELOAD(k_fold_accum);
+  H2V_PRELOAD(k_window_group);
   H2V_PRELOAD(k_pack_partial);
   H2V_PRELOAD(k_sum_partials);
   H2V_PRELOAD(k_pp_mul);
@@ -1631,7 +1689,7 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   const MsmGeom& g = ctx->geom;
   const u32 nb = g.nb() * g.G;  // buckets of all fold groups
   {
-    int lrc = ensure_lines(ctx);
+    int lrc = ensure_lines(ctx, groups);
     if (lrc) return lrc;
   }
   trace(ctx, "lines ready");
@@ -1650,6 +1708,7 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   CKC(ctx->d_r.ensure(32 * (size_t)gcount * groups));
   CKC(ctx->d_partial_out.ensure((size_t)H2V_PARTIAL_BYTES * groups));
   CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
+  CKC(ctx->d_gsums.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
   CKC(ensure_msm_bufs(g, ctx->mb, hd.n_shared));
   CKC(ctx->d_M.ensure(sizeof(E12) * H2V_ATE_ITERS * (size_t)g.G));
   CKC(ctx->d_verdict.ensure(4 * (size_t)g.G + 16));
@@ -1818,6 +1877,7 @@ static u64 graph_key(const h2v_ctx* ctx, int mode) {
                           &ctx->d_M, &ctx->d_partial_out, &ctx->mb.tiles, &ctx->d_wsums_fin};
   for (const DevBuf* b : bufs) mix((u64)(size_t)b->p);
   mix((u64)(size_t)ctx->d_lines());
+  mix((u64)(size_t)ctx->d_gsums.p | (u64)line_run(ctx->geom.G ? ctx->geom.G : 1) << 56);
   mix((u64)(size_t)ctx->comm.window);
   return h | 1;
 }
@@ -2088,8 +2148,9 @@ static int finalize_impl(h2v_ctx* ctx, u32 n_partials, u32 groups, const u8* par
     }
     g.wbase[1] = g.W[0];
   }
+  const int lines_of_batch = ctx->lines_cur;  // the resident batch of this context keeps its own line geometry (restored below)
   {
-    int lrc = ensure_lines(ctx);
+    int lrc = ensure_lines(ctx, groups);
     if (lrc) return lrc;
   }
   const MsmGeom& g = ctx->geom;
@@ -2097,12 +2158,14 @@ static int finalize_impl(h2v_ctx* ctx, u32 n_partials, u32 groups, const u8* par
   CKC(ctx->d_verdict.ensure(4 * (size_t)groups + 16));
   CKC(ctx->d_M.ensure(sizeof(E12) * H2V_ATE_ITERS * (size_t)groups));
   CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
+  CKC(ctx->d_gsums.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
   CKC(cudaMemsetAsync(ctx->d_verdict.p, 0, 4 * (size_t)groups + 16, s));
   ctx->verdicts_on_device = false;  // d_verdict now belongs to the global batches being finalized
   k_sum_partials<<<groups, 128, 0, s>>>(n_partials, g.c[0] | g.c[1] << 16, g.W[0] | g.W[1] << 16, npts, d_parts, (size_t)groups * H2V_PARTIAL_BYTES,
                                         ctx->d_wsums_fin.as<G1Jac>(), ctx->d_verdict.as<u32>() + groups, nullptr, nullptr);
   LAUNCH_CHECK();
   int prc = launch_pairing(ctx, ctx->d_wsums_fin.as<G1Jac>(), groups);
+  if (lines_of_batch >= 0 && ctx->n) ctx->lines_cur = lines_of_batch;
   if (prc) return prc;
   if (batch_accum) {
     FoldArgs fa{{g.W[0], g.W[1]}, {g.c[0], g.c[1]}, {0, g.W[0]}};
