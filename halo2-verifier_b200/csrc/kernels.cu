@@ -88,13 +88,13 @@ __global__ void k_init(PlanView pv, u32 n, const u64* inst_off, const u32* ncols
   status[j] = st;
 }
 
-__global__ void __launch_bounds__(128) k_decompress(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, G1Affine* pts, u32* bad) {
+__global__ void __launch_bounds__(128) k_decompress(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, G1Affine* pts, u32* bad, u32 blk_off, u32 blk_total) {
   pdl_prologue();
   TlScope tl_(1, pts);
   const PlanHeader& hd = pv.h();
   // grid-stride: the grid may be capped below the work (wide_grid) so that this multiplier-bound kernel leaves block
   // slots on every SM to the latency-bound kernels of the other contexts in flight
-  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < n * hd.n_points; t += gridDim.x * blockDim.x) {
+  for (u32 t = (blk_off + blockIdx.x) * blockDim.x + threadIdx.x; t < n * hd.n_points; t += blk_total * blockDim.x) {
     const u32 j = t % n, slot = t / n;
     const u64 off = proof_off[j];
     const u32 len = (u32)(proof_off[j + 1] - off);
@@ -426,10 +426,10 @@ __global__ void __launch_bounds__(256) k_msm_scatter(MsmGeom g, const int16_t* d
 
 // thread per bucket: sum of its (signed) points, Jacobian += affine
 __global__ void __launch_bounds__(128) k_msm_bucket_sum(MsmGeom g, u32 nb, const u32* off, const u32* order, const u32* sorted,
-                                                        const G1Affine* pts, const G1Affine* shared_pts, G1Jac* buckets) {
+                                                        const G1Affine* pts, const G1Affine* shared_pts, G1Jac* buckets, u32 blk_off, u32 blk_total) {
   pdl_prologue();
   TlScope tl_(6, pts);
-  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < nb; t += gridDim.x * blockDim.x) {  // grid-stride, see k_decompress
+  for (u32 t = (blk_off + blockIdx.x) * blockDim.x + threadIdx.x; t < nb; t += blk_total * blockDim.x) {  // grid-stride, see k_decompress
     const u32 b = order[t];
     G1Jac acc = G1Jac::identity();
     const u32 e0 = off[b], e1 = off[b + 1];
@@ -1027,6 +1027,17 @@ static u32 wide_grid(u64 items, u32 dflt_per_sm) {
   return per_sm ? std::min<u32>(full, (u32)sms * per_sm) : full;
 }
 
+// H2V_WIDE_SPLIT = K > 1: a multiplier-bound kernel is launched as K consecutive grids (diagnosis of how kernels of
+// several contexts interleave: the block scheduler serves the oldest grid first)
+static u32 wide_split() {
+  static const u32 k = [] {
+    const char* e = getenv("H2V_WIDE_SPLIT");
+    const int v = e ? atoi(e) : 1;
+    return (u32)(v >= 1 && v <= 64 ? v : 1);
+  }();
+  return k;
+}
+
 // `len` bytes from the kernel's CSPRNG; 0 on success
 static int os_entropy(void* out, size_t len) {
   u8* p = (u8*)out;
@@ -1607,8 +1618,12 @@ static int enqueue_msm(h2v_ctx* ctx, const MsmGeom& g, h2v_ctx::MsmBufs& B, cuda
   KLAUNCH(k_scan_apply, n_tiles, SCAN_NT, 0, s, nb, n_tiles, B.tiles.as<u32>(), B.off.as<u32>(), B.cursor.as<u32>());
   KLAUNCH(k_bucket_order, n_tiles, SCAN_NT, 0, s, nb, B.hist.as<u32>(), B.hist.as<u32>() + nb, B.hist.as<u32>() + nb + SIZE_BINS, B.order.as<u32>());
   KLAUNCH(k_msm_scatter, std::min<u32>(cdiv((u64)g.G * g.T * g.Wmax, 256), 148 * 16), 256, 0, s, g, B.dig.as<int16_t>(), B.cursor.as<u32>(), B.sorted.as<u32>());
-  KLAUNCH(k_msm_bucket_sum, wide_grid(nb, 0), 128, 0, s, g, nb, B.off.as<u32>(), B.order.as<u32>(), B.sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
-          pv.sec<G1Affine>(hd.off_shared_pts), B.buckets.as<G1Jac>());
+  {
+    const u32 total = wide_grid(nb, 0), K = std::min(wide_split(), total), per = cdiv(total, K);
+    for (u32 off = 0; off < total; off += per)
+      KLAUNCH(k_msm_bucket_sum, std::min(per, total - off), 128, 0, s, g, nb, B.off.as<u32>(), B.order.as<u32>(), B.sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
+              pv.sec<G1Affine>(hd.off_shared_pts), B.buckets.as<G1Jac>(), off, total);
+  }
   KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, B.buckets.as<G1Jac>(), B.partials_msm.as<G1Jac>());
   KLAUNCH(k_msm_window_reduce, (g.W[0] + g.W[1]) * g.G, 128, 0, s, g, B.partials_msm.as<G1Jac>(), B.wsums.as<G1Jac>());
   return 0;
@@ -1789,8 +1804,12 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
   // (one-warp blocks were measured for the two multiplier-bound kernels: no change, 0.300 ms / 0.364 ms alone.  A single
   // batch is 2.6 warps of decompression per SM sub-partition: the quantisation to 3 bounds the kernel at ~86 % of the pipe.)
-  KLAUNCH(k_decompress, wide_grid((u64)n * hd.n_points, 0), 128, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(),
-                                                                ctx->d_pts.as<G1Affine>(), ctx->d_bad.as<u32>());
+  {
+    const u32 total = wide_grid((u64)n * hd.n_points, 0), K = std::min(wide_split(), total), per = cdiv(total, K);
+    for (u32 off = 0; off < total; off += per)
+      KLAUNCH(k_decompress, std::min(per, total - off), 128, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_pts.as<G1Affine>(),
+              ctx->d_bad.as<u32>(), off, total);
+  }
   nvtxRangePop();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[1], s));
   nvtxRangePushA("h2v:transcript");
