@@ -340,12 +340,17 @@ static constexpr u32 SIZE_BINS = 1024;
 __device__ __forceinline__ u32 size_bin(u32 count) { return SIZE_BINS - 1 - (count < SIZE_BINS - 1 ? count : SIZE_BINS - 1); }
 __global__ void __launch_bounds__(SCAN_NT) k_scan_tiles(const u32* hist, u32 nb, u32* off, u32* tile_total, u32* size_hist) {
   pdl_prologue();
+  // the bucket sizes of a uniform MSM crowd into a few dozen size bins: the per-bucket global atomics on those few
+  // addresses were 100 us per launch set (ncu, 16 fold groups); the tile counts its bins in shared memory first
+  __shared__ u32 bins[SIZE_BINS];
+  for (u32 i = threadIdx.x; i < SIZE_BINS; i += SCAN_NT) bins[i] = 0;
+  __syncthreads();
   const u32 i0 = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER;
   u32 v[SCAN_PER], sum = 0;
 #pragma unroll
   for (u32 q = 0; q < SCAN_PER; q++) {
     v[q] = i0 + q < nb ? hist[i0 + q] : 0;
-    if (i0 + q < nb) atomicAdd(&size_hist[size_bin(v[q])], 1u);
+    if (i0 + q < nb) atomicAdd(&bins[size_bin(v[q])], 1u);
     sum += v[q];
   }
   u32 total;
@@ -356,6 +361,9 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_tiles(const u32* hist, u32 nb,
     e += v[q];
   }
   if (threadIdx.x == 0) tile_total[blockIdx.x] = total;
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < SIZE_BINS; i += SCAN_NT)
+    if (bins[i]) atomicAdd(&size_hist[i], bins[i]);
 }
 __global__ void __launch_bounds__(SCAN_NT) k_scan_apply(u32 nb, u32 n_tiles, const u32* tile_total, u32* off, u32* cursor) {
   pdl_prologue();
@@ -385,11 +393,13 @@ __global__ void __launch_bounds__(SCAN_NT) k_bucket_order(u32 nb, const u32* his
   pdl_prologue();
   static_assert(SIZE_BINS == SCAN_TILE, "one tile of size bins");
   __shared__ u32 base[SIZE_BINS];
+  __shared__ u32 cnt[SIZE_BINS];  // buckets of this tile per size bin, then the tile's first slot inside the bin
   u32 v[SCAN_PER], sum = 0, total;
 #pragma unroll
   for (u32 q = 0; q < SCAN_PER; q++) {
     v[q] = size_hist[threadIdx.x * SCAN_PER + q];
     sum += v[q];
+    cnt[threadIdx.x * SCAN_PER + q] = 0;
   }
   u32 e = block_excl_scan<SCAN_NT>(sum, &total);
 #pragma unroll
@@ -398,13 +408,28 @@ __global__ void __launch_bounds__(SCAN_NT) k_bucket_order(u32 nb, const u32* his
     e += v[q];
   }
   __syncthreads();
+  // slots inside a bin: first within the tile (shared-memory atomics), then ONE global atomic per (tile, bin) instead
+  // of one per bucket (the buckets crowd into a few dozen bins: 100 us per launch set of 16 fold groups, ncu)
+  u32 bin[SCAN_PER], local[SCAN_PER];
 #pragma unroll
   for (u32 q = 0; q < SCAN_PER; q++) {
     const u32 i = blockIdx.x * SCAN_TILE + q * SCAN_NT + threadIdx.x;
     if (i < nb) {
-      const u32 bin = size_bin(hist[i]);
-      order[base[bin] + atomicAdd(&size_cursor[bin], 1u)] = i;
+      bin[q] = size_bin(hist[i]);
+      local[q] = atomicAdd(&cnt[bin[q]], 1u);
     }
+  }
+  __syncthreads();
+#pragma unroll
+  for (u32 q = 0; q < SCAN_PER; q++) {
+    const u32 b = threadIdx.x * SCAN_PER + q;
+    if (cnt[b]) cnt[b] = atomicAdd(&size_cursor[b], cnt[b]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (u32 q = 0; q < SCAN_PER; q++) {
+    const u32 i = blockIdx.x * SCAN_TILE + q * SCAN_NT + threadIdx.x;
+    if (i < nb) order[base[bin[q]] + cnt[bin[q]] + local[q]] = i;
   }
 }
 
