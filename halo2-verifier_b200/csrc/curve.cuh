@@ -150,7 +150,9 @@ H2V_HDN inline G1Jac g1_mul_canonical(const G1Affine& p, const u32* k) {
 // 32 bytes little-endian x; bit 7 of byte 31 = parity of canonical y; bit 6 must be clear.
 // Returns false for every encoding the reference's read_point rejects (invalid encoding, or the
 // identity, which common_point refuses: transcript/mod.rs:161-163,218-219).
-H2V_HDN inline bool g1_decompress(const u8* b, G1Affine& out) {
+// canon (optional): the CANONICAL coordinates x | y as the transcript absorbs them (transcript/mod.rs:216-224), which fall
+// out of the decompression anyway (x is the input, y's canonical form decides the sign).
+H2V_HDN inline bool g1_decompress(const u8* b, G1Affine& out, Fq* canon = nullptr) {
   Fq x = Fq::load_le(b);
   const bool sign = (x.l[7] >> 31) & 1;
   const bool inf_bit = (x.l[7] >> 30) & 1;
@@ -161,7 +163,19 @@ H2V_HDN inline bool g1_decompress(const u8* b, G1Affine& out) {
   Fq y = fq_sqrt_candidate(rhs);
   if (y.sqr() != rhs) return false;  // also rejects the all-zero string: 3 is a non-residue
   Fq yc = y.to_canonical();
-  if ((bool)(yc.l[0] & 1) != sign) y = y.neg();
+  if ((bool)(yc.l[0] & 1) != sign) {
+    y = y.neg();
+    if (canon) {  // y != 0 here (0 is even: a set sign bit on y = 0 cannot occur since 3 is a non-residue, x^3 + 3 != 0)
+      u32 m[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) m[i] = FqP::mod(i);
+      Fq::sub_raw(yc.l, m, yc.l);
+    }
+  }
+  if (canon) {
+    canon[0] = x;
+    canon[1] = yc;
+  }
   out.x = xm;
   out.y = y;
   return true;

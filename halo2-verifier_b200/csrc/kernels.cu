@@ -36,6 +36,7 @@
 #include "timeline.cuh"
 #include "pairing_cta.cuh"
 #include "exchange.cuh"
+#include "transcript_quad.cuh"
 
 using namespace h2v;
 
@@ -88,7 +89,7 @@ __global__ void k_init(PlanView pv, u32 n, const u64* inst_off, const u32* ncols
   status[j] = st;
 }
 
-__global__ void __launch_bounds__(128) k_decompress(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, G1Affine* pts, u32* bad, u32 blk_off, u32 blk_total) {
+__global__ void __launch_bounds__(128) k_decompress(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, G1Affine* pts, u32* ptsc, u32* bad, u32 blk_off, u32 blk_total) {
   pdl_prologue();
   TlScope tl_(1, pts);
   const PlanHeader& hd = pv.h();
@@ -99,12 +100,22 @@ __global__ void __launch_bounds__(128) k_decompress(PlanView pv, u32 n, const u8
     const u64 off = proof_off[j];
     const u32 len = (u32)(proof_off[j + 1] - off);
     G1Affine p;
-    if (!decompress_stage(pv, proofs + off, len, slot, p)) {
+    Fq canon[2];  // canonical x | y for the quad transcript replay (ptsc == null: not wanted)
+    if (!decompress_stage(pv, proofs + off, len, slot, p, ptsc ? canon : nullptr)) {
       p.x = Fq::zero();
       p.y = Fq::zero();
+      canon[0] = Fq::zero();
+      canon[1] = Fq::zero();
       atomicMin(&bad[j], pv.sec<u32>(hd.off_pt_item)[slot]);
     }
     pts[t] = p;
+    if (ptsc) {
+      uint4* o = (uint4*)(ptsc + 16 * (size_t)t);
+      o[0] = make_uint4(canon[0].l[0], canon[0].l[1], canon[0].l[2], canon[0].l[3]);
+      o[1] = make_uint4(canon[0].l[4], canon[0].l[5], canon[0].l[6], canon[0].l[7]);
+      o[2] = make_uint4(canon[1].l[0], canon[1].l[1], canon[1].l[2], canon[1].l[3]);
+      o[3] = make_uint4(canon[1].l[4], canon[1].l[5], canon[1].l[6], canon[1].l[7]);
+    }
   }
 }
 
@@ -123,6 +134,28 @@ __global__ void __launch_bounds__(64, H2V_TRANSCRIPT_MINB) k_transcript(PlanView
                                     (u32)(inst_off[j + 1] - inst_off[j]), pts, vals, j, n, bad[j], inst_bad);
   if (inst_bad) status[j] = ST_INVALID_INSTANCES;
   else if (b != H2V_NO_BAD_ITEM) status[j] = b < hd.first_mo_item ? ST_TRANSCRIPT : ST_OPENING;
+}
+
+// Blake2b transcripts: four lanes per proof (transcript_quad.cuh)
+__global__ void __launch_bounds__(4 * TQ_PROOFS_PER_BLOCK) k_transcript_quad(PlanView pv, u32 n, const u8* proofs, const u64* proof_off, const u8* inst, const u64* inst_off,
+                                                                             const u32* ptsc, Fr* vals, u32* status, const u32* bad) {
+  pdl_prologue();
+  TlScope tl_(2, ptsc);
+  __shared__ __align__(16) u8 bufs[TQ_PROOFS_PER_BLOCK][128];
+  const u32 j = blockIdx.x * TQ_PROOFS_PER_BLOCK + (threadIdx.x >> 2);
+  if (j >= n) return;                // quad-uniform
+  if (status[j] != ST_OK) return;    // quad-uniform
+  const PlanHeader& hd = pv.h();
+  TqState st;
+  tq_setup(st, bufs[threadIdx.x >> 2]);
+  const u64 off = proof_off[j];
+  bool inst_bad;
+  const u32 b = transcript_quad(pv, proofs + off, (u32)(proof_off[j + 1] - off), inst + 32 * inst_off[j], (u32)(inst_off[j + 1] - inst_off[j]), ptsc, vals, j, n,
+                                bad[j], inst_bad, st);
+  if (st.q == 0) {
+    if (inst_bad) status[j] = ST_INVALID_INSTANCES;
+    else if (b != H2V_NO_BAD_ITEM) status[j] = b < hd.first_mo_item ? ST_TRANSCRIPT : ST_OPENING;
+  }
 }
 
 __global__ void __launch_bounds__(64, H2V_SCALAR_MINB) k_scalar(PlanView pv, u32 n, const u8* inst, const u64* inst_off, const u32* col_len, Fr* vals,
@@ -986,12 +1019,12 @@ struct h2v_ctx {
   } mb, ab;
   DevBuf d_plan, d_proofs, d_proof_off, d_inst, d_inst_off, d_ncols, d_col_len, d_pts, d_bad, d_status, d_vals, d_scratch, d_right,
       d_shared, d_left, d_rlc_bytes, d_r, d_acc_bytes, d_verdict, d_partials, d_pp_prod, d_pp_lr, d_pp_bytes, d_hook, d_chal, d_flush, d_M, d_partial_out,
-      d_wsums_fin, d_sub_pairs, d_sub_verdict, d_sub_M, d_gsums;
+      d_wsums_fin, d_sub_pairs, d_sub_verdict, d_sub_M, d_gsums, d_ptsc;
   const G2Line* d_lines() const { return lines_cur >= 0 ? lines[lines_cur].buf.as<G2Line>() : nullptr; }
   std::vector<DevBuf*> all_bufs() {
     std::vector<DevBuf*> v = {&d_plan, &d_proofs, &d_proof_off, &d_inst, &d_inst_off, &d_ncols, &d_col_len, &d_pts, &d_bad, &d_status, &d_vals, &d_scratch,
                               &d_right, &d_shared, &d_left, &d_rlc_bytes, &d_r, &d_acc_bytes, &d_verdict, &d_partials, &d_pp_prod, &d_pp_lr, &d_pp_bytes,
-                              &d_hook, &d_chal, &d_flush, &d_M, &d_partial_out, &d_wsums_fin, &d_sub_pairs, &d_sub_verdict, &d_sub_M, &d_gsums,
+                              &d_hook, &d_chal, &d_flush, &d_M, &d_partial_out, &d_wsums_fin, &d_sub_pairs, &d_sub_verdict, &d_sub_M, &d_gsums, &d_ptsc,
                               &lines[0].buf, &lines[1].buf, &lines[2].buf, &lines[3].buf};
     for (MsmBufs* m : {&mb, &ab})
       for (DevBuf* d : {&m->coef, &m->shared_sum, &m->dig, &m->hist, &m->off, &m->cursor, &m->order, &m->sorted, &m->buckets, &m->wsums, &m->partials_msm, &m->tiles})
@@ -1320,6 +1353,7 @@ static cudaError_t preload_kernels() {
   H2V_PRELOAD(k_decompress);
   H2V_PRELOAD(k_transcript<Blake2b>);
   H2V_PRELOAD(k_transcript<Keccak256>);
+  H2V_PRELOAD(k_transcript_quad);
   H2V_PRELOAD(k_scalar);
   H2V_PRELOAD(k_rlc_expand);
   H2V_PRELOAD(k_rlc_scan);
@@ -1738,6 +1772,7 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   CKC(ctx->d_inst.ensure(32 * iscal + 64));
   CKC(ctx->d_inst_off.ensure(8 * (size_t)(n + 1)));
   CKC(ctx->d_pts.ensure(sizeof(G1Affine) * (size_t)n * hd.n_points));
+  if (hd.hash == HASH_BLAKE2B) CKC(ctx->d_ptsc.ensure(64 * (size_t)n * hd.n_points));
   CKC(ctx->d_bad.ensure(4 * (size_t)n));
   CKC(ctx->d_status.ensure(4 * (size_t)n));
   CKC(ctx->d_vals.ensure(32 * (size_t)n * hd.n_vals));
@@ -1829,16 +1864,21 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
   // (one-warp blocks were measured for the two multiplier-bound kernels: no change, 0.300 ms / 0.364 ms alone.  A single
   // batch is 2.6 warps of decompression per SM sub-partition: the quantisation to 3 bounds the kernel at ~86 % of the pipe.)
+  static const bool quad_off = getenv("H2V_TRANSCRIPT_THREAD") != nullptr;  // diagnosis: the thread-per-proof replay for Blake2b too
+  const bool use_quad = hd.hash == HASH_BLAKE2B && !quad_off;
   {
     const u32 total = wide_grid((u64)n * hd.n_points, 0), K = std::min(wide_split(), total), per = cdiv(total, K);
     for (u32 off = 0; off < total; off += per)
       KLAUNCH(k_decompress, std::min(per, total - off), 128, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_pts.as<G1Affine>(),
-              ctx->d_bad.as<u32>(), off, total);
+              use_quad ? ctx->d_ptsc.as<u32>() : nullptr, ctx->d_bad.as<u32>(), off, total);
   }
   nvtxRangePop();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[1], s));
   nvtxRangePushA("h2v:transcript");
-  if (hd.hash == HASH_BLAKE2B)
+  if (use_quad)
+    KLAUNCH(k_transcript_quad, cdiv(n, TQ_PROOFS_PER_BLOCK), 4 * TQ_PROOFS_PER_BLOCK, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
+            ctx->d_inst_off.as<u64>(), ctx->d_ptsc.as<u32>(), ctx->d_vals.as<Fr>(), ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
+  else if (hd.hash == HASH_BLAKE2B)
     KLAUNCH((k_transcript<Blake2b>), cdiv(n, 64), 64, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
                                                      ctx->d_inst_off.as<u64>(), ctx->d_pts.as<G1Affine>(), ctx->d_vals.as<Fr>(),
                                                      ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
@@ -1918,7 +1958,7 @@ static u64 graph_key(const h2v_ctx* ctx, int mode) {
                           &ctx->d_pts, &ctx->d_bad, &ctx->d_status, &ctx->d_vals, &ctx->d_scratch, &ctx->d_right, &ctx->d_shared, &ctx->d_left,
                           &ctx->d_r, &ctx->mb.coef, &ctx->mb.shared_sum, &ctx->mb.dig, &ctx->mb.hist, &ctx->mb.off, &ctx->mb.cursor, &ctx->mb.order,
                           &ctx->mb.sorted, &ctx->mb.buckets, &ctx->mb.wsums, &ctx->d_acc_bytes, &ctx->d_verdict, &ctx->mb.partials_msm,
-                          &ctx->d_M, &ctx->d_partial_out, &ctx->mb.tiles, &ctx->d_wsums_fin};
+                          &ctx->d_M, &ctx->d_partial_out, &ctx->mb.tiles, &ctx->d_wsums_fin, &ctx->d_ptsc};
   for (const DevBuf* b : bufs) mix((u64)(size_t)b->p);
   mix((u64)(size_t)ctx->d_lines());
   mix((u64)(size_t)ctx->d_gsums.p | (u64)line_run(ctx->geom.G ? ctx->geom.G : 1) << 56);

@@ -22,10 +22,10 @@ static constexpr u32 H2V_NO_BAD_ITEM = 0xFFFFFFFFu;
 // ---------------------------------------------------------------------------------------------
 // Point slot `slot` of one proof -> affine point.  Returns false when the reference's read_point
 // would fail at this item (truncated proof, invalid encoding, identity).
-H2V_HDN inline bool decompress_stage(const PlanView& pv, const u8* proof, u32 len, u32 slot, G1Affine& out) {
+H2V_HDN inline bool decompress_stage(const PlanView& pv, const u8* proof, u32 len, u32 slot, G1Affine& out, Fq* canon = nullptr) {
   const u32 item = pv.sec<u32>(pv.h().off_pt_item)[slot];
   if ((item + 1) * 32 > len) return false;
-  return g1_decompress(proof + item * 32, out);
+  return g1_decompress(proof + item * 32, out, canon);
 }
 
 // ---------------------------------------------------------------------------------------------
