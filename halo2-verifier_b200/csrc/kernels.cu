@@ -1182,7 +1182,7 @@ static u32 lift_range(u32 c, u32 W) {
 
 // n_geom >= n: the window geometry is chosen as for a batch of n_geom proofs (sharded batches: every
 // rank must use the same windows so that partial window sums add up, see h2v_batch_set_shard_hint)
-static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom, u32 groups = 1) {
+static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom, u32 groups = 1, u32 force_c = 0) {
   MsmGeom g{};
   g.n = n;
   g.G = groups;
@@ -1199,7 +1199,10 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom, u32 groups =
   const char* f1 = getenv("H2V_MSM_WINDOW_LEFT");
   for (int ch = 0; ch < 2; ch++) {
     const char* f = ch == 0 ? f0 : f1;
-    if (f && atoi(f) >= 4 && atoi(f) <= 15) {
+    if (force_c) {  // attribution sub-batches: both channels with the same window size (one reduction chunk per window)
+      g.c[ch] = force_c;
+      g.W[ch] = (255 + g.c[ch] - 1) / g.c[ch];
+    } else if (f && atoi(f) >= 4 && atoi(f) <= 15) {
       g.c[ch] = (u32)atoi(f);
       g.W[ch] = (255 + g.c[ch] - 1) / g.c[ch];
     }
@@ -1216,6 +1219,7 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom, u32 groups =
     const int m = atoi(fm);
     if (m == 2 || m == 4 || m == 8) g.m = (u32)m;
   }
+  if (force_c) g.m = g.B[0];  // the whole window is one chunk: its weighted sum IS the window sum (enqueue_msm skips the second step)
   return g;
 }
 
@@ -1683,8 +1687,13 @@ static int enqueue_msm(h2v_ctx* ctx, const MsmGeom& g, h2v_ctx::MsmBufs& B, cuda
       KLAUNCH(k_msm_bucket_sum, std::min(per, total - off), 128, 0, s, g, nb, B.off.as<u32>(), B.order.as<u32>(), B.sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
               pv.sec<G1Affine>(hd.off_shared_pts), B.buckets.as<G1Jac>(), off, total);
   }
-  KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, B.buckets.as<G1Jac>(), B.partials_msm.as<G1Jac>());
-  KLAUNCH(k_msm_window_reduce, (g.W[0] + g.W[1]) * g.G, 128, 0, s, g, B.partials_msm.as<G1Jac>(), B.wsums.as<G1Jac>());
+  if (g.B[0] == g.m && g.B[1] == g.m) {
+    // one chunk per window (the tiny windows of the attribution sub-batches): chunk q is window q, offset 0
+    KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, B.buckets.as<G1Jac>(), B.wsums.as<G1Jac>());
+  } else {
+    KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, B.buckets.as<G1Jac>(), B.partials_msm.as<G1Jac>());
+    KLAUNCH(k_msm_window_reduce, (g.W[0] + g.W[1]) * g.G, 128, 0, s, g, B.partials_msm.as<G1Jac>(), B.wsums.as<G1Jac>());
+  }
   return 0;
 }
 
@@ -2087,7 +2096,7 @@ static int attribute_impl(h2v_ctx* ctx) {
   if (const char* e = getenv("H2V_ATTR_SUB")) msub = (u32)atoi(e);  // (tuning: 0 = no sub-batch level)
   if (msub >= 2 && g.n >= 4 * msub && g.n % msub == 0) {
     const u32 subs = g.n / msub, SG = N / msub;
-    MsmGeom sg = choose_geom(msub, hd, 0, SG);
+    MsmGeom sg = choose_geom(msub, hd, 0, SG, 4);
     CKC(ensure_msm_bufs(sg, ctx->ab, hd.n_shared));
     CKC(ctx->d_sub_verdict.ensure(4 * (size_t)SG + sizeof(G1Jac) * 2 * (size_t)SG + 64));
     u32* sv = ctx->d_sub_verdict.as<u32>();
