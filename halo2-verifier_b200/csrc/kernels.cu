@@ -124,16 +124,18 @@ __global__ void __launch_bounds__(64, H2V_TRANSCRIPT_MINB) k_transcript(PlanView
                                                    const u64* inst_off, const G1Affine* pts, Fr* vals, u32* status, const u32* bad) {
   pdl_prologue();
   TlScope tl_(2, pts);
-  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  if (status[j] != ST_OK) return;
   const PlanHeader& hd = pv.h();
-  const u64 off = proof_off[j];
-  bool inst_bad;
-  const u32 b = transcript_stage<H>(pv, proofs + off, (u32)(proof_off[j + 1] - off), inst + 32 * inst_off[j],
-                                    (u32)(inst_off[j + 1] - inst_off[j]), pts, vals, j, n, bad[j], inst_bad);
-  if (inst_bad) status[j] = ST_INVALID_INSTANCES;
-  else if (b != H2V_NO_BAD_ITEM) status[j] = b < hd.first_mo_item ? ST_TRANSCRIPT : ST_OPENING;
+  // grid-stride: the grid may be capped (narrow_grid) so that this latency-bound kernel shares the SMs with the
+  // multiplier-bound kernels of the other contexts in flight instead of displacing them
+  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    if (status[j] != ST_OK) continue;
+    const u64 off = proof_off[j];
+    bool inst_bad;
+    const u32 b = transcript_stage<H>(pv, proofs + off, (u32)(proof_off[j + 1] - off), inst + 32 * inst_off[j],
+                                      (u32)(inst_off[j + 1] - inst_off[j]), pts, vals, j, n, bad[j], inst_bad);
+    if (inst_bad) status[j] = ST_INVALID_INSTANCES;
+    else if (b != H2V_NO_BAD_ITEM) status[j] = b < hd.first_mo_item ? ST_TRANSCRIPT : ST_OPENING;
+  }
 }
 
 // Blake2b transcripts: four lanes per proof (transcript_quad.cuh)
@@ -142,19 +144,20 @@ __global__ void __launch_bounds__(4 * TQ_PROOFS_PER_BLOCK) k_transcript_quad(Pla
   pdl_prologue();
   TlScope tl_(2, ptsc);
   __shared__ __align__(16) u8 bufs[TQ_PROOFS_PER_BLOCK][128];
-  const u32 j = blockIdx.x * TQ_PROOFS_PER_BLOCK + (threadIdx.x >> 2);
-  if (j >= n) return;                // quad-uniform
-  if (status[j] != ST_OK) return;    // quad-uniform
   const PlanHeader& hd = pv.h();
-  TqState st;
-  tq_setup(st, bufs[threadIdx.x >> 2]);
-  const u64 off = proof_off[j];
-  bool inst_bad;
-  const u32 b = transcript_quad(pv, proofs + off, (u32)(proof_off[j + 1] - off), inst + 32 * inst_off[j], (u32)(inst_off[j + 1] - inst_off[j]), ptsc, vals, j, n,
-                                bad[j], inst_bad, st);
-  if (st.q == 0) {
-    if (inst_bad) status[j] = ST_INVALID_INSTANCES;
-    else if (b != H2V_NO_BAD_ITEM) status[j] = b < hd.first_mo_item ? ST_TRANSCRIPT : ST_OPENING;
+  // grid-stride over the proofs (see k_transcript); every quad is on its own: shuffles and barriers use the quad's mask
+  for (u32 j = blockIdx.x * TQ_PROOFS_PER_BLOCK + (threadIdx.x >> 2); j < n; j += gridDim.x * TQ_PROOFS_PER_BLOCK) {  // quad-uniform
+    if (status[j] != ST_OK) continue;  // quad-uniform
+    TqState st;
+    tq_setup(st, bufs[threadIdx.x >> 2]);
+    const u64 off = proof_off[j];
+    bool inst_bad;
+    const u32 b = transcript_quad(pv, proofs + off, (u32)(proof_off[j + 1] - off), inst + 32 * inst_off[j], (u32)(inst_off[j + 1] - inst_off[j]), ptsc, vals, j,
+                                  n, bad[j], inst_bad, st);
+    if (st.q == 0) {
+      if (inst_bad) status[j] = ST_INVALID_INSTANCES;
+      else if (b != H2V_NO_BAD_ITEM) status[j] = b < hd.first_mo_item ? ST_TRANSCRIPT : ST_OPENING;
+    }
   }
 }
 
@@ -162,20 +165,20 @@ __global__ void __launch_bounds__(64, H2V_SCALAR_MINB) k_scalar(PlanView pv, u32
                                                Fr* scratch, Fr* right, Fr* shared, Fr* left, u32* status) {
   pdl_prologue();
   TlScope tl_(3, right);
-  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
   const PlanHeader& hd = pv.h();
-  u32 st = status[j];
-  if (st == ST_OK) {
-    ScalarIO io{j, n, vals, scratch, right, shared, left};
-    st = scalar_stage(pv, io, inst + 32 * inst_off[j], col_len ? col_len + (size_t)j * hd.n_inst_cols : nullptr,
-                      (u32)(inst_off[j + 1] - inst_off[j]));
-    if (st != ST_OK) status[j] = st;
-  }
-  if (st != ST_OK) {  // excluded from the fold
-    for (u32 i = 0; i < hd.n_points; i++) right[(size_t)i * n + j] = Fr::zero();
-    for (u32 i = 0; i < hd.n_shared; i++) shared[(size_t)i * n + j] = Fr::zero();
-    for (u32 i = 0; i < hd.n_mo; i++) left[(size_t)i * n + j] = Fr::zero();
+  for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {  // grid-stride, see k_transcript
+    u32 st = status[j];
+    if (st == ST_OK) {
+      ScalarIO io{j, n, vals, scratch, right, shared, left};
+      st = scalar_stage(pv, io, inst + 32 * inst_off[j], col_len ? col_len + (size_t)j * hd.n_inst_cols : nullptr,
+                        (u32)(inst_off[j + 1] - inst_off[j]));
+      if (st != ST_OK) status[j] = st;
+    }
+    if (st != ST_OK) {  // excluded from the fold
+      for (u32 i = 0; i < hd.n_points; i++) right[(size_t)i * n + j] = Fr::zero();
+      for (u32 i = 0; i < hd.n_shared; i++) shared[(size_t)i * n + j] = Fr::zero();
+      for (u32 i = 0; i < hd.n_mo; i++) left[(size_t)i * n + j] = Fr::zero();
+    }
   }
 }
 
@@ -514,18 +517,18 @@ __device__ G1Jac g1_mul_small(const G1Jac& p, u32 k) {
 __global__ void __launch_bounds__(128) k_msm_chunk_reduce(MsmGeom g, u32 n_chunks, const G1Jac* buckets, G1Jac* partials) {
   pdl_prologue();
   TlScope tl_(7, buckets);
-  const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n_chunks) return;
-  const u32 b0 = q * g.m, bl = b0 % g.nb();  // bl: inside its fold group
-  const u32 ch = bl >= g.bbase[1] ? 1u : 0u;
-  const u32 i0 = (bl - g.bbase[ch]) % g.B[ch];  // index of the chunk's first bucket inside its window
-  G1Jac run = G1Jac::identity(), acc = G1Jac::identity();
-  for (u32 i = g.m; i-- > 0;) {
-    run = g1_add(run, buckets[b0 + i]);
-    acc = g1_add(acc, run);
+  for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < n_chunks; q += gridDim.x * blockDim.x) {  // grid-stride, see k_transcript
+    const u32 b0 = q * g.m, bl = b0 % g.nb();  // bl: inside its fold group
+    const u32 ch = bl >= g.bbase[1] ? 1u : 0u;
+    const u32 i0 = (bl - g.bbase[ch]) % g.B[ch];  // index of the chunk's first bucket inside its window
+    G1Jac run = G1Jac::identity(), acc = G1Jac::identity();
+    for (u32 i = g.m; i-- > 0;) {
+      run = g1_add(run, buckets[b0 + i]);
+      acc = g1_add(acc, run);
+    }
+    if (i0) acc = g1_add(acc, g1_mul_small(run, i0));
+    partials[q] = acc;
   }
-  if (i0) acc = g1_add(acc, g1_mul_small(run, i0));
-  partials[q] = acc;
 }
 
 __global__ void __launch_bounds__(128) k_msm_window_reduce(MsmGeom g, const G1Jac* partials, G1Jac* window_sums) {
@@ -1096,6 +1099,18 @@ static u32 wide_split() {
   return k;
 }
 
+// Grid of a latency-bound kernel over `units` blocks of work: H2V_NARROW_BLOCKS_PER_SM caps it (the kernels are grid-stride)
+// so that, launched ahead of the multiplier-bound kernels (H2V_PRIO), it takes a slice of every SM instead of all of it.
+static u32 narrow_grid(u64 units) {
+  static const u32 cap = [] {
+    const char* e = getenv("H2V_NARROW_BLOCKS_PER_SM");
+    const int v = e ? atoi(e) : 0;
+    return (u32)(v > 0 ? v * 148 : 0);
+  }();
+  const u32 u = (u32)std::min<u64>(units, 0x7FFFFFFFu);
+  return cap ? std::min(u, cap) : u;
+}
+
 // `len` bytes from the kernel's CSPRNG; 0 on success
 static int os_entropy(void* out, size_t len) {
   u8* p = (u8*)out;
@@ -1111,7 +1126,16 @@ static int os_entropy(void* out, size_t len) {
   return 0;
 }
 
-// kernel launch with (pdl) or without the programmatic-stream-serialization attribute
+// kernel launch with (pdl) or without the programmatic-stream-serialization attribute, and with an optional launch
+// priority (H2V_PRIO, diagnosis: 0 = none; the latency-bound kernels of a launch set ahead of the multiplier-bound ones)
+static int prio_mode() {
+  static const int v = [] {
+    const char* e = getenv("H2V_PRIO");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+static thread_local int tl_launch_prio = 0;  // 0 = no attribute; otherwise the priority value + 100
 template <class... KArgs, class... Args>
 static cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
@@ -1119,12 +1143,33 @@ static cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 bl
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  unsigned na = 0;
+  if (pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
+  if (tl_launch_prio) {
+    at[na].id = cudaLaunchAttributePriority;
+    at[na].val.priority = tl_launch_prio - 100;
+    na++;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+// priority class of the launches that follow: 'W' = multiplier-bound (wide), 'M' = mid (transcript / scalar), 'N' = narrow
+static void set_launch_class(char cls) {
+  const int m = prio_mode();
+  if (!m) return;
+  static int lo = 0, hi = 0;
+  static const bool init = [] { cudaDeviceGetStreamPriorityRange(&lo, &hi); return true; }();
+  (void)init;
+  int p = lo;  // lo = least priority (numerically largest)
+  if (cls == 'N') p = hi;
+  else if (cls == 'M') p = m == 1 ? hi : (m == 2 ? lo : (hi + lo) / 2);
+  tl_launch_prio = p + 100;
 }
 #define KLAUNCH_P(pdl, kern, grid, block, smem, st, ...)                       \
   do {                                                                         \
@@ -1682,16 +1727,18 @@ static int enqueue_msm(h2v_ctx* ctx, const MsmGeom& g, h2v_ctx::MsmBufs& B, cuda
   KLAUNCH(k_bucket_order, n_tiles, SCAN_NT, 0, s, nb, B.hist.as<u32>(), B.hist.as<u32>() + nb, B.hist.as<u32>() + nb + SIZE_BINS, B.order.as<u32>());
   KLAUNCH(k_msm_scatter, std::min<u32>(cdiv((u64)g.G * g.T * g.Wmax, 256), 148 * 16), 256, 0, s, g, B.dig.as<int16_t>(), B.cursor.as<u32>(), B.sorted.as<u32>());
   {
+    set_launch_class('W');
     const u32 total = wide_grid(nb, 0), K = std::min(wide_split(), total), per = cdiv(total, K);
     for (u32 off = 0; off < total; off += per)
       KLAUNCH(k_msm_bucket_sum, std::min(per, total - off), 128, 0, s, g, nb, B.off.as<u32>(), B.order.as<u32>(), B.sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
               pv.sec<G1Affine>(hd.off_shared_pts), B.buckets.as<G1Jac>(), off, total);
   }
+  set_launch_class('N');
   if (g.B[0] == g.m && g.B[1] == g.m) {
     // one chunk per window (the tiny windows of the attribution sub-batches): chunk q is window q, offset 0
-    KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, B.buckets.as<G1Jac>(), B.wsums.as<G1Jac>());
+    KLAUNCH(k_msm_chunk_reduce, narrow_grid(cdiv(nb / g.m, 128)), 128, 0, s, g, nb / g.m, B.buckets.as<G1Jac>(), B.wsums.as<G1Jac>());
   } else {
-    KLAUNCH(k_msm_chunk_reduce, cdiv(nb / g.m, 128), 128, 0, s, g, nb / g.m, B.buckets.as<G1Jac>(), B.partials_msm.as<G1Jac>());
+    KLAUNCH(k_msm_chunk_reduce, narrow_grid(cdiv(nb / g.m, 128)), 128, 0, s, g, nb / g.m, B.buckets.as<G1Jac>(), B.partials_msm.as<G1Jac>());
     KLAUNCH(k_msm_window_reduce, (g.W[0] + g.W[1]) * g.G, 128, 0, s, g, B.partials_msm.as<G1Jac>(), B.wsums.as<G1Jac>());
   }
   return 0;
@@ -1861,6 +1908,7 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
     ctx->err = "the folded accumulator hook is defined for a single fold group";
     return -1;
   }
+  set_launch_class('N');
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[0], s));
   // c_j = prod_{i>j} r_i depends only on the coefficients: scanned on the auxiliary stream while the proofs are parsed
   CKC(cudaEventRecord(ctx->ev_fork, s));
@@ -1876,6 +1924,7 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   static const bool quad_off = getenv("H2V_TRANSCRIPT_THREAD") != nullptr;  // diagnosis: the thread-per-proof replay for Blake2b too
   const bool use_quad = hd.hash == HASH_BLAKE2B && !quad_off;
   {
+    set_launch_class('W');
     const u32 total = wide_grid((u64)n * hd.n_points, 0), K = std::min(wide_split(), total), per = cdiv(total, K);
     for (u32 off = 0; off < total; off += per)
       KLAUNCH(k_decompress, std::min(per, total - off), 128, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_pts.as<G1Affine>(),
@@ -1884,24 +1933,26 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   nvtxRangePop();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[1], s));
   nvtxRangePushA("h2v:transcript");
+  set_launch_class('M');
   if (use_quad)
-    KLAUNCH(k_transcript_quad, cdiv(n, TQ_PROOFS_PER_BLOCK), 4 * TQ_PROOFS_PER_BLOCK, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
+    KLAUNCH(k_transcript_quad, narrow_grid(cdiv(n, TQ_PROOFS_PER_BLOCK)), 4 * TQ_PROOFS_PER_BLOCK, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
             ctx->d_inst_off.as<u64>(), ctx->d_ptsc.as<u32>(), ctx->d_vals.as<Fr>(), ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
   else if (hd.hash == HASH_BLAKE2B)
-    KLAUNCH((k_transcript<Blake2b>), cdiv(n, 64), 64, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
+    KLAUNCH((k_transcript<Blake2b>), narrow_grid(cdiv(n, 64)), 64, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
                                                      ctx->d_inst_off.as<u64>(), ctx->d_pts.as<G1Affine>(), ctx->d_vals.as<Fr>(),
                                                      ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
   else
-    KLAUNCH((k_transcript<Keccak256>), cdiv(n, 64), 64, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
+    KLAUNCH((k_transcript<Keccak256>), narrow_grid(cdiv(n, 64)), 64, 0, s, pv, n, ctx->d_proofs.as<u8>(), ctx->d_proof_off.as<u64>(), ctx->d_inst.as<u8>(),
                                                        ctx->d_inst_off.as<u64>(), ctx->d_pts.as<G1Affine>(), ctx->d_vals.as<Fr>(),
                                                        ctx->d_status.as<u32>(), ctx->d_bad.as<u32>());
   nvtxRangePop();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[2], s));
   nvtxRangePushA("h2v:scalar");
-  KLAUNCH(k_scalar, cdiv(n, 64), 64, 0, s, pv, n, ctx->d_inst.as<u8>(), ctx->d_inst_off.as<u64>(),
+  KLAUNCH(k_scalar, narrow_grid(cdiv(n, 64)), 64, 0, s, pv, n, ctx->d_inst.as<u8>(), ctx->d_inst_off.as<u64>(),
                                       ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_vals.as<Fr>(), ctx->d_scratch.as<Fr>(),
                                       ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_status.as<u32>());
   nvtxRangePop();
+  set_launch_class('N');
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[3], s));
   CKC(cudaStreamWaitEvent(s, ctx->ev_join, 0));
   {
@@ -2019,7 +2070,7 @@ static int run_impl(h2v_ctx* ctx, int mode) {
       return rc;
     }
     CKC(ce);
-    const cudaError_t ie = cudaGraphInstantiate(&gs.exec, graph, 0);
+    const cudaError_t ie = cudaGraphInstantiate(&gs.exec, graph, prio_mode() ? cudaGraphInstantiateFlagUseNodePriority : 0);
     cudaGraphDestroy(graph);
     CKC(ie);
     gs.key = key;
