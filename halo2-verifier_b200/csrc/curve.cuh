@@ -38,21 +38,24 @@ H2V_HD bool g1_on_curve(const G1Affine& p) {
   return p.y.sqr() == rhs;
 }
 
-// dbl-2009-l (a = 0): 2M + 5S
+// dbl-2009-l (a = 0): 2M + 5S.  Products through the out-of-line multiplication (Fq::mul_c / sqr_c): g1_double and g1_add serve
+// the latency-bound kernels (bucket reduction, window combination, attribution), where a few warps per SM walk the code once
+// per point: with every product inlined the pair was ~4.6 k instructions and 27 % of k_msm_chunk_reduce's warp stalls were
+// instruction fetches (ncu, profiles/r2b_narrow_summary.txt).  The multiplier-bound kernels use g1_add_mixed (inlined).
 H2V_HDN inline G1Jac g1_double(const G1Jac& p) {
   if (p.is_identity()) return p;
-  Fq A = p.X.sqr();
-  Fq B = p.Y.sqr();
-  Fq C = B.sqr();
+  Fq A = Fq::sqr_c(p.X);
+  Fq B = Fq::sqr_c(p.Y);
+  Fq C = Fq::sqr_c(B);
   Fq t = p.X + B;
-  Fq D = (t.sqr() - A - C).dbl();
+  Fq D = (Fq::sqr_c(t) - A - C).dbl();
   Fq E = A.dbl() + A;
-  Fq F = E.sqr();
+  Fq F = Fq::sqr_c(E);
   G1Jac r;
   r.X = F - D.dbl();
   Fq C8 = C.dbl().dbl().dbl();
-  r.Y = E * (D - r.X) - C8;
-  r.Z = (p.Y * p.Z).dbl();
+  r.Y = Fq::mul_c(E, D - r.X) - C8;
+  r.Z = Fq::mul_c(p.Y, p.Z).dbl();
   return r;
 }
 
@@ -90,25 +93,25 @@ H2V_HDN inline G1Jac g1_add_mixed(const G1Jac& p, const G1Affine& q, bool negate
 H2V_HDN inline G1Jac g1_add(const G1Jac& p, const G1Jac& q) {
   if (p.is_identity()) return q;
   if (q.is_identity()) return p;
-  Fq Z1Z1 = p.Z.sqr();
-  Fq Z2Z2 = q.Z.sqr();
-  Fq U1 = p.X * Z2Z2;
-  Fq U2 = q.X * Z1Z1;
-  Fq S1 = p.Y * q.Z * Z2Z2;
-  Fq S2 = q.Y * p.Z * Z1Z1;
+  Fq Z1Z1 = Fq::sqr_c(p.Z);
+  Fq Z2Z2 = Fq::sqr_c(q.Z);
+  Fq U1 = Fq::mul_c(p.X, Z2Z2);
+  Fq U2 = Fq::mul_c(q.X, Z1Z1);
+  Fq S1 = Fq::mul_c(Fq::mul_c(p.Y, q.Z), Z2Z2);
+  Fq S2 = Fq::mul_c(Fq::mul_c(q.Y, p.Z), Z1Z1);
   Fq H = U2 - U1;
   Fq rr = S2 - S1;
   if (H.is_zero()) {
     if (rr.is_zero()) return g1_double(p);
     return G1Jac::identity();
   }
-  Fq HH = H.sqr();
-  Fq HHH = HH * H;
-  Fq V = U1 * HH;
+  Fq HH = Fq::sqr_c(H);
+  Fq HHH = Fq::mul_c(HH, H);
+  Fq V = Fq::mul_c(U1, HH);
   G1Jac r;
-  r.X = rr.sqr() - HHH - V.dbl();
-  r.Y = rr * (V - r.X) - S1 * HHH;
-  r.Z = p.Z * q.Z * H;
+  r.X = Fq::sqr_c(rr) - HHH - V.dbl();
+  r.Y = Fq::mul_c(rr, V - r.X) - Fq::mul_c(S1, HHH);
+  r.Z = Fq::mul_c(Fq::mul_c(p.Z, q.Z), H);
   return r;
 }
 

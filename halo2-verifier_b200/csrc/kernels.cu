@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(4 * TQ_PROOFS_PER_BLOCK) k_transcript_quad(Pla
                                                                              const u32* ptsc, Fr* vals, u32* status, const u32* bad) {
   pdl_prologue();
   TlScope tl_(2, ptsc);
-  __shared__ __align__(16) u8 bufs[TQ_PROOFS_PER_BLOCK][128];
+  __shared__ __align__(16) u8 bufs[TQ_PROOFS_PER_BLOCK][TQ_BUF_STRIDE];
   const PlanHeader& hd = pv.h();
   // grid-stride over the proofs (see k_transcript); every quad is on its own: shuffles and barriers use the quad's mask
   for (u32 j = blockIdx.x * TQ_PROOFS_PER_BLOCK + (threadIdx.x >> 2); j < n; j += gridDim.x * TQ_PROOFS_PER_BLOCK) {  // quad-uniform
@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(4 * TQ_PROOFS_PER_BLOCK) k_transcript_quad(Pla
   }
 }
 
-__global__ void __launch_bounds__(64, H2V_SCALAR_MINB) k_scalar(PlanView pv, u32 n, const u8* inst, const u64* inst_off, const u32* col_len, Fr* vals,
+template <int MINB>
+__global__ void __launch_bounds__(64, MINB) k_scalar(PlanView pv, u32 n, const u8* inst, const u64* inst_off, const u32* col_len, Fr* vals,
                                                Fr* scratch, Fr* right, Fr* shared, Fr* left, u32* status) {
   pdl_prologue();
   TlScope tl_(3, right);
@@ -514,7 +515,7 @@ __device__ G1Jac g1_mul_small(const G1Jac& p, u32 k) {
 
 // S_w = sum_{k=1..B} k * bucket_k, in two steps.  Step A, thread per chunk of m buckets: running-sum
 // trick inside the chunk plus (offset * chunk sum).  Step B, block per window: tree reduction.
-__global__ void __launch_bounds__(128) k_msm_chunk_reduce(MsmGeom g, u32 n_chunks, const G1Jac* buckets, G1Jac* partials) {
+__global__ void __launch_bounds__(128, 4) k_msm_chunk_reduce(MsmGeom g, u32 n_chunks, const G1Jac* buckets, G1Jac* partials) {
   pdl_prologue();
   TlScope tl_(7, buckets);
   for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < n_chunks; q += gridDim.x * blockDim.x) {  // grid-stride, see k_transcript
@@ -1403,7 +1404,8 @@ static cudaError_t preload_kernels() {
   H2V_PRELOAD(k_transcript<Blake2b>);
   H2V_PRELOAD(k_transcript<Keccak256>);
   H2V_PRELOAD(k_transcript_quad);
-  H2V_PRELOAD(k_scalar);
+  H2V_PRELOAD(k_scalar<H2V_SCALAR_MINB>);
+  H2V_PRELOAD(k_scalar<12>);
   H2V_PRELOAD(k_rlc_expand);
   H2V_PRELOAD(k_rlc_scan);
   H2V_PRELOAD(k_shared_reduce);
@@ -1948,9 +1950,18 @@ static int enqueue_batch(h2v_ctx* ctx, int mode) {
   nvtxRangePop();
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[2], s));
   nvtxRangePushA("h2v:scalar");
-  KLAUNCH(k_scalar, narrow_grid(cdiv(n, 64)), 64, 0, s, pv, n, ctx->d_inst.as<u8>(), ctx->d_inst_off.as<u64>(),
-                                      ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_vals.as<Fr>(), ctx->d_scratch.as<Fr>(),
-                                      ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_status.as<u32>());
+  {
+    // register cap of the scalar stage (see H2V_SCALAR_MINB): 80 registers = 24 warps per SM for launch sets of several fold
+    // groups, uncapped for a single batch (64 blocks: the cap cannot add warps there)
+    static const int cap = [] {
+      const char* e = getenv("H2V_SCALAR_CAP");
+      return e ? atoi(e) : 1;
+    }();
+    auto kern = (cap && n > 148 * 64) ? k_scalar<12> : k_scalar<H2V_SCALAR_MINB>;
+    KLAUNCH(kern, narrow_grid(cdiv(n, 64)), 64, 0, s, pv, n, ctx->d_inst.as<u8>(), ctx->d_inst_off.as<u64>(),
+            ctx->has_col_len ? ctx->d_col_len.as<u32>() : nullptr, ctx->d_vals.as<Fr>(), ctx->d_scratch.as<Fr>(), ctx->d_right.as<Fr>(),
+            ctx->d_shared.as<Fr>(), ctx->d_left.as<Fr>(), ctx->d_status.as<u32>());
+  }
   nvtxRangePop();
   set_launch_class('N');
   if (!ctx->capturing) CKC(cudaEventRecord(ctx->ev[3], s));

@@ -17,6 +17,8 @@ namespace h2v {
 #if defined(__CUDACC__)
 
 static constexpr int TQ_PROOFS_PER_BLOCK = 32;  // 128 threads
+static constexpr int TQ_BUF_STRIDE = 144;       // bytes between the 128-byte block buffers of neighbouring proofs: the eight quads of a warp then hit
+                                                // disjoint banks (a 128-byte stride put all of them on the same banks: 88 M conflict cycles per launch set, ncu)
 __constant__ u64 c_tq_iv[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,
                                0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
 __constant__ u8 c_tq_sigma[12][16] = {
@@ -67,28 +69,41 @@ __device__ __forceinline__ void tq_g(u64& a, u64& b, u64& c, u64& d, u64 x, u64 
   b = rotr64(b ^ c, 63);
 }
 
-// one compression of the block buffer into (a, b); `last`: final block of a digest
-__device__ __forceinline__ void tq_compress(const TqState& st, u64& ha, u64& hb, u64 t, bool last) {
-  const u64* m = (const u64*)st.buf;
-  u64 a = ha, b = hb, c = c_tq_iv[st.q], d = c_tq_iv[st.q + 4];
+// one compression of the block buffer into (a, b); `last`: final block of a digest.
+// NOT inlined: the replay reaches it from five places (byte / word absorption, flush, digest) and an inlined copy is ~1.2 k
+// instructions; ncu (profiles/r2b_narrow_summary.txt) showed 96 k static instructions, 14.5 k of them hot, and 19.5 % of the
+// warp-stall samples on instruction fetch.  Arguments by value (registers), the buffer as a shared-memory address.
+__device__ __noinline__ ulonglong2 tq_compress_ni(u64 ha, u64 hb, u64 t, u32 last, u32 sbuf, u32 s0, u32 s1, u32 s2, u32 s3, u32 s4_, u32 s5) {
+  const u32 lane = threadIdx.x & 31, q = lane & 3, lane0 = lane & ~3u, qmask = 0xFu << lane0;
+  const u32 sig[6] = {s0, s1, s2, s3, s4_, s5};
+  u64 a = ha, b = hb, c = c_tq_iv[q], d = c_tq_iv[q + 4];
   // v[12] ^= t (low word), v[13] ^= 0 (high word of the counter), v[14] inverted on the last block
-  d ^= st.q == 0 ? t : 0ull;
-  if (last && st.q == 2) d = ~d;
+  d ^= q == 0 ? t : 0ull;
+  if (last && q == 2) d = ~d;
+  auto ldm = [sbuf](u32 w) {
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(sbuf + 8 * w));
+    return v;
+  };
 #pragma unroll
   for (int r = 0; r < 12; r++) {
-    const u32 s4 = (st.sig[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
-    tq_g(a, b, c, d, m[s4 & 15], m[(s4 >> 4) & 15]);
+    const u32 s4 = (sig[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
+    tq_g(a, b, c, d, ldm(s4 & 15), ldm((s4 >> 4) & 15));
     // diagonalise: lane q takes b from q + 1, c from q + 2, d from q + 3
-    b = tq_shfl(st, b, (st.q + 1) & 3);
-    c = tq_shfl(st, c, (st.q + 2) & 3);
-    d = tq_shfl(st, d, (st.q + 3) & 3);
-    tq_g(a, b, c, d, m[(s4 >> 8) & 15], m[(s4 >> 12) & 15]);
-    b = tq_shfl(st, b, (st.q + 3) & 3);
-    c = tq_shfl(st, c, (st.q + 2) & 3);
-    d = tq_shfl(st, d, (st.q + 1) & 3);
+    b = __shfl_sync(qmask, b, (int)(lane0 + ((q + 1) & 3)));
+    c = __shfl_sync(qmask, c, (int)(lane0 + ((q + 2) & 3)));
+    d = __shfl_sync(qmask, d, (int)(lane0 + ((q + 3) & 3)));
+    tq_g(a, b, c, d, ldm((s4 >> 8) & 15), ldm((s4 >> 12) & 15));
+    b = __shfl_sync(qmask, b, (int)(lane0 + ((q + 3) & 3)));
+    c = __shfl_sync(qmask, c, (int)(lane0 + ((q + 2) & 3)));
+    d = __shfl_sync(qmask, d, (int)(lane0 + ((q + 1) & 3)));
   }
-  ha ^= a ^ c;
-  hb ^= b ^ d;
+  return make_ulonglong2(ha ^ a ^ c, hb ^ b ^ d);
+}
+__device__ __forceinline__ void tq_compress(const TqState& st, u64& ha, u64& hb, u64 t, bool last) {
+  const ulonglong2 r = tq_compress_ni(ha, hb, t, last ? 1u : 0u, (u32)__cvta_generic_to_shared(st.buf), st.sig[0], st.sig[1], st.sig[2], st.sig[3], st.sig[4], st.sig[5]);
+  ha = r.x;
+  hb = r.y;
 }
 
 __device__ __forceinline__ void tq_zero_buf(const TqState& st) {
@@ -173,42 +188,11 @@ __device__ __forceinline__ u32 transcript_quad(const PlanView& pv, const u8* pro
   tq_zero_buf(st);
   u32 item = 0, pslot = 0, cidx = 0;
   inst_bad = false;
+  // ONE absorption site for every kind of item (prefix byte + one or two 32-byte words): with a site per kind the inlined
+  // buffer handling was most of the kernel's 14 k instructions and 28 % of its warp stalls were instruction fetches (ncu)
   for (u32 o = 0; o < hd.n_tops; o++) {
     const u32 kind = ops[o].kind, count = ops[o].count;
-    if (kind == T_ABS_VK) {
-      const Fr c = pv.cst(hd.c_vk_repr).to_canonical();
-      tq_byte(st, 2);
-      tq_word32(st, (u64)c.l[2 * st.q] | ((u64)c.l[2 * st.q + 1] << 32));
-    } else if (kind == T_ABS_INST) {
-      for (u32 i = 0; i < inst_total; i++) {
-        const u64 w = tq_load8(inst + 32 * (size_t)i + 8 * st.q);
-        if (tq_geq_r(st, w)) inst_bad = true;
-        tq_byte(st, 2);
-        tq_word32(st, w);
-      }
-    } else if (kind == T_POINTS) {
-      for (u32 i = 0; i < count; i++, item++, pslot++) {
-        const u64* c = (const u64*)(ptsc + 16 * ((size_t)pslot * n + j));  // canonical x | y (zeros when the point was rejected)
-        tq_byte(st, 1);
-        tq_word32(st, c[st.q]);
-        tq_word32(st, c[4 + st.q]);
-      }
-    } else if (kind == T_SCALARS) {
-      for (u32 i = 0; i < count; i++, item++) {
-        u64 w = 0;
-        if ((item + 1) * 32 <= len) {
-          w = tq_load8(proof + item * 32 + 8 * st.q);
-          if (tq_geq_r(st, w)) {
-            if (item < bad_item) bad_item = item;
-            w = 0;
-          }
-        } else if (item < bad_item) {
-          bad_item = item;
-        }
-        tq_byte(st, 2);
-        tq_word32(st, w);
-      }
-    } else {  // T_SQUEEZE
+    if (kind == T_SQUEEZE) {
       for (u32 i = 0; i < count; i++, cidx++) {
         tq_byte(st, 0);
         u64 lo, hi;
@@ -225,6 +209,40 @@ __device__ __forceinline__ u32 transcript_quad(const PlanView& pv, const u8* pro
         }
         if (st.q == (cidx & 3)) vals[(size_t)(hd.v_chal + cidx) * n + j] = Fr::from_uniform_words(d);
       }
+      continue;
+    }
+    const u32 reps = kind == T_ABS_VK ? 1u : kind == T_ABS_INST ? inst_total : count;
+    for (u32 i = 0; i < reps; i++) {
+      u64 w = 0, w2 = 0;
+      u32 prefix = 2, words = 1;
+      if (kind == T_ABS_VK) {
+        const Fr c = pv.cst(hd.c_vk_repr).to_canonical();
+        w = (u64)c.l[2 * st.q] | ((u64)c.l[2 * st.q + 1] << 32);
+      } else if (kind == T_ABS_INST) {
+        w = tq_load8(inst + 32 * (size_t)i + 8 * st.q);
+        if (tq_geq_r(st, w)) inst_bad = true;
+      } else if (kind == T_POINTS) {
+        const u64* c = (const u64*)(ptsc + 16 * ((size_t)pslot * n + j));  // canonical x | y (zeros when the point was rejected)
+        prefix = 1;
+        words = 2;
+        w = c[st.q];
+        w2 = c[4 + st.q];
+        item++;
+        pslot++;
+      } else {  // T_SCALARS
+        if ((item + 1) * 32 <= len) {
+          w = tq_load8(proof + item * 32 + 8 * st.q);
+          if (tq_geq_r(st, w)) {
+            if (item < bad_item) bad_item = item;
+            w = 0;
+          }
+        } else if (item < bad_item) {
+          bad_item = item;
+        }
+        item++;
+      }
+      tq_byte(st, (u8)prefix);
+      for (u32 k = 0; k < words; k++) tq_word32(st, k ? w2 : w);
     }
   }
   // Montgomery form of the proof scalars, spread over the lanes (values the hashing above replaced by zero stay zero)
