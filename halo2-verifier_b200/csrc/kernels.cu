@@ -37,6 +37,7 @@
 #include "pairing_cta.cuh"
 #include "exchange.cuh"
 #include "transcript_quad.cuh"
+#include "glv.cuh"
 
 using namespace h2v;
 
@@ -200,6 +201,7 @@ static constexpr u32 RLC_NT = 256;
 //     coefficients of sub-batch b % subs of fold group b / subs: the fold restarts inside every sub-batch
 __global__ void __launch_bounds__(RLC_NT) k_rlc_scan(const Fr* r, u64 count, u64 base, u32 n, Fr* coef, u32 subs, u64 group_stride, u64 offset) {
   pdl_prologue();
+  TlScope tl_(14, coef);
   __shared__ Fr sh[RLC_NT];
   r += (size_t)(blockIdx.x / subs) * group_stride + offset + (size_t)(blockIdx.x % subs) * count;
   coef += (size_t)blockIdx.x * n;
@@ -228,6 +230,7 @@ __global__ void __launch_bounds__(RLC_NT) k_rlc_scan(const Fr* r, u64 count, u64
 // shared_sum[b] = sum_j c_j * shared[b][j]  (canonical form, ready for digit extraction)
 __global__ void __launch_bounds__(256) k_shared_reduce(u32 n, u32 N, u32 Sh, const Fr* shared, const Fr* coef, Fr* shared_sum) {
   pdl_prologue();
+  TlScope tl_(15, shared_sum);
   __shared__ Fr sh[256];
   const u32 b = blockIdx.x, grp = blockIdx.y, t = threadIdx.x;
   Fr acc = Fr::zero();
@@ -255,6 +258,8 @@ struct MsmGeom {
   u32 Z[2];  // scalar lift range: k'' = k + z*r, z in [0, Z), keeps every window (also the top one) uniformly filled
   u32 Wmax;  // row stride of the digit table
   u32 m;     // buckets per reduction chunk
+  u32 glv;   // 1: every term is split into its two GLV halves (glv.cuh), rows / entries 2 t + half; windows cover 130 bits
+             // (the attribution sub-batches: half the windows -> half the doublings of their explicit window combination)
   __host__ __device__ u32 nb() const { return W[0] * B[0] + W[1] * B[1]; }
   __host__ __device__ u32 channel_of_term(u32 tl) const { return (tl >= n * P && tl < n * P + n * n_mo) ? 1u : 0u; }  // tl = term inside its group
 };
@@ -271,6 +276,32 @@ __device__ __forceinline__ const G1Affine& msm_point(const MsmGeom& g, u32 t, co
   return shared_pts[tl - nP - nL];
 }
 
+// signed c-bit digits of a little-endian magnitude kk[0..NL) (bits beyond NL limbs are zero), negated when `neg`; row of
+// the digit table + bucket histogram of the term's channel
+template <int NL>
+__device__ __forceinline__ void msm_emit_digits(const MsmGeom& g, u32 ch, u32 grp, const u32* kk, bool neg, int16_t* row, u32* hist) {
+  u32 carry = 0;
+  const u32 c = g.c[ch], mask = (1u << c) - 1, half = 1u << (c - 1);
+  for (u32 w = 0; w < g.W[ch]; w++) {
+    const u32 bit = w * c;
+    const u32 li = bit >> 5, sh = bit & 31;
+    u64 two = li < NL ? kk[li] : 0;
+    if (li + 1 < NL) two |= (u64)kk[li + 1] << 32;
+    u32 v = ((u32)(two >> sh) & mask) + carry;
+    int d;
+    if (v > half) {
+      d = (int)v - (int)(1u << c);
+      carry = 1;
+    } else {
+      d = (int)v;
+      carry = 0;
+    }
+    if (neg) d = -d;
+    row[w] = (int16_t)d;
+    if (d != 0) atomicAdd(&hist[grp * g.nb() + g.bbase[ch] + w * g.B[ch] + (u32)(d < 0 ? -d : d) - 1], 1u);
+  }
+}
+
 // signed c-bit digits of every term's scalar (already multiplied by c_j) + bucket histogram
 __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, const Fr* left, const Fr* coef, const Fr* shared_sum,
                                                     const G1Affine* shared_pts, int16_t* dig, u32* hist, const u32* parent_verdict, u32 parent_size) {
@@ -280,11 +311,12 @@ __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, 
   if (t >= g.G * g.T) return;
   const u32 grp = t / g.T, tl = t % g.T;
   const u32 nP = g.n * g.P, nL = g.n * g.n_mo;
+  const u32 rows = 1 + g.glv;  // digit rows of this term
   Fr k;
   u32 ch = 0;
   if (parent_verdict && parent_verdict[(u32)(((u64)grp * g.n) / parent_size)]) {  // sub-batch of an accepted fold group: nothing to re-check
     ch = g.channel_of_term(tl);
-    for (u32 w = 0; w < g.W[ch]; w++) dig[(size_t)t * g.Wmax + w] = 0;
+    for (u32 w = 0; w < rows * g.Wmax; w++) dig[(size_t)t * rows * g.Wmax + w] = 0;
     return;
   }
   if (tl < nP) {
@@ -299,7 +331,14 @@ __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, 
     k = (sp.x.is_zero() && sp.y.is_zero()) ? Fr::zero() : shared_sum[grp * g.Sh + tl - nP - nL];  // identity base (all-zero fixed column)
   }
   if (k.is_zero()) {  // excluded proof / unused slot / identity base: no bucket entries at all
-    for (u32 w = 0; w < g.W[ch]; w++) dig[(size_t)t * g.Wmax + w] = 0;
+    for (u32 w = 0; w < rows * g.Wmax; w++) dig[(size_t)t * rows * g.Wmax + w] = 0;
+    return;
+  }
+  if (g.glv) {  // k = k1 + k2 lambda: row 2 t of P, row 2 t + 1 of phi(P)
+    GlvHalf h1, h2;
+    glv_decompose(k.l, h1, h2);
+    msm_emit_digits<5>(g, ch, grp, h1.l, h1.neg, dig + (size_t)(2 * t) * g.Wmax, hist);
+    msm_emit_digits<5>(g, ch, grp, h2.l, h2.neg, dig + (size_t)(2 * t + 1) * g.Wmax, hist);
     return;
   }
   // k'' = k + z*r (r*P = identity: same group element), z spread over [0, Z) so that k'' is uniform in
@@ -316,25 +355,7 @@ __global__ void __launch_bounds__(128) k_msm_digits(MsmGeom g, const Fr* right, 
     }
     kk[8] = (u32)acc;
   }
-  u32 carry = 0;
-  const u32 c = g.c[ch], mask = (1u << c) - 1, half = 1u << (c - 1);
-  for (u32 w = 0; w < g.W[ch]; w++) {
-    const u32 bit = w * c;
-    const u32 li = bit >> 5, sh = bit & 31;
-    u64 two = li < 9 ? kk[li] : 0;
-    if (li + 1 < 9) two |= (u64)kk[li + 1] << 32;
-    u32 v = ((u32)(two >> sh) & mask) + carry;
-    int d;
-    if (v > half) {
-      d = (int)v - (int)(1u << c);
-      carry = 1;
-    } else {
-      d = (int)v;
-      carry = 0;
-    }
-    dig[(size_t)t * g.Wmax + w] = (int16_t)d;
-    if (d != 0) atomicAdd(&hist[grp * g.nb() + g.bbase[ch] + w * g.B[ch] + (u32)(d < 0 ? -d : d) - 1], 1u);
-  }
+  msm_emit_digits<9>(g, ch, grp, kk, false, dig + (size_t)t * g.Wmax, hist);
 }
 
 // exclusive scan of the bucket histogram in two launches: tiles of 1024 counters are scanned with coalesced
@@ -428,6 +449,7 @@ __global__ void __launch_bounds__(SCAN_NT) k_scan_apply(u32 nb, u32 n_tiles, con
 // k_msm_bucket_sum then walk chains of (nearly) equal length, and the longest chains start first.
 __global__ void __launch_bounds__(SCAN_NT) k_bucket_order(u32 nb, const u32* hist, const u32* size_hist, u32* size_cursor, u32* order) {
   pdl_prologue();
+  TlScope tl_(16, order);
   static_assert(SIZE_BINS == SCAN_TILE, "one tile of size bins");
   __shared__ u32 base[SIZE_BINS];
   __shared__ u32 cnt[SIZE_BINS];  // buckets of this tile per size bin, then the tile's first slot inside the bin
@@ -473,33 +495,73 @@ __global__ void __launch_bounds__(SCAN_NT) k_bucket_order(u32 nb, const u32* his
 __global__ void __launch_bounds__(256) k_msm_scatter(MsmGeom g, const int16_t* dig, u32* cursor, u32* sorted) {
   pdl_prologue();
   TlScope tl_(5, sorted);
-  const u64 total = (u64)g.G * g.T * g.Wmax;
+  const u64 total = ((u64)g.G * g.T << g.glv) * g.Wmax;
   for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (u64)gridDim.x * blockDim.x) {
-    const u32 t = (u32)(idx / g.Wmax), w = (u32)(idx % g.Wmax);
+    const u32 row = (u32)(idx / g.Wmax), w = (u32)(idx % g.Wmax);  // row = term, or 2 term + GLV half
+    const u32 t = row >> g.glv;
     const u32 ch = g.channel_of_term(t % g.T);
     if (w >= g.W[ch]) continue;
     const int d = dig[idx];
     if (d == 0) continue;
     const u32 b = (t / g.T) * g.nb() + g.bbase[ch] + w * g.B[ch] + (u32)(d < 0 ? -d : d) - 1;
     const u32 pos = atomicAdd(&cursor[b], 1u);
-    sorted[pos] = t | (d < 0 ? 0x80000000u : 0u);
+    sorted[pos] = row | (d < 0 ? 0x80000000u : 0u);
   }
 }
 
 // thread per bucket: sum of its (signed) points, Jacobian += affine
+__device__ __forceinline__ G1Jac shfl_down_jac(const G1Jac& p, u32 delta) {
+  G1Jac r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.X.l[i] = __shfl_down_sync(0xFFFFFFFFu, p.X.l[i], delta);
+    r.Y.l[i] = __shfl_down_sync(0xFFFFFFFFu, p.Y.l[i], delta);
+    r.Z.l[i] = __shfl_down_sync(0xFFFFFFFFu, p.Z.l[i], delta);
+  }
+  return r;
+}
+
+// GLV = true (attribution sub-batches): entry 2 t + 1 stands for phi(P_t) = (beta x, y); few, long buckets (56 entries with 4-bit
+// windows), so GLV_BUCKET_LANES lanes share a bucket (entries e0 + q, e0 + q + LANES, ...) and add their partial sums with shuffles
+#ifndef GLV_BUCKET_LANES
+#define GLV_BUCKET_LANES 2
+#endif
+template <bool GLV>
 __global__ void __launch_bounds__(128) k_msm_bucket_sum(MsmGeom g, u32 nb, const u32* off, const u32* order, const u32* sorted,
                                                         const G1Affine* pts, const G1Affine* shared_pts, G1Jac* buckets, u32 blk_off, u32 blk_total) {
   pdl_prologue();
   TlScope tl_(6, pts);
-  for (u32 t = (blk_off + blockIdx.x) * blockDim.x + threadIdx.x; t < nb; t += blk_total * blockDim.x) {  // grid-stride, see k_decompress
-    const u32 b = order[t];
-    G1Jac acc = G1Jac::identity();
-    const u32 e0 = off[b], e1 = off[b + 1];
-    for (u32 e = e0; e < e1; e++) {
-      const u32 ent = sorted[e];
-      acc = g1_add_mixed(acc, msm_point(g, ent & 0x7FFFFFFFu, pts, shared_pts), (ent >> 31) != 0);
+  if constexpr (GLV) {
+    constexpr u32 LANES = GLV_BUCKET_LANES;
+    for (u32 t0 = (blk_off + blockIdx.x) * blockDim.x; t0 < LANES * nb; t0 += blk_total * blockDim.x) {  // block-uniform bound: every lane reaches the shuffles
+      const u32 t = t0 + threadIdx.x, q = t % LANES;
+      const bool live = t / LANES < nb;
+      const u32 b = live ? order[t / LANES] : 0;
+      G1Jac acc = G1Jac::identity();
+      if (live) {
+        const u32 e1 = off[b + 1];
+        for (u32 e = off[b] + q; e < e1; e += LANES) {
+          const u32 ent = sorted[e], row = ent & 0x7FFFFFFFu;
+          G1Affine pt = msm_point(g, row >> 1, pts, shared_pts);
+          if (row & 1) pt.x = Fq::mul_c(pt.x, glv_beta());
+          acc = g1_add_mixed(acc, pt, (ent >> 31) != 0);
+        }
+      }
+#pragma unroll
+      for (u32 d = LANES / 2; d >= 1; d >>= 1) acc = g1_add(acc, shfl_down_jac(acc, d));
+      if (live && q == 0) buckets[b] = acc;
     }
-    buckets[b] = acc;
+  } else {
+    for (u32 t = (blk_off + blockIdx.x) * blockDim.x + threadIdx.x; t < nb; t += blk_total * blockDim.x) {  // grid-stride, see k_decompress
+      const u32 b = order[t];
+      G1Jac acc = G1Jac::identity();
+      const u32 e0 = off[b], e1 = off[b + 1];
+      for (u32 e = e0; e < e1; e++) {
+        const u32 ent = sorted[e];
+        acc = g1_add_mixed(acc, msm_point(g, ent & 0x7FFFFFFFu, pts, shared_pts), (ent >> 31) != 0);
+      }
+      buckets[b] = acc;
+    }
   }
 }
 
@@ -727,19 +789,28 @@ __global__ void __launch_bounds__(128) k_pp_reduce(PlanView pv, u32 n, const G1J
 // (SingleStrategy semantics, strategy.rs:164-176).  With 1 % bad proofs level 2 sees ~15 % of the batch.
 static constexpr u32 ATTR_SUB = 16;
 
-// explicit window combination of a sub-batch: thread per (sub-batch, channel), acc = sum_w 2^(c w) S_w  (the batch path
-// avoids this serial chain through bilinearity; here 128 windows per sub-batch would cost far more line products)
+// explicit window combination of a sub-batch, acc = sum_w 2^(c w) S_w  (the batch path avoids this serial chain through
+// bilinearity; here one pair per window and sub-batch would cost far more line products).  FOUR lanes per (sub-batch, channel):
+// lane q combines its quarter of the windows and shifts it into place, top quarter 128 doublings + 6 additions instead of
+// 132 + 33 for the whole chain; the quarters are added with shuffles.
 __global__ void __launch_bounds__(64) k_window_combine(u32 groups, FoldArgs fa, const G1Jac* __restrict__ wsums, G1Jac* __restrict__ pairs) {
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 2 * groups) return;
-  const u32 grp = t >> 1, ch = t & 1;  // ch 0 = right, 1 = left: the pair order of the unit lines
-  const G1Jac* ws = wsums + (size_t)grp * (fa.W[0] + fa.W[1]) + fa.wbase[ch];
+  TlScope tl_(11, wsums);
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x, item = t >> 2, q = t & 3;
+  const bool live = item < 2 * groups;  // no early exit: every lane takes part in the shuffles
   G1Jac acc = G1Jac::identity();
-  for (u32 w = fa.W[ch]; w-- > 0;) {
-    for (u32 i = 0; i < fa.c[ch]; i++) g1_double_inl(acc);
-    acc = g1_add(acc, ws[w]);
+  if (live) {
+    const u32 grp = item >> 1, ch = item & 1;  // ch 0 = right, 1 = left: the pair order of the unit lines
+    const G1Jac* ws = wsums + (size_t)grp * (fa.W[0] + fa.W[1]) + fa.wbase[ch];
+    const u32 W = fa.W[ch], per = (W + 3) / 4, w0 = q * per < W ? q * per : W, w1 = w0 + per < W ? w0 + per : W;
+    for (u32 w = w1; w-- > w0;) {
+      for (u32 i = 0; i < fa.c[ch]; i++) g1_double_inl(acc);
+      acc = g1_add(acc, ws[w]);
+    }
+    for (u32 i = 0; i < w0 * fa.c[ch]; i++) g1_double_inl(acc);
   }
-  pairs[t] = acc;
+  acc = g1_add(acc, shfl_down_jac(acc, 2));
+  acc = g1_add(acc, shfl_down_jac(acc, 1));
+  if (live && q == 0) pairs[item] = acc;
 }
 
 // suspects [base, base + cap) of the compacted list are processed per pass
@@ -757,38 +828,53 @@ __global__ void __launch_bounds__(128) k_pp_suspects(u32 n, const u32* status, c
   list[atomicAdd(count, 1u)] = j;
 }
 
-// thread per (base, suspect): unscaled scalar * point, plain double-and-add -> prod[base][slot]
+// FOUR lanes per (base, suspect): unscaled scalar * point through the GLV decomposition (glv.cuh), lane q walks half of the
+// bits of one 128-bit half (129 dependent doublings instead of 254), the four summands are added with warp shuffles
+// -> prod[base][slot]
 __global__ void __launch_bounds__(128) k_pp_mul_list(PlanView pv, u32 n, const G1Affine* pts, const Fr* right, const Fr* shared, const Fr* left,
                                                      const u32* list, const u32* count, u32 base, u32 cap, G1Jac* out) {
+  TlScope tl_(12, out);
   const PlanHeader& hd = pv.h();
   const u32 nb = hd.n_points + hd.n_shared + hd.n_mo;
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 cnt = chunk_count(*count, base, cap);
-  if (t >= nb * cnt) return;
-  const u32 slot = t % cnt, b = t / cnt, j = list[base + slot];
+  const u32 item = t >> 2, q = t & 3;  // item = (base, suspect); no early exit: all lanes take part in the shuffles
+  const bool live = item < nb * cnt;
   G1Jac r = G1Jac::identity();
-  Fr k;
-  const G1Affine* p;
-  if (b < hd.n_points) {
-    k = right[(size_t)b * n + j];
-    p = &pts[(size_t)b * n + j];
-  } else if (b < hd.n_points + hd.n_shared) {
-    k = shared[(size_t)(b - hd.n_points) * n + j];
-    p = &pv.sec<G1Affine>(hd.off_shared_pts)[b - hd.n_points];
-  } else {
-    const u32 q = b - hd.n_points - hd.n_shared;
-    k = left[(size_t)q * n + j];
-    p = &pts[(size_t)(hd.n_points - hd.n_mo + q) * n + j];
+  u32 slot = 0, b = 0;
+  if (live) {
+    slot = item % cnt;
+    b = item / cnt;
+    const u32 j = list[base + slot];
+    Fr k;
+    const G1Affine* p;
+    if (b < hd.n_points) {
+      k = right[(size_t)b * n + j];
+      p = &pts[(size_t)b * n + j];
+    } else if (b < hd.n_points + hd.n_shared) {
+      k = shared[(size_t)(b - hd.n_points) * n + j];
+      p = &pv.sec<G1Affine>(hd.off_shared_pts)[b - hd.n_points];
+    } else {
+      const u32 qq = b - hd.n_points - hd.n_shared;
+      k = left[(size_t)qq * n + j];
+      p = &pts[(size_t)(hd.n_points - hd.n_mo + qq) * n + j];
+    }
+    if (!k.is_zero() && !(p->x.is_zero() && p->y.is_zero())) {
+      k = k.to_canonical();
+      GlvHalf h1, h2;
+      glv_decompose(k.l, h1, h2);
+      const bool endo = (q & 1) != 0, top = (q >> 1) != 0;
+      r = g1_mul_glv_part(*p, endo ? h2 : h1, endo, top ? 64u : 0u, top ? 65u : 64u, top ? 64u : 0u);
+    }
   }
-  if (!k.is_zero() && !(p->x.is_zero() && p->y.is_zero())) {
-    k = k.to_canonical();
-    r = g1_mul_canonical(*p, k.l);
-  }
-  out[(size_t)b * cap + slot] = r;
+  r = g1_add(r, shfl_down_jac(r, 2));
+  r = g1_add(r, shfl_down_jac(r, 1));
+  if (live && q == 0) out[(size_t)b * cap + slot] = r;
 }
 
 // thread per (channel, suspect): sum of the per-base products -> pairs[slot][0] = R_j, pairs[slot][1] = L_j
 __global__ void __launch_bounds__(128) k_pp_reduce_list(PlanView pv, const u32* count, u32 base, u32 cap, const G1Jac* prod, G1Jac* pairs) {
+  TlScope tl_(13, prod);
   const PlanHeader& hd = pv.h();
   const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 cnt = chunk_count(*count, base, cap);
@@ -1245,15 +1331,15 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom, u32 groups =
   const char* f1 = getenv("H2V_MSM_WINDOW_LEFT");
   for (int ch = 0; ch < 2; ch++) {
     const char* f = ch == 0 ? f0 : f1;
-    if (force_c) {  // attribution sub-batches: both channels with the same window size (one reduction chunk per window)
-      g.c[ch] = force_c;
-      g.W[ch] = (255 + g.c[ch] - 1) / g.c[ch];
+    if (force_c) {  // attribution sub-batches: both channels with the same window size (one reduction chunk per window),
+      g.c[ch] = force_c;  // GLV halves of 129 bits + the carry of the signed digits
+      g.W[ch] = (130 + g.c[ch] - 1) / g.c[ch];
     } else if (f && atoi(f) >= 4 && atoi(f) <= 15) {
       g.c[ch] = (u32)atoi(f);
       g.W[ch] = (255 + g.c[ch] - 1) / g.c[ch];
     }
     g.B[ch] = 1u << (g.c[ch] - 1);
-    g.Z[ch] = lift_range(g.c[ch], g.W[ch]);
+    g.Z[ch] = force_c ? 1u : lift_range(g.c[ch], g.W[ch]);
   }
   g.wbase[0] = 0;
   g.wbase[1] = g.W[0];
@@ -1265,6 +1351,7 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom, u32 groups =
     const int m = atoi(fm);
     if (m == 2 || m == 4 || m == 8) g.m = (u32)m;
   }
+  g.glv = force_c ? 1u : 0u;
   if (force_c) g.m = g.B[0];  // the whole window is one chunk: its weighted sum IS the window sum (enqueue_msm skips the second step)
   return g;
 }
@@ -1414,7 +1501,8 @@ static cudaError_t preload_kernels() {
   H2V_PRELOAD(k_scan_apply);
   H2V_PRELOAD(k_bucket_order);
   H2V_PRELOAD(k_msm_scatter);
-  H2V_PRELOAD(k_msm_bucket_sum);
+  H2V_PRELOAD(k_msm_bucket_sum<false>);
+  H2V_PRELOAD(k_msm_bucket_sum<true>);
   H2V_PRELOAD(k_msm_chunk_reduce);
   H2V_PRELOAD(k_msm_window_reduce);
   H2V_PRELOAD(k_fold_accum);
@@ -1727,13 +1815,13 @@ static int enqueue_msm(h2v_ctx* ctx, const MsmGeom& g, h2v_ctx::MsmBufs& B, cuda
   KLAUNCH(k_scan_tiles, n_tiles, SCAN_NT, 0, s, B.hist.as<u32>(), nb, B.off.as<u32>(), B.tiles.as<u32>(), B.hist.as<u32>() + nb);
   KLAUNCH(k_scan_apply, n_tiles, SCAN_NT, 0, s, nb, n_tiles, B.tiles.as<u32>(), B.off.as<u32>(), B.cursor.as<u32>());
   KLAUNCH(k_bucket_order, n_tiles, SCAN_NT, 0, s, nb, B.hist.as<u32>(), B.hist.as<u32>() + nb, B.hist.as<u32>() + nb + SIZE_BINS, B.order.as<u32>());
-  KLAUNCH(k_msm_scatter, std::min<u32>(cdiv((u64)g.G * g.T * g.Wmax, 256), 148 * 16), 256, 0, s, g, B.dig.as<int16_t>(), B.cursor.as<u32>(), B.sorted.as<u32>());
+  KLAUNCH(k_msm_scatter, std::min<u32>(cdiv(((u64)g.G * g.T << g.glv) * g.Wmax, 256), 148 * 16), 256, 0, s, g, B.dig.as<int16_t>(), B.cursor.as<u32>(), B.sorted.as<u32>());
   {
     set_launch_class('W');
-    const u32 total = wide_grid(nb, 0), K = std::min(wide_split(), total), per = cdiv(total, K);
+    const u32 total = wide_grid(g.glv ? GLV_BUCKET_LANES * (u64)nb : nb, 0), K = std::min(wide_split(), total), per = cdiv(total, K);  // GLV: several lanes per bucket
     for (u32 off = 0; off < total; off += per)
-      KLAUNCH(k_msm_bucket_sum, std::min(per, total - off), 128, 0, s, g, nb, B.off.as<u32>(), B.order.as<u32>(), B.sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
-              pv.sec<G1Affine>(hd.off_shared_pts), B.buckets.as<G1Jac>(), off, total);
+      KLAUNCH(g.glv ? k_msm_bucket_sum<true> : k_msm_bucket_sum<false>, std::min(per, total - off), 128, 0, s, g, nb, B.off.as<u32>(), B.order.as<u32>(),
+              B.sorted.as<u32>(), ctx->d_pts.as<G1Affine>(), pv.sec<G1Affine>(hd.off_shared_pts), B.buckets.as<G1Jac>(), off, total);
   }
   set_launch_class('N');
   if (g.B[0] == g.m && g.B[1] == g.m) {
@@ -1751,13 +1839,13 @@ static cudaError_t ensure_msm_bufs(const MsmGeom& g, h2v_ctx::MsmBufs& B, u32 n_
   cudaError_t e;
   if ((e = B.coef.ensure(32 * (size_t)g.N)) != cudaSuccess) return e;
   if ((e = B.shared_sum.ensure(32 * (size_t)n_shared * g.G + 32)) != cudaSuccess) return e;
-  if ((e = B.dig.ensure(2 * (size_t)g.G * g.T * g.Wmax)) != cudaSuccess) return e;
+  if ((e = B.dig.ensure(2 * ((size_t)g.G * g.T << g.glv) * g.Wmax)) != cudaSuccess) return e;
   if ((e = B.hist.ensure(4 * (nb + 2 * SIZE_BINS))) != cudaSuccess) return e;
   if ((e = B.order.ensure(4 * nb)) != cudaSuccess) return e;
   if ((e = B.off.ensure(4 * (nb + 1))) != cudaSuccess) return e;
   if ((e = B.cursor.ensure(4 * nb)) != cudaSuccess) return e;
   if ((e = B.tiles.ensure(4 * (nb / 1024 + 2))) != cudaSuccess) return e;
-  if ((e = B.sorted.ensure(4 * (size_t)g.G * g.T * g.Wmax)) != cudaSuccess) return e;
+  if ((e = B.sorted.ensure(4 * ((size_t)g.G * g.T << g.glv) * g.Wmax)) != cudaSuccess) return e;
   if ((e = B.buckets.ensure(sizeof(G1Jac) * nb)) != cudaSuccess) return e;
   if ((e = B.wsums.ensure(sizeof(G1Jac) * (size_t)(g.W[0] + g.W[1]) * g.G)) != cudaSuccess) return e;
   return B.partials_msm.ensure(sizeof(G1Jac) * (nb / g.m));
@@ -2156,9 +2244,16 @@ static int attribute_impl(h2v_ctx* ctx) {
   // ---- level 1: sub-batches of ATTR_SUB proofs through the bucket MSM, one 2-pair check each
   u32 msub = ATTR_SUB;
   if (const char* e = getenv("H2V_ATTR_SUB")) msub = (u32)atoi(e);  // (tuning: 0 = no sub-batch level)
-  if (msub >= 2 && g.n >= 4 * msub && g.n % msub == 0) {
+  // (level 1 needs twice the term ids of the batch pass - two GLV halves per term - inside the 31-bit id space)
+  if (msub >= 2 && g.n >= 4 * msub && g.n % msub == 0 &&
+      2 * ((u64)N * (hd.n_points + hd.n_mo) + (u64)hd.n_shared * (N / msub)) < (1ull << 31)) {
     const u32 subs = g.n / msub, SG = N / msub;
-    MsmGeom sg = choose_geom(msub, hd, 0, SG, 4);
+    // window bits of the re-fold: dependent chain = bucket chain (2 * 14 * msub / 2^(c-1) entries) + in-window reduction
+    // (2^c additions) + window combination (130 doublings + 130 / c additions); measured (B200, sub-batches of 16): MSM + combination
+    // 1.35 + 0.73 ms at c = 4, 1.73 + 0.68 at c = 5, 2.71 + 0.64 at c = 6
+    u32 attr_c = 4;
+    if (const char* e = getenv("H2V_ATTR_WINDOW")) attr_c = (u32)std::min(8, std::max(3, atoi(e)));
+    MsmGeom sg = choose_geom(msub, hd, 0, SG, attr_c);
     CKC(ensure_msm_bufs(sg, ctx->ab, hd.n_shared));
     CKC(ctx->d_sub_verdict.ensure(4 * (size_t)SG + sizeof(G1Jac) * 2 * (size_t)SG + 64));
     u32* sv = ctx->d_sub_verdict.as<u32>();
@@ -2175,7 +2270,7 @@ static int attribute_impl(h2v_ctx* ctx) {
     }
     if (trace_on()) { ctx_sync(ctx); trace(ctx, "attr: sub-batch msm done"); }
     FoldArgs fa{{sg.W[0], sg.W[1]}, {sg.c[0], sg.c[1]}, {sg.wbase[0], sg.wbase[1]}};
-    KLAUNCH_P(false, k_window_combine, cdiv(2 * (u64)SG, 64), 64, 0, s, SG, fa, ctx->ab.wsums.as<G1Jac>(), sub_pairs);
+    KLAUNCH_P(false, k_window_combine, cdiv(8 * (u64)SG, 64), 64, 0, s, SG, fa, ctx->ab.wsums.as<G1Jac>(), sub_pairs);
     if (trace_on()) { ctx_sync(ctx); trace(ctx, "attr: window combine done"); }
     for (u32 base = 0; base < SG; base += CHUNK) {
       const u32 cnt = std::min(CHUNK, SG - base);
@@ -2196,7 +2291,7 @@ static int attribute_impl(h2v_ctx* ctx) {
   if (trace_on()) { char b[64]; snprintf(b, sizeof b, "attr: level 1 done, %u suspects", total); trace(ctx, b); }
   for (u32 base = 0; base < total; base += CHUNK) {
     const u32 cnt = std::min(CHUNK, total - base);
-    KLAUNCH_P(false, k_pp_mul_list, cdiv((u64)cnt * nbases, 128), 128, 0, s, pv, N, ctx->d_pts.as<G1Affine>(), ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(),
+    KLAUNCH_P(false, k_pp_mul_list, cdiv((u64)4 * cnt * nbases, 128), 128, 0, s, pv, N, ctx->d_pts.as<G1Affine>(), ctx->d_right.as<Fr>(), ctx->d_shared.as<Fr>(),
               ctx->d_left.as<Fr>(), list, count, base, CHUNK, ctx->d_pp_prod.as<G1Jac>());
     KLAUNCH_P(false, k_pp_reduce_list, cdiv(2 * (u64)cnt, 128), 128, 0, s, pv, count, base, CHUNK, ctx->d_pp_prod.as<G1Jac>(), ctx->d_pp_lr.as<G1Jac>());
     if (trace_on()) { ctx_sync(ctx); trace(ctx, "attr: suspects' accumulators done"); }

@@ -1,7 +1,8 @@
 // Per-block timeline (diagnostics and bench timing; off unless h2v_debug_timeline_start was called): thread 0 of
 // every block of an instrumented kernel appends {kernel id, block, SM, context tag, start, end} on the global
 // nanosecond timer.  Kernel ids: 1 decompress, 2 transcript, 3 scalar, 4 digits, 5 scatter, 6 bucket_sum,
-// 7 chunk_reduce, 8 window_reduce, 9 lines, 10 pairing_check.
+// 7 chunk_reduce, 8 window_reduce, 9 lines, 10 pairing_check, 11 window_combine, 12 pp_mul_list, 13 pp_reduce_list, 14 rlc_scan,
+// 15 shared_reduce, 16 bucket_order.
 #pragma once
 #include "field.cuh"
 

@@ -2,6 +2,7 @@
 #include "tower.cuh"
 #include "pairing_cta.cuh"
 #include "hash.cuh"
+#include "glv.cuh"
 #include <string.h>
 using namespace h2v;
 extern "C" {
@@ -29,6 +30,19 @@ void t_g1_mul(const u32* pxy, const u32* k, u32* out) {
   G1Affine p; Fq t; memcpy(t.l, pxy, 32); p.x = Fq::from_canonical(t); memcpy(t.l, pxy + 8, 32); p.y = Fq::from_canonical(t);
   G1Jac r = g1_mul_canonical(p, k); G1Affine a; g1_to_affine(r, a);
   Fq x = a.x.to_canonical(), y = a.y.to_canonical(); memcpy(out, x.l, 32); memcpy(out + 8, y.l, 32);
+}
+// GLV (glv.cuh): the two halves of a canonical scalar (5 limbs + sign each), and [k]P as the sum of the two half-length parts
+void t_glv_decompose(const u32* k, u32* out12) {
+  GlvHalf a, b; glv_decompose(k, a, b);
+  memcpy(out12, a.l, 20); out12[5] = a.neg; memcpy(out12 + 6, b.l, 20); out12[11] = b.neg;
+}
+void t_g1_mul_glv(const u32* pxy, const u32* k, u32* out) {
+  G1Affine p; Fq t; memcpy(t.l, pxy, 32); p.x = Fq::from_canonical(t); memcpy(t.l, pxy + 8, 32); p.y = Fq::from_canonical(t);
+  GlvHalf a, b; glv_decompose(k, a, b);
+  G1Jac r = g1_add(g1_add(g1_mul_glv_part(p, a, false, 64, 65, 64), g1_mul_glv_part(p, a, false, 0, 64, 0)),
+                   g1_add(g1_mul_glv_part(p, b, true, 64, 65, 64), g1_mul_glv_part(p, b, true, 0, 64, 0)));
+  G1Affine q; const bool ok = g1_to_affine(r, q);
+  Fq x = q.x.to_canonical(), y = q.y.to_canonical(); memcpy(out, x.l, 32); memcpy(out + 8, y.l, 32); (void)ok;
 }
 void t_g1_add(const u32* pxy, const u32* qxy, int neg, u32* out) {
   G1Affine p, q; Fq t; memcpy(t.l, pxy, 32); p.x = Fq::from_canonical(t); memcpy(t.l, pxy + 8, 32); p.y = Fq::from_canonical(t);

@@ -97,6 +97,31 @@ def test_decompression_and_group_law(prim):
         prim.t_g1_add(L16(*pt), L16(*q), 1, out); assert (I(out), I(out, 8)) == bn.g1_neg(bn.g1_mul(pt, 2))
 
 
+def test_glv_decomposition_and_split_multiplication(prim):
+    """glv.cuh: k = k1 + k2 * lambda (mod r) with both halves below 2^128, and [k]P rebuilt from the two half-length parts
+    (the attribution kernels' scalar multiplication) equals the oracle's [k]P."""
+    lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    beta = 0x59e26bcea0d48bacd4f263f1acdb5c4f5763473177fffffe
+    assert pow(lam, 3, bn.R) == 1 and lam != 1 and pow(beta, 3, bn.P) == 1 and beta != 1
+    g = bn.g1_mul_gen(1)
+    assert bn.g1_mul(g, lam) == (beta * g[0] % bn.P, g[1])  # phi(P) = (beta x, y) = [lambda] P
+    rng = random.Random(9)
+    out12 = (ctypes.c_uint32 * 12)()
+    ks = [0, 1, 2, bn.R - 1, bn.R - 2, lam, bn.R - lam, (bn.R - 1) // 2] + [rng.randrange(bn.R) for _ in range(3000)] + \
+         [rng.randrange(1 << b) for b in range(1, 254)]
+    for k in ks:
+        prim.t_glv_decompose(L(k), out12)
+        k1 = sum(out12[i] << (32 * i) for i in range(5)) * (-1 if out12[5] else 1)
+        k2 = sum(out12[6 + i] << (32 * i) for i in range(5)) * (-1 if out12[11] else 1)
+        assert (k1 + k2 * lam) % bn.R == k, hex(k)
+        assert abs(k1) < 1 << 128 and abs(k2) < 1 << 128, hex(k)
+    out = (ctypes.c_uint32 * 16)()
+    for k in [1, 2, lam, bn.R - 1, (1 << 64) - 1, 1 << 64, (1 << 128) + 5] + [rng.randrange(bn.R) for _ in range(12)]:
+        pt = bn.g1_mul_gen(rng.randrange(1, bn.R))
+        prim.t_g1_mul_glv(L16(*pt), L(k), out)
+        assert (I(out), I(out, 8)) == bn.g1_mul(pt, k), hex(k)
+
+
 def test_pairing_value_equals_oracle(prim):
     S = sim.FIXTURE_SRS_SECRET
     sg2, ng2 = bn.g2_mul(bn.G2_GEN, S), bn.g2_neg(bn.G2_GEN)

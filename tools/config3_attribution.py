@@ -35,6 +35,32 @@ def main():
     res, ms_bad = timed(bad, insts, 1)
     assert not res.verdict and [i for i, s_ in enumerate(res.status) if s_] == idx
     print("GWC, 4096 proofs, 1 %% corrupted:        %.2f ms per batch (batch check rejects -> attribution), %d flagged == injected" % (ms_bad, len(idx)))
+    if os.environ.get("H2V_TL"):  # per-kernel spans of ONE rejected batch incl. its attribution (block timeline, csrc/timeline.cuh)
+        import ctypes
+        import numpy as np
+        lib, cap = pkg._lib, 1 << 20
+        assert lib.h2v_debug_timeline_start(0, cap) == 0
+        bv.verify_batch(bad, insts)
+        buf, cnt = np.zeros(cap * 8, dtype=np.uint32), ctypes.c_uint32(0)
+        assert lib.h2v_debug_timeline_stop(0, buf.ctypes.data, cap, ctypes.byref(cnt)) == 0
+        rec = buf[: cnt.value * 8].reshape(-1, 8).astype(np.uint64)
+        kid, t0, t1 = rec[:, 0], rec[:, 4] | (rec[:, 5] << np.uint64(32)), rec[:, 6] | (rec[:, 7] << np.uint64(32))
+        names = {1: "decompress", 2: "transcript", 3: "scalar", 4: "digits", 5: "scatter", 6: "bucket_sum", 7: "chunk_reduce", 8: "window_reduce", 9: "lines",
+                 10: "pairing", 11: "window_combine", 12: "pp_mul_list", 13: "pp_reduce_list", 14: "rlc_scan", 15: "shared_reduce", 16: "bucket_order"}
+        base = int(t0.min())
+        ev = []
+        for k_ in np.unique(kid):
+            m = kid == k_
+            s0, s1 = np.sort(t0[m]), t1[m][np.argsort(t0[m])]
+            start, mx = 0, int(s1[0])
+            for i in range(1, len(s0)):
+                if int(s0[i]) > mx + 20000:
+                    ev.append((int(s0[start]) - base, int(s1[start:i].max()) - base, int(k_), i - start)); start = i
+                mx = max(mx, int(s1[i]))
+            ev.append((int(s0[start]) - base, int(s1[start:].max()) - base, int(k_), len(s0) - start))
+        for a, b, k_, nblk in sorted(ev):
+            print("  %8.3f -> %8.3f ms  (%6.3f)  %-14s blocks %d" % (a * 1e-6, b * 1e-6, (b - a) * 1e-6, names.get(k_, k_), nblk))
+        return
     if os.environ.get("H2V_TRACE"):
         return
     G = 8
