@@ -1406,7 +1406,7 @@ static int ensure_lines(h2v_ctx* ctx, const MsmGeom& g, int* slot_out) {
   CKC(ctx_sync(ctx));  // the victim's lines may still be read by queued work
   sl.key = ~0ull;
   CKC(sl.buf.ensure(tab.size()));
-  CKC(ctx->d_M.ensure(sizeof(E12) * H2V_ATE_ITERS));
+  CKC(ctx->d_M.ensure(sizeof(E12) * (H2V_ATE_ITERS + MILLER_SEGS)));
   CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128));
   CKC(ctx->d_partial_out.ensure(H2V_PARTIAL_BYTES));
   CKC(cudaMemcpyAsync(sl.buf.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -1434,7 +1434,15 @@ static int launch_pairing(h2v_ctx* ctx, const G1Jac* wsums, u32 groups) {
   }
   KLAUNCH((k_lines<LINES_GROUPS>), dim3(H2V_ATE_ITERS, groups), 64 * LINES_GROUPS, k_lines_smem<LINES_GROUPS>(), s, LinesArgs{np}, pairs, ctx->d_lines(),
                                                                                        ctx->d_M.as<E12>(), none);
-  KLAUNCH(k_pairing_check, groups, 128, 0, s, ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>(), none);
+  // (parallel Miller segments on four blocks per group when the launch is small, pairing_cta.cuh)
+  static const bool seg_off = getenv("H2V_MILLER_SEGMENTS_OFF") != nullptr;
+  if (groups * MILLER_SEGS <= 148 && !seg_off) {
+    E12* seg = ctx->d_M.as<E12>() + (size_t)groups * H2V_ATE_ITERS;  // behind the iteration products (d_M holds ATE_ITERS + MILLER_SEGS per group)
+    KLAUNCH(k_miller_segments, dim3(MILLER_SEGS, groups), 128, 0, s, ctx->d_M.as<E12>(), seg);
+    KLAUNCH(k_pairing_check<true>, groups, 128, 0, s, seg, ctx->d_verdict.as<u32>(), none);
+  } else {
+    KLAUNCH(k_pairing_check<false>, groups, 128, 0, s, ctx->d_M.as<E12>(), ctx->d_verdict.as<u32>(), none);
+  }
   return 0;
 }
 
@@ -1443,7 +1451,7 @@ static int launch_pairing(h2v_ctx* ctx, const G1Jac* wsums, u32 groups) {
 static int launch_pair_checks(h2v_ctx* ctx, const G1Jac* pairs, u32 count, const G2Line* unit_lines, E12* M, u32* verdict, PairSkip sk) {
   cudaStream_t s = ctx->stream;
   KLAUNCH_P(false, (k_lines<2>), dim3(H2V_ATE_ITERS, count), 128, k_lines_smem<2>(), s, LinesArgs{2}, pairs, unit_lines, M, sk);
-  KLAUNCH_P(false, k_pairing_check, count, 128, 0, s, M, verdict, sk);
+  KLAUNCH_P(false, k_pairing_check<false>, count, 128, 0, s, M, verdict, sk);
   return 0;
 }
 
@@ -1520,7 +1528,9 @@ static cudaError_t preload_kernels() {
   H2V_PRELOAD(k_gather_scalars);
   H2V_PRELOAD(k_gather_challenges);
   H2V_PRELOAD(k_lines<LINES_GROUPS>);
-  H2V_PRELOAD(k_pairing_check);
+  H2V_PRELOAD(k_pairing_check<false>);
+  H2V_PRELOAD(k_pairing_check<true>);
+  H2V_PRELOAD(k_miller_segments);
   H2V_PRELOAD(k_pack_partial_x);
   H2V_PRELOAD(k_bcast_verdict);
   H2V_PRELOAD(k_wait_verdict);
@@ -1931,7 +1941,7 @@ static int upload_impl(h2v_ctx* ctx, u32 n, const u8* proofs, const u64* proof_o
   CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
   CKC(ctx->d_gsums.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
   CKC(ensure_msm_bufs(g, ctx->mb, hd.n_shared));
-  CKC(ctx->d_M.ensure(sizeof(E12) * H2V_ATE_ITERS * (size_t)g.G));
+  CKC(ctx->d_M.ensure(sizeof(E12) * (H2V_ATE_ITERS + MILLER_SEGS) * (size_t)g.G));
   CKC(ctx->d_verdict.ensure(4 * (size_t)g.G + 16));
   cudaStream_t s = ctx->stream;
   CKC(cudaMemcpyAsync(ctx->d_proofs.p, proofs, pbytes, cudaMemcpyHostToDevice, s));
@@ -2406,7 +2416,7 @@ static int finalize_impl(h2v_ctx* ctx, u32 n_partials, u32 groups, const u8* par
   const MsmGeom& g = ctx->geom;
   const u32 npts = g.W[0] + g.W[1];
   CKC(ctx->d_verdict.ensure(4 * (size_t)groups + 16));
-  CKC(ctx->d_M.ensure(sizeof(E12) * H2V_ATE_ITERS * (size_t)groups));
+  CKC(ctx->d_M.ensure(sizeof(E12) * (H2V_ATE_ITERS + MILLER_SEGS) * (size_t)groups));
   CKC(ctx->d_wsums_fin.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
   CKC(ctx->d_gsums.ensure(sizeof(G1Jac) * 128 * (size_t)groups));
   CKC(cudaMemsetAsync(ctx->d_verdict.p, 0, 4 * (size_t)groups + 16, s));
