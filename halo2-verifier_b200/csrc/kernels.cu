@@ -526,13 +526,14 @@ __device__ __forceinline__ G1Jac shfl_down_jac(const G1Jac& p, u32 delta) {
 #ifndef GLV_BUCKET_LANES
 #define GLV_BUCKET_LANES 2
 #endif
-template <bool GLV>
+template <bool GLV, int LANES>
 __global__ void __launch_bounds__(128) k_msm_bucket_sum(MsmGeom g, u32 nb, const u32* off, const u32* order, const u32* sorted,
                                                         const G1Affine* pts, const G1Affine* shared_pts, G1Jac* buckets, u32 blk_off, u32 blk_total) {
   pdl_prologue();
   TlScope tl_(6, pts);
-  if constexpr (GLV) {
-    constexpr u32 LANES = GLV_BUCKET_LANES;
+  if constexpr (LANES > 1) {
+    // LANES lanes per bucket (entries e0 + q, e0 + q + LANES, ...), partial sums added with shuffles: for launches whose bucket
+    // chains are the critical path (a single batch; the attribution sub-batches)
     for (u32 t0 = (blk_off + blockIdx.x) * blockDim.x; t0 < LANES * nb; t0 += blk_total * blockDim.x) {  // block-uniform bound: every lane reaches the shuffles
       const u32 t = t0 + threadIdx.x, q = t % LANES;
       const bool live = t / LANES < nb;
@@ -542,9 +543,13 @@ __global__ void __launch_bounds__(128) k_msm_bucket_sum(MsmGeom g, u32 nb, const
         const u32 e1 = off[b + 1];
         for (u32 e = off[b] + q; e < e1; e += LANES) {
           const u32 ent = sorted[e], row = ent & 0x7FFFFFFFu;
-          G1Affine pt = msm_point(g, row >> 1, pts, shared_pts);
-          if (row & 1) pt.x = Fq::mul_c(pt.x, glv_beta());
-          acc = g1_add_mixed(acc, pt, (ent >> 31) != 0);
+          if constexpr (GLV) {
+            G1Affine pt = msm_point(g, row >> 1, pts, shared_pts);
+            if (row & 1) pt.x = Fq::mul_c(pt.x, glv_beta());
+            acc = g1_add_mixed(acc, pt, (ent >> 31) != 0);
+          } else {
+            acc = g1_add_mixed(acc, msm_point(g, row, pts, shared_pts), (ent >> 31) != 0);
+          }
         }
       }
 #pragma unroll
@@ -552,6 +557,7 @@ __global__ void __launch_bounds__(128) k_msm_bucket_sum(MsmGeom g, u32 nb, const
       if (live && q == 0) buckets[b] = acc;
     }
   } else {
+    static_assert(!GLV, "the GLV variant shares its buckets between lanes");
     for (u32 t = (blk_off + blockIdx.x) * blockDim.x + threadIdx.x; t < nb; t += blk_total * blockDim.x) {  // grid-stride, see k_decompress
       const u32 b = order[t];
       G1Jac acc = G1Jac::identity();
@@ -1346,7 +1352,10 @@ static MsmGeom choose_geom(u32 n, const PlanHeader& hd, u32 n_geom, u32 groups =
   g.bbase[0] = 0;
   g.bbase[1] = g.W[0] * g.B[0];
   g.Wmax = std::max(g.W[0], g.W[1]);
-  g.m = 8;  // every B is a power of two >= 8
+  // buckets per reduction chunk (every B is a power of two >= 8): 8 for launch sets of several fold groups (least work), 4 for a
+  // single batch, where the chunk kernel is a latency chain (measured alone: chunk + window reduction 0.236 + 0.069 ms with 8,
+  // 0.153 + 0.088 with 4, 0.169 + 0.124 with 2)
+  g.m = (groups == 1 && n_geom <= 8192) ? 4 : 8;
   if (const char* fm = getenv("H2V_MSM_CHUNK")) {
     const int m = atoi(fm);
     if (m == 2 || m == 4 || m == 8) g.m = (u32)m;
@@ -1509,8 +1518,10 @@ static cudaError_t preload_kernels() {
   H2V_PRELOAD(k_scan_apply);
   H2V_PRELOAD(k_bucket_order);
   H2V_PRELOAD(k_msm_scatter);
-  H2V_PRELOAD(k_msm_bucket_sum<false>);
-  H2V_PRELOAD(k_msm_bucket_sum<true>);
+  H2V_PRELOAD((k_msm_bucket_sum<false, 1>));
+  H2V_PRELOAD((k_msm_bucket_sum<false, 2>));
+  H2V_PRELOAD((k_msm_bucket_sum<false, 4>));
+  H2V_PRELOAD((k_msm_bucket_sum<true, GLV_BUCKET_LANES>));
   H2V_PRELOAD(k_msm_chunk_reduce);
   H2V_PRELOAD(k_msm_window_reduce);
   H2V_PRELOAD(k_fold_accum);
@@ -1828,10 +1839,15 @@ static int enqueue_msm(h2v_ctx* ctx, const MsmGeom& g, h2v_ctx::MsmBufs& B, cuda
   KLAUNCH(k_msm_scatter, std::min<u32>(cdiv(((u64)g.G * g.T << g.glv) * g.Wmax, 256), 148 * 16), 256, 0, s, g, B.dig.as<int16_t>(), B.cursor.as<u32>(), B.sorted.as<u32>());
   {
     set_launch_class('W');
-    const u32 total = wide_grid(g.glv ? GLV_BUCKET_LANES * (u64)nb : nb, 0), K = std::min(wide_split(), total), per = cdiv(total, K);  // GLV: several lanes per bucket
+    // lanes per bucket: 1 for launch sets of several fold groups (throughput: no shuffle additions), 2 for a single batch and
+    // for the attribution sub-batches (their bucket chains are latency)
+    static const int lanes_env = getenv("H2V_BUCKET_LANES") ? atoi(getenv("H2V_BUCKET_LANES")) : 0;
+    const u32 lanes = g.glv ? GLV_BUCKET_LANES : (lanes_env ? (u32)lanes_env : (g.G == 1 && g.n <= 8192 ? 2u : 1u));
+    auto kern = g.glv ? k_msm_bucket_sum<true, GLV_BUCKET_LANES> : lanes == 2 ? k_msm_bucket_sum<false, 2> : lanes == 4 ? k_msm_bucket_sum<false, 4> : k_msm_bucket_sum<false, 1>;
+    const u32 total = wide_grid((u64)(lanes == 2 || lanes == 4 || g.glv ? lanes : 1u) * nb, 0), K = std::min(wide_split(), total), per = cdiv(total, K);
     for (u32 off = 0; off < total; off += per)
-      KLAUNCH(g.glv ? k_msm_bucket_sum<true> : k_msm_bucket_sum<false>, std::min(per, total - off), 128, 0, s, g, nb, B.off.as<u32>(), B.order.as<u32>(),
-              B.sorted.as<u32>(), ctx->d_pts.as<G1Affine>(), pv.sec<G1Affine>(hd.off_shared_pts), B.buckets.as<G1Jac>(), off, total);
+      KLAUNCH(kern, std::min(per, total - off), 128, 0, s, g, nb, B.off.as<u32>(), B.order.as<u32>(), B.sorted.as<u32>(), ctx->d_pts.as<G1Affine>(),
+              pv.sec<G1Affine>(hd.off_shared_pts), B.buckets.as<G1Jac>(), off, total);
   }
   set_launch_class('N');
   if (g.B[0] == g.m && g.B[1] == g.m) {
