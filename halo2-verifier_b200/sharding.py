@@ -98,6 +98,12 @@ def _gather_to_root(part: torch.Tensor, root: int, rank: int, world: int, group=
     if rank == root:
         out = torch.empty(world * part.numel(), dtype=torch.uint8, device=part.device)
         dist.gather(part, list(out.chunk(world)), dst=root, group=group)
+        # The collective is asynchronous to the host and ordered only against torch's current stream; the context's own stream
+        # (cudaStreamNonBlocking) reads `out` next (h2v_finalize*), so the host waits for the gather here.  Without this wait the
+        # finalize raced the incoming partials (2-GPU test: a rejected / accepted pair of fold groups came out wrong once the
+        # root's kernels got faster than the peer's send).
+        if out.is_cuda:
+            torch.cuda.current_stream(out.device).synchronize()
         return out
     dist.gather(part, None, dst=root, group=group)
     return None
