@@ -5,16 +5,18 @@
 // one CUDA graph, no host round trip until the verdicts:
 //   k_init            instance-shape checks                                    lib.rs:51-55
 //   k_decompress      thread per (proof, point): sqrt + curve check            transcript/mod.rs:158-166
-//   k_transcript      thread per proof: Blake2b / Keccak replay -> challenges  lib.rs:66-253
+//   k_transcript_quad four lanes per proof (Blake2b; k_transcript: thread per proof, Keccak): replay -> challenges   lib.rs:66-253
 //   k_scalar          thread per proof: Lagrange, h(x), multi-open scalars     lib.rs:173-347, shplonk.rs / gwc.rs
 //   k_rlc_*           r_i expansion + suffix products c_j per fold group       strategy.rs:125-136
 //   k_shared_reduce   column sums of the shared-base scalars
 //   k_msm_digits, k_scan_*, k_bucket_order, k_msm_scatter, k_msm_bucket_sum, k_msm_chunk_reduce, k_msm_window_reduce
 //                     one signed-digit Pippenger per fold group over its proofs' points   arithmetic.rs:7-108, msm.rs:81-86
-//   k_lines           per Miller iteration: product of the lines of every (channel, window) pair
-//   k_pairing_check   f = f^2 M_i, division-free final exponentiation test     msm.rs:185-203
+//   k_window_group    runs of consecutive windows combined (the pairing then sees one pair per run)
+//   k_lines           per Miller iteration: product of the lines of every (channel, run) pair
+//   k_miller_segments four blocks per group walk segments of f = f^2 M_i in parallel
+//   k_pairing_check   product of the segments, division-free final exponentiation test   msm.rs:185-203
 //   (k_pack_partial / k_sum_partials: shards of a multi-GPU batch; k_fold_accum: explicit (L, R), parity hook only)
-//   (k_pp_*           per-proof accumulators / pairings: parity hook and rejection attribution)
+//   (k_pp_*, k_window_combine: per-proof accumulators / pairings: parity hook and rejection attribution, glv.cuh)
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
 #include <errno.h>
