@@ -71,7 +71,7 @@ __device__ __forceinline__ void tq_g(u64& a, u64& b, u64& c, u64& d, u64 x, u64 
 
 // one compression of the block buffer into (a, b); `last`: final block of a digest.
 // NOT inlined: the replay reaches it from five places (byte / word absorption, flush, digest) and an inlined copy is ~1.2 k
-// instructions; ncu (profiles/r2b_narrow_summary.txt) showed 96 k static instructions, 14.5 k of them hot, and 19.5 % of the
+// instructions; the kernel was 48 k instructions, ncu (profiles/r2b_narrow_summary.txt) showed 7 k of them hot and 19.5 % of the
 // warp-stall samples on instruction fetch.  Arguments by value (registers), the buffer as a shared-memory address.
 __device__ __noinline__ ulonglong2 tq_compress_ni(u64 ha, u64 hb, u64 t, u32 last, u32 sbuf, u32 s0, u32 s1, u32 s2, u32 s3, u32 s4_, u32 s5) {
   const u32 lane = threadIdx.x & 31, q = lane & 3, lane0 = lane & ~3u, qmask = 0xFu << lane0;
@@ -189,7 +189,7 @@ __device__ __forceinline__ u32 transcript_quad(const PlanView& pv, const u8* pro
   u32 item = 0, pslot = 0, cidx = 0;
   inst_bad = false;
   // ONE absorption site for every kind of item (prefix byte + one or two 32-byte words): with a site per kind the inlined
-  // buffer handling was most of the kernel's 14 k instructions and 28 % of its warp stalls were instruction fetches (ncu)
+  // buffer handling was most of the kernel's then 7 k instructions and 28 % of its warp stalls were instruction fetches (ncu); 6.4 k now
   for (u32 o = 0; o < hd.n_tops; o++) {
     const u32 kind = ops[o].kind, count = ops[o].count;
     if (kind == T_SQUEEZE) {
